@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY. ctypes bindings for oracle/_ref/libjaero_ref.so — the reference's
+own hot-path sources compiled verbatim (oracle/Makefile). Only tests/, bench.py's cpu_baseline /
+--impl reference legs and __graft_entry__.smoke() may import this."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libjaero_ref.so")
+_lib = None
+c_dp = ctypes.POINTER(ctypes.c_double)
+STATE_FIELDS = ["mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse",
+                "ebno", "marg", "cfe_est", "n_sig_true", "n_sig_false", "center_wtptr", "st_ref_wtptr"]
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(_SO)
+        vp, d, i, l = ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_long
+        for name in ("jref_oqpsk_new", "jref_msk_new"):
+            f = getattr(L, name); f.restype = vp; f.argtypes = [d, d, d, d, i, d, i, i, i]
+        L.jref_write.argtypes = [vp, vp, l]
+        L.jref_set_dcd.argtypes = [vp, i]
+        L.jref_soft_count.restype = l; L.jref_soft_count.argtypes = [vp]
+        L.jref_soft_take.restype = l; L.jref_soft_take.argtypes = [vp, vp, l]
+        L.jref_emit_count.restype = l; L.jref_emit_count.argtypes = [vp]
+        L.jref_cfe_log_take.restype = l; L.jref_cfe_log_take.argtypes = [vp, vp, l]
+        L.jref_state.argtypes = [vp, vp]
+        L.jref_free.argtypes = [vp]
+        L.jref_rrc_design.argtypes = [d, i, d, d, vp, i]
+        L.jref_trig_tables.argtypes = [vp, vp]
+        L.jref_fir.argtypes = [vp, i, vp, vp, l]
+        L.jref_qround.argtypes = [d]
+        L.jref_fft.argtypes = [i, i, vp, vp]
+        L.jref_fftr_forward.argtypes = [i, vp, vp]
+        L.jref_fftr_inverse.argtypes = [i, vp, vp]
+        L.jref_jfastfir_rrc.argtypes = [d, i, d, d, i, vp, l]
+        L.jref_cfe_new.restype = vp; L.jref_cfe_new.argtypes = [i, d, d, d]
+        L.jref_cfe_process.restype = d; L.jref_cfe_process.argtypes = [vp, vp, vp]
+        L.jref_cfe_bigchange.argtypes = [vp]; L.jref_cfe_free.argtypes = [vp]
+        L.jref_codec_new.restype = vp; L.jref_codec_new.argtypes = [i]
+        L.jref_codec_decode_continuous.argtypes = [vp, vp, i, vp]
+        L.jref_codec_decode_soft.argtypes = [vp, vp, i, vp]
+        L.jref_codec_free.argtypes = [vp]
+        L.jref_golden_jfastfir_len.restype = l
+        L.jref_golden_jfastfir_Fs.restype = d; L.jref_golden_jfastfir_fb.restype = d
+        L.jref_golden_jfastfir.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class RefDemod:
+    """One verbatim reference demodulator. kind: 'oqpsk' | 'msk'.
+    NB OQPSK keeps function-local statics: ONE instance per process."""
+
+    def __init__(self, kind, fb, Fs=48000.0, freq_center=8000.0, lockingbw=10500.0, fft_power=14,
+                 signalthreshold=0.65, afc=False, sql=False, cpureduce=False):
+        L = lib()
+        new = L.jref_oqpsk_new if kind == "oqpsk" else L.jref_msk_new
+        self.h = new(fb, Fs, freq_center, lockingbw, fft_power, signalthreshold, int(afc), int(sql), int(cpureduce))
+        self.kind = kind
+
+    def write(self, pcm):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        lib().jref_write(self.h, _p(pcm), len(pcm))
+
+    def set_dcd(self, dcd):
+        lib().jref_set_dcd(self.h, int(dcd))
+
+    def take_soft(self):
+        n = lib().jref_soft_count(self.h)
+        out = np.zeros(n, dtype=np.int16)
+        if n:
+            lib().jref_soft_take(self.h, _p(out), n)
+        return out
+
+    def take_cfe_log(self):
+        out = np.zeros(1 << 16, dtype=np.float64)
+        n = lib().jref_cfe_log_take(self.h, _p(out), len(out))
+        return out[:n].copy()
+
+    def state(self):
+        o = np.zeros(16, dtype=np.float64)
+        n = lib().jref_state(self.h, _p(o))
+        return dict(zip(STATE_FIELDS, o[:n]))
+
+    def close(self):
+        if self.h:
+            lib().jref_free(self.h); self.h = None
+
+
+class RefCodec:
+    """JConvolutionalCodec (jconvolutionalcodec.cpp) over the restated libcorrect."""
+
+    def __init__(self, paddinglength=24):
+        self.h = lib().jref_codec_new(paddinglength)
+
+    def decode_continuous(self, soft):
+        soft = np.ascontiguousarray(soft, dtype=np.uint8)
+        out = np.zeros(len(soft), dtype=np.int32)
+        n = lib().jref_codec_decode_continuous(self.h, _p(soft), len(soft), _p(out))
+        return out[:n].copy()
+
+    def decode_soft(self, soft):
+        soft = np.ascontiguousarray(soft, dtype=np.uint8)
+        out = np.zeros(len(soft), dtype=np.int32)
+        n = lib().jref_codec_decode_soft(self.h, _p(soft), len(soft), _p(out))
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            lib().jref_codec_free(self.h); self.h = None
+
+
+def run_demod_job(args):
+    """Process-pool worker: (kind, kwargs, pcm, chunk, dcd_schedule) -> (soft, state, cfe_log).
+    dcd_schedule: list of (sample_index, dcd) applied at chunk boundaries (index must be a multiple of chunk)."""
+    kind, kw, pcm, chunk, dcd_schedule = args
+    d = RefDemod(kind, **kw)
+    sched = dict(dcd_schedule or [])
+    for a in range(0, len(pcm), chunk):
+        if a in sched:
+            d.set_dcd(sched[a])
+        d.write(pcm[a:a + chunk])
+    out = (d.take_soft(), d.state(), d.take_cfe_log())
+    d.close()
+    return out
