@@ -1,0 +1,154 @@
+"""TEST INFRASTRUCTURE ONLY. ctypes bindings for oracle/_build/libjaero_oracle.so — this repo's CPU
+restatement of the reference's hot path (oracle/restated/*.cpp, oracle/correct_restated.c).
+Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() may import this."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libjaero_oracle.so")
+_lib = None
+STATE_FIELDS = ["mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse",
+                "ebno", "marg", "cfe_est", "n_sig_true", "n_sig_false", "center_wtptr", "st_ref_wtptr"]
+
+
+def available():
+    return os.path.exists(_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(_SO)
+        vp, d, i, l = ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_long
+        L.jor_demod_new.restype = vp; L.jor_demod_new.argtypes = [i, d, d, d, d, i, d, i, i, i]
+        L.jor_write.argtypes = [vp, vp, l]; L.jor_set_dcd.argtypes = [vp, i]
+        L.jor_soft_count.restype = l; L.jor_soft_count.argtypes = [vp]
+        L.jor_soft_take.restype = l; L.jor_soft_take.argtypes = [vp, vp, l]
+        L.jor_cfe_log_take.restype = l; L.jor_cfe_log_take.argtypes = [vp, vp, l]
+        L.jor_state.argtypes = [vp, vp]; L.jor_free.argtypes = [vp]
+        L.jor_rrc_design.argtypes = [d, i, d, d, vp, i]
+        L.jor_trig_tables.argtypes = [vp, vp]; L.jor_qround.argtypes = [d]
+        L.jor_fft.argtypes = [i, i, vp, vp]
+        L.jor_cfe_new.restype = vp; L.jor_cfe_new.argtypes = [i, d, d, d]
+        L.jor_cfe_process.restype = d; L.jor_cfe_process.argtypes = [vp, vp, vp, vp]
+        L.jor_cfe_bigchange.argtypes = [vp]; L.jor_cfe_free.argtypes = [vp]
+        L.jor_deinterleave.argtypes = [vp, i, vp]
+        L.jor_viterbi_new.restype = vp; L.jor_viterbi_new.argtypes = [i]
+        L.jor_viterbi_decode_continuous.argtypes = [vp, vp, i, vp]; L.jor_viterbi_free.argtypes = [vp]
+        L.jor_conv_decode_soft.argtypes = [vp, i, vp]; L.jor_conv_encode.argtypes = [vp, i, vp]
+        L.jor_pchan_new.restype = vp; L.jor_pchan_new.argtypes = [i]
+        L.jor_pchan_process.argtypes = [vp, vp, i]; L.jor_pchan_update_dcd.argtypes = [vp]
+        L.jor_pchan_dcd.argtypes = [vp]
+        L.jor_pchan_su_count.restype = l; L.jor_pchan_su_count.argtypes = [vp]
+        L.jor_pchan_su_take.restype = l; L.jor_pchan_su_take.argtypes = [vp, vp, vp, vp, l]
+        L.jor_pchan_free.argtypes = [vp]
+        L.jor_crc16.restype = ctypes.c_uint16; L.jor_crc16.argtypes = [vp, i]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class OracleDemod:
+    def __init__(self, kind, fb, Fs=48000.0, freq_center=8000.0, lockingbw=10500.0, fft_power=14,
+                 signalthreshold=0.65, afc=False, sql=False, cpureduce=False):
+        self.kind = kind
+        self.h = lib().jor_demod_new(0 if kind == "oqpsk" else 1, fb, Fs, freq_center, lockingbw, fft_power,
+                                     signalthreshold, int(afc), int(sql), int(cpureduce))
+
+    def write(self, pcm):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        lib().jor_write(self.h, _p(pcm), len(pcm))
+
+    def set_dcd(self, dcd):
+        lib().jor_set_dcd(self.h, int(dcd))
+
+    def take_soft(self):
+        n = lib().jor_soft_count(self.h)
+        out = np.zeros(n, dtype=np.int16)
+        if n:
+            lib().jor_soft_take(self.h, _p(out), n)
+        return out
+
+    def take_cfe_log(self):
+        out = np.zeros(1 << 16, dtype=np.float64)
+        n = lib().jor_cfe_log_take(self.h, _p(out), len(out))
+        return out[:n].copy()
+
+    def state(self):
+        o = np.zeros(16, dtype=np.float64)
+        n = lib().jor_state(self.h, _p(o))
+        return dict(zip(STATE_FIELDS, o[:n]))
+
+    def close(self):
+        if self.h:
+            lib().jor_free(self.h); self.h = None
+
+
+class OracleViterbi:
+    def __init__(self, paddinglength=24):
+        self.h = lib().jor_viterbi_new(paddinglength)
+
+    def decode_continuous(self, soft):
+        soft = np.ascontiguousarray(soft, dtype=np.uint8)
+        out = np.zeros(len(soft), dtype=np.int32)
+        n = lib().jor_viterbi_decode_continuous(self.h, _p(soft), len(soft), _p(out))
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            lib().jor_viterbi_free(self.h); self.h = None
+
+
+def conv_encode(msg_bytes):
+    msg = np.ascontiguousarray(msg_bytes, dtype=np.uint8)
+    enc = np.zeros(2 * (len(msg) + 2) + 8, dtype=np.uint8)
+    nbits = lib().jor_conv_encode(_p(msg), len(msg), _p(enc))
+    return np.unpackbits(enc)[:nbits]
+
+
+def conv_decode_soft(soft):
+    soft = np.ascontiguousarray(soft, dtype=np.uint8)
+    msg = np.zeros(len(soft) // 16 + 8, dtype=np.uint8)
+    nbytes = lib().jor_conv_decode_soft(_p(soft), len(soft), _p(msg))
+    return np.unpackbits(msg[:nbytes])
+
+
+def deinterleave(block, cols):
+    block = np.ascontiguousarray(block, dtype=np.int32)
+    out = np.zeros(64 * cols, dtype=np.uint8)
+    lib().jor_deinterleave(_p(block), cols, _p(out))
+    return out
+
+
+class OraclePChannel:
+    """Restated AeroL::Decode (continuous P-channel): soft bits -> signal units + CRC flags + DCD."""
+
+    def __init__(self, fb):
+        self.h = lib().jor_pchan_new(int(fb))
+
+    def process(self, soft):
+        soft = np.ascontiguousarray(soft, dtype=np.int16)
+        lib().jor_pchan_process(self.h, _p(soft), len(soft))
+
+    def update_dcd(self):
+        lib().jor_pchan_update_dcd(self.h)
+
+    @property
+    def dcd(self):
+        return bool(lib().jor_pchan_dcd(self.h))
+
+    def take_sus(self):
+        n = lib().jor_pchan_su_count(self.h)
+        b = np.zeros((n, 12), dtype=np.uint8); ok = np.zeros(n, dtype=np.int32); fr = np.zeros(n, dtype=np.int64)
+        if n:
+            lib().jor_pchan_su_take(self.h, _p(b), _p(ok), _p(fr), n)
+        return b, ok, fr
+
+    def close(self):
+        if self.h:
+            lib().jor_pchan_free(self.h); self.h = None

@@ -1,0 +1,57 @@
+// TEST INFRASTRUCTURE ONLY (oracle): CPU restatement, never linked into the product.
+// De-interleaver + continuous K=7 r=1/2 soft Viterbi wrapper + P-channel framing of the reference.
+#ifndef JAERO_FEC_ORACLE_H
+#define JAERO_FEC_ORACLE_H
+#include <cstdint>
+#include <vector>
+extern "C" {
+#include "correct.h"
+}
+
+// AeroLInterleaver::deinterleave_ba  (JAERO/aerol.cpp:523-538 row permutation, :603-625 gather)
+void oracle_deinterleave(const int *block, int cols, uint8_t *out);
+
+// JConvolutionalCodec::Decode_Continuous  (JAERO/jconvolutionalcodec.cpp:151-201)
+struct ContinuousViterbiOracle
+{
+    correct_convolutional *conv;
+    int paddinglength;                 // AeroL passes 24 (JAERO/aerol.cpp:940)
+    std::vector<uint8_t> overlap;      // last 62 soft values of the previous block
+    ContinuousViterbiOracle(int paddinglength = 24);
+    ~ContinuousViterbiOracle();
+    // soft: n values 0..255 ; returns n/2 bits (0/1)
+    std::vector<int> decode(const uint8_t *soft, int n);
+};
+
+struct SignalUnit { uint8_t bytes[12]; int crc_ok; long frame; };
+
+// AeroL::Decode, continuous (non-burst) P-channel branch for 600 / 1200 / 10500 bps
+// (JAERO/aerol.cpp:1124-1322 UW + header, :1540-1610 block/FEC/CRC, :1990-2039 sync), minus all text output.
+struct PChannelOracle
+{
+    int ifb; bool useingOQPSK;
+    int NumberOfBits, BitsInHeader, TotalNumberOfBits, cols;
+    std::vector<int> block;
+    ContinuousViterbiOracle codec;
+    std::vector<int> dl2; int dl2_ptr;             // DelayLine (aerol.h:451-481)
+    std::vector<int> scr; int scr_pos;             // AeroLScrambler (aerol.h:397-437)
+    // preamble detectors
+    std::vector<int> preamble, buf_plain, buf_imag, buf_real;
+    bool inv_imag, inv_real;
+    int realimag, gotsync_last;
+    long cntr; int blockcnt;
+    uint16_t frameinfo, lastframeinfo; int formatid, supfrmaker, framecounter1, framecounter2;
+    std::vector<uint8_t> infofield;
+    int datacdcountdown; bool datacd;
+    long nframes;
+    // outputs
+    std::vector<SignalUnit> sus;
+    std::vector<long> dcd_events;                  // (bit index<<1)|dcd at every DataCarrierDetect emit
+    long bits_seen;
+    explicit PChannelOracle(int fb);
+    void process(const short *soft, int n);        // AeroL::processDemodulatedSoftBits -> Decode(bits,true)
+    void updateDCD();                              // AeroL::updateDCD (aerol.cpp:1109-1122), 1 s tick
+    void lostSignal();                             // AeroL::LostSignal (aerol.h:925-931)
+};
+uint16_t oracle_crc16(const uint8_t *bytes, int n);   // AeroLcrc16::calcusingbytes (aerol.h:334-362)
+#endif

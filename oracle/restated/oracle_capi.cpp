@@ -1,0 +1,104 @@
+// TEST INFRASTRUCTURE ONLY (oracle): extern "C" surface of the CPU restatement for ctypes.
+#include "demod_oracle.h"
+#include "fec_oracle.h"
+#include <cstring>
+using namespace jor;
+
+struct OrHandle { int kind; OqpskDemodOracle *oq; MskDemodOracle *msk; };
+
+extern "C" {
+void *jor_demod_new(int kind, double fb, double Fs, double freq_center, double lockingbw, int fft_power,
+                    double signalthreshold, int afc, int sql, int cpureduce)
+{
+    DemodSettings s; s.coarsefreqest_fft_power = fft_power; s.freq_center = freq_center; s.lockingbw = lockingbw;
+    s.fb = fb; s.Fs = Fs; s.signalthreshold = signalthreshold; s.afc = afc; s.sql = sql; s.cpuReduce = cpureduce;
+    OrHandle *h = new OrHandle(); h->kind = kind; h->oq = 0; h->msk = 0;
+    if (kind == 0) h->oq = new OqpskDemodOracle(s); else h->msk = new MskDemodOracle(s);
+    return h;
+}
+void jor_write(void *hv, const int16_t *pcm, long n)
+{ OrHandle *h = (OrHandle *)hv; if (h->kind == 0) h->oq->writeData(pcm, n); else h->msk->writeData(pcm, n); }
+void jor_set_dcd(void *hv, int d)
+{ OrHandle *h = (OrHandle *)hv; if (h->kind == 0) h->oq->DCDstatSlot(d != 0); else h->msk->DCDstatSlot(d != 0); }
+long jor_soft_count(void *hv)
+{ OrHandle *h = (OrHandle *)hv; return (long)(h->kind == 0 ? h->oq->soft_out.size() : h->msk->soft_out.size()); }
+long jor_soft_take(void *hv, short *out, long cap)
+{
+    OrHandle *h = (OrHandle *)hv; std::vector<short> &v = h->kind == 0 ? h->oq->soft_out : h->msk->soft_out;
+    long n = (long)v.size(); if (n > cap) n = cap;
+    memcpy(out, v.data(), n * sizeof(short)); v.erase(v.begin(), v.begin() + n); return n;
+}
+long jor_cfe_log_take(void *hv, double *out, long cap)
+{
+    OrHandle *h = (OrHandle *)hv; std::vector<double> &v = h->kind == 0 ? h->oq->cfe_log : h->msk->cfe_log;
+    long n = (long)v.size(); if (n > cap) n = cap;
+    memcpy(out, v.data(), n * sizeof(double)); v.erase(v.begin(), v.begin() + n); return n;
+}
+// same layout as jref_state (oracle/ref_driver.cpp)
+int jor_state(void *hv, double *o)
+{
+    OrHandle *h = (OrHandle *)hv;
+    if (h->kind == 0) {
+        OqpskDemodOracle *d = h->oq;
+        o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer_center.freq; o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr;
+        o[5] = d->agc.AGCVal; o[6] = d->mse; o[7] = d->ebno.EbNo; o[8] = d->marg.Val; o[9] = d->cfe.freq_offset_est;
+        o[10] = (double)d->n_sig_true; o[11] = (double)d->n_sig_false; o[12] = d->mixer_center.WTptr; o[13] = d->st_osc_ref.WTptr;
+    } else {
+        MskDemodOracle *d = h->msk;
+        o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer_center.freq; o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr;
+        o[5] = d->agc.AGCVal; o[6] = d->mse; o[7] = d->ebno.EbNo; o[8] = d->marg.Val; o[9] = d->cfe.freq_offset_est;
+        o[10] = (double)d->n_sig_true; o[11] = (double)d->n_sig_false; o[12] = d->mixer_center.WTptr; o[13] = 0;
+    }
+    return 14;
+}
+void jor_free(void *hv) { OrHandle *h = (OrHandle *)hv; delete h->oq; delete h->msk; delete h; }
+
+int jor_rrc_design(double alpha, int firsize, double Fs, double symbol_freq, double *out, int cap)
+{ std::vector<double> p = rrc_design(alpha, firsize, Fs, symbol_freq); int n = (int)p.size(); for (int i = 0; i < n && i < cap; i++) out[i] = p[i]; return n; }
+void jor_trig_tables(double *s, double *c) { for (int i = 0; i < WTSIZE; i++) { s[i] = trig().SinWT[i]; c[i] = trig().CosWT[i]; } }
+int jor_qround(double d) { return qRound(d); }
+void jor_fft(int n, int inverse, const double *in_ri, double *out_ri)
+{ std::vector<cpx> x(n); for (int i = 0; i < n; i++) x[i] = cpx(in_ri[2 * i], in_ri[2 * i + 1]); fft_pow2(x.data(), n, inverse != 0);
+  for (int i = 0; i < n; i++) { out_ri[2 * i] = x[i].real(); out_ri[2 * i + 1] = x[i].imag(); } }
+
+void *jor_cfe_new(int power, double lockingbw, double fb, double Fs) { CoarseFreqEstimate *c = new CoarseFreqEstimate(); c->setSettings(power, lockingbw, fb, Fs); return c; }
+double jor_cfe_process(void *cv, const double *ri, double *y_out, double *raw_est)
+{
+    CoarseFreqEstimate *c = (CoarseFreqEstimate *)cv; std::vector<cpx> d(c->nfft);
+    for (int i = 0; i < c->nfft; i++) d[i] = cpx(ri[2 * i], ri[2 * i + 1]);
+    double e = c->ProcessBasebandData(d);
+    if (y_out) for (int i = 0; i < c->nfft; i++) y_out[i] = c->y[i];
+    if (raw_est) *raw_est = c->freq_offset_est;
+    return e;
+}
+void jor_cfe_bigchange(void *cv) { ((CoarseFreqEstimate *)cv)->bigchange(); }
+void jor_cfe_free(void *cv) { delete (CoarseFreqEstimate *)cv; }
+
+// ---- FEC ----
+void jor_deinterleave(const int *block, int cols, uint8_t *out) { oracle_deinterleave(block, cols, out); }
+void *jor_viterbi_new(int pad) { return new ContinuousViterbiOracle(pad); }
+int jor_viterbi_decode_continuous(void *v, const uint8_t *soft, int n, int *bits)
+{ std::vector<int> r = ((ContinuousViterbiOracle *)v)->decode(soft, n); for (size_t i = 0; i < r.size(); i++) bits[i] = r[i]; return (int)r.size(); }
+void jor_viterbi_free(void *v) { delete (ContinuousViterbiOracle *)v; }
+// raw libcorrect-restated entry points for block tests
+int jor_conv_decode_soft(const uint8_t *soft, int nbits, uint8_t *msg)
+{ correct_convolutional_polynomial_t poly[2] = {109, 79}; correct_convolutional *c = correct_convolutional_create(2, 7, poly);
+  int r = (int)correct_convolutional_decode_soft(c, soft, nbits, msg); correct_convolutional_destroy(c); return r; }
+int jor_conv_encode(const uint8_t *msg, int msg_len, uint8_t *enc)
+{ correct_convolutional_polynomial_t poly[2] = {109, 79}; correct_convolutional *c = correct_convolutional_create(2, 7, poly);
+  int r = (int)correct_convolutional_encode(c, msg, msg_len, enc); correct_convolutional_destroy(c); return r; }
+
+void *jor_pchan_new(int fb) { return new PChannelOracle(fb); }
+void jor_pchan_process(void *p, const short *soft, int n) { ((PChannelOracle *)p)->process(soft, n); }
+void jor_pchan_update_dcd(void *p) { ((PChannelOracle *)p)->updateDCD(); }
+int jor_pchan_dcd(void *p) { return ((PChannelOracle *)p)->datacd ? 1 : 0; }
+long jor_pchan_su_count(void *p) { return (long)((PChannelOracle *)p)->sus.size(); }
+long jor_pchan_su_take(void *p, uint8_t *bytes12, int *crc_ok, long *frame, long cap)
+{
+    PChannelOracle *o = (PChannelOracle *)p; long n = (long)o->sus.size(); if (n > cap) n = cap;
+    for (long i = 0; i < n; i++) { memcpy(bytes12 + 12 * i, o->sus[i].bytes, 12); crc_ok[i] = o->sus[i].crc_ok; frame[i] = o->sus[i].frame; }
+    o->sus.erase(o->sus.begin(), o->sus.begin() + n); return n;
+}
+void jor_pchan_free(void *p) { delete (PChannelOracle *)p; }
+uint16_t jor_crc16(const uint8_t *b, int n) { return oracle_crc16(b, n); }
+}
