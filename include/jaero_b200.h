@@ -1,0 +1,147 @@
+/* jaero_b200 — C ABI of the B200-native JAERO demodulator / Viterbi hot path.
+ *
+ * Drop-in boundary. Every entry point below replaces a piece of the reference's
+ * per-instance C++/Qt interface with a *batched* call over many independent channels; a single
+ * reference object is a batch of one. Plain pointers and sizes only — no Qt, no torch, no CUDA
+ * types. All functions return 0 on success or a negative JAERO_E_* code; jaero_last_error()
+ * gives the message for the calling thread. There is NO CPU fallback: if no CUDA device is
+ * usable the create calls fail with JAERO_E_CUDA.
+ *
+ *   reference interface (file:line)                               this header
+ *   -------------------------------------------------------------  ---------------------------
+ *   OqpskDemodulator::Settings  JAERO/oqpskdemodulator.h:20-39      jaero_settings
+ *   MskDemodulator::Settings    JAERO/mskdemodulator.h:24-45        jaero_settings
+ *   ctor + setSettings + setAFC/setSQL/setCPUReduce + start()
+ *     JAERO/oqpskdemodulator.cpp:8-117,149-163,175-289,312-315      jaero_batch_create
+ *     JAERO/mskdemodulator.cpp:9-84,105-118,135-263,296-299
+ *   qint64 writeData(const char*, qint64)
+ *     JAERO/oqpskdemodulator.cpp:334-627, mskdemodulator.cpp:313-488 jaero_batch_write[_device]
+ *   signal processDemodulatedSoftBits(const QVector<short>&)
+ *     JAERO/oqpskdemodulator.h:67, mskdemodulator.h:152             jaero_batch_read_softbits
+ *   slot DCDstatSlot(bool)  oqpskdemodulator.cpp:679-684            jaero_batch_set_dcd
+ *   slot CenterFreqChangedSlot(double) oqpskdemodulator.cpp:291-310 jaero_batch_set_center_freq
+ *   signals MSESignal / EbNoMeasurmentSignal / SignalStatus / Plottables,
+ *     getCurrentFreq()  oqpskdemodulator.cpp:322-325,670-675         jaero_batch_get_status
+ *   CoarseFreqEstimate::ProcessBasebandData + FreqOffsetEstimateSlot
+ *     JAERO/coarsefreqestimate.cpp:90-137, oqpskdemodulator.cpp:629-677   (inside jaero_batch_write)
+ *   AeroLInterleaver::deinterleave_ba  JAERO/aerol.cpp:603-625       jaero_viterbi_decode_continuous(cols>0)
+ *   JConvolutionalCodec::SetCode / Decode_Continuous / Decode_soft
+ *     JAERO/jconvolutionalcodec.cpp:20-29,151-201,98-125            jaero_viterbi_*
+ *   destructor                                                      jaero_batch_destroy / jaero_viterbi_destroy
+ */
+#ifndef JAERO_B200_H
+#define JAERO_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JAERO_OK 0
+#define JAERO_E_ARG (-1)      /* bad argument */
+#define JAERO_E_CUDA (-2)     /* CUDA runtime error / no device (no CPU fallback exists) */
+#define JAERO_E_STATE (-3)    /* call not valid in this state */
+#define JAERO_E_OVERFLOW (-4) /* a soft-bit ring overflowed because the caller did not drain it */
+
+#define JAERO_KIND_OQPSK 0 /* continuous 8400/10500 bps OQPSK, JAERO/oqpskdemodulator.cpp */
+#define JAERO_KIND_MSK 1   /* continuous 600/1200 bps MSK,     JAERO/mskdemodulator.cpp */
+
+/* Same fields, defaults and units as the reference's Settings structs. */
+typedef struct jaero_settings {
+    int kind;                    /* JAERO_KIND_* */
+    int coarsefreqest_fft_power; /* 14 (OQPSK) / 13 (MSK) */
+    double freq_center;          /* Hz; used for every channel unless per-channel values are given */
+    double lockingbw;            /* Hz */
+    double fb;                   /* bits/s: 600, 1200, 8400, 10500 */
+    double Fs;                   /* Hz, 48000 */
+    double signalthreshold;      /* 0.65 (OQPSK) / 0.5 (MSK) */
+    int afc;                     /* setAFC */
+    int sql;                     /* setSQL */
+    int cpu_reduce;              /* setCPUReduce */
+    int report_ebno;             /* 1: keep the two 2 s EbNo moving averages (observable only) */
+} jaero_settings;
+
+/* Per-channel telemetry: what the reference emits as MSESignal, EbNoMeasurmentSignal,
+ * SignalStatus, Plottables(freq_est, freq_center, bw) plus the loop state used by parity tests. */
+typedef struct jaero_status {
+    double mixer2_freq;   /* Hz  (Plottables freq_est) */
+    double mixer2_wtptr;  /* NCO table pointer [0,19999) */
+    double center_freq;   /* Hz  (getCurrentFreq) */
+    double st_freq;       /* symbol-timing oscillator Hz */
+    double st_wtptr;
+    double agc;           /* AGC::AGCVal */
+    double mse;           /* MSESignal */
+    double ebno;          /* EbNoMeasurmentSignal (0 if report_ebno==0) */
+    double marg;          /* residual-bias moving average */
+    double cfe_est;       /* last coarse frequency estimate (Hz offset) */
+    double n_sig_true;    /* SignalStatus(true) count */
+    double n_sig_false;   /* SignalStatus(false) count */
+    double center_wtptr;
+    double st_ref_wtptr;
+    int64_t samples;      /* samples consumed so far */
+    int64_t softbits;     /* soft bits emitted so far */
+    int32_t dcd;
+    int32_t reserved;
+} jaero_status;
+
+typedef struct jaero_batch jaero_batch;
+typedef struct jaero_viterbi jaero_viterbi;
+
+const char *jaero_last_error(void);
+int jaero_device_count(void);
+
+/* n_channels independent demodulators of one mode on one GPU. freq_center_per_channel may be NULL. */
+int jaero_batch_create(const jaero_settings *settings, int n_channels,
+                       const double *freq_center_per_channel, int device_ordinal, jaero_batch **out);
+void jaero_batch_destroy(jaero_batch *b);
+int jaero_batch_channels(const jaero_batch *b);
+
+/* writeData for every channel: pcm[ch*channel_stride + i], i < n_samples, little-endian int16 mono,
+ * HOST memory (the call stages it to the GPU). Asynchronous with respect to the host unless
+ * followed by a read/status call; ordering between calls is preserved. */
+int jaero_batch_write(jaero_batch *b, const int16_t *pcm, size_t n_samples, size_t channel_stride);
+/* Same, pcm already resident in this GPU's memory (device pointer). */
+int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n_samples, size_t channel_stride);
+/* Block until everything queued so far has executed. */
+int jaero_batch_sync(jaero_batch *b);
+
+/* Drain the soft bits emitted since the last read (the concatenated payloads of the reference's
+ * processDemodulatedSoftBits emits: multiples of 32 (OQPSK) / 12 (MSK) values 0..255).
+ * out[ch*cap + k]; counts[ch] = number written for that channel. HOST pointers. */
+int jaero_batch_read_softbits(jaero_batch *b, int16_t *out, size_t cap_per_channel, int32_t *counts);
+/* Device-resident view of the same rings for on-GPU consumers (d_soft[ch*ring_cap + k], d_counts[ch]);
+ * valid until the next write. jaero_batch_reset_softbits() marks them consumed. */
+int jaero_batch_softbits_device(jaero_batch *b, const int16_t **d_soft, const int32_t **d_counts, size_t *ring_cap);
+int jaero_batch_reset_softbits(jaero_batch *b);
+
+int jaero_batch_set_dcd(jaero_batch *b, int channel, int dcd);            /* channel<0: all */
+int jaero_batch_set_center_freq(jaero_batch *b, int channel, double hz);  /* CenterFreqChangedSlot */
+int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out);
+int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out /* [n_channels] */);
+/* kernel launches issued by this batch so far (for bench.py's gpu_launches) */
+int64_t jaero_batch_launch_count(const jaero_batch *b);
+
+/* ---- K=7 r=1/2 soft Viterbi (polys 109,79), one independent decoder per channel ---- */
+int jaero_viterbi_create(int n_channels, int paddinglength, int device_ordinal, jaero_viterbi **out);
+void jaero_viterbi_destroy(jaero_viterbi *v);
+/* Decode_Continuous for every channel: soft[ch*n_soft + k] (0..255, 128 = erasure), n_soft even.
+ * interleaver_cols > 0: soft is the *interleaved* 64 x cols block and the de-interleave gather
+ * (AeroLInterleaver::deinterleave_ba) is fused in front; 0: soft is already in code order.
+ * bits_out[ch*(n_soft/2) + k] in {0,1}. The 62-value overlap is carried per channel. HOST pointers.
+ * n_valid[ch] (may be NULL) = number of bits Decode_Continuous returns for that channel: n_soft/2,
+ * except on a channel's first call after create/reset, where QVector::mid() truncates the result to
+ * n_soft/2 - (paddinglength/2 + 1) (jconvolutionalcodec.cpp:194) — AeroL's frame alignment relies on it. */
+int jaero_viterbi_decode_continuous(jaero_viterbi *v, const uint8_t *soft, size_t n_soft,
+                                    int interleaver_cols, uint8_t *bits_out, int32_t *n_valid);
+int jaero_viterbi_decode_continuous_device(jaero_viterbi *v, const uint8_t *d_soft, size_t n_soft,
+                                           int interleaver_cols, uint8_t *d_bits_out, int32_t *d_n_valid);
+/* Decode_soft (one-shot, no overlap / padding): n_soft/2 bits out per channel. */
+int jaero_viterbi_decode_block(jaero_viterbi *v, const uint8_t *soft, size_t n_soft, uint8_t *bits_out);
+int jaero_viterbi_reset(jaero_viterbi *v);   /* SetCode(): clears the overlap of every channel */
+int jaero_viterbi_sync(jaero_viterbi *v);
+int64_t jaero_viterbi_launch_count(const jaero_viterbi *v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

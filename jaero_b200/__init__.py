@@ -1,0 +1,208 @@
+"""jaero_b200 — B200-native (sm_100a) batched implementation of JAERO's demodulator + Viterbi hot path.
+
+This module is a thin ctypes loader over the C ABI in include/jaero_b200.h (libjaero_b200.so, built
+in-tree by jaero_b200/build.py). There is no CPU fallback: constructing a batch without the CUDA
+library or without a GPU raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjaero_b200.so")
+KIND_OQPSK, KIND_MSK = 0, 1
+_lib = None
+
+
+class JaeroError(RuntimeError):
+    pass
+
+
+class Settings(ctypes.Structure):
+    """Mirror of jaero_settings == the reference's Settings structs (oqpskdemodulator.h:20-39, mskdemodulator.h:24-45)."""
+    _fields_ = [("kind", ctypes.c_int), ("coarsefreqest_fft_power", ctypes.c_int), ("freq_center", ctypes.c_double),
+                ("lockingbw", ctypes.c_double), ("fb", ctypes.c_double), ("Fs", ctypes.c_double),
+                ("signalthreshold", ctypes.c_double), ("afc", ctypes.c_int), ("sql", ctypes.c_int),
+                ("cpu_reduce", ctypes.c_int), ("report_ebno", ctypes.c_int)]
+
+
+class Status(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ("mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse", "ebno", "marg",
+                 "cfe_est", "n_sig_true", "n_sig_false", "center_wtptr", "st_ref_wtptr")] + \
+               [("samples", ctypes.c_int64), ("softbits", ctypes.c_int64), ("dcd", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaero_batch_destroy", "jaero_batch_channels",
+           "jaero_batch_write", "jaero_batch_write_device", "jaero_batch_sync", "jaero_batch_read_softbits",
+           "jaero_batch_softbits_device", "jaero_batch_reset_softbits", "jaero_batch_set_dcd",
+           "jaero_batch_set_center_freq", "jaero_batch_get_status", "jaero_batch_get_status_all",
+           "jaero_batch_launch_count", "jaero_viterbi_create", "jaero_viterbi_destroy",
+           "jaero_viterbi_decode_continuous", "jaero_viterbi_decode_continuous_device", "jaero_viterbi_decode_block",
+           "jaero_viterbi_reset", "jaero_viterbi_sync", "jaero_viterbi_launch_count"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JaeroError("libjaero_b200.so is not built (run `python -m jaero_b200.build`); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i, d, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+        L.jaero_last_error.restype = ctypes.c_char_p
+        L.jaero_batch_create.argtypes = [ctypes.POINTER(Settings), i, vp, i, ctypes.POINTER(vp)]
+        L.jaero_batch_destroy.argtypes = [vp]; L.jaero_batch_destroy.restype = None
+        L.jaero_batch_channels.argtypes = [vp]
+        L.jaero_batch_write.argtypes = [vp, vp, sz, sz]
+        L.jaero_batch_write_device.argtypes = [vp, vp, sz, sz]
+        L.jaero_batch_sync.argtypes = [vp]
+        L.jaero_batch_read_softbits.argtypes = [vp, vp, sz, vp]
+        L.jaero_batch_softbits_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(sz)]
+        L.jaero_batch_reset_softbits.argtypes = [vp]
+        L.jaero_batch_set_dcd.argtypes = [vp, i, i]
+        L.jaero_batch_set_center_freq.argtypes = [vp, i, d]
+        L.jaero_batch_get_status.argtypes = [vp, i, ctypes.POINTER(Status)]
+        L.jaero_batch_get_status_all.argtypes = [vp, vp]
+        L.jaero_batch_launch_count.argtypes = [vp]; L.jaero_batch_launch_count.restype = ctypes.c_int64
+        L.jaero_viterbi_create.argtypes = [i, i, i, ctypes.POINTER(vp)]
+        L.jaero_viterbi_destroy.argtypes = [vp]; L.jaero_viterbi_destroy.restype = None
+        L.jaero_viterbi_decode_continuous.argtypes = [vp, vp, sz, i, vp, vp]
+        L.jaero_viterbi_decode_continuous_device.argtypes = [vp, vp, sz, i, vp, vp]
+        L.jaero_viterbi_decode_block.argtypes = [vp, vp, sz, vp]
+        L.jaero_viterbi_reset.argtypes = [vp]; L.jaero_viterbi_sync.argtypes = [vp]
+        L.jaero_viterbi_launch_count.argtypes = [vp]; L.jaero_viterbi_launch_count.restype = ctypes.c_int64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise JaeroError("jaero_b200 error %d: %s" % (rc, lib().jaero_last_error().decode()))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class DemodBatch:
+    """n_channels independent continuous demodulators on one GPU (kind 'oqpsk' or 'msk').
+
+    write() == the reference's writeData() for every channel; read_softbits() returns what the
+    reference would have emitted through processDemodulatedSoftBits since the previous read."""
+
+    def __init__(self, kind, n_channels, fb, Fs=48000.0, freq_center=8000.0, lockingbw=10500.0, fft_power=None,
+                 signalthreshold=None, afc=False, sql=False, cpu_reduce=False, report_ebno=True, device=0):
+        k = KIND_OQPSK if kind == "oqpsk" else KIND_MSK
+        if fft_power is None:
+            fft_power = 14 if k == KIND_OQPSK else 13
+        if signalthreshold is None:
+            signalthreshold = 0.65 if k == KIND_OQPSK else 0.5
+        fc = np.ascontiguousarray(np.broadcast_to(np.asarray(freq_center, dtype=np.float64), (n_channels,)))
+        s = Settings(k, fft_power, float(fc[0]), lockingbw, fb, Fs, signalthreshold, int(afc), int(sql), int(cpu_reduce), int(report_ebno))
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        self.kind = kind
+        self.soft_cap = max(4096, int(2 * fb) + 64)
+        _check(lib().jaero_batch_create(ctypes.byref(s), n_channels, _p(fc), device, ctypes.byref(self.h)))
+
+    def write(self, pcm):
+        """pcm: int16 array [n_channels, n_samples] (host)."""
+        pcm = np.asarray(pcm)
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n
+        if not pcm.flags.c_contiguous:
+            pcm = np.ascontiguousarray(pcm)
+        _check(lib().jaero_batch_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2))
+
+    def write_device(self, dev_ptr, n_samples, stride):
+        _check(lib().jaero_batch_write_device(self.h, ctypes.c_void_p(dev_ptr), n_samples, stride))
+
+    def sync(self):
+        _check(lib().jaero_batch_sync(self.h))
+
+    def read_softbits(self):
+        out = np.zeros((self.n, self.soft_cap), dtype=np.int16)
+        counts = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_batch_read_softbits(self.h, _p(out), self.soft_cap, _p(counts)))
+        return [out[c, :counts[c]].copy() for c in range(self.n)]
+
+    def reset_softbits(self):
+        _check(lib().jaero_batch_reset_softbits(self.h))
+
+    def softbits_device(self):
+        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        _check(lib().jaero_batch_softbits_device(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def set_dcd(self, dcd, channel=-1):
+        _check(lib().jaero_batch_set_dcd(self.h, channel, int(dcd)))
+
+    def set_center_freq(self, hz, channel=-1):
+        _check(lib().jaero_batch_set_center_freq(self.h, channel, float(hz)))
+
+    def status(self):
+        arr = (Status * self.n)()
+        _check(lib().jaero_batch_get_status_all(self.h, ctypes.cast(arr, ctypes.c_void_p)))
+        return [{f[0]: getattr(arr[c], f[0]) for f in Status._fields_} for c in range(self.n)]
+
+    @property
+    def launches(self):
+        return lib().jaero_batch_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().jaero_batch_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ViterbiBatch:
+    """Batched JConvolutionalCodec (K=7, r=1/2, polys 109/79): Decode_Continuous / Decode_soft."""
+
+    def __init__(self, n_channels, paddinglength=24, device=0):
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        _check(lib().jaero_viterbi_create(n_channels, paddinglength, device, ctypes.byref(self.h)))
+
+    def decode_continuous(self, soft, interleaver_cols=0):
+        soft = np.ascontiguousarray(soft, dtype=np.uint8)
+        assert soft.ndim == 2 and soft.shape[0] == self.n
+        out = np.zeros((self.n, soft.shape[1] // 2), dtype=np.uint8)
+        valid = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_viterbi_decode_continuous(self.h, _p(soft), soft.shape[1], interleaver_cols, _p(out), _p(valid)))
+        self.last_valid = valid
+        return out
+
+    def decode_continuous_device(self, d_soft, n_soft, interleaver_cols, d_bits, d_valid=None):
+        _check(lib().jaero_viterbi_decode_continuous_device(self.h, ctypes.c_void_p(d_soft), n_soft, interleaver_cols,
+                                                            ctypes.c_void_p(d_bits), ctypes.c_void_p(d_valid)))
+
+    def decode_block(self, soft):
+        soft = np.ascontiguousarray(soft, dtype=np.uint8)
+        out = np.zeros((self.n, soft.shape[1] // 2), dtype=np.uint8)
+        _check(lib().jaero_viterbi_decode_block(self.h, _p(soft), soft.shape[1], _p(out)))
+        return out
+
+    def reset(self):
+        _check(lib().jaero_viterbi_reset(self.h))
+
+    def sync(self):
+        _check(lib().jaero_viterbi_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().jaero_viterbi_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().jaero_viterbi_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

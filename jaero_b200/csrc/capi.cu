@@ -1,0 +1,599 @@
+// extern "C" boundary of libjaero_b200.so (declared in include/jaero_b200.h).
+// Host-side object management only: device allocation, staging copies, stream ordering, kernel
+// launches. No CPU implementation of any DSP lives here — without a CUDA device every create
+// call fails loudly.
+#include "../../include/jaero_b200.h"
+#include "common.cuh"
+#include "viterbi.cuh"
+#include "demod.cuh"
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace jb {
+static thread_local std::string g_err;
+void set_error(const std::string &m) { g_err = m; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    return JAERO_E_CUDA;
+}
+} // namespace jb
+using namespace jb;
+
+struct jaero_viterbi {
+    int n_channels, pad, device;
+    cudaStream_t stream;
+    uint8_t *d_overlap; int *d_overlap_len; int *d_renorm;
+    uint8_t *d_soft, *d_bits; size_t soft_cap, bits_cap;
+    int *d_valid;
+    int64_t launches;
+};
+
+extern "C" {
+
+const char *jaero_last_error(void) { return g_err.c_str(); }
+int jaero_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------ Viterbi
+int jaero_viterbi_create(int n_channels, int paddinglength, int device, jaero_viterbi **out)
+{
+    if (!out || n_channels <= 0 || paddinglength < 0 || (paddinglength & 1)) { set_error("jaero_viterbi_create: bad argument"); return JAERO_E_ARG; }
+    int ndev = 0;
+    JB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("jaero_viterbi_create: no such CUDA device"); return JAERO_E_CUDA; }
+    JB_CUDA(cudaSetDevice(device));
+    jaero_viterbi *v = new (std::nothrow) jaero_viterbi();
+    if (!v) { set_error("out of host memory"); return JAERO_E_ARG; }
+    memset(v, 0, sizeof *v);
+    v->n_channels = n_channels; v->pad = paddinglength; v->device = device;
+    JB_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    JB_CUDA(cudaMalloc(&v->d_overlap, (size_t)n_channels * 64));
+    JB_CUDA(cudaMalloc(&v->d_overlap_len, (size_t)n_channels * sizeof(int)));
+    JB_CUDA(cudaMalloc(&v->d_renorm, (size_t)n_channels * sizeof(int)));
+    JB_CUDA(cudaMalloc(&v->d_valid, (size_t)n_channels * sizeof(int)));
+    JB_CUDA(cudaMemsetAsync(v->d_overlap, 0, (size_t)n_channels * 64, v->stream));
+    JB_CUDA(cudaMemsetAsync(v->d_overlap_len, 0, (size_t)n_channels * sizeof(int), v->stream));
+    JB_CUDA(cudaMemsetAsync(v->d_renorm, 0, (size_t)n_channels * sizeof(int), v->stream));
+    *out = v;
+    return JAERO_OK;
+}
+void jaero_viterbi_destroy(jaero_viterbi *v)
+{
+    if (!v) return;
+    cudaSetDevice(v->device);
+    cudaStreamSynchronize(v->stream);
+    cudaFree(v->d_overlap); cudaFree(v->d_overlap_len); cudaFree(v->d_renorm); cudaFree(v->d_valid); cudaFree(v->d_soft); cudaFree(v->d_bits);
+    cudaStreamDestroy(v->stream);
+    delete v;
+}
+int jaero_viterbi_reset(jaero_viterbi *v)
+{
+    if (!v) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(v->device));
+    JB_CUDA(cudaMemsetAsync(v->d_overlap_len, 0, (size_t)v->n_channels * sizeof(int), v->stream));
+    return JAERO_OK;
+}
+int jaero_viterbi_sync(jaero_viterbi *v)
+{
+    if (!v) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(v->device));
+    JB_CUDA(cudaStreamSynchronize(v->stream));
+    return JAERO_OK;
+}
+int64_t jaero_viterbi_launch_count(const jaero_viterbi *v) { return v ? v->launches : 0; }
+
+static int vit_check(jaero_viterbi *v, size_t n_soft, int cols)
+{
+    if (!v) { set_error("null handle"); return JAERO_E_ARG; }
+    if (n_soft < 32 || (n_soft & 1) || n_soft > 60000) { set_error("viterbi: n_soft must be even, 32..60000"); return JAERO_E_ARG; }
+    if (cols < 0 || (cols > 0 && (size_t)cols * 64 != n_soft)) { set_error("viterbi: interleaver_cols*64 must equal n_soft"); return JAERO_E_ARG; }
+    return JAERO_OK;
+}
+int jaero_viterbi_decode_continuous_device(jaero_viterbi *v, const uint8_t *d_soft, size_t n_soft, int cols, uint8_t *d_bits, int32_t *d_n_valid)
+{
+    int r = vit_check(v, n_soft, cols); if (r) return r;
+    JB_CUDA(cudaSetDevice(v->device));
+    if (viterbi_launch(d_soft, (int)n_soft, cols, 0, v->pad, v->d_overlap, v->d_overlap_len, v->d_renorm, d_bits, d_n_valid, v->n_channels, v->stream)) return JAERO_E_CUDA;
+    v->launches++;
+    return JAERO_OK;
+}
+static int vit_stage(jaero_viterbi *v, size_t n_soft)
+{
+    size_t need = (size_t)v->n_channels * n_soft;
+    if (need > v->soft_cap) { cudaFree(v->d_soft); v->d_soft = 0; JB_CUDA(cudaMalloc(&v->d_soft, need)); v->soft_cap = need; }
+    size_t needb = (size_t)v->n_channels * (n_soft / 2);
+    if (needb > v->bits_cap) { cudaFree(v->d_bits); v->d_bits = 0; JB_CUDA(cudaMalloc(&v->d_bits, needb)); v->bits_cap = needb; }
+    return JAERO_OK;
+}
+int jaero_viterbi_decode_continuous(jaero_viterbi *v, const uint8_t *soft, size_t n_soft, int cols, uint8_t *bits_out, int32_t *n_valid)
+{
+    int r = vit_check(v, n_soft, cols); if (r) return r;
+    if (!soft || !bits_out) { set_error("null buffer"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(v->device));
+    r = vit_stage(v, n_soft); if (r) return r;
+    JB_CUDA(cudaMemcpyAsync(v->d_soft, soft, (size_t)v->n_channels * n_soft, cudaMemcpyHostToDevice, v->stream));
+    r = jaero_viterbi_decode_continuous_device(v, v->d_soft, n_soft, cols, v->d_bits, v->d_valid); if (r) return r;
+    JB_CUDA(cudaMemcpyAsync(bits_out, v->d_bits, (size_t)v->n_channels * (n_soft / 2), cudaMemcpyDeviceToHost, v->stream));
+    if (n_valid) JB_CUDA(cudaMemcpyAsync(n_valid, v->d_valid, (size_t)v->n_channels * sizeof(int), cudaMemcpyDeviceToHost, v->stream));
+    JB_CUDA(cudaStreamSynchronize(v->stream));
+    return JAERO_OK;
+}
+int jaero_viterbi_decode_block(jaero_viterbi *v, const uint8_t *soft, size_t n_soft, uint8_t *bits_out)
+{
+    int r = vit_check(v, n_soft, 0); if (r) return r;
+    if (!soft || !bits_out) { set_error("null buffer"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(v->device));
+    r = vit_stage(v, n_soft); if (r) return r;
+    JB_CUDA(cudaMemcpyAsync(v->d_soft, soft, (size_t)v->n_channels * n_soft, cudaMemcpyHostToDevice, v->stream));
+    if (viterbi_launch(v->d_soft, (int)n_soft, 0, 1, 0, v->d_overlap, v->d_overlap_len, v->d_renorm, v->d_bits, v->d_valid, v->n_channels, v->stream)) return JAERO_E_CUDA;
+    v->launches++;
+    JB_CUDA(cudaMemcpyAsync(bits_out, v->d_bits, (size_t)v->n_channels * (n_soft / 2), cudaMemcpyDeviceToHost, v->stream));
+    JB_CUDA(cudaStreamSynchronize(v->stream));
+    return JAERO_OK;
+}
+
+} // extern "C"
+
+// ====================================================================== demodulator batches
+#include <cmath>
+#include <algorithm>
+
+namespace {
+
+// RootRaisedCosine::design (JAERO/DSP.h:316-338): closed-form RRC taps, firsize forced odd.
+std::vector<double> rrc_taps(double alpha, int firsize, double samplerate, double symbol_freq)
+{
+    if ((firsize % 2) == 0) firsize += 1;
+    std::vector<double> pts(firsize);
+    const double T = (samplerate) / (symbol_freq);
+    for (int i = 0; i < firsize; i++) {
+        if (i == ((firsize - 1) / 2)) pts[i] = (4.0 * alpha + M_PI - M_PI * alpha) / (M_PI * sqrt(T));
+        else {
+            const double fi = (((double)i) - ((double)(firsize - 1)) / 2.0);
+            if (fabs(1.0 - pow(4.0 * alpha * fi / T, 2)) < 0.0000000001)
+                pts[i] = (alpha * ((M_PI - 2.0) * cos(M_PI / (4.0 * alpha)) + (M_PI + 2.0) * sin(M_PI / (4.0 * alpha))) / (M_PI * sqrt(2.0 * T)));
+            else
+                pts[i] = (4.0 * alpha / (M_PI * sqrt(T)) * (cos((1.0 + alpha) * M_PI * fi / T) + T / (4.0 * alpha * fi) * sin((1.0 - alpha) * M_PI * fi / T)) / (1.0 - pow(4.0 * alpha * fi / T, 2)));
+        }
+    }
+    return pts;
+}
+
+// Delay<T>::update interpolation weight (JAERO/DSP.h:357-374) for every ring position; the kernels keep
+// the delay line as a shift register, which is only equivalent if the weight does not depend on the
+// ring position (true for every delay the reference configures) — verified here.
+bool delay_weight(double fractdelay, int *k_out, double *w_out)
+{
+    const int size = (int)std::ceil(fractdelay) + 1;
+    double w0 = 0;
+    for (int bp = 0; bp < size; bp++) {
+        double dptr = ((double)bp) - fractdelay;
+        while (std::floor(dptr) < 0) dptr += ((double)size);
+        const int iptr = (int)std::floor(dptr);
+        const double w = dptr - ((double)iptr);
+        if (bp == 0) w0 = w; else if (w != w0) return false;
+    }
+    *k_out = (int)std::ceil(fractdelay);
+    *w_out = w0;
+    return true;
+}
+
+template <class T> int dev_alloc_zero(T **p, size_t count, cudaStream_t s)
+{
+    JB_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    JB_CUDA(cudaMemsetAsync(*p, 0, count * sizeof(T), s));
+    return 0;
+}
+} // namespace
+
+struct jaero_batch {
+    jaero_settings set;
+    int device;
+    cudaStream_t stream;
+    DemodParams p;
+    CfePlan cfe;
+    std::vector<void *> allocs;
+    // lock-step counters mirrored on the host
+    long long samples;          // samples fully processed
+    int bb_pos, coarse_counter;
+    int16_t *d_stage; size_t stage_cap;
+    int16_t *h_soft_stage;      // pinned
+    int *h_ints; double *h_dbls;   // pinned mirrors of I / D
+    long long launches;
+};
+
+namespace {
+template <class T> int batch_alloc(jaero_batch *b, T **p, size_t count)
+{
+    int r = dev_alloc_zero(p, count, b->stream);
+    if (r == 0) b->allocs.push_back((void *)*p);
+    return r;
+}
+
+__global__ void init_state_kernel(DemodParams p, const double *freq_center, double st_freq, double ebno_init)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels) return;
+    auto D = [&](int i) -> double & { return p.D[(size_t)i * p.cpad + ch]; };
+    auto I = [&](int i) -> int & { return p.I[(size_t)i * p.cpad + ch]; };
+    // WaveTable::SetFreq(double,int) (DSP.cpp:142-149): WTstep = freq*WTSIZE/(float)samplerate
+    double fc = freq_center[ch];
+    if (fc > ((p.Fs / 2.0) - (p.lockingbw / 2.0))) fc = ((p.Fs / 2.0) - (p.lockingbw / 2.0));   // oqpskdemodulator.cpp:183
+    if (fc < 0) fc = 0;
+    const double sr = (double)((float)((int)p.Fs));
+    D(D_M2_FREQ) = fc; D(D_M2_STEP) = (fc) * ((double)jb::WTSIZE) / sr;
+    D(D_MC_FREQ) = fc; D(D_MC_STEP) = (fc) * ((double)jb::WTSIZE) / sr;
+    D(D_ST_FREQ) = st_freq; D(D_ST_STEP) = (st_freq) * ((double)jb::WTSIZE) / sr;
+    D(D_SR_FREQ) = st_freq; D(D_SR_STEP) = (st_freq) * ((double)jb::WTSIZE) / sr;
+    D(D_MSE) = (p.kind == JAERO_KIND_OQPSK) ? 100.0 : 10.0;       // oqpskdemodulator.cpp:17 / mskdemodulator.cpp:180
+    D(D_DIFF_LAST) = -1.0;                                        // DSP.cpp:520
+    D(D_EB_EBNO) = ebno_init;
+    I(I_COUNTDOWN) = 4; I(I_COUNTDOWN2) = 5;                      // oqpskdemodulator.cpp:641,652 / mskdemodulator.cpp:493
+    I(I_EMPTYING) = 1;                                            // coarsefreqestimate.cpp:24
+}
+
+// after a host read: move the not-yet-emitted (<32 / <12) soft bits to the front of each ring
+__global__ void soft_reset_kernel(DemodParams p)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels) return;
+    int &count = p.I[(size_t)I_SOFT_COUNT * p.cpad + ch];
+    const int pending = p.I[(size_t)I_SOFT_PENDING * p.cpad + ch];
+    int16_t *ring = p.soft + (size_t)ch * p.soft_cap;
+    for (int k = 0; k < pending; k++) ring[k] = ring[count + k];
+    count = 0;
+}
+__global__ void set_int_kernel(DemodParams p, int idx, int channel, int value)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels) return;
+    if (channel < 0 || channel == ch) p.I[(size_t)idx * p.cpad + ch] = value;
+}
+// CenterFreqChangedSlot (oqpskdemodulator.cpp:291-310 / mskdemodulator.cpp:265-282)
+__global__ void center_freq_kernel(DemodParams p, int channel, double freq_center)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels || (channel >= 0 && channel != ch)) return;
+    auto D = [&](int i) -> double & { return p.D[(size_t)i * p.cpad + ch]; };
+    double fc = freq_center;
+    if (p.kind == JAERO_KIND_OQPSK) {
+        if (p.fb != 8400) { if (fc < (0.5 * p.fb)) fc = 0.5 * p.fb; if (fc > (p.Fs / 2.0 - 0.5 * p.fb)) fc = p.Fs / 2.0 - 0.5 * p.fb; }
+    } else { if (fc < (0.75 * p.fb)) fc = 0.75 * p.fb; if (fc > (p.Fs / 2.0 - 0.75 * p.fb)) fc = p.Fs / 2.0 - 0.75 * p.fb; }
+    if (fc < 0) fc = 0;
+    const double srf = (double)((float)((int)p.Fs));
+    D(D_MC_FREQ) = fc; D(D_MC_STEP) = (fc) * ((double)jb::WTSIZE) / srf;   // SetFreq(freq,Fs)
+    auto set_m2 = [&](double f) { if (f < 0) f = 0; D(D_M2_FREQ) = f; D(D_M2_STEP) = (f) * ((double)jb::WTSIZE) / p.Fs; };
+    if (p.afc) set_m2(D(D_MC_FREQ));
+    if ((D(D_M2_FREQ) - D(D_MC_FREQ)) > (p.lockingbw / 2.0)) set_m2(D(D_MC_FREQ) + (p.lockingbw / 2.0));
+    if ((D(D_M2_FREQ) - D(D_MC_FREQ)) < (-p.lockingbw / 2.0)) set_m2(D(D_MC_FREQ) - (p.lockingbw / 2.0));
+    double2 *row = p.bb + (size_t)ch * p.bbnfft;
+    for (int j = 0; j < p.bbnfft; j++) row[j] = make_double2(0.0, 0.0);
+}
+} // namespace
+
+extern "C" {
+
+int jaero_batch_create(const jaero_settings *s, int n_channels, const double *freq_center_per_channel, int device, jaero_batch **out)
+{
+    if (!s || !out || n_channels <= 0) { set_error("jaero_batch_create: bad argument"); return JAERO_E_ARG; }
+    if (s->kind != JAERO_KIND_OQPSK && s->kind != JAERO_KIND_MSK) { set_error("jaero_batch_create: unknown kind"); return JAERO_E_ARG; }
+    if (s->Fs <= 0 || s->fb <= 0 || s->coarsefreqest_fft_power < 10 || s->coarsefreqest_fft_power > 14) {
+        set_error("jaero_batch_create: Fs/fb must be positive and coarsefreqest_fft_power in 10..14"); return JAERO_E_ARG; }
+    if (s->kind == JAERO_KIND_OQPSK && s->fb == 8400) { set_error("jaero_batch_create: the 8400 bps FFT pre-filter path is not implemented yet"); return JAERO_E_ARG; }
+    int ndev = 0;
+    JB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("jaero_batch_create: no such CUDA device"); return JAERO_E_CUDA; }
+    JB_CUDA(cudaSetDevice(device));
+    jaero_batch *b = new (std::nothrow) jaero_batch();
+    if (!b) { set_error("out of host memory"); return JAERO_E_ARG; }
+    b->set = *s; b->device = device; b->samples = 0; b->bb_pos = 0; b->coarse_counter = 0;
+    b->d_stage = 0; b->stage_cap = 0; b->launches = 0;
+    JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    DemodParams &p = b->p;
+    memset(&p, 0, sizeof p);
+    p.kind = s->kind; p.n_channels = n_channels; p.cpad = (n_channels + 31) & ~31;
+    p.Fs = s->Fs; p.fb = s->fb; p.lockingbw = s->lockingbw; p.signalthreshold = s->signalthreshold;
+    p.afc = s->afc; p.sql = s->sql; p.cpu_reduce = s->cpu_reduce; p.report_ebno = s->report_ebno;
+    p.bbnfft = 1 << s->coarsefreqest_fft_power;
+    std::vector<double> taps;
+    double st_freq;
+    if (s->kind == JAERO_KIND_OQPSK) {
+        taps = rrc_taps(1.0, 55, s->Fs, s->fb / 2);                           // oqpskdemodulator.cpp:209-211
+        p.agc_len = (int)round(4 * s->Fs);                                    // :197 AGC(4,Fs)
+        p.ebno_len = 2 * 48000;                                               // :42 (built in the ctor with Fs=48000)
+        p.marg_len = 800; p.dt_len = 401; p.mse_len = 400;                    // :44-45,53
+        const double T = s->Fs / (s->fb / 2);                                 // :221
+        if (!delay_weight(T / 4.0, &p.k41, &p.w41) || !delay_weight(T / 8.0, &p.k8, &p.w8) || p.k41 > 3 || p.k8 > 3) {
+            set_error("unsupported fractional delay for this Fs/fb"); delete b; return JAERO_E_ARG; }
+        p.res_b0 = 0.00032714218939589035; p.res_b1 = 0; p.res_b2 = 0.00032714218939589035;   // :256-261
+        p.res_a1 = -0.39005299948210803; p.res_a2 = 0.99934571562120822;
+        p.ee = 0.4;                                                           // :263
+        p.lf_b0 = 0.0010275610653672064; p.lf_b1 = 0.0020551221307344128; p.lf_b2 = 0.0010275610653672064;   // :95-100
+        p.lf_a1 = -1.9207386815577139; p.lf_a2 = 0.92509247310306331;
+        st_freq = s->fb;                                                      // :270
+    } else {
+        p.sps = (int)(s->Fs / s->fb);                                         // mskdemodulator.cpp:149
+        if (2 * p.sps > MAX_TAPS) { set_error("MSK: 2*SamplesPerSymbol exceeds the supported FIR length"); delete b; return JAERO_E_ARG; }
+        taps.resize(2 * p.sps);
+        for (int i = 0; i < 2 * p.sps; i++) taps[i] = sin(M_PI * i / (2.0 * p.sps)) / (2.0 * p.sps);   // :164-170
+        p.agc_len = (int)round(1 * s->Fs);                                    // :173
+        p.ebno_len = (int)(2.0 * s->Fs);                                      // :176
+        p.marg_len = p.sps; p.dt_len = p.sps / 2 + 1; p.mse_len = 600;        // :254-256, ctor :64
+        if (s->fb >= 1200) {                                                  // :189-250
+            p.correctionfactor = 0.6;
+            if (s->Fs == 48000) { p.res_a1 = -1.993312819378528; p.res_a2 = 0.999476538254407; p.res_b0 = 2.617308727964618e-04; p.res_b2 = -2.617308727964618e-04; p.ee = 0.025; }
+            else { p.res_a1 = -1.974342917561558; p.res_a2 = 0.998953350377616; p.res_b0 = 5.233248111921052e-04; p.res_b2 = -5.233248111921052e-04; p.ee = 0.05; }
+        } else {
+            p.correctionfactor = 1.0;
+            if (s->Fs == 48000) { p.res_a1 = -1.998196509168551; p.res_a2 = 0.999738234875681; p.res_b0 = 1.308825621597620e-04; p.res_b2 = -1.308825621597620e-04; p.ee = 0.025; }
+            else { p.res_a1 = -1.974342917561558; p.res_a2 = 0.998953350377616; p.res_b0 = 5.233248111921052e-04; p.res_b2 = -5.233248111921052e-04; p.ee = 0.0125; }
+        }
+        p.res_b1 = 0;
+        st_freq = s->fb / 2;                                                  // :159
+    }
+    p.ntaps = (int)taps.size();
+    p.soft_cap = std::max(4096, (int)(2 * s->fb) + 64);
+    if (demod_set_taps(taps.data(), p.ntaps)) { delete b; return JAERO_E_CUDA; }
+
+    const size_t cp = p.cpad;
+    int rc = 0;
+    rc |= batch_alloc(b, &p.D, (size_t)D_COUNT * cp);
+    rc |= batch_alloc(b, &p.I, (size_t)I_COUNT * cp);
+    rc |= batch_alloc(b, &p.agc_ring, (size_t)p.agc_len * cp);
+    if (p.report_ebno) { rc |= batch_alloc(b, &p.ebno_e1, (size_t)p.ebno_len * cp); rc |= batch_alloc(b, &p.ebno_e2, (size_t)p.ebno_len * cp); }
+    rc |= batch_alloc(b, &p.fir_re, (size_t)(p.ntaps + 1) * cp);
+    rc |= batch_alloc(b, &p.fir_im, (size_t)(p.ntaps + 1) * cp);
+    rc |= batch_alloc(b, &p.bb, (size_t)n_channels * p.bbnfft);
+    rc |= batch_alloc(b, &p.marg_ring, (size_t)p.marg_len * cp);
+    rc |= batch_alloc(b, &p.mse_pm, (size_t)p.mse_len * cp);
+    rc |= batch_alloc(b, &p.mse_ma, (size_t)p.mse_len * cp);
+    rc |= batch_alloc(b, &p.dt_ring, (size_t)p.dt_len * cp);
+    if (s->kind == JAERO_KIND_MSK) {
+        rc |= batch_alloc(b, &p.dsmpl_ring, (size_t)(p.sps + 1) * cp);
+        rc |= batch_alloc(b, &p.dly8_ring, (size_t)(p.sps / 2 + 1) * cp);
+    }
+    rc |= batch_alloc(b, &p.soft, (size_t)n_channels * p.soft_cap);
+    rc |= batch_alloc(b, &p.cfe_est_out, (size_t)cp);
+    if (rc) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+
+    // trig tables exactly as TrigLookUp builds them (DSP.cpp:19-20), computed with the host libm
+    {
+        std::vector<double> sn(jb::WTSIZE), cs(jb::WTSIZE);
+        for (int i = 0; i < jb::WTSIZE; i++) sn[i] = (sin(2 * M_PI * ((double)i) / jb::WTSIZE));
+        for (int i = 0; i < jb::WTSIZE; i++) cs[i] = (sin(M_PI_2 + 2 * M_PI * ((double)i) / jb::WTSIZE));
+        double *ds, *dc;
+        if (batch_alloc(b, &ds, (size_t)jb::WTSIZE) || batch_alloc(b, &dc, (size_t)jb::WTSIZE)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+        JB_CUDA(cudaMemcpyAsync(ds, sn.data(), sn.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaMemcpyAsync(dc, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        p.sin_t = ds; p.cos_t = dc;
+    }
+    // coarse estimator plan (CoarseFreqEstimate::setSettings, coarsefreqestimate.cpp:39-76)
+    {
+        CfePlan &c = b->cfe;
+        memset(&c, 0, sizeof c);
+        c.nfft = p.bbnfft;
+        const int lg = s->coarsefreqest_fft_power;
+        c.n1 = 1 << ((lg + 1) / 2); c.n2 = 1 << (lg / 2);
+        c.hzperbin = s->Fs / ((double)c.nfft);
+        const double lbw = (s->kind == JAERO_KIND_OQPSK) ? 2.0 * s->lockingbw / 2.0 : s->lockingbw;   // oqpskdemodulator.cpp:191
+        c.startbin = (int)std::max(round(lbw / c.hzperbin), 1.0);
+        c.stopbin = c.nfft - c.startbin;
+        c.expectedpeakbin = (int)round(s->fb / (2.0 * c.hzperbin));
+        c.lo = (int)round((-lbw / c.hzperbin) + ((double)(c.nfft / 2)));
+        c.hi = (int)round((lbw / c.hzperbin) + ((double)(c.nfft / 2)));
+        c.is8400 = (s->fb == 8400);
+        std::vector<double2> tw(c.nfft);
+        for (int k = 0; k < c.nfft; k++) { const double a = -2.0 * M_PI * (double)k / (double)c.nfft; tw[k] = make_double2(cos(a), sin(a)); }
+        c.group = std::min(n_channels, 512);
+        if (batch_alloc(b, &c.tw, (size_t)c.nfft) || batch_alloc(b, &c.work_a, (size_t)c.group * c.nfft) ||
+            batch_alloc(b, &c.work_b, (size_t)c.group * c.nfft) || batch_alloc(b, &c.y, (size_t)n_channels * c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+        JB_CUDA(cudaMemcpyAsync(c.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    // per-channel initial state
+    {
+        std::vector<double> fc(n_channels);
+        for (int i = 0; i < n_channels; i++) fc[i] = freq_center_per_channel ? freq_center_per_channel[i] : s->freq_center;
+        double *dfc;
+        JB_CUDA(cudaMalloc(&dfc, n_channels * sizeof(double)));
+        JB_CUDA(cudaMemcpyAsync(dfc, fc.data(), n_channels * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        init_state_kernel<<<(n_channels + 127) / 128, 128, 0, b->stream>>>(p, dfc, st_freq, 0.0);
+        JB_CUDA(cudaGetLastError());
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        cudaFree(dfc);
+    }
+    JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)I_COUNT * cp * sizeof(int)));
+    JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)D_COUNT * cp * sizeof(double)));
+    JB_CUDA(cudaMallocHost(&b->h_soft_stage, (size_t)n_channels * p.soft_cap * sizeof(int16_t)));
+    *out = b;
+    return JAERO_OK;
+}
+
+void jaero_batch_destroy(jaero_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    for (void *q : b->allocs) cudaFree(q);
+    cudaFree(b->d_stage);
+    cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage);
+    cudaStreamDestroy(b->stream);
+    delete b;
+}
+int jaero_batch_channels(const jaero_batch *b) { return b ? b->p.n_channels : 0; }
+int64_t jaero_batch_launch_count(const jaero_batch *b) { return b ? b->launches : 0; }
+
+int jaero_batch_sync(jaero_batch *b)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    return JAERO_OK;
+}
+
+int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, size_t stride)
+{
+    if (!b || !d_pcm) { set_error("jaero_batch_write_device: null argument"); return JAERO_E_ARG; }
+    if (n == 0) return JAERO_OK;                                   // `if(!len)return 0;` oqpskdemodulator.cpp:337
+    if (stride < n || n > 0x7fffffff) { set_error("jaero_batch_write_device: bad stride / length"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const DemodParams &p = b->p;
+    const int N = p.bbnfft, trig_every = p.cpu_reduce ? N : N / 4;
+    SegmentArgs a;
+    memset(&a, 0, sizeof a);
+    a.new_write = 1;
+    int seg_start = 0; bool resume = false;
+    auto launch = [&](int i0, int i1, bool stop_after_a, int bb0, int cc0) -> int {
+        a.sample0 = b->samples; a.i0 = i0; a.i1 = i1; a.skip_a_first = resume ? 1 : 0; a.stop_after_a = stop_after_a ? 1 : 0;
+        a.apply_cfe = resume ? 1 : 0; a.bb_pos = bb0; a.coarse_counter = cc0;
+        int r = (p.kind == JAERO_KIND_OQPSK) ? oqpsk_segment_launch(p, a, d_pcm, stride, b->stream)
+                                             : msk_segment_launch(p, a, d_pcm, stride, b->stream);
+        b->launches++;
+        a.new_write = 0;
+        return r;
+    };
+    int bb = b->bb_pos, cc = b->coarse_counter;
+    int seg_bb = bb, seg_cc = cc;                                  // counters at the start of the open segment
+    for (int i = 0; i < (int)n; i++) {
+        // A(i): ring write + trigger test (oqpskdemodulator.cpp:410-429) — lock-step for the whole batch
+        bool trigger = false;
+        if (cc >= p.Fs || !p.cpu_reduce) {
+            bb++; if (bb >= N) bb = 0;
+            if (bb % trig_every == 0) trigger = true;
+        }
+        if (trigger) {
+            if (launch(seg_start, i + 1, true, seg_bb, seg_cc)) return JAERO_E_CUDA;
+            b->samples += (i - seg_start);                         // samples whose B part has run
+            if (cfe_run(b->cfe, p, bb, b->stream, &b->launches)) return JAERO_E_CUDA;
+            cc = 0;                                                // :426
+            seg_start = i; resume = true; seg_bb = bb; seg_cc = 0;
+        }
+        cc++;                                                      // :431
+    }
+    if (launch(seg_start, (int)n, false, seg_bb, seg_cc)) return JAERO_E_CUDA;
+    b->samples += ((int)n - seg_start);
+    b->bb_pos = bb; b->coarse_counter = cc;
+    return JAERO_OK;
+}
+
+int jaero_batch_write(jaero_batch *b, const int16_t *pcm, size_t n, size_t stride)
+{
+    if (!b || !pcm) { set_error("jaero_batch_write: null argument"); return JAERO_E_ARG; }
+    if (n == 0) return JAERO_OK;
+    if (stride < n) { set_error("jaero_batch_write: channel_stride < n_samples"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t C = b->p.n_channels;
+    const size_t pitch = (n + 7) & ~(size_t)7;
+    if (C * pitch > b->stage_cap) {
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_stage); b->d_stage = 0;
+        JB_CUDA(cudaMalloc(&b->d_stage, C * pitch * sizeof(int16_t)));
+        b->stage_cap = C * pitch;
+    }
+    JB_CUDA(cudaMemcpy2DAsync(b->d_stage, pitch * sizeof(int16_t), pcm, stride * sizeof(int16_t), n * sizeof(int16_t), C,
+                              cudaMemcpyHostToDevice, b->stream));
+    return jaero_batch_write_device(b, b->d_stage, n, pitch);
+}
+
+static int pull_ints(jaero_batch *b)
+{
+    const size_t cp = b->p.cpad;
+    JB_CUDA(cudaMemcpyAsync(b->h_ints, b->p.I, (size_t)I_COUNT * cp * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+
+int jaero_batch_read_softbits(jaero_batch *b, int16_t *out, size_t cap, int32_t *counts)
+{
+    if (!b || !out || !counts) { set_error("jaero_batch_read_softbits: null argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    if (pull_ints(b)) return JAERO_E_CUDA;
+    const DemodParams &p = b->p;
+    const size_t cp = p.cpad;
+    const int *cnt = b->h_ints + (size_t)I_SOFT_COUNT * cp, *ovf = b->h_ints + (size_t)I_SOFT_OVERFLOW * cp;
+    int maxc = 0; bool overflow = false;
+    for (int ch = 0; ch < p.n_channels; ch++) { maxc = std::max(maxc, cnt[ch]); overflow |= (ovf[ch] != 0) || ((size_t)cnt[ch] > cap); }
+    if (overflow) { set_error("soft-bit ring overflow: drain more often or pass a larger buffer"); return JAERO_E_OVERFLOW; }
+    if (maxc > 0) {
+        JB_CUDA(cudaMemcpy2DAsync(b->h_soft_stage, (size_t)p.soft_cap * 2, p.soft, (size_t)p.soft_cap * 2, (size_t)maxc * 2, p.n_channels,
+                                  cudaMemcpyDeviceToHost, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    for (int ch = 0; ch < p.n_channels; ch++) {
+        counts[ch] = cnt[ch];
+        if (cnt[ch]) memcpy(out + (size_t)ch * cap, b->h_soft_stage + (size_t)ch * p.soft_cap, (size_t)cnt[ch] * 2);
+    }
+    soft_reset_kernel<<<(p.n_channels + 127) / 128, 128, 0, b->stream>>>(p);
+    JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_batch_softbits_device(jaero_batch *b, const int16_t **d_soft, const int32_t **d_counts, size_t *ring_cap)
+{
+    if (!b || !d_soft || !d_counts || !ring_cap) { set_error("null argument"); return JAERO_E_ARG; }
+    *d_soft = b->p.soft; *d_counts = b->p.I + (size_t)I_SOFT_COUNT * b->p.cpad; *ring_cap = (size_t)b->p.soft_cap;
+    return JAERO_OK;
+}
+int jaero_batch_reset_softbits(jaero_batch *b)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    soft_reset_kernel<<<(b->p.n_channels + 127) / 128, 128, 0, b->stream>>>(b->p);
+    JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_batch_set_dcd(jaero_batch *b, int channel, int dcd)
+{
+    if (!b || channel >= b->p.n_channels) { set_error("jaero_batch_set_dcd: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    set_int_kernel<<<(b->p.n_channels + 127) / 128, 128, 0, b->stream>>>(b->p, I_DCD, channel, dcd ? 1 : 0);
+    JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_batch_set_center_freq(jaero_batch *b, int channel, double hz)
+{
+    if (!b || channel >= b->p.n_channels) { set_error("jaero_batch_set_center_freq: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    center_freq_kernel<<<(b->p.n_channels + 127) / 128, 128, 0, b->stream>>>(b->p, channel, hz);
+    JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out)
+{
+    if (!b || !out) { set_error("null argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t cp = b->p.cpad;
+    JB_CUDA(cudaMemcpyAsync(b->h_dbls, b->p.D, (size_t)D_COUNT * cp * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (pull_ints(b)) return JAERO_E_CUDA;
+    for (int ch = 0; ch < b->p.n_channels; ch++) {
+        auto D = [&](int i) { return b->h_dbls[(size_t)i * cp + ch]; };
+        auto I = [&](int i) { return b->h_ints[(size_t)i * cp + ch]; };
+        jaero_status &s = out[ch];
+        s.mixer2_freq = D(D_M2_FREQ); s.mixer2_wtptr = D(D_M2_PTR); s.center_freq = D(D_MC_FREQ);
+        s.st_freq = D(D_ST_FREQ); s.st_wtptr = D(D_ST_PTR); s.agc = D(D_AGC_VAL); s.mse = D(D_MSE);
+        s.ebno = D(D_EB_EBNO); s.marg = D(D_MARG_VAL); s.cfe_est = D(D_CFE_EST);
+        s.n_sig_true = I(I_SIG_TRUE); s.n_sig_false = I(I_SIG_FALSE);
+        s.center_wtptr = D(D_MC_PTR); s.st_ref_wtptr = D(D_SR_PTR);
+        s.samples = b->samples; s.softbits = 0; s.dcd = I(I_DCD); s.reserved = 0;
+    }
+    return JAERO_OK;
+}
+int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out)
+{
+    if (!b || !out || channel < 0 || channel >= b->p.n_channels) { set_error("jaero_batch_get_status: bad argument"); return JAERO_E_ARG; }
+    std::vector<jaero_status> all(b->p.n_channels);
+    int r = jaero_batch_get_status_all(b, all.data());
+    if (r) return r;
+    *out = all[channel];
+    return JAERO_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,4 @@
+// Single translation unit for the two segment kernels (they share the __constant__ tap table).
+// Built with -fmad=false: see demod_device.cuh.
+#include "oqpsk_demod.cu"
+#include "msk_demod.cu"

@@ -1,0 +1,311 @@
+// K1a — fused continuous OQPSK demodulator segment kernel (8400* / 10500 bps), one thread per channel.
+//   (* the 8400 bps FFT pre-filter, oqpskdemodulator.cpp:343-381, is not part of this kernel yet)
+//
+// Replaces OqpskDemodulator::writeData (JAERO/oqpskdemodulator.cpp:334-627) and
+// OqpskDemodulator::FreqOffsetEstimateSlot (:629-677) for a whole batch of channels:
+// int16 -> coarse-estimator ring write -> NCO mix (table NCO, DSP.cpp:79-85) -> 55-tap RRC FIR x2
+// (DSP.cpp:292-304) -> EbNo (DSP.cpp:729-744) -> AGC (DSP.cpp:370-379) -> clip -> symbol-timing chain
+// (delays, resonator, T/8 quadrature, arg, PLL nudges :473-484) -> strobe interpolation (:488-494)
+// -> carrier loop (:512-532) -> bias rotate / 400-symbol delay (:535-537) -> MSE gate (:563-565)
+// -> soft bits (:569-592).
+//
+// The per-sample recursion is serial per channel (the carrier loop feeds the NCO ahead of the
+// FIR), so the parallel axis is the channel: lane = channel, all sample-rate ring positions are
+// warp-uniform, every HBM ring access is a coalesced 256 B row. FIR delay lines live in shared
+// memory ([tap][lane], conflict-free), everything else in registers.
+#include "demod_device.cuh"
+
+namespace jb {
+
+__constant__ double c_taps[MAX_TAPS];
+
+int demod_set_taps(const double *taps, int n)
+{
+    if (n > MAX_TAPS) { set_error("too many FIR taps"); return -1; }
+    JB_CUDA(cudaMemcpyToSymbol(c_taps, taps, n * sizeof(double)));
+    return 0;
+}
+
+static const int OQ_THREADS = 32;
+static const int OQ_NT1 = 56;             // 55 taps + 1 (FIR ring, DSP.cpp:277)
+
+#define LD(idx) p.D[(size_t)(idx) * p.cpad + ch]
+#define LI(idx) p.I[(size_t)(idx) * p.cpad + ch]
+
+__global__ void __launch_bounds__(OQ_THREADS)
+oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
+{
+    __shared__ double s_re[OQ_NT1][OQ_THREADS];
+    __shared__ double s_im[OQ_NT1][OQ_THREADS];
+    const int lane = threadIdx.x;
+    const int ch = blockIdx.x * OQ_THREADS + lane;
+    const bool live = ch < p.n_channels;
+    if (!live) return;                    // no block-level barriers below
+
+    // ---------------- load state
+    Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
+    Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+    Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
+    Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
+    double agc_sum = LD(D_AGC_SUM), agc_val = LD(D_AGC_VAL);
+    double eb_sum1 = LD(D_EB_SUM1), eb_sum2 = LD(D_EB_SUM2), eb_ebno = LD(D_EB_EBNO);
+    double dly_s0 = LD(D_DLY_S0);
+    double d41_0 = LD(D_DLY41_0), d41_1 = LD(D_DLY41_1), d41_2 = LD(D_DLY41_2);
+    double d42_0 = LD(D_DLY42_0), d42_1 = LD(D_DLY42_1), d42_2 = LD(D_DLY42_2);
+    double d8_0 = LD(D_DLY8_0), d8_1 = LD(D_DLY8_1), d8_2 = LD(D_DLY8_2);
+    Biquad res = {LD(D_RES_X1), LD(D_RES_X2), LD(D_RES_Y1), LD(D_RES_Y2)};
+    Biquad lf = {LD(D_LF_X1), LD(D_LF_X2), LD(D_LF_Y1), LD(D_LF_Y2)};
+    double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
+    double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
+    double marg_sum = LD(D_MARG_SUM), marg_val = LD(D_MARG_VAL);
+    double pm_sum = LD(D_MSE_PM_SUM), ma_sum = LD(D_MSE_MA_SUM), mse = LD(D_MSE);
+    double lastmse = LD(D_LASTMSE);
+    int yui = LI(I_YUI), countdown = LI(I_COUNTDOWN), countdown2 = LI(I_COUNTDOWN2), dcd = LI(I_DCD);
+    int sig2l_init = LI(I_SIG2L_INIT);
+    int marg_pos = LI(I_MARG_POS), dt_pos = LI(I_DT_POS), mse_pos = LI(I_MSE_POS);
+    int soft_count = LI(I_SOFT_COUNT), soft_pending = LI(I_SOFT_PENDING), soft_overflow = LI(I_SOFT_OVERFLOW);
+    int sig_true = LI(I_SIG_TRUE), sig_false = LI(I_SIG_FALSE);
+
+    for (int k = 0; k < OQ_NT1; k++) {
+        s_re[k][lane] = p.fir_re[(size_t)k * p.cpad + ch];
+        s_im[k][lane] = p.fir_im[(size_t)k * p.cpad + ch];
+    }
+    if (a.new_write) lastmse = mse;                                       // oqpskdemodulator.cpp:339
+
+    // ---------------- FreqOffsetEstimateSlot (oqpskdemodulator.cpp:629-677), re-entrant in the reference:
+    // it runs after the ring write and before the mixer of the same sample.
+    if (a.apply_cfe) {
+        const double est = p.cfe_est_out[ch];
+        if ((mse < p.signalthreshold) && (!dcd)) {                        // :642-650
+            if (countdown2 > 0) countdown2--;
+            else osc_set_freq(m2, mc.freq + est, p.Fs);
+        } else countdown2 = 5;
+        if ((mse > p.signalthreshold) && (fabs(m2.freq - (mc.freq + est)) > 3.0))    // :653-657
+            osc_set_freq(m2, mc.freq + est, p.Fs);
+        if ((p.afc) && (mse < p.signalthreshold) && (fabs(m2.freq - mc.freq) > 3.0)) {   // :658-669
+            if (countdown > 0) countdown--;
+            else {
+                osc_set_freq(mc, m2.freq, p.Fs);
+                if (mc.freq < p.lockingbw / 2.0) osc_set_freq(mc, p.lockingbw / 2.0, p.Fs);
+                if (mc.freq > (p.Fs / 2.0 - p.lockingbw / 2.0)) osc_set_freq(mc, p.Fs / 2.0 - p.lockingbw / 2.0, p.Fs);
+                LI(I_EMPTYING) = 4;                                       // CoarseFreqEstimate::bigchange (coarsefreqestimate.cpp:84-88)
+                LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
+                double2 *row = p.bb + (size_t)ch * p.bbnfft;              // :667 bbcycbuff[j]=0
+                for (int j = 0; j < p.bbnfft; j++) row[j] = make_double2(0.0, 0.0);
+            }
+        } else countdown = 4;
+        if (mse > p.signalthreshold) sig_false++; else sig_true++;       // :674-675
+    }
+
+    // ---------------- uniform ring positions
+    const int agc_len = p.agc_len, eb_len = p.ebno_len;
+    int agc_pos = (int)(a.sample0 % agc_len);
+    int eb_pos = (int)(a.sample0 % eb_len);
+    int fir_pos = (int)(a.sample0 % OQ_NT1);
+    int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
+    const bool ebno_on = p.report_ebno != 0;
+    const int16_t *row = pcm + (size_t)ch * stride;
+
+    for (int i = a.i0; i < a.i1; i++) {
+        const double dval = ((double)row[i]) / 32768.0;                   // :390
+
+        // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
+        if (!(i == a.i0 && a.skip_a_first)) {
+            if (coarse_counter >= p.Fs || !p.cpu_reduce) {
+                const int t = osc_index(mc.ptr);
+                p.bb[(size_t)ch * p.bbnfft + bb_pos] = make_double2(p.cos_t[t] * dval, p.sin_t[t] * dval);
+                bb_pos++; if (bb_pos >= p.bbnfft) bb_pos = 0;
+            }
+        }
+        if (i == a.i1 - 1 && a.stop_after_a) break;
+        coarse_counter++;                                                 // :431
+
+        // ---- B
+        const int t2 = osc_index(m2.ptr);
+        const double cre = p.cos_t[t2] * dval, cim = p.sin_t[t2] * dval;   // :453 cval = CIS * dval
+        // FIR x2 (DSP.cpp:292-304): write, advance, sum oldest -> newest excluding the sample just written
+        s_re[fir_pos][lane] = cre; s_im[fir_pos][lane] = cim;
+        fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
+        double sre = 0, sim = 0;
+        {
+            int tp = fir_pos;
+#pragma unroll 11
+            for (int k = 0; k < 55; k++) {
+                sre += c_taps[k] * s_re[tp][lane];
+                sim += c_taps[k] * s_im[tp][lane];
+                tp++; if (tp >= OQ_NT1) tp = 0;
+            }
+        }
+        const double dabval = sqrt(sre * sre + sim * sim);                // :461
+
+        if (ebno_on) {                                                    // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
+            const size_t e = (size_t)eb_pos * p.cpad + ch;
+            const double sq = dabval * dabval;
+            eb_sum2 = eb_sum2 - p.ebno_e2[e]; eb_sum2 = eb_sum2 + fabs(sq); p.ebno_e2[e] = fabs(sq);
+            eb_sum1 = eb_sum1 - p.ebno_e1[e]; eb_sum1 = eb_sum1 + fabs(dabval); p.ebno_e1[e] = fabs(dabval);
+            const double e2val = eb_sum2 / ((double)eb_len), mean = eb_sum1 / ((double)eb_len);
+            const double mean_sq = mean * mean;
+            double var = (e2val) - (mean * mean);
+            var -= (0.024709 * mean_sq);
+            double mvr = (((p.Fs * mean_sq / (2.0 * p.fb * var))) * 0.13743);
+            if (mvr < 0.000000001) mvr = 0.000000001;
+            double tebno = 10.0 * log10(mvr);
+            if (isnan(tebno)) tebno = 50;
+            if (tebno > 50.0) tebno = 50;
+            if (tebno < 0.0) tebno = 0;
+            eb_ebno = eb_ebno * 0.8 + 0.2 * tebno;
+        }
+        eb_pos++; if (eb_pos >= eb_len) eb_pos = 0;
+
+        {   // AGC::Update (DSP.cpp:370-379)
+            const size_t e = (size_t)agc_pos * p.cpad + ch;
+            agc_sum = agc_sum - p.agc_ring[e];
+            agc_sum = agc_sum + fabs(dabval);
+            p.agc_ring[e] = fabs(dabval);
+            agc_pos++; if (agc_pos >= agc_len) agc_pos = 0;
+            agc_val = 1.414213562 / fmax(agc_sum / ((double)agc_len), 0.000001);
+            agc_val = fmax(agc_val, 0.000001);
+        }
+        double2 sig2 = make_double2(sre * agc_val, sim * agc_val);        // :466
+        const double abval = hypot(sig2.x, sig2.y);                       // :469 std::abs
+        if (abval > 2.84) { const double g = (2.84 / abval); sig2 = make_double2(g * sig2.x, g * sig2.y); }   // :470
+
+        // ---- symbol timing (:473-484)
+        const double ab2 = abval * abval;
+        const double st_diff = (0.0 * ab2 + (1.0 - 0.0) * dly_s0) - (ab2);    // Delay(1): weighting 0 -> x[n-1]
+        dly_s0 = ab2;
+        // Delay(T/4): older = x[n-k41], newer = x[n-k41+1]  (DSP.h:357-374)
+        double st_d1out, st_d2out;
+        {
+            const double older = (p.k41 == 3) ? d41_2 : (p.k41 == 2 ? d41_1 : d41_0);
+            const double newer = (p.k41 == 3) ? d41_1 : (p.k41 == 2 ? d41_0 : st_diff);
+            st_d1out = (p.w41 * newer + (1.0 - p.w41) * older);
+            d41_2 = d41_1; d41_1 = d41_0; d41_0 = st_diff;
+        }
+        {
+            const double older = (p.k41 == 3) ? d42_2 : (p.k41 == 2 ? d42_1 : d42_0);
+            const double newer = (p.k41 == 3) ? d42_1 : (p.k41 == 2 ? d42_0 : st_d1out);
+            st_d2out = (p.w41 * newer + (1.0 - p.w41) * older);
+            d42_2 = d42_1; d42_1 = d42_0; d42_0 = st_d1out;
+        }
+        double st_eta = (st_d2out - st_diff) * st_d1out;
+        st_eta = biquad_update(res, st_eta, p.res_a1, p.res_a2, p.res_b0, p.res_b1, p.res_b2);
+        double d8out;
+        {
+            const double older = (p.k8 == 3) ? d8_2 : (p.k8 == 2 ? d8_1 : d8_0);
+            const double newer = (p.k8 == 3) ? d8_1 : (p.k8 == 2 ? d8_0 : st_eta);
+            d8out = (p.w8 * newer + (1.0 - p.w8) * older);
+            d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta;
+        }
+        const int ts = osc_index(st.ptr);
+        const double2 st_out = cmul(make_double2(p.cos_t[ts], p.sin_t[ts]), make_double2(st_eta, -d8out));   // :478-479
+        const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
+        osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, p.Fs); // :481 IncreseFreqHz
+        osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0); // :482
+        if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), p.Fs);
+        if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), p.Fs);
+
+        if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
+        double frac;
+        if (osc_have_passed_point(st, p.ee, frac)) {                      // :488
+            const double pt_last = frac, pt_this = 1.0 - pt_last;
+            const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
+            yui++; yui %= 2;
+            if (!yui) pt_d = pt;
+            else {
+                double2 pt_qpsk = make_double2(pt.x, pt_d.y);             // :503
+                const double ct_xt = tanh(pt.y) * pt.x;
+                const double ct_xt_d = tanh(pt_d.x) * pt_d.y;
+                double ct_ec = ct_xt_d - ct_xt;
+                if (ct_ec > M_PI) ct_ec = M_PI;
+                if (ct_ec < -M_PI) ct_ec = -M_PI;
+                if (p.fb > 8400) {                                        // :518-525
+                    ct_ec = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
+                    if (ct_ec > M_PI_2) ct_ec = M_PI_2;
+                    if (ct_ec < -M_PI_2) ct_ec = -M_PI_2;
+                    osc_increase_phase_deg(m2, 1.0 * ct_ec);
+                    osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, p.Fs);
+                } else {                                                  // :526-532
+                    osc_increase_phase_deg(m2, 1.0 * ct_ec);
+                    const double lfo = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
+                    osc_set_freq(m2, (0.5 * 0.01 * lfo) + m2.freq, p.Fs);
+                }
+                {   // marg->UpdateSigned(ct_ec)  MA(800)  (:535, DSP.cpp:418-426)
+                    const size_t e = (size_t)marg_pos * p.cpad + ch;
+                    marg_sum = marg_sum - p.marg_ring[e];
+                    marg_sum = marg_sum + (ct_ec);
+                    p.marg_ring[e] = (ct_ec);
+                    marg_pos++; marg_pos %= p.marg_len;
+                    marg_val = marg_sum / ((double)p.marg_len);
+                }
+                {   // dt.update(pt_qpsk): 400-symbol delay (:536, DSP.h:455-460)
+                    p.dt_ring[(size_t)dt_pos * p.cpad + ch] = pt_qpsk;
+                    dt_pos++; dt_pos %= p.dt_len;
+                    pt_qpsk = p.dt_ring[(size_t)dt_pos * p.cpad + ch];
+                }
+                pt_qpsk = cmul(pt_qpsk, make_double2(cos(marg_val), sin(marg_val)));   // :537
+                {   // MSEcalc::Update (DSP.cpp:451-463)
+                    const size_t e = (size_t)mse_pos * p.cpad + ch;
+                    const double ab = hypot(pt_qpsk.x, pt_qpsk.y);
+                    pm_sum = pm_sum - p.mse_pm[e]; pm_sum = pm_sum + fabs(ab); p.mse_pm[e] = fabs(ab);
+                    double mu = pm_sum / ((double)p.mse_len);
+                    if (mu < 0.000001) mu = 0.000001;
+                    const double r2 = sqrt(2.0);
+                    const double tre = (r2 * pt_qpsk.x) / mu, tim = (r2 * pt_qpsk.y) / mu;
+                    const double tda = (fabs(tre) - 1.0), tdb = (fabs(tim) - 1.0);
+                    const double v = (tda * tda) + (tdb * tdb);
+                    ma_sum = ma_sum - p.mse_ma[e]; ma_sum = ma_sum + fabs(v); p.mse_ma[e] = fabs(v);
+                    mse_pos++; mse_pos %= p.mse_len;
+                    mse = ma_sum / ((double)p.mse_len);
+                }
+                if (mse < p.signalthreshold) {                            // :565
+                    push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.y * 127.0 + 128.0));
+                    push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.x * 127.0 + 128.0));
+                    if (soft_pending >= 32) {                             // :583-592
+                        if (!p.sql || mse < p.signalthreshold || lastmse < p.signalthreshold) soft_count += soft_pending;
+                        soft_pending = 0;
+                    }
+                }
+            }
+        }
+        sig2_last = sig2;                                                 // :596
+        osc_next_frame(m2); osc_next_frame(mc); osc_next_frame(st); osc_next_frame(sr);   // :600-603
+    }
+
+    // ---------------- store state
+    LD(D_M2_PTR) = m2.ptr; LD(D_M2_STEP) = m2.step; LD(D_M2_FREQ) = m2.freq; LD(D_M2_LAST) = m2.last;
+    LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
+    LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
+    LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
+    LD(D_AGC_SUM) = agc_sum; LD(D_AGC_VAL) = agc_val;
+    LD(D_EB_SUM1) = eb_sum1; LD(D_EB_SUM2) = eb_sum2; LD(D_EB_EBNO) = eb_ebno;
+    LD(D_DLY_S0) = dly_s0;
+    LD(D_DLY41_0) = d41_0; LD(D_DLY41_1) = d41_1; LD(D_DLY41_2) = d41_2;
+    LD(D_DLY42_0) = d42_0; LD(D_DLY42_1) = d42_1; LD(D_DLY42_2) = d42_2;
+    LD(D_DLY8_0) = d8_0; LD(D_DLY8_1) = d8_1; LD(D_DLY8_2) = d8_2;
+    LD(D_RES_X1) = res.x1; LD(D_RES_X2) = res.x2; LD(D_RES_Y1) = res.y1; LD(D_RES_Y2) = res.y2;
+    LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
+    LD(D_SIG2L_RE) = sig2_last.x; LD(D_SIG2L_IM) = sig2_last.y;
+    LD(D_PTD_RE) = pt_d.x; LD(D_PTD_IM) = pt_d.y;
+    LD(D_MARG_SUM) = marg_sum; LD(D_MARG_VAL) = marg_val;
+    LD(D_MSE_PM_SUM) = pm_sum; LD(D_MSE_MA_SUM) = ma_sum; LD(D_MSE) = mse;
+    LD(D_LASTMSE) = lastmse;
+    LI(I_YUI) = yui; LI(I_COUNTDOWN) = countdown; LI(I_COUNTDOWN2) = countdown2; LI(I_SIG2L_INIT) = sig2l_init;
+    LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
+    LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
+    LI(I_SIG_TRUE) = sig_true; LI(I_SIG_FALSE) = sig_false;
+    for (int k = 0; k < OQ_NT1; k++) {
+        p.fir_re[(size_t)k * p.cpad + ch] = s_re[k][lane];
+        p.fir_im[(size_t)k * p.cpad + ch] = s_im[k][lane];
+    }
+}
+
+int oqpsk_segment_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s)
+{
+    const int grid = (p.n_channels + OQ_THREADS - 1) / OQ_THREADS;
+    oqpsk_segment_kernel<<<grid, OQ_THREADS, 0, s>>>(p, a, d_pcm, stride);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace jb

@@ -1,0 +1,194 @@
+// K5 — batched K=7, r=1/2 soft-decision Viterbi decoder, one warp per channel.
+//
+// Replaces (reference): AeroLInterleaver::deinterleave_ba (JAERO/aerol.cpp:603-625, row permutation
+// (i*27)%64 at :531-535) + JConvolutionalCodec::Decode_Continuous / Decode_soft
+// (JAERO/jconvolutionalcodec.cpp:151-201, 98-125), whose arithmetic lives in the un-vendored
+// quiet/libcorrect. The decoding schedule below is the written spec shared with the CPU oracle
+// (oracle/correct_restated.c): warm-up (K-1 steps), add-compare-select with ties to the
+// "low" predecessor, a zero-tail of K-1 steps with ties to the "high" predecessor, a 140-slice
+// history ring that emits 105 decisions after walking back 35, min-subtraction every 128 steps,
+// final flush from state 0. Integer arithmetic only -> bit-exact against the oracle.
+//
+// Mapping: lane l owns successor states 2l and 2l+1 (both have predecessors l and l+32), path
+// metrics are two uint16 packed in one register so a step needs two warp shuffles; the 64
+// decision bits of a step are two __ballot_sync words kept in a shared-memory ring; the
+// best-state search is one __reduce_min_sync on (metric<<6 | state).
+#include "common.cuh"
+#include "viterbi.cuh"
+
+namespace jb {
+
+static const int VK = 7;
+static const int V_MIN_TB = 5 * VK;              // 35
+static const int V_GROUP = 15 * VK;              // 105
+static const int V_CAP = V_MIN_TB + V_GROUP;     // 140
+static const int V_RENORM = 65535 / (2 * 255);   // 128
+static const unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned parity7(unsigned x) { return __popc(x) & 1u; }
+// table[sr] bit p = parity(sr & poly[p]), polys 109, 79 (jconvolutionalcodec.cpp:13-14)
+__device__ __forceinline__ unsigned conv_out(unsigned sr) { return parity7(sr & 109u) | (parity7(sr & 79u) << 1); }
+
+struct WarpHist {
+    unsigned *h0, *h1;       // decision words of even / odd successors, V_CAP entries each
+    uint8_t *obits;          // decoded bits, oldest first
+    int index, len, nout;
+};
+
+// history_buffer_traceback: every lane walks the same survivor (no divergence); lane 0 stores.
+__device__ __forceinline__ void traceback(WarpHist &H, unsigned state, int min_tb, int lane)
+{
+    int idx = H.index;
+    const int len = H.len;
+    const int g = len - min_tb;
+    for (int j = 0; j < len; j++) {
+        idx = (idx == 0) ? V_CAP - 1 : idx - 1;
+        unsigned w = (state & 1u) ? H.h1[idx] : H.h0[idx];
+        unsigned h = (w >> (state >> 1)) & 1u;
+        state = (state >> 1) | (h << 5);
+        if (j >= min_tb && lane == 0) H.obits[H.nout + (g - 1 - (j - min_tb))] = (uint8_t)h;
+    }
+    if (g > 0) { H.nout += g; H.len -= g; }
+}
+
+__global__ void __launch_bounds__(128)
+viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, int n_soft, int cols, int mode, int pad,
+                  uint8_t *__restrict__ overlap, int *__restrict__ overlap_len,
+                  int *__restrict__ renorm_counter, uint8_t *__restrict__ bits_out, int *__restrict__ n_valid, int n_channels,
+                  int smem_per_warp, int sbuf_bytes)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ch >= n_channels) return;
+    unsigned char *base = smem + (size_t)warp * smem_per_warp;
+    uint8_t *sbuf = base;
+    unsigned *h0 = reinterpret_cast<unsigned *>(base + sbuf_bytes);
+    unsigned *h1 = h0 + V_CAP;
+    uint8_t *obits = reinterpret_cast<uint8_t *>(h1 + V_CAP);
+
+    // ---- stage the code-order soft buffer: overlap ‖ (de-interleaved) block ‖ erasure padding
+    const int ov = (mode == 0) ? overlap_len[ch] : 0;
+    const int padn = (mode == 0) ? pad : 0;
+    const int total = ov + n_soft + padn;
+    const uint8_t *src = soft_in + (size_t)ch * n_soft;
+    for (int k = lane; k < total; k += 32) {
+        uint8_t v;
+        if (k < ov) v = overlap[ch * 64 + k];
+        else if (k < ov + n_soft) {
+            int q = k - ov;
+            if (cols > 0) { int i = q & 63, j = q >> 6; v = src[((i * 27) & 63) * cols + j]; }   // deinterleave_ba
+            else v = src[q];
+        } else v = 128;
+        sbuf[k] = v;
+    }
+    __syncwarp();
+    const int sets = total >> 1;
+    for (int k = lane; k < sets; k += 32) obits[k] = 0;
+
+    // per-lane branch outputs for successors 2l (e=0) and 2l+1 (e=1)
+    const unsigned s0 = 2u * lane, s1 = 2u * lane + 1u;
+    const unsigned tl0 = conv_out(s0), th0 = conv_out(s0 | 64u), tl1 = conv_out(s1), th1 = conv_out(s1 | 64u);
+    const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
+    const bool odd = lane & 1;
+
+    unsigned m = 0;                       // packed metrics: e0 | e1<<16 (error_buffer_reset -> 0)
+    WarpHist H; H.h0 = h0; H.h1 = h1; H.obits = obits; H.index = 0; H.len = 0; H.nout = 0;
+    int rc = renorm_counter[ch];
+
+    for (int i = 0; i < sets; i++) {
+        const unsigned a0 = sbuf[2 * i], b0 = sbuf[2 * i + 1];
+        const unsigned a1 = 255u - a0, b1 = 255u - b0;    // |soft-255|
+        const unsigned vlo = __shfl_sync(FULL, m, src_lo), vhi = __shfl_sync(FULL, m, src_hi);
+        const unsigned mlo = odd ? (vlo >> 16) : (vlo & 0xffffu);
+        const unsigned mhi = odd ? (vhi >> 16) : (vhi & 0xffffu);
+#define DSEL(t) (((t) & 1u ? a1 : a0) + ((t) & 2u ? b1 : b0))
+        if (i < VK - 1) {
+            // warm-up: errors[j] = dist(table[j]) + errors[j>>1] for the states reachable so far; no history
+            unsigned e0 = (DSEL(tl0) + mlo) & 0xffffu, e1 = (DSEL(tl1) + mlo) & 0xffffu;
+            unsigned lim = 1u << (i + 1);
+            unsigned o0 = m & 0xffffu, o1 = m >> 16;
+            if (s0 < lim) o0 = e0;
+            if (s1 < lim) o1 = e1;
+            m = o0 | (o1 << 16);
+            continue;
+        }
+        const bool tail = (i + (VK - 1) >= sets);
+        const unsigned lo0 = (DSEL(tl0) + mlo) & 0xffffu, hi0 = (DSEL(th0) + mhi) & 0xffffu;
+        const unsigned lo1 = (DSEL(tl1) + mlo) & 0xffffu, hi1 = (DSEL(th1) + mhi) & 0xffffu;
+#undef DSEL
+        // inner: ties -> low predecessor (<=); tail: ties -> high predecessor (<)
+        const bool pick_lo0 = tail ? (lo0 < hi0) : (lo0 <= hi0);
+        const bool pick_lo1 = tail ? (lo1 < hi1) : (lo1 <= hi1);
+        unsigned e0 = pick_lo0 ? lo0 : hi0, e1 = pick_lo1 ? lo1 : hi1;
+        const unsigned w0 = __ballot_sync(FULL, !pick_lo0), w1 = __ballot_sync(FULL, !pick_lo1);
+        if (lane == 0) { h0[H.index] = w0; h1[H.index] = w1; }
+        __syncwarp();
+        const unsigned skip = tail ? (1u << (VK - (sets - i))) : 1u;
+        // history_buffer_process_skip
+        H.index++; if (H.index == V_CAP) H.index = 0;
+        rc++; H.len++;
+        const bool renorm = (rc == V_RENORM);
+        const bool tb = (H.len == V_CAP);
+        if (renorm || tb) {
+            unsigned k0 = ((s0 & (skip - 1u)) == 0u) ? ((e0 << 6) | s0) : 0xffffffffu;
+            unsigned k1 = ((s1 & (skip - 1u)) == 0u) ? ((e1 << 6) | s1) : 0xffffffffu;
+            unsigned best = __reduce_min_sync(FULL, min(k0, k1));
+            if (renorm) {
+                rc = 0;
+                unsigned mn = best >> 6;
+                if ((s0 & (skip - 1u)) == 0u) e0 = (e0 - mn) & 0xffffu;
+                if ((s1 & (skip - 1u)) == 0u) e1 = (e1 - mn) & 0xffffu;
+            }
+            if (tb) traceback(H, best & 63u, V_MIN_TB, lane);
+        }
+        m = e0 | (e1 << 16);
+    }
+    traceback(H, 0u, 0, lane);            // history_buffer_flush
+    renorm_counter[ch] = rc;
+    __syncwarp();
+
+    // ---- outputs
+    const int nbits = n_soft >> 1;
+    uint8_t *out = bits_out + (size_t)ch * nbits;
+    if (mode == 0) {
+        // Decode_Continuous: mid(paddinglength+1, n/2); positions never written by the decoder read as 0
+        const int pos = pad + 1;
+        for (int k = lane; k < nbits; k += 32) out[k] = (pos + k < sets) ? obits[pos + k] : (uint8_t)0;
+        if (lane == 0 && n_valid) n_valid[ch] = (sets - pos < nbits) ? (sets - pos) : nbits;   // QVector::mid truncation
+        // keep right(62) of the new (code-order) block, zero-extended to 62
+        const int kk = n_soft < 62 ? n_soft : 62;
+        for (int k = lane; k < 62; k += 32) overlap[ch * 64 + k] = (k < kk) ? sbuf[ov + n_soft - kk + k] : (uint8_t)0;
+        if (lane == 0) overlap_len[ch] = 62;
+    } else {
+        for (int k = lane; k < nbits; k += 32) out[k] = obits[k];   // last K-1 positions stay 0
+        if (lane == 0 && n_valid) n_valid[ch] = nbits;
+    }
+}
+
+size_t viterbi_smem_per_warp(int n_soft, int pad, int *sbuf_bytes)
+{
+    int total = 62 + n_soft + pad;
+    int sb = (total + 15) & ~15;
+    int ob = ((total / 2) + 15) & ~15;
+    *sbuf_bytes = sb;
+    return (size_t)sb + 2 * V_CAP * sizeof(unsigned) + ob;
+}
+
+int viterbi_launch(const uint8_t *d_soft, int n_soft, int cols, int mode, int pad, uint8_t *d_overlap,
+                   int *d_overlap_len, int *d_renorm, uint8_t *d_bits, int *d_valid, int n_channels, cudaStream_t stream)
+{
+    int sbuf_bytes = 0;
+    size_t per_warp = viterbi_smem_per_warp(n_soft, pad, &sbuf_bytes);
+    const int warps = 4;
+    size_t smem = per_warp * warps;
+    if (smem > 200 * 1024) { set_error("viterbi: block too long for shared memory"); return -1; }
+    JB_CUDA(cudaFuncSetAttribute(viterbi_k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int grid = (n_channels + warps - 1) / warps;
+    viterbi_k7_kernel<<<grid, warps * 32, smem, stream>>>(d_soft, n_soft, cols, mode, pad, d_overlap, d_overlap_len,
+                                                          d_renorm, d_bits, d_valid, n_channels, (int)per_warp, sbuf_bytes);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+} // namespace jb

@@ -1,0 +1,8 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+namespace jb {
+// mode 0: Decode_Continuous (overlap + erasure padding carried per channel); mode 1: one-shot Decode_soft
+int viterbi_launch(const uint8_t *d_soft, int n_soft, int cols, int mode, int pad, uint8_t *d_overlap,
+                   int *d_overlap_len, int *d_renorm, uint8_t *d_bits, int *d_valid, int n_channels, cudaStream_t stream);
+}

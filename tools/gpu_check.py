@@ -1,0 +1,111 @@
+"""First-contact GPU check (development aid, not a test): CUDA path vs the CPU oracle with verbose diffs."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import jaero_b200  # noqa: E402
+from oracle import restated  # noqa: E402
+
+
+def check_viterbi():
+    rng = np.random.default_rng(1)
+    C, n = 8, 4992
+    vb = jaero_b200.ViterbiBatch(C, 24)
+    orc = [restated.OracleViterbi(24) for _ in range(C)]
+    ok = True
+    for it in range(3):
+        soft = np.zeros((C, n), dtype=np.uint8)
+        for c in range(C):
+            msg = rng.integers(0, 256, size=n // 16, dtype=np.uint8)
+            enc = restated.conv_encode(msg)[:n].astype(np.float64)
+            noisy = (enc * 2 - 1) * 60 + 128 + rng.normal(0, 45 + 10 * c, size=n)
+            soft[c] = np.clip(np.round(noisy), 0, 255).astype(np.uint8)
+        # interleave so that cols=78 de-interleaves back to `soft`
+        inter = np.zeros_like(soft)
+        for c in range(C):
+            k = np.arange(n); i = k % 64; j = k // 64
+            inter[c, ((i * 27) % 64) * 78 + j] = soft[c, k]
+        t = time.time()
+        got = vb.decode_continuous(inter, 78)
+        dt = time.time() - t
+        for c in range(C):
+            ref = orc[c].decode_continuous(soft[c])
+            same = np.array_equal(ref.astype(np.uint8), got[c][:len(ref)]) and vb.last_valid[c] == len(ref)
+            ok &= same
+            if not same:
+                bad = np.nonzero(ref.astype(np.uint8) != got[c][:len(ref)])[0]
+                print("  viterbi it", it, "ch", c, "mismatch at", bad[:10], "count", len(bad))
+        print("viterbi iteration", it, "ok" if ok else "FAIL", "%.1f ms" % (dt * 1e3))
+    blk = rng.integers(0, 256, size=(C, 600), dtype=np.uint8)
+    got = vb.decode_block(blk)
+    for c in range(C):
+        ref = restated.conv_decode_soft(blk[c])[:294]
+        if not np.array_equal(ref, got[c][:294]):
+            ok = False; print("  decode_block mismatch ch", c)
+    print("VITERBI", "PASS" if ok else "FAIL")
+    return ok
+
+
+def check_demod(kind, name, kw, nch=3, seconds=None):
+    pcm = np.load(os.path.join(ROOT, "tests", "golden", name + "_excerpt.npz"))["pcm"]
+    if seconds:
+        pcm = pcm[:int(seconds * 48000)]
+    rng = np.random.default_rng(7)
+    chans = [pcm]
+    for c in range(1, nch):
+        x = pcm.astype(np.float64) * (0.5 + 0.4 * c / nch) + rng.normal(0, 150 * c, size=len(pcm))
+        chans.append(np.clip(np.round(x), -32768, 32767).astype(np.int16))
+    pcm2 = np.stack(chans)
+    b = jaero_b200.DemodBatch(kind, nch, device=0, report_ebno=True, **kw)
+    orc = [restated.OracleDemod(kind, **kw) for _ in range(nch)]
+    chunk = 4800
+    t = time.time()
+    acc = [[] for _ in range(nch)]
+    for a in range(0, pcm2.shape[1], chunk):
+        b.write(pcm2[:, a:a + chunk])
+        if (a // chunk) % 8 == 7:
+            for c, s_ in enumerate(b.read_softbits()):
+                acc[c].append(s_)
+    b.sync()
+    tg = time.time() - t
+    for c, s_ in enumerate(b.read_softbits()):
+        acc[c].append(s_)
+    soft = [np.concatenate(x) for x in acc]
+    st = b.status()
+    ok = True
+    for c in range(nch):
+        t = time.time()
+        for a in range(0, pcm2.shape[1], chunk):
+            orc[c].write(pcm2[c, a:a + chunk])
+        tc = time.time() - t
+        s_ref = orc[c].take_soft(); o = orc[c].state()
+        n = min(len(s_ref), len(soft[c]))
+        hard_same = np.array_equal(s_ref[:n] >= 128, soft[c][:n] >= 128) and len(s_ref) == len(soft[c])
+        exact = np.array_equal(s_ref, soft[c])
+        maxd = int(np.abs(s_ref[:n].astype(int) - soft[c][:n].astype(int)).max()) if n else -1
+        rel = {k: abs(st[c][k] - o[k]) / max(abs(o[k]), 1e-12) for k in o if k in st[c]}
+        worst = max(rel, key=rel.get)
+        print(f"{kind} ch{c}: soft n={len(soft[c])}/{len(s_ref)} exact={exact} hard_same={hard_same} max|d|={maxd} "
+              f"worst state {worst} rel={rel[worst]:.3e}  mse={st[c]['mse']:.5f}/{o['mse']:.5f} f={st[c]['mixer2_freq']:.4f}/{o['mixer2_freq']:.4f} "
+              f"ebno={st[c]['ebno']:.3f}/{o['ebno']:.3f} cpu={tc:.2f}s")
+        ok &= hard_same and rel[worst] < 1e-4
+    print(kind.upper(), "PASS" if ok else "FAIL", "gpu wall %.2fs for %d ch x %d samples, launches=%d" % (tg, nch, pcm2.shape[1], b.launches))
+    b.close()
+    return ok
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["viterbi", "oqpsk", "msk"]
+    ok = True
+    if "viterbi" in which:
+        ok &= check_viterbi()
+    if "oqpsk" in which:
+        ok &= check_demod("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
+    if "msk" in which:
+        ok &= check_demod("msk", "msk_600", dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True))
+    print("ALL", "PASS" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
