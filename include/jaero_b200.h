@@ -141,6 +141,27 @@ int jaero_viterbi_reset(jaero_viterbi *v);   /* SetCode(): clears the overlap of
 int jaero_viterbi_sync(jaero_viterbi *v);
 int64_t jaero_viterbi_launch_count(const jaero_viterbi *v);
 
+/* ---- P-channel frame layer (600 / 1200 / 10500 bps, continuous): soft bits -> CRC-checked signal units ----
+ * Replaces AeroL::processDemodulatedSoftBits -> AeroL::Decode(bits,true) (JAERO/aerol.cpp:2077-2090,1124-2039,
+ * non-burst branch), AeroL::updateDCD (:1109-1122) and the DataCarrierDetect -> DCDstatSlot feedback
+ * (JAERO/mainwindow.cpp:234-237). */
+typedef struct jaero_pchannel jaero_pchannel;
+int jaero_pchannel_create(int n_channels, double fb, int device_ordinal, jaero_pchannel **out);
+void jaero_pchannel_destroy(jaero_pchannel *p);
+/* Consume everything the batch's demodulators emitted since the last call (device-resident, no host hop),
+ * run framing + de-interleave + Viterbi + descramble + CRC, and write each channel's DCD back into the batch. */
+int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b);
+/* Same for soft bits supplied by the host: soft[ch*cap + k], counts[ch] (drop-in for processDemodulatedSoftBits). */
+int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
+/* AeroL::updateDCD: call once per second of signal (the reference's 1 s QTimer). b may be NULL. */
+int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b);
+/* Drain decoded signal units: out[(ch*cap + k)*16 + 0..11] = SU bytes, [12] = CRC ok, [13] = index in frame,
+ * [14..15] = frame number (LE). counts[ch] = SUs written. HOST pointers. */
+int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap_per_channel, int32_t *counts);
+/* dcd[ch], su_total[ch], su_ok[ch] (any may be NULL) */
+int jaero_pchannel_get_stats(jaero_pchannel *p, int32_t *dcd, int64_t *su_total, int64_t *su_ok);
+int64_t jaero_pchannel_launch_count(const jaero_pchannel *p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,10 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_batch_set_center_freq", "jaero_batch_get_status", "jaero_batch_get_status_all",
            "jaero_batch_launch_count", "jaero_viterbi_create", "jaero_viterbi_destroy",
            "jaero_viterbi_decode_continuous", "jaero_viterbi_decode_continuous_device", "jaero_viterbi_decode_block",
-           "jaero_viterbi_reset", "jaero_viterbi_sync", "jaero_viterbi_launch_count"]
+           "jaero_viterbi_reset", "jaero_viterbi_sync", "jaero_viterbi_launch_count",
+           "jaero_pchannel_create", "jaero_pchannel_destroy", "jaero_pchannel_process_batch",
+           "jaero_pchannel_process_softbits", "jaero_pchannel_tick", "jaero_pchannel_read_sus",
+           "jaero_pchannel_get_stats", "jaero_pchannel_launch_count"]
 
 
 def lib():
@@ -72,6 +75,14 @@ def lib():
         L.jaero_viterbi_decode_block.argtypes = [vp, vp, sz, vp]
         L.jaero_viterbi_reset.argtypes = [vp]; L.jaero_viterbi_sync.argtypes = [vp]
         L.jaero_viterbi_launch_count.argtypes = [vp]; L.jaero_viterbi_launch_count.restype = ctypes.c_int64
+        L.jaero_pchannel_create.argtypes = [i, d, i, ctypes.POINTER(vp)]
+        L.jaero_pchannel_destroy.argtypes = [vp]; L.jaero_pchannel_destroy.restype = None
+        L.jaero_pchannel_process_batch.argtypes = [vp, vp]
+        L.jaero_pchannel_process_softbits.argtypes = [vp, vp, sz, vp]
+        L.jaero_pchannel_tick.argtypes = [vp, vp]
+        L.jaero_pchannel_read_sus.argtypes = [vp, vp, sz, vp]
+        L.jaero_pchannel_get_stats.argtypes = [vp, vp, vp, vp]
+        L.jaero_pchannel_launch_count.argtypes = [vp]; L.jaero_pchannel_launch_count.restype = ctypes.c_int64
         _lib = L
     return _lib
 
@@ -200,6 +211,61 @@ class ViterbiBatch:
     def close(self):
         if self.h:
             lib().jaero_viterbi_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PChannelBatch:
+    """Batched AeroL P-channel frame layer (600/1200/10500 bps, continuous): soft bits -> CRC-checked SUs + DCD."""
+
+    def __init__(self, n_channels, fb, device=0):
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        self.su_cap = 4 * (int({600: 1152, 1200: 1152, 10500: 4992}[int(fb)]) // 2 // 96) + 8
+        _check(lib().jaero_pchannel_create(n_channels, float(fb), device, ctypes.byref(self.h)))
+
+    def process_batch(self, batch):
+        _check(lib().jaero_pchannel_process_batch(self.h, batch.h))
+
+    def process_softbits(self, soft_list):
+        cap = max(1, max(len(s) for s in soft_list))
+        buf = np.zeros((self.n, cap), dtype=np.int16)
+        counts = np.zeros(self.n, dtype=np.int32)
+        for c, s in enumerate(soft_list):
+            buf[c, :len(s)] = s; counts[c] = len(s)
+        _check(lib().jaero_pchannel_process_softbits(self.h, _p(buf), cap, _p(counts)))
+
+    def tick(self, batch=None):
+        _check(lib().jaero_pchannel_tick(self.h, batch.h if batch is not None else None))
+
+    def read_sus(self):
+        """-> per channel: (bytes[n,12], crc_ok[n], index_in_frame[n], frame[n])"""
+        out = np.zeros((self.n, self.su_cap, 16), dtype=np.uint8)
+        counts = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_pchannel_read_sus(self.h, _p(out), self.su_cap, _p(counts)))
+        res = []
+        for c in range(self.n):
+            r = out[c, :counts[c]]
+            res.append((r[:, :12].copy(), r[:, 12].astype(np.int32), r[:, 13].astype(np.int32),
+                        r[:, 14].astype(np.int32) | (r[:, 15].astype(np.int32) << 8)))
+        return res
+
+    def stats(self):
+        dcd = np.zeros(self.n, dtype=np.int32); tot = np.zeros(self.n, dtype=np.int64); ok = np.zeros(self.n, dtype=np.int64)
+        _check(lib().jaero_pchannel_get_stats(self.h, _p(dcd), _p(tot), _p(ok)))
+        return dcd, tot, ok
+
+    @property
+    def launches(self):
+        return lib().jaero_pchannel_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().jaero_pchannel_destroy(self.h); self.h = None
 
     def __del__(self):
         try:

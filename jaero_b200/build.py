@@ -15,6 +15,7 @@ UNITS = [
     ("capi.cu", []),
     ("viterbi.cu", []),
     ("cfe.cu", []),
+    ("pchannel.cu", []),
     ("demod_kernels.cu", ["-fmad=false"]),
 ]
 

@@ -597,3 +597,178 @@ int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out)
 }
 
 } // extern "C"
+
+// ====================================================================== P-channel frame layer
+#include "pchannel.cuh"
+
+struct jaero_pchannel {
+    int device; cudaStream_t stream;
+    PChanParams pp;
+    std::vector<void *> allocs;
+    uint8_t *vit_overlap; int *vit_overlap_len, *vit_renorm, *vit_valid;
+    int16_t *d_soft_stage; int *d_count_stage; size_t stage_cap;
+    PChanState *h_state; uint8_t *h_su;
+    long long launches;
+};
+
+namespace {
+template <class T> int pc_alloc(jaero_pchannel *p, T **ptr, size_t count)
+{
+    int r = dev_alloc_zero(ptr, count, p->stream);
+    if (r == 0) p->allocs.push_back((void *)*ptr);
+    return r;
+}
+__global__ void pchan_su_reset_kernel(PChanParams pp)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < pp.n_channels) pp.state[ch].su_count = 0;
+}
+} // namespace
+
+extern "C" {
+
+int jaero_pchannel_create(int n_channels, double fb, int device, jaero_pchannel **out)
+{
+    if (!out || n_channels <= 0) { set_error("jaero_pchannel_create: bad argument"); return JAERO_E_ARG; }
+    const int ifb = (int)(fb + 0.5);
+    if (ifb != 600 && ifb != 1200 && ifb != 10500) { set_error("jaero_pchannel_create: P-channel rates are 600, 1200, 10500"); return JAERO_E_ARG; }
+    int ndev = 0;
+    JB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("jaero_pchannel_create: no such CUDA device"); return JAERO_E_CUDA; }
+    JB_CUDA(cudaSetDevice(device));
+    jaero_pchannel *p = new (std::nothrow) jaero_pchannel();
+    if (!p) { set_error("out of host memory"); return JAERO_E_ARG; }
+    p->device = device; p->launches = 0; p->d_soft_stage = 0; p->d_count_stage = 0; p->stage_cap = 0;
+    JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    PChanParams &pp = p->pp;
+    memset(&pp, 0, sizeof pp);
+    pp.n_channels = n_channels; pp.paddinglength = 24;                          // aerol.cpp:940
+    switch (ifb) {                                                               // AeroL::setSettings, aerol.cpp:1013-1052
+    case 600: pp.cols = 6; pp.number_of_bits = 1152; pp.bits_in_header = 16; pp.total_number_of_bits = 16 + 1152 + 32; pp.oqpsk = 0; pp.dl2_len = 576 - 6 + 1; break;
+    case 1200: pp.cols = 9; pp.number_of_bits = 1152; pp.bits_in_header = 16; pp.total_number_of_bits = 16 + 1152 + 32; pp.oqpsk = 0; pp.dl2_len = 576 - 6 + 1; break;
+    default: pp.cols = 78; pp.number_of_bits = 4992; pp.bits_in_header = 16 + 178; pp.total_number_of_bits = 16 + 178 + 4992 + 64; pp.oqpsk = 1; pp.dl2_len = 4992 - 6 + 1; break;
+    }
+    pp.block_len = pp.cols * 64;
+    pp.info_cap = pp.number_of_bits / 16 + 16;
+    pp.su_cap = 4 * (pp.number_of_bits / 2 / 96) + 8;
+    const size_t C = n_channels;
+    int rc = 0;
+    rc |= pc_alloc(p, &pp.state, C);
+    rc |= pc_alloc(p, &pp.blocks, C * PCHAN_QUEUE * pp.block_len);
+    rc |= pc_alloc(p, &pp.decoded, C * PCHAN_QUEUE * (pp.block_len / 2));
+    rc |= pc_alloc(p, &pp.meta, C * PCHAN_QUEUE);
+    rc |= pc_alloc(p, &pp.ready, C);
+    rc |= pc_alloc(p, &pp.dl2, C * pp.dl2_len);
+    rc |= pc_alloc(p, &pp.infofield, C * pp.info_cap);
+    rc |= pc_alloc(p, &pp.su_out, C * pp.su_cap * 16);
+    rc |= pc_alloc(p, &p->vit_overlap, C * 64);
+    rc |= pc_alloc(p, &p->vit_overlap_len, C);
+    rc |= pc_alloc(p, &p->vit_renorm, C);
+    rc |= pc_alloc(p, &p->vit_valid, C);
+    if (rc) { jaero_pchannel_destroy(p); return JAERO_E_CUDA; }
+    {   // AeroLScrambler::pre_state (aerol.h:397-419)
+        int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
+        std::vector<uint8_t> seq(5000);
+        for (int a = 0; a < 5000; a++) { int v = st[0] ^ st[14]; seq[a] = (uint8_t)v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
+        if (pchan_set_scrambler(seq.data())) { jaero_pchannel_destroy(p); return JAERO_E_CUDA; }
+    }
+    if (pchan_init(pp, p->stream)) { jaero_pchannel_destroy(p); return JAERO_E_CUDA; }
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    JB_CUDA(cudaMallocHost(&p->h_state, C * sizeof(PChanState)));
+    JB_CUDA(cudaMallocHost(&p->h_su, C * pp.su_cap * 16));
+    *out = p;
+    return JAERO_OK;
+}
+void jaero_pchannel_destroy(jaero_pchannel *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (void *q : p->allocs) cudaFree(q);
+    cudaFree(p->d_soft_stage); cudaFree(p->d_count_stage);
+    cudaFreeHost(p->h_state); cudaFreeHost(p->h_su);
+    cudaStreamDestroy(p->stream);
+    delete p;
+}
+int64_t jaero_pchannel_launch_count(const jaero_pchannel *p) { return p ? p->launches : 0; }
+
+int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b)
+{
+    if (!p || !b || p->pp.n_channels != b->p.n_channels || p->device != b->device) { set_error("jaero_pchannel_process_batch: batch mismatch"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    const DemodParams &dp = b->p;
+    int *dcd = dp.I + (size_t)I_DCD * dp.cpad;
+    // everything runs on the batch's stream so it is ordered after the demodulator segments
+    if (pchan_process(p->pp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, dp.soft_cap, dcd, p->vit_overlap, p->vit_overlap_len,
+                      p->vit_renorm, p->vit_valid, PCHAN_QUEUE, b->stream, &p->launches)) return JAERO_E_CUDA;
+    soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
+    JB_CUDA(cudaGetLastError());
+    p->launches++;
+    return JAERO_OK;
+}
+int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size_t cap, const int32_t *counts)
+{
+    if (!p || !soft || !counts || cap == 0) { set_error("jaero_pchannel_process_softbits: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    const size_t C = p->pp.n_channels;
+    if (C * cap > p->stage_cap) {
+        JB_CUDA(cudaStreamSynchronize(p->stream));
+        cudaFree(p->d_soft_stage); cudaFree(p->d_count_stage); p->d_soft_stage = 0; p->d_count_stage = 0;
+        JB_CUDA(cudaMalloc(&p->d_soft_stage, C * cap * sizeof(int16_t)));
+        JB_CUDA(cudaMalloc(&p->d_count_stage, C * sizeof(int)));
+        p->stage_cap = C * cap;
+    }
+    JB_CUDA(cudaMemcpyAsync(p->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
+    JB_CUDA(cudaMemcpyAsync(p->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    if (pchan_process(p->pp, p->d_soft_stage, p->d_count_stage, (int)cap, nullptr, p->vit_overlap, p->vit_overlap_len,
+                      p->vit_renorm, p->vit_valid, PCHAN_QUEUE, p->stream, &p->launches)) return JAERO_E_CUDA;
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    return JAERO_OK;
+}
+int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b)
+{
+    if (!p || (b && b->p.n_channels != p->pp.n_channels)) { set_error("jaero_pchannel_tick: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    if (pchan_tick(p->pp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->stream)) return JAERO_E_CUDA;
+    p->launches++;
+    return JAERO_OK;
+}
+static int pc_pull_state(jaero_pchannel *p)
+{
+    JB_CUDA(cudaDeviceSynchronize());
+    JB_CUDA(cudaMemcpy(p->h_state, p->pp.state, (size_t)p->pp.n_channels * sizeof(PChanState), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap, int32_t *counts)
+{
+    if (!p || !out || !counts) { set_error("jaero_pchannel_read_sus: null argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    if (pc_pull_state(p)) return JAERO_E_CUDA;
+    const PChanParams &pp = p->pp;
+    bool overflow = false; int maxc = 0;
+    for (int ch = 0; ch < pp.n_channels; ch++) { maxc = std::max(maxc, p->h_state[ch].su_count); overflow |= p->h_state[ch].queue_overflow != 0 || (size_t)p->h_state[ch].su_count > cap; }
+    if (overflow) { set_error("P-channel queue overflow: call process/read more often"); return JAERO_E_OVERFLOW; }
+    if (maxc) JB_CUDA(cudaMemcpy(p->h_su, pp.su_out, (size_t)pp.n_channels * pp.su_cap * 16, cudaMemcpyDeviceToHost));
+    for (int ch = 0; ch < pp.n_channels; ch++) {
+        counts[ch] = p->h_state[ch].su_count;
+        if (counts[ch]) memcpy(out + (size_t)ch * cap * 16, p->h_su + (size_t)ch * pp.su_cap * 16, (size_t)counts[ch] * 16);
+    }
+    pchan_su_reset_kernel<<<(pp.n_channels + 127) / 128, 128, 0, p->stream>>>(pp);
+    JB_CUDA(cudaGetLastError());
+    JB_CUDA(cudaStreamSynchronize(p->stream));
+    return JAERO_OK;
+}
+int jaero_pchannel_get_stats(jaero_pchannel *p, int32_t *dcd, int64_t *su_total, int64_t *su_ok)
+{
+    if (!p) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    if (pc_pull_state(p)) return JAERO_E_CUDA;
+    for (int ch = 0; ch < p->pp.n_channels; ch++) {
+        if (dcd) dcd[ch] = p->h_state[ch].datacd;
+        if (su_total) su_total[ch] = p->h_state[ch].su_total;
+        if (su_ok) su_ok[ch] = p->h_state[ch].su_ok;
+    }
+    return JAERO_OK;
+}
+
+} // extern "C"

@@ -52,7 +52,8 @@ __device__ __forceinline__ void traceback(WarpHist &H, unsigned state, int min_t
 }
 
 __global__ void __launch_bounds__(128)
-viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, int n_soft, int cols, int mode, int pad,
+viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, size_t in_stride, size_t out_stride,
+                  const int *__restrict__ active_count, int active_q, int n_soft, int cols, int mode, int pad,
                   uint8_t *__restrict__ overlap, int *__restrict__ overlap_len,
                   int *__restrict__ renorm_counter, uint8_t *__restrict__ bits_out, int *__restrict__ n_valid, int n_channels,
                   int smem_per_warp, int sbuf_bytes)
@@ -61,6 +62,7 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, int n_soft, int cols, int
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ch = blockIdx.x * (blockDim.x >> 5) + warp;
     if (ch >= n_channels) return;
+    if (active_count && active_count[ch] <= active_q) return;      // nothing queued for this channel
     unsigned char *base = smem + (size_t)warp * smem_per_warp;
     uint8_t *sbuf = base;
     unsigned *h0 = reinterpret_cast<unsigned *>(base + sbuf_bytes);
@@ -71,7 +73,7 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, int n_soft, int cols, int
     const int ov = (mode == 0) ? overlap_len[ch] : 0;
     const int padn = (mode == 0) ? pad : 0;
     const int total = ov + n_soft + padn;
-    const uint8_t *src = soft_in + (size_t)ch * n_soft;
+    const uint8_t *src = soft_in + (size_t)ch * in_stride;
     for (int k = lane; k < total; k += 32) {
         uint8_t v;
         if (k < ov) v = overlap[ch * 64 + k];
@@ -150,7 +152,7 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, int n_soft, int cols, int
 
     // ---- outputs
     const int nbits = n_soft >> 1;
-    uint8_t *out = bits_out + (size_t)ch * nbits;
+    uint8_t *out = bits_out + (size_t)ch * out_stride;
     if (mode == 0) {
         // Decode_Continuous: mid(paddinglength+1, n/2); positions never written by the decoder read as 0
         const int pos = pad + 1;
@@ -176,8 +178,11 @@ size_t viterbi_smem_per_warp(int n_soft, int pad, int *sbuf_bytes)
 }
 
 int viterbi_launch(const uint8_t *d_soft, int n_soft, int cols, int mode, int pad, uint8_t *d_overlap,
-                   int *d_overlap_len, int *d_renorm, uint8_t *d_bits, int *d_valid, int n_channels, cudaStream_t stream)
+                   int *d_overlap_len, int *d_renorm, uint8_t *d_bits, int *d_valid, int n_channels, cudaStream_t stream,
+                   size_t in_stride, size_t out_stride, const int *d_active_count, int active_q)
 {
+    if (in_stride == 0) in_stride = (size_t)n_soft;
+    if (out_stride == 0) out_stride = (size_t)(n_soft / 2);
     int sbuf_bytes = 0;
     size_t per_warp = viterbi_smem_per_warp(n_soft, pad, &sbuf_bytes);
     const int warps = 4;
@@ -185,7 +190,7 @@ int viterbi_launch(const uint8_t *d_soft, int n_soft, int cols, int mode, int pa
     if (smem > 200 * 1024) { set_error("viterbi: block too long for shared memory"); return -1; }
     JB_CUDA(cudaFuncSetAttribute(viterbi_k7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (n_channels + warps - 1) / warps;
-    viterbi_k7_kernel<<<grid, warps * 32, smem, stream>>>(d_soft, n_soft, cols, mode, pad, d_overlap, d_overlap_len,
+    viterbi_k7_kernel<<<grid, warps * 32, smem, stream>>>(d_soft, in_stride, out_stride, d_active_count, active_q, n_soft, cols, mode, pad, d_overlap, d_overlap_len,
                                                           d_renorm, d_bits, d_valid, n_channels, (int)per_warp, sbuf_bytes);
     JB_CUDA(cudaGetLastError());
     return 0;

@@ -98,8 +98,55 @@ def check_demod(kind, name, kw, nch=3, seconds=None):
     return ok
 
 
+def check_pchannel():
+    """demod -> device framing/Viterbi/CRC vs oracle P-channel on the same soft bits, incl. DCD feedback."""
+    from jaero_b200 import synth
+    ok = True
+    cases = [("oqpsk", 10500, np.load(os.path.join(ROOT, "tests", "golden", "oqpsk_10500_excerpt.npz"))["pcm"],
+              dict(fb=10500, freq_center=5760, lockingbw=10500, afc=True)),
+             ("oqpsk", 10500, synth.oqpsk_pchannel_pcm(10, fc=8000.0, seed=5, ebn0_db=9.0), dict(fb=10500, freq_center=8000, lockingbw=10500)),
+             ("msk", 600, np.load(os.path.join(ROOT, "tests", "golden", "msk_600_excerpt.npz"))["pcm"],
+              dict(fb=600, freq_center=1000, lockingbw=900, afc=True))]
+    for kind, fb, pcm, kw in cases:
+        b = jaero_b200.DemodBatch(kind, 2, **kw)
+        pc = jaero_b200.PChannelBatch(2, fb)
+        od = [restated.OracleDemod(kind, fft_power=14 if kind == "oqpsk" else 13, signalthreshold=0.65 if kind == "oqpsk" else 0.5, **kw) for _ in range(2)]
+        op = [restated.OraclePChannel(fb) for _ in range(2)]
+        pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 3 // 4).astype(np.int16)])
+        chunk = 4096
+        got = [[], []]
+        for a in range(0, pcm2.shape[1], chunk):
+            b.write(pcm2[:, a:a + chunk])
+            pc.process_batch(b)
+            for c in range(2):
+                od[c].set_dcd(op[c].dcd)          # the DCD the GPU pipeline sees: state at the end of the previous chunk
+                od[c].write(pcm2[c, a:a + chunk])
+                op[c].process(od[c].take_soft())
+            if (a // chunk) % 11 == 10:
+                for c, r in enumerate(pc.read_sus()):
+                    got[c].append(r)
+            if (a + chunk) % 48000 < chunk:       # ~1 s tick on both sides at the same chunk boundary
+                pc.tick(b)
+                for c in range(2):
+                    op[c].update_dcd()
+        for c, r in enumerate(pc.read_sus()):
+            got[c].append(r)
+        dcd, tot, okc = pc.stats()
+        for c in range(2):
+            gb = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]])
+            rb, rok, rfr = op[c].take_sus()
+            same = gb.shape == rb.shape and np.array_equal(gb, rb) and np.array_equal(gok, rok)
+            st = b.status()[c]; o = od[c].state()
+            print(f"pchannel {kind}{fb} ch{c}: SUs gpu={len(gok)} oracle={len(rok)} crc_ok gpu={int(gok.sum())} oracle={int(rok.sum())} identical={same} "
+                  f"dcd gpu={dcd[c]} oracle={int(op[c].dcd)} f={st['mixer2_freq']:.4f}/{o['mixer2_freq']:.4f}")
+            ok &= same and dcd[c] == int(op[c].dcd)
+        b.close(); pc.close()
+    print("PCHANNEL", "PASS" if ok else "FAIL")
+    return ok
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["viterbi", "oqpsk", "msk"]
+    which = sys.argv[1:] or ["viterbi", "oqpsk", "msk", "pchannel"]
     ok = True
     if "viterbi" in which:
         ok &= check_viterbi()
@@ -107,5 +154,7 @@ if __name__ == "__main__":
         ok &= check_demod("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
     if "msk" in which:
         ok &= check_demod("msk", "msk_600", dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True))
+    if "pchannel" in which:
+        ok &= check_pchannel()
     print("ALL", "PASS" if ok else "FAIL")
     sys.exit(0 if ok else 1)
