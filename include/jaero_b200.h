@@ -120,6 +120,15 @@ int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out);
 int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out /* [n_channels] */);
 /* kernel launches issued by this batch so far (for bench.py's gpu_launches) */
 int64_t jaero_batch_launch_count(const jaero_batch *b);
+/* Run on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL = back to the batch's own stream),
+ * so the caller's events / other work order against the demodulator kernels. */
+int jaero_batch_set_stream(jaero_batch *b, void *cuda_stream);
+/* Measurement aid: when enabled, every segment-kernel launch and every coarse-estimator run is bracketed by CUDA
+ * events on the launch stream; get_profile() synchronises and returns the accumulated device milliseconds and
+ * launch counts since the last call: out[0]=segment ms, out[1]=segment launches, out[2]=estimator ms,
+ * out[3]=estimator runs, out[4]=samples per channel covered by the segment launches. */
+int jaero_batch_set_profiling(jaero_batch *b, int enabled);
+int jaero_batch_get_profile(jaero_batch *b, double out[5]);
 
 /* ---- K=7 r=1/2 soft Viterbi (polys 109,79), one independent decoder per channel ---- */
 int jaero_viterbi_create(int n_channels, int paddinglength, int device_ordinal, jaero_viterbi **out);
@@ -158,6 +167,8 @@ int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b);
 /* Drain decoded signal units: out[(ch*cap + k)*16 + 0..11] = SU bytes, [12] = CRC ok, [13] = index in frame,
  * [14..15] = frame number (LE). counts[ch] = SUs written. HOST pointers. */
 int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap_per_channel, int32_t *counts);
+/* Drop the queued signal units without copying them (device-side consumers / benchmarks). Asynchronous. */
+int jaero_pchannel_discard_sus(jaero_pchannel *p);
 /* dcd[ch], su_total[ch], su_ok[ch] (any may be NULL) */
 int jaero_pchannel_get_stats(jaero_pchannel *p, int32_t *dcd, int64_t *su_total, int64_t *su_ok);
 int64_t jaero_pchannel_launch_count(const jaero_pchannel *p);

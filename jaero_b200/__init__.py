@@ -38,12 +38,13 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_batch_write", "jaero_batch_write_device", "jaero_batch_sync", "jaero_batch_read_softbits",
            "jaero_batch_softbits_device", "jaero_batch_reset_softbits", "jaero_batch_set_dcd",
            "jaero_batch_set_center_freq", "jaero_batch_get_status", "jaero_batch_get_status_all",
-           "jaero_batch_launch_count", "jaero_viterbi_create", "jaero_viterbi_destroy",
+           "jaero_batch_launch_count", "jaero_batch_set_stream", "jaero_batch_set_profiling",
+           "jaero_batch_get_profile", "jaero_viterbi_create", "jaero_viterbi_destroy",
            "jaero_viterbi_decode_continuous", "jaero_viterbi_decode_continuous_device", "jaero_viterbi_decode_block",
            "jaero_viterbi_reset", "jaero_viterbi_sync", "jaero_viterbi_launch_count",
            "jaero_pchannel_create", "jaero_pchannel_destroy", "jaero_pchannel_process_batch",
            "jaero_pchannel_process_softbits", "jaero_pchannel_tick", "jaero_pchannel_read_sus",
-           "jaero_pchannel_get_stats", "jaero_pchannel_launch_count"]
+           "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count"]
 
 
 def lib():
@@ -68,6 +69,9 @@ def lib():
         L.jaero_batch_get_status.argtypes = [vp, i, ctypes.POINTER(Status)]
         L.jaero_batch_get_status_all.argtypes = [vp, vp]
         L.jaero_batch_launch_count.argtypes = [vp]; L.jaero_batch_launch_count.restype = ctypes.c_int64
+        L.jaero_batch_set_stream.argtypes = [vp, vp]
+        L.jaero_batch_set_profiling.argtypes = [vp, i]
+        L.jaero_batch_get_profile.argtypes = [vp, vp]
         L.jaero_viterbi_create.argtypes = [i, i, i, ctypes.POINTER(vp)]
         L.jaero_viterbi_destroy.argtypes = [vp]; L.jaero_viterbi_destroy.restype = None
         L.jaero_viterbi_decode_continuous.argtypes = [vp, vp, sz, i, vp, vp]
@@ -81,6 +85,7 @@ def lib():
         L.jaero_pchannel_process_softbits.argtypes = [vp, vp, sz, vp]
         L.jaero_pchannel_tick.argtypes = [vp, vp]
         L.jaero_pchannel_read_sus.argtypes = [vp, vp, sz, vp]
+        L.jaero_pchannel_discard_sus.argtypes = [vp]
         L.jaero_pchannel_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_pchannel_launch_count.argtypes = [vp]; L.jaero_pchannel_launch_count.restype = ctypes.c_int64
         _lib = L
@@ -109,6 +114,8 @@ class DemodBatch:
             fft_power = 14 if k == KIND_OQPSK else 13
         if signalthreshold is None:
             signalthreshold = 0.65 if k == KIND_OQPSK else 0.5
+        if n_channels <= 0:
+            raise JaeroError("n_channels must be positive")
         fc = np.ascontiguousarray(np.broadcast_to(np.asarray(freq_center, dtype=np.float64), (n_channels,)))
         s = Settings(k, fft_power, float(fc[0]), lockingbw, fb, Fs, signalthreshold, int(afc), int(sql), int(cpu_reduce), int(report_ebno))
         self.h = ctypes.c_void_p()
@@ -155,6 +162,17 @@ class DemodBatch:
         arr = (Status * self.n)()
         _check(lib().jaero_batch_get_status_all(self.h, ctypes.cast(arr, ctypes.c_void_p)))
         return [{f[0]: getattr(arr[c], f[0]) for f in Status._fields_} for c in range(self.n)]
+
+    def set_stream(self, cuda_stream):
+        _check(lib().jaero_batch_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def set_profiling(self, on):
+        _check(lib().jaero_batch_set_profiling(self.h, int(on)))
+
+    def get_profile(self):
+        o = np.zeros(5, dtype=np.float64)
+        _check(lib().jaero_batch_get_profile(self.h, _p(o)))
+        return dict(segment_ms=o[0], segment_launches=int(o[1]), cfe_ms=o[2], cfe_runs=int(o[3]), samples=int(o[4]))
 
     @property
     def launches(self):
@@ -253,6 +271,9 @@ class PChannelBatch:
             res.append((r[:, :12].copy(), r[:, 12].astype(np.int32), r[:, 13].astype(np.int32),
                         r[:, 14].astype(np.int32) | (r[:, 15].astype(np.int32) << 8)))
         return res
+
+    def discard_sus(self):
+        _check(lib().jaero_pchannel_discard_sus(self.h))
 
     def stats(self):
         dcd = np.zeros(self.n, dtype=np.int32); tot = np.zeros(self.n, dtype=np.int64); ok = np.zeros(self.n, dtype=np.int64)

@@ -208,6 +208,10 @@ struct jaero_batch {
     int16_t *h_soft_stage;      // pinned
     int *h_ints; double *h_dbls;   // pinned mirrors of I / D
     long long launches;
+    cudaStream_t own_stream;
+    bool profiling;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_seg, ev_cfe;
+    double prof_samples;
 };
 
 namespace {
@@ -297,6 +301,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     b->set = *s; b->device = device; b->samples = 0; b->bb_pos = 0; b->coarse_counter = 0;
     b->d_stage = 0; b->stage_cap = 0; b->launches = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    b->own_stream = b->stream; b->profiling = false; b->prof_samples = 0;
     DemodParams &p = b->p;
     memset(&p, 0, sizeof p);
     p.kind = s->kind; p.n_channels = n_channels; p.cpad = (n_channels + 31) & ~31;
@@ -426,12 +431,40 @@ void jaero_batch_destroy(jaero_batch *b)
     for (void *q : b->allocs) cudaFree(q);
     cudaFree(b->d_stage);
     cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage);
-    cudaStreamDestroy(b->stream);
+    for (auto &e : b->ev_seg) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : b->ev_cfe) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaStreamDestroy(b->own_stream);
     delete b;
 }
 int jaero_batch_channels(const jaero_batch *b) { return b ? b->p.n_channels : 0; }
 int64_t jaero_batch_launch_count(const jaero_batch *b) { return b ? b->launches : 0; }
 
+int jaero_batch_set_stream(jaero_batch *b, void *cuda_stream)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return JAERO_OK;
+}
+int jaero_batch_set_profiling(jaero_batch *b, int enabled)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    b->profiling = enabled != 0;
+    return JAERO_OK;
+}
+int jaero_batch_get_profile(jaero_batch *b, double out[5])
+{
+    if (!b || !out) { set_error("null argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    double seg = 0, cfe = 0;
+    for (auto &e : b->ev_seg) { float ms = 0; cudaEventElapsedTime(&ms, e.first, e.second); seg += ms; cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto &e : b->ev_cfe) { float ms = 0; cudaEventElapsedTime(&ms, e.first, e.second); cfe += ms; cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    out[0] = seg; out[1] = (double)b->ev_seg.size(); out[2] = cfe; out[3] = (double)b->ev_cfe.size(); out[4] = b->prof_samples;
+    b->ev_seg.clear(); b->ev_cfe.clear(); b->prof_samples = 0;
+    return JAERO_OK;
+}
 int jaero_batch_sync(jaero_batch *b)
 {
     if (!b) { set_error("null handle"); return JAERO_E_ARG; }
@@ -455,8 +488,11 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
     auto launch = [&](int i0, int i1, bool stop_after_a, int bb0, int cc0) -> int {
         a.sample0 = b->samples; a.i0 = i0; a.i1 = i1; a.skip_a_first = resume ? 1 : 0; a.stop_after_a = stop_after_a ? 1 : 0;
         a.apply_cfe = resume ? 1 : 0; a.bb_pos = bb0; a.coarse_counter = cc0;
+        cudaEvent_t e0 = 0, e1 = 0;
+        if (b->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
         int r = (p.kind == JAERO_KIND_OQPSK) ? oqpsk_segment_launch(p, a, d_pcm, stride, b->stream)
                                              : msk_segment_launch(p, a, d_pcm, stride, b->stream);
+        if (b->profiling) { cudaEventRecord(e1, b->stream); b->ev_seg.push_back({e0, e1}); b->prof_samples += (i1 - i0 - (stop_after_a ? 1 : 0)); }
         b->launches++;
         a.new_write = 0;
         return r;
@@ -473,7 +509,10 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         if (trigger) {
             if (launch(seg_start, i + 1, true, seg_bb, seg_cc)) return JAERO_E_CUDA;
             b->samples += (i - seg_start);                         // samples whose B part has run
+            cudaEvent_t c0 = 0, c1 = 0;
+            if (b->profiling) { cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventRecord(c0, b->stream); }
             if (cfe_run(b->cfe, p, bb, b->stream, &b->launches)) return JAERO_E_CUDA;
+            if (b->profiling) { cudaEventRecord(c1, b->stream); b->ev_cfe.push_back({c0, c1}); }
             cc = 0;                                                // :426
             seg_start = i; resume = true; seg_bb = bb; seg_cc = 0;
         }
@@ -609,6 +648,7 @@ struct jaero_pchannel {
     int16_t *d_soft_stage; int *d_count_stage; size_t stage_cap;
     PChanState *h_state; uint8_t *h_su;
     long long launches;
+    cudaStream_t cur_stream;     // stream of the most recent process call (the batch's stream for process_batch)
 };
 
 namespace {
@@ -621,7 +661,7 @@ template <class T> int pc_alloc(jaero_pchannel *p, T **ptr, size_t count)
 __global__ void pchan_su_reset_kernel(PChanParams pp)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch < pp.n_channels) pp.state[ch].su_count = 0;
+    if (ch < pp.n_channels) { pp.state[ch].su_count = 0; pp.state[ch].queue_overflow = 0; }
 }
 } // namespace
 
@@ -640,6 +680,7 @@ int jaero_pchannel_create(int n_channels, double fb, int device, jaero_pchannel 
     if (!p) { set_error("out of host memory"); return JAERO_E_ARG; }
     p->device = device; p->launches = 0; p->d_soft_stage = 0; p->d_count_stage = 0; p->stage_cap = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    p->cur_stream = p->stream;
     PChanParams &pp = p->pp;
     memset(&pp, 0, sizeof pp);
     pp.n_channels = n_channels; pp.paddinglength = 24;                          // aerol.cpp:940
@@ -699,6 +740,7 @@ int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b)
     const DemodParams &dp = b->p;
     int *dcd = dp.I + (size_t)I_DCD * dp.cpad;
     // everything runs on the batch's stream so it is ordered after the demodulator segments
+    p->cur_stream = b->stream;
     if (pchan_process(p->pp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, dp.soft_cap, dcd, p->vit_overlap, p->vit_overlap_len,
                       p->vit_renorm, p->vit_valid, PCHAN_QUEUE, b->stream, &p->launches)) return JAERO_E_CUDA;
     soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
@@ -718,6 +760,8 @@ int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size
         JB_CUDA(cudaMalloc(&p->d_count_stage, C * sizeof(int)));
         p->stage_cap = C * cap;
     }
+    JB_CUDA(cudaStreamSynchronize(p->cur_stream));
+    p->cur_stream = p->stream;
     JB_CUDA(cudaMemcpyAsync(p->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
     JB_CUDA(cudaMemcpyAsync(p->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     if (pchan_process(p->pp, p->d_soft_stage, p->d_count_stage, (int)cap, nullptr, p->vit_overlap, p->vit_overlap_len,
@@ -753,9 +797,18 @@ int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap, int32_t
         counts[ch] = p->h_state[ch].su_count;
         if (counts[ch]) memcpy(out + (size_t)ch * cap * 16, p->h_su + (size_t)ch * pp.su_cap * 16, (size_t)counts[ch] * 16);
     }
-    pchan_su_reset_kernel<<<(pp.n_channels + 127) / 128, 128, 0, p->stream>>>(pp);
+    pchan_su_reset_kernel<<<(pp.n_channels + 127) / 128, 128, 0, p->cur_stream>>>(pp);
     JB_CUDA(cudaGetLastError());
-    JB_CUDA(cudaStreamSynchronize(p->stream));
+    JB_CUDA(cudaStreamSynchronize(p->cur_stream));
+    return JAERO_OK;
+}
+int jaero_pchannel_discard_sus(jaero_pchannel *p)
+{
+    if (!p) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    pchan_su_reset_kernel<<<(p->pp.n_channels + 127) / 128, 128, 0, p->cur_stream>>>(p->pp);
+    JB_CUDA(cudaGetLastError());
+    p->launches++;
     return JAERO_OK;
 }
 int jaero_pchannel_get_stats(jaero_pchannel *p, int32_t *dcd, int64_t *su_total, int64_t *su_ok)

@@ -106,14 +106,45 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     const bool ebno_on = p.report_ebno != 0;
     const int16_t *row = pcm + (size_t)ch * stride;
 
+    // ---- software-pipelined operands. The GPU issues in order: a load only stalls the thread when its result is
+    // used, so everything whose address is known early (lock-step ring slots, the next PCM sample, the NCO table
+    // entries for the already-advanced phases, the symbol-rate ring slots of the next strobe) is requested one
+    // iteration ahead and consumed from registers. One DRAM round trip per sample instead of a chain of them.
+    const bool ring_on0 = (coarse_counter >= p.Fs || !p.cpu_reduce);
+    int cur_pcm = row[a.i0];
+    double cur_agc_old = p.agc_ring[(size_t)agc_pos * p.cpad + ch];
+    double cur_e1_old = ebno_on ? p.ebno_e1[(size_t)eb_pos * p.cpad + ch] : 0.0;
+    double cur_e2_old = ebno_on ? p.ebno_e2[(size_t)eb_pos * p.cpad + ch] : 0.0;
+    double c2_re, c2_im, cs_re, cs_im, cc_re, cc_im;
+    { const int t = osc_index(m2.ptr); c2_re = p.cos_t[t]; c2_im = p.sin_t[t]; }
+    { const int t = osc_index(st.ptr); cs_re = p.cos_t[t]; cs_im = p.sin_t[t]; }
+    { const int t = osc_index(mc.ptr); cc_re = p.cos_t[t]; cc_im = p.sin_t[t]; }
+    (void)ring_on0;
+    double sy_marg_old = p.marg_ring[(size_t)marg_pos * p.cpad + ch];
+    double sy_pm_old = p.mse_pm[(size_t)mse_pos * p.cpad + ch];
+    double sy_ma_old = p.mse_ma[(size_t)mse_pos * p.cpad + ch];
+    double2 sy_dt_old = p.dt_ring[(size_t)((dt_pos + 1) % p.dt_len) * p.cpad + ch];
+
     for (int i = a.i0; i < a.i1; i++) {
-        const double dval = ((double)row[i]) / 32768.0;                   // :390
+        const double dval = ((double)cur_pcm) / 32768.0;                  // :390
+        // requests for the next iteration (slots that this iteration does not write)
+        int nxt_pcm = cur_pcm;
+        double nxt_agc_old = 0, nxt_e1_old = 0, nxt_e2_old = 0;
+        if (i + 1 < a.i1) {
+            nxt_pcm = row[i + 1];
+            int np_ = agc_pos + 1; if (np_ >= agc_len) np_ = 0;
+            nxt_agc_old = p.agc_ring[(size_t)np_ * p.cpad + ch];
+            if (ebno_on) {
+                int ne_ = eb_pos + 1; if (ne_ >= eb_len) ne_ = 0;
+                nxt_e1_old = p.ebno_e1[(size_t)ne_ * p.cpad + ch];
+                nxt_e2_old = p.ebno_e2[(size_t)ne_ * p.cpad + ch];
+            }
+        }
 
         // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
         if (!(i == a.i0 && a.skip_a_first)) {
             if (coarse_counter >= p.Fs || !p.cpu_reduce) {
-                const int t = osc_index(mc.ptr);
-                p.bb[(size_t)ch * p.bbnfft + bb_pos] = make_double2(p.cos_t[t] * dval, p.sin_t[t] * dval);
+                p.bb[(size_t)ch * p.bbnfft + bb_pos] = make_double2(cc_re * dval, cc_im * dval);
                 bb_pos++; if (bb_pos >= p.bbnfft) bb_pos = 0;
             }
         }
@@ -121,14 +152,13 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         coarse_counter++;                                                 // :431
 
         // ---- B
-        const int t2 = osc_index(m2.ptr);
-        const double cre = p.cos_t[t2] * dval, cim = p.sin_t[t2] * dval;   // :453 cval = CIS * dval
-        // FIR x2 (DSP.cpp:292-304): write, advance, sum oldest -> newest excluding the sample just written
-        s_re[fir_pos][lane] = cre; s_im[fir_pos][lane] = cim;
-        fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
+        const double cre = c2_re * dval, cim = c2_im * dval;               // :453 cval = CIS * dval
+        // FIR x2 (DSP.cpp:292-304): the reference writes the new sample, advances, then sums the 55 OLDER entries
+        // (oldest -> newest, excluding the one just written). Summing first and storing afterwards reads the same
+        // entries in the same order and keeps the NCO table load off the critical path.
         double sre = 0, sim = 0;
         {
-            int tp = fir_pos;
+            int tp = fir_pos + 1; if (tp >= OQ_NT1) tp = 0;
 #pragma unroll 11
             for (int k = 0; k < 55; k++) {
                 sre += c_taps[k] * s_re[tp][lane];
@@ -136,13 +166,15 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 tp++; if (tp >= OQ_NT1) tp = 0;
             }
         }
+        s_re[fir_pos][lane] = cre; s_im[fir_pos][lane] = cim;
+        fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
         const double dabval = sqrt(sre * sre + sim * sim);                // :461
 
         if (ebno_on) {                                                    // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
             const size_t e = (size_t)eb_pos * p.cpad + ch;
             const double sq = dabval * dabval;
-            eb_sum2 = eb_sum2 - p.ebno_e2[e]; eb_sum2 = eb_sum2 + fabs(sq); p.ebno_e2[e] = fabs(sq);
-            eb_sum1 = eb_sum1 - p.ebno_e1[e]; eb_sum1 = eb_sum1 + fabs(dabval); p.ebno_e1[e] = fabs(dabval);
+            eb_sum2 = eb_sum2 - cur_e2_old; eb_sum2 = eb_sum2 + fabs(sq); p.ebno_e2[e] = fabs(sq);
+            eb_sum1 = eb_sum1 - cur_e1_old; eb_sum1 = eb_sum1 + fabs(dabval); p.ebno_e1[e] = fabs(dabval);
             const double e2val = eb_sum2 / ((double)eb_len), mean = eb_sum1 / ((double)eb_len);
             const double mean_sq = mean * mean;
             double var = (e2val) - (mean * mean);
@@ -159,7 +191,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
 
         {   // AGC::Update (DSP.cpp:370-379)
             const size_t e = (size_t)agc_pos * p.cpad + ch;
-            agc_sum = agc_sum - p.agc_ring[e];
+            agc_sum = agc_sum - cur_agc_old;
             agc_sum = agc_sum + fabs(dabval);
             p.agc_ring[e] = fabs(dabval);
             agc_pos++; if (agc_pos >= agc_len) agc_pos = 0;
@@ -197,8 +229,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
             d8out = (p.w8 * newer + (1.0 - p.w8) * older);
             d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta;
         }
-        const int ts = osc_index(st.ptr);
-        const double2 st_out = cmul(make_double2(p.cos_t[ts], p.sin_t[ts]), make_double2(st_eta, -d8out));   // :478-479
+        const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
         const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
         osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, p.Fs); // :481 IncreseFreqHz
         osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0); // :482
@@ -232,7 +263,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 }
                 {   // marg->UpdateSigned(ct_ec)  MA(800)  (:535, DSP.cpp:418-426)
                     const size_t e = (size_t)marg_pos * p.cpad + ch;
-                    marg_sum = marg_sum - p.marg_ring[e];
+                    marg_sum = marg_sum - sy_marg_old;
                     marg_sum = marg_sum + (ct_ec);
                     p.marg_ring[e] = (ct_ec);
                     marg_pos++; marg_pos %= p.marg_len;
@@ -241,23 +272,28 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 {   // dt.update(pt_qpsk): 400-symbol delay (:536, DSP.h:455-460)
                     p.dt_ring[(size_t)dt_pos * p.cpad + ch] = pt_qpsk;
                     dt_pos++; dt_pos %= p.dt_len;
-                    pt_qpsk = p.dt_ring[(size_t)dt_pos * p.cpad + ch];
+                    pt_qpsk = sy_dt_old;                                  // requested after the previous strobe
                 }
                 pt_qpsk = cmul(pt_qpsk, make_double2(cos(marg_val), sin(marg_val)));   // :537
                 {   // MSEcalc::Update (DSP.cpp:451-463)
                     const size_t e = (size_t)mse_pos * p.cpad + ch;
                     const double ab = hypot(pt_qpsk.x, pt_qpsk.y);
-                    pm_sum = pm_sum - p.mse_pm[e]; pm_sum = pm_sum + fabs(ab); p.mse_pm[e] = fabs(ab);
+                    pm_sum = pm_sum - sy_pm_old; pm_sum = pm_sum + fabs(ab); p.mse_pm[e] = fabs(ab);
                     double mu = pm_sum / ((double)p.mse_len);
                     if (mu < 0.000001) mu = 0.000001;
                     const double r2 = sqrt(2.0);
                     const double tre = (r2 * pt_qpsk.x) / mu, tim = (r2 * pt_qpsk.y) / mu;
                     const double tda = (fabs(tre) - 1.0), tdb = (fabs(tim) - 1.0);
                     const double v = (tda * tda) + (tdb * tdb);
-                    ma_sum = ma_sum - p.mse_ma[e]; ma_sum = ma_sum + fabs(v); p.mse_ma[e] = fabs(v);
+                    ma_sum = ma_sum - sy_ma_old; ma_sum = ma_sum + fabs(v); p.mse_ma[e] = fabs(v);
                     mse_pos++; mse_pos %= p.mse_len;
                     mse = ma_sum / ((double)p.mse_len);
                 }
+                // operands of the next strobe pair (slots written >= 400 symbols ago)
+                sy_marg_old = p.marg_ring[(size_t)marg_pos * p.cpad + ch];
+                sy_pm_old = p.mse_pm[(size_t)mse_pos * p.cpad + ch];
+                sy_ma_old = p.mse_ma[(size_t)mse_pos * p.cpad + ch];
+                sy_dt_old = p.dt_ring[(size_t)((dt_pos + 1) % p.dt_len) * p.cpad + ch];
                 if (mse < p.signalthreshold) {                            // :565
                     push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.y * 127.0 + 128.0));
                     push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.x * 127.0 + 128.0));
@@ -270,6 +306,10 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         }
         sig2_last = sig2;                                                 // :596
         osc_next_frame(m2); osc_next_frame(mc); osc_next_frame(st); osc_next_frame(sr);   // :600-603
+        { const int t = osc_index(m2.ptr); c2_re = p.cos_t[t]; c2_im = p.sin_t[t]; }
+        { const int t = osc_index(st.ptr); cs_re = p.cos_t[t]; cs_im = p.sin_t[t]; }
+        { const int t = osc_index(mc.ptr); cc_re = p.cos_t[t]; cc_im = p.sin_t[t]; }
+        cur_pcm = nxt_pcm; cur_agc_old = nxt_agc_old; cur_e1_old = nxt_e1_old; cur_e2_old = nxt_e2_old;
     }
 
     // ---------------- store state

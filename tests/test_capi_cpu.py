@@ -1,0 +1,55 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/jaero_b200.h declares; without a GPU the product fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, has_cuda
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "jaero_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jaero_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from jaero_b200 import build
+    so = build.build()
+    L = ctypes.CDLL(so)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), "missing export " + n
+    import jaero_b200
+    assert set(jaero_b200.EXPORTS) <= set(names)
+
+
+def test_python_structs_match_header_layout():
+    import jaero_b200
+    assert ctypes.sizeof(jaero_b200.Settings) == 4 + 4 + 5 * 8 + 4 * 4          # kind, fft_power, 5 doubles, 4 ints
+    assert ctypes.sizeof(jaero_b200.Status) == 14 * 8 + 2 * 8 + 2 * 4
+
+
+@pytest.mark.skipif(has_cuda(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    import jaero_b200
+    with pytest.raises(jaero_b200.JaeroError):
+        jaero_b200.DemodBatch("oqpsk", 4, fb=10500)
+    with pytest.raises(jaero_b200.JaeroError):
+        jaero_b200.ViterbiBatch(4)
+    with pytest.raises(jaero_b200.JaeroError):
+        jaero_b200.PChannelBatch(4, 10500)
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under jaero_b200/ may include, import or link it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jaero_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r'#include\s*[<"][^>"]*oracle', txt), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+                assert "libjaero_oracle" not in txt and "libjaero_ref" not in txt, f

@@ -1,0 +1,55 @@
+"""Generate tests/golden/expected_outputs.json by running the VERBATIM reference (oracle/_ref, built from
+/root/reference by oracle/Makefile) over the committed PCM excerpts. Build container only.
+
+For each excerpt: SHA-256 of the emitted soft-bit stream, its length, the final loop state, the coarse
+estimator log digest, and the signal units + CRC flags that the restated AeroL P-channel framing decodes
+from those soft bits (the Viterbi arithmetic inside is the restated libcorrect: parity unpinned upstream,
+pinned here by CRC-16-valid SUs)."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref, restated  # noqa: E402
+
+CASES = {
+    "oqpsk_10500": dict(kind="oqpsk", kw=dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)),
+    "oqpsk_10500_noafc_dcd": dict(kind="oqpsk", excerpt="oqpsk_10500", dcd_at=96000,
+                                  kw=dict(fb=10500, freq_center=5757, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=False)),
+    "msk_600": dict(kind="msk", kw=dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True)),
+}
+
+
+def run_case(name, case, chunk=4800):
+    import multiprocessing as mp
+    pcm = np.load(os.path.join(ROOT, "tests", "golden", case.get("excerpt", name) + "_excerpt.npz"))["pcm"]
+    sched = [(case["dcd_at"], 1)] if "dcd_at" in case else None
+    ctx = mp.get_context("spawn")            # fresh process: the reference keeps function-local statics
+    with ctx.Pool(1) as pool:
+        soft, state, cfe = pool.apply(ref.run_demod_job, ((case["kind"], case["kw"], pcm, chunk, sched),))
+    p = restated.OraclePChannel(case["kw"]["fb"])
+    p.process(soft)
+    su, ok, fr = p.take_sus()
+    return {
+        "kind": case["kind"], "kw": case["kw"], "excerpt": case.get("excerpt", name), "chunk": chunk,
+        "dcd_schedule": sched or [],
+        "n_soft": int(len(soft)), "soft_sha256": hashlib.sha256(soft.astype("<i2").tobytes()).hexdigest(),
+        "soft_head": [int(x) for x in soft[:64]],
+        "state": {k: float(v) for k, v in state.items()},
+        "cfe_log_sha256": hashlib.sha256(np.asarray(cfe, dtype="<f8").tobytes()).hexdigest(), "n_cfe": int(len(cfe)),
+        "n_su": int(len(ok)), "n_su_crc_ok": int(ok.sum()),
+        "su_sha256": hashlib.sha256(su.tobytes() + ok.astype("<i4").tobytes()).hexdigest(),
+        "su_first_ok": [int(x) for x in su[np.argmax(ok)]] if ok.any() else [],
+    }
+
+
+if __name__ == "__main__":
+    out = {name: run_case(name, case) for name, case in CASES.items()}
+    for k, v in out.items():
+        print(k, v["n_soft"], v["n_su"], v["n_su_crc_ok"], v["state"]["mse"])
+    with open(os.path.join(ROOT, "tests", "golden", "expected_outputs.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
