@@ -31,7 +31,16 @@ __device__ __forceinline__ void osc_next_frame(Osc &o)               // DSP.cpp:
     if (o.step < 0) o.step = 0;
     o.last = o.ptr;
     o.ptr += o.step;
-    while (((int)o.ptr) >= WTSIZE) o.ptr -= WTSIZE;
+    // `while(((int)WTptr)>=WTSIZE)`: for the non-negative finite pointer, (int)x >= N  <=>  x >= (double)N
+    while (o.ptr >= (double)WTSIZE) o.ptr -= WTSIZE;
+}
+// table index the oscillator will have after its next WTnextFrame(), without committing the advance
+__device__ __forceinline__ int osc_next_index(const Osc &o)
+{
+    double s = o.step; if (s < 0) s = 0;
+    double q = o.ptr + s;
+    while (q >= (double)WTSIZE) q -= WTSIZE;
+    return osc_index(q);
 }
 __device__ __forceinline__ void osc_set_phase_deg(Osc &o, double p)  // DSP.cpp:175-180
 {

@@ -28,19 +28,46 @@ int demod_set_taps(const double *taps, int n)
 
 static const int OQ_THREADS = 32;
 static const int OQ_NT1 = 56;             // 55 taps + 1 (FIR ring, DSP.cpp:277)
+static const int OQ_FIRROWS = 2 * OQ_NT1; // every entry is stored twice so any 55-entry window is contiguous
+static const int OQ_EBNO_TAIL = 256;      // samples before the end of a launch over which the EbNo read-out is evaluated
 
-#define LD(idx) p.D[(size_t)(idx) * p.cpad + ch]
-#define LI(idx) p.I[(size_t)(idx) * p.cpad + ch]
+#define LD(idx) p.D[(size_t)(idx) * cpad + ch]
+#define LI(idx) p.I[(size_t)(idx) * cpad + ch]
+
+// 55-tap FIR over a contiguous window (oldest first), exactly the accumulation order of
+// FIR::FIRUpdateAndProcess (DSP.cpp:296-303): outsum += points[i]*buff[tptr], i = 0..54.
+__device__ __forceinline__ void fir55(const double *__restrict__ wre, const double *__restrict__ wim, double &ore, double &oim)
+{
+    double sre = 0, sim = 0;
+#pragma unroll
+    for (int k = 0; k < 55; k++) {
+        sre += c_taps[k] * wre[k * OQ_THREADS];
+        sim += c_taps[k] * wim[k * OQ_THREADS];
+    }
+    ore = sre; oim = sim;
+}
+// the first 54 terms of the same sum (everything except the newest sample, which is still being mixed)
+__device__ __forceinline__ void fir54(const double *__restrict__ wre, const double *__restrict__ wim, double &ore, double &oim)
+{
+    double sre = 0, sim = 0;
+#pragma unroll
+    for (int k = 0; k < 54; k++) {
+        sre += c_taps[k] * wre[k * OQ_THREADS];
+        sim += c_taps[k] * wim[k * OQ_THREADS];
+    }
+    ore = sre; oim = sim;
+}
 
 __global__ void __launch_bounds__(OQ_THREADS)
 oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
 {
-    __shared__ double s_re[OQ_NT1][OQ_THREADS];
-    __shared__ double s_im[OQ_NT1][OQ_THREADS];
+    extern __shared__ double oq_smem[];
+    double *s_re = oq_smem;                                   // [OQ_FIRROWS][32]
+    double *s_im = oq_smem + OQ_FIRROWS * OQ_THREADS;
     const int lane = threadIdx.x;
     const int ch = blockIdx.x * OQ_THREADS + lane;
-    const bool live = ch < p.n_channels;
-    if (!live) return;                    // no block-level barriers below
+    if (ch >= p.n_channels) return;       // no block-level barriers below
+    const size_t cpad = p.cpad;
 
     // ---------------- load state
     Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
@@ -67,8 +94,9 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     int sig_true = LI(I_SIG_TRUE), sig_false = LI(I_SIG_FALSE);
 
     for (int k = 0; k < OQ_NT1; k++) {
-        s_re[k][lane] = p.fir_re[(size_t)k * p.cpad + ch];
-        s_im[k][lane] = p.fir_im[(size_t)k * p.cpad + ch];
+        const double vr = p.fir_re[(size_t)k * cpad + ch], vi = p.fir_im[(size_t)k * cpad + ch];
+        s_re[k * OQ_THREADS + lane] = vr; s_re[(k + OQ_NT1) * OQ_THREADS + lane] = vr;
+        s_im[k * OQ_THREADS + lane] = vi; s_im[(k + OQ_NT1) * OQ_THREADS + lane] = vi;
     }
     if (a.new_write) lastmse = mse;                                       // oqpskdemodulator.cpp:339
 
@@ -90,111 +118,137 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 if (mc.freq > (p.Fs / 2.0 - p.lockingbw / 2.0)) osc_set_freq(mc, p.Fs / 2.0 - p.lockingbw / 2.0, p.Fs);
                 LI(I_EMPTYING) = 4;                                       // CoarseFreqEstimate::bigchange (coarsefreqestimate.cpp:84-88)
                 LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
-                double2 *row = p.bb + (size_t)ch * p.bbnfft;              // :667 bbcycbuff[j]=0
-                for (int j = 0; j < p.bbnfft; j++) row[j] = make_double2(0.0, 0.0);
+                double2 *rowz = p.bb + (size_t)ch * p.bbnfft;             // :667 bbcycbuff[j]=0
+                for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);
             }
         } else countdown = 4;
         if (mse > p.signalthreshold) sig_false++; else sig_true++;       // :674-675
     }
 
-    // ---------------- uniform ring positions
+    // ---------------- lock-step ring cursors (pointer + position), advanced by one row per sample
     const int agc_len = p.agc_len, eb_len = p.ebno_len;
     int agc_pos = (int)(a.sample0 % agc_len);
     int eb_pos = (int)(a.sample0 % eb_len);
-    int fir_pos = (int)(a.sample0 % OQ_NT1);
+    int fir_pos = (int)(a.sample0 % OQ_NT1);                  // next FIR slot to write
     int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
     const bool ebno_on = p.report_ebno != 0;
     const int16_t *row = pcm + (size_t)ch * stride;
+    double *agc_p = p.agc_ring + (size_t)agc_pos * cpad + ch;
+    double *agc_base = p.agc_ring + ch, *agc_end = p.agc_ring + (size_t)agc_len * cpad + ch;
+    double *e1_p = ebno_on ? p.ebno_e1 + (size_t)eb_pos * cpad + ch : nullptr;
+    double *e2_p = ebno_on ? p.ebno_e2 + (size_t)eb_pos * cpad + ch : nullptr;
+    const size_t eb_span = (size_t)eb_len * cpad;
+    double2 *bb_row = p.bb + (size_t)ch * p.bbnfft;
+    const int bbn = p.bbnfft;
+    const bool cpu_reduce = p.cpu_reduce != 0;
+    const double Fs = p.Fs, fbr = p.fb, thr = p.signalthreshold, ee = p.ee;
+    const double res_a1 = p.res_a1, res_a2 = p.res_a2, res_b0 = p.res_b0, res_b1 = p.res_b1, res_b2 = p.res_b2;
+    const double w41 = p.w41, w8 = p.w8;
+    const int k41 = p.k41, k8 = p.k8;
+    const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
+    const int marg_len = p.marg_len, dt_len = p.dt_len, mse_len = p.mse_len;
+    const int eb_from = a.i1 - OQ_EBNO_TAIL;
 
-    // ---- software-pipelined operands. The GPU issues in order: a load only stalls the thread when its result is
-    // used, so everything whose address is known early (lock-step ring slots, the next PCM sample, the NCO table
-    // entries for the already-advanced phases, the symbol-rate ring slots of the next strobe) is requested one
-    // iteration ahead and consumed from registers. One DRAM round trip per sample instead of a chain of them.
-    const bool ring_on0 = (coarse_counter >= p.Fs || !p.cpu_reduce);
+    // ---- software-pipelined operands. The SM issues a warp's instructions in order: a load only stalls the warp
+    // when its result is used, so everything whose address is known early (lock-step ring slots, the next PCM sample,
+    // the NCO table entries of the already-advanced phases, the symbol-rate ring slots of the next strobe) is requested
+    // one iteration ahead and consumed from registers: one DRAM round trip per sample instead of a chain of them.
     int cur_pcm = row[a.i0];
-    double cur_agc_old = p.agc_ring[(size_t)agc_pos * p.cpad + ch];
-    double cur_e1_old = ebno_on ? p.ebno_e1[(size_t)eb_pos * p.cpad + ch] : 0.0;
-    double cur_e2_old = ebno_on ? p.ebno_e2[(size_t)eb_pos * p.cpad + ch] : 0.0;
+    double cur_agc_old = *agc_p;
+    double cur_e1_old = ebno_on ? *e1_p : 0.0;
+    double cur_e2_old = ebno_on ? *e2_p : 0.0;
     double c2_re, c2_im, cs_re, cs_im, cc_re, cc_im;
-    { const int t = osc_index(m2.ptr); c2_re = p.cos_t[t]; c2_im = p.sin_t[t]; }
-    { const int t = osc_index(st.ptr); cs_re = p.cos_t[t]; cs_im = p.sin_t[t]; }
-    { const int t = osc_index(mc.ptr); cc_re = p.cos_t[t]; cc_im = p.sin_t[t]; }
-    (void)ring_on0;
-    double sy_marg_old = p.marg_ring[(size_t)marg_pos * p.cpad + ch];
-    double sy_pm_old = p.mse_pm[(size_t)mse_pos * p.cpad + ch];
-    double sy_ma_old = p.mse_ma[(size_t)mse_pos * p.cpad + ch];
-    double2 sy_dt_old = p.dt_ring[(size_t)((dt_pos + 1) % p.dt_len) * p.cpad + ch];
+    { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
+    { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+    { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+    double sy_marg_old = p.marg_ring[(size_t)marg_pos * cpad + ch];
+    double sy_pm_old = p.mse_pm[(size_t)mse_pos * cpad + ch];
+    double sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
+    double2 sy_dt_old;
+    { int r = dt_pos + 1; if (r >= dt_len) r = 0; sy_dt_old = p.dt_ring[(size_t)r * cpad + ch]; }
+
+    // FIR output of the first sample of this launch: the 55 entries older than the slot about to be written
+    // (DSP.cpp:292-304: the output excludes the sample just stored). The window that ends at logical slot q starts at
+    // row q+2 of the doubled buffer.
+    double fre, fim;
+    {
+        int newest = fir_pos - 1; if (newest < 0) newest += OQ_NT1;
+        fir55(s_re + (newest + 2) * OQ_THREADS + lane, s_im + (newest + 2) * OQ_THREADS + lane, fre, fim);
+    }
 
     for (int i = a.i0; i < a.i1; i++) {
         const double dval = ((double)cur_pcm) / 32768.0;                  // :390
-        // requests for the next iteration (slots that this iteration does not write)
+        // requests for the next iteration (slots this iteration does not write)
         int nxt_pcm = cur_pcm;
         double nxt_agc_old = 0, nxt_e1_old = 0, nxt_e2_old = 0;
+        double *agc_n = agc_p + cpad; if (agc_n >= agc_end) agc_n = agc_base;
         if (i + 1 < a.i1) {
             nxt_pcm = row[i + 1];
-            int np_ = agc_pos + 1; if (np_ >= agc_len) np_ = 0;
-            nxt_agc_old = p.agc_ring[(size_t)np_ * p.cpad + ch];
+            nxt_agc_old = *agc_n;
             if (ebno_on) {
-                int ne_ = eb_pos + 1; if (ne_ >= eb_len) ne_ = 0;
-                nxt_e1_old = p.ebno_e1[(size_t)ne_ * p.cpad + ch];
-                nxt_e2_old = p.ebno_e2[(size_t)ne_ * p.cpad + ch];
+                const bool wrap = (eb_pos + 1 >= eb_len);
+                nxt_e1_old = wrap ? *(e1_p + cpad - eb_span) : *(e1_p + cpad);
+                nxt_e2_old = wrap ? *(e2_p + cpad - eb_span) : *(e2_p + cpad);
             }
         }
 
         // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
         if (!(i == a.i0 && a.skip_a_first)) {
-            if (coarse_counter >= p.Fs || !p.cpu_reduce) {
-                p.bb[(size_t)ch * p.bbnfft + bb_pos] = make_double2(cc_re * dval, cc_im * dval);
-                bb_pos++; if (bb_pos >= p.bbnfft) bb_pos = 0;
+            if (coarse_counter >= Fs || !cpu_reduce) {
+                bb_row[bb_pos] = make_double2(cc_re * dval, cc_im * dval);
+                bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
             }
         }
         if (i == a.i1 - 1 && a.stop_after_a) break;
         coarse_counter++;                                                 // :431
+        // mixer_center only free-runs inside the loop: advance it now (:601) and request its next table entry a whole
+        // iteration before the ring write that consumes it
+        osc_next_frame(mc);
+        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+        // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
+        const int m2_spec = osc_next_index(m2);
+        double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
 
-        // ---- B
-        const double cre = c2_re * dval, cim = c2_im * dval;               // :453 cval = CIS * dval
-        // FIR x2 (DSP.cpp:292-304): the reference writes the new sample, advances, then sums the 55 OLDER entries
-        // (oldest -> newest, excluding the one just written). Summing first and storing afterwards reads the same
-        // entries in the same order and keeps the NCO table load off the critical path.
-        double sre = 0, sim = 0;
-        {
-            int tp = fir_pos + 1; if (tp >= OQ_NT1) tp = 0;
-#pragma unroll 11
-            for (int k = 0; k < 55; k++) {
-                sre += c_taps[k] * s_re[tp][lane];
-                sim += c_taps[k] * s_im[tp][lane];
-                tp++; if (tp >= OQ_NT1) tp = 0;
-            }
-        }
-        s_re[fir_pos][lane] = cre; s_im[fir_pos][lane] = cim;
-        fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
+        // ---- B. cval = CIS * dval (:453) goes into the FIR ring; the output for THIS sample (fre,fim) was formed from
+        // the older entries in the previous iteration, the output for the NEXT sample is formed now — an independent
+        // dependency chain the scheduler interleaves with the serial loop arithmetic below.
+        // The 54 older terms are summed first (same order as DSP.cpp:296-303), the newest term is appended once the mixed
+        // sample is available.
+        double nfre, nfim;
+        fir54(s_re + (fir_pos + 2) * OQ_THREADS + lane, s_im + (fir_pos + 2) * OQ_THREADS + lane, nfre, nfim);
+
+        const double sre = fre, sim = fim;
         const double dabval = sqrt(sre * sre + sim * sim);                // :461
 
         if (ebno_on) {                                                    // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
-            const size_t e = (size_t)eb_pos * p.cpad + ch;
             const double sq = dabval * dabval;
-            eb_sum2 = eb_sum2 - cur_e2_old; eb_sum2 = eb_sum2 + fabs(sq); p.ebno_e2[e] = fabs(sq);
-            eb_sum1 = eb_sum1 - cur_e1_old; eb_sum1 = eb_sum1 + fabs(dabval); p.ebno_e1[e] = fabs(dabval);
-            const double e2val = eb_sum2 / ((double)eb_len), mean = eb_sum1 / ((double)eb_len);
-            const double mean_sq = mean * mean;
-            double var = (e2val) - (mean * mean);
-            var -= (0.024709 * mean_sq);
-            double mvr = (((p.Fs * mean_sq / (2.0 * p.fb * var))) * 0.13743);
-            if (mvr < 0.000000001) mvr = 0.000000001;
-            double tebno = 10.0 * log10(mvr);
-            if (isnan(tebno)) tebno = 50;
-            if (tebno > 50.0) tebno = 50;
-            if (tebno < 0.0) tebno = 0;
-            eb_ebno = eb_ebno * 0.8 + 0.2 * tebno;
+            eb_sum2 = eb_sum2 - cur_e2_old; eb_sum2 = eb_sum2 + fabs(sq); *e2_p = fabs(sq);
+            eb_sum1 = eb_sum1 - cur_e1_old; eb_sum1 = eb_sum1 + fabs(dabval); *e1_p = fabs(dabval);
+            // The smoothed read-out EbNo <- 0.8 EbNo + 0.2 tebno forgets its past by 0.8^k: evaluating it over the last
+            // 256 samples of a launch reproduces the value a per-sample evaluation has at the end of the launch to
+            // below 1e-24 relative, without a log10 and three divisions on every sample. Observable only (DSP.h:250).
+            if (i >= eb_from) {
+                const double e2val = eb_sum2 / ((double)eb_len), mean = eb_sum1 / ((double)eb_len);
+                const double mean_sq = mean * mean;
+                double var = (e2val) - (mean * mean);
+                var -= (0.024709 * mean_sq);
+                double mvr = (((Fs * mean_sq / (2.0 * fbr * var))) * 0.13743);
+                if (mvr < 0.000000001) mvr = 0.000000001;
+                double tebno = 10.0 * log10(mvr);
+                if (isnan(tebno)) tebno = 50;
+                if (tebno > 50.0) tebno = 50;
+                if (tebno < 0.0) tebno = 0;
+                eb_ebno = eb_ebno * 0.8 + 0.2 * tebno;
+            }
+            e1_p += cpad; e2_p += cpad; eb_pos++;
+            if (eb_pos >= eb_len) { eb_pos = 0; e1_p -= eb_span; e2_p -= eb_span; }
         }
-        eb_pos++; if (eb_pos >= eb_len) eb_pos = 0;
 
         {   // AGC::Update (DSP.cpp:370-379)
-            const size_t e = (size_t)agc_pos * p.cpad + ch;
             agc_sum = agc_sum - cur_agc_old;
             agc_sum = agc_sum + fabs(dabval);
-            p.agc_ring[e] = fabs(dabval);
-            agc_pos++; if (agc_pos >= agc_len) agc_pos = 0;
+            *agc_p = fabs(dabval);
+            agc_p = agc_n;
             agc_val = 1.414213562 / fmax(agc_sum / ((double)agc_len), 0.000001);
             agc_val = fmax(agc_val, 0.000001);
         }
@@ -209,39 +263,39 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         // Delay(T/4): older = x[n-k41], newer = x[n-k41+1]  (DSP.h:357-374)
         double st_d1out, st_d2out;
         {
-            const double older = (p.k41 == 3) ? d41_2 : (p.k41 == 2 ? d41_1 : d41_0);
-            const double newer = (p.k41 == 3) ? d41_1 : (p.k41 == 2 ? d41_0 : st_diff);
-            st_d1out = (p.w41 * newer + (1.0 - p.w41) * older);
+            const double older = (k41 == 3) ? d41_2 : (k41 == 2 ? d41_1 : d41_0);
+            const double newer = (k41 == 3) ? d41_1 : (k41 == 2 ? d41_0 : st_diff);
+            st_d1out = (w41 * newer + (1.0 - w41) * older);
             d41_2 = d41_1; d41_1 = d41_0; d41_0 = st_diff;
         }
         {
-            const double older = (p.k41 == 3) ? d42_2 : (p.k41 == 2 ? d42_1 : d42_0);
-            const double newer = (p.k41 == 3) ? d42_1 : (p.k41 == 2 ? d42_0 : st_d1out);
-            st_d2out = (p.w41 * newer + (1.0 - p.w41) * older);
+            const double older = (k41 == 3) ? d42_2 : (k41 == 2 ? d42_1 : d42_0);
+            const double newer = (k41 == 3) ? d42_1 : (k41 == 2 ? d42_0 : st_d1out);
+            st_d2out = (w41 * newer + (1.0 - w41) * older);
             d42_2 = d42_1; d42_1 = d42_0; d42_0 = st_d1out;
         }
         double st_eta = (st_d2out - st_diff) * st_d1out;
-        st_eta = biquad_update(res, st_eta, p.res_a1, p.res_a2, p.res_b0, p.res_b1, p.res_b2);
+        st_eta = biquad_update(res, st_eta, res_a1, res_a2, res_b0, res_b1, res_b2);
         double d8out;
         {
-            const double older = (p.k8 == 3) ? d8_2 : (p.k8 == 2 ? d8_1 : d8_0);
-            const double newer = (p.k8 == 3) ? d8_1 : (p.k8 == 2 ? d8_0 : st_eta);
-            d8out = (p.w8 * newer + (1.0 - p.w8) * older);
+            const double older = (k8 == 3) ? d8_2 : (k8 == 2 ? d8_1 : d8_0);
+            const double newer = (k8 == 3) ? d8_1 : (k8 == 2 ? d8_0 : st_eta);
+            d8out = (w8 * newer + (1.0 - w8) * older);
             d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta;
         }
         const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
         const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
-        osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, p.Fs); // :481 IncreseFreqHz
+        osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
         osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0); // :482
-        if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), p.Fs);
-        if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), p.Fs);
+        if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);
+        if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), Fs);
 
         if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
         double frac;
-        if (osc_have_passed_point(st, p.ee, frac)) {                      // :488
+        if (osc_have_passed_point(st, ee, frac)) {                        // :488
             const double pt_last = frac, pt_this = 1.0 - pt_last;
             const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
-            yui++; yui %= 2;
+            yui ^= 1;                                                     // yui++; yui%=2;
             if (!yui) pt_d = pt;
             else {
                 double2 pt_qpsk = make_double2(pt.x, pt_d.y);             // :503
@@ -250,66 +304,75 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 double ct_ec = ct_xt_d - ct_xt;
                 if (ct_ec > M_PI) ct_ec = M_PI;
                 if (ct_ec < -M_PI) ct_ec = -M_PI;
-                if (p.fb > 8400) {                                        // :518-525
+                if (fbr > 8400) {                                         // :518-525
                     ct_ec = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
                     if (ct_ec > M_PI_2) ct_ec = M_PI_2;
                     if (ct_ec < -M_PI_2) ct_ec = -M_PI_2;
                     osc_increase_phase_deg(m2, 1.0 * ct_ec);
-                    osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, p.Fs);
+                    osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, Fs);
                 } else {                                                  // :526-532
                     osc_increase_phase_deg(m2, 1.0 * ct_ec);
                     const double lfo = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
-                    osc_set_freq(m2, (0.5 * 0.01 * lfo) + m2.freq, p.Fs);
+                    osc_set_freq(m2, (0.5 * 0.01 * lfo) + m2.freq, Fs);
                 }
                 {   // marg->UpdateSigned(ct_ec)  MA(800)  (:535, DSP.cpp:418-426)
-                    const size_t e = (size_t)marg_pos * p.cpad + ch;
                     marg_sum = marg_sum - sy_marg_old;
                     marg_sum = marg_sum + (ct_ec);
-                    p.marg_ring[e] = (ct_ec);
-                    marg_pos++; marg_pos %= p.marg_len;
-                    marg_val = marg_sum / ((double)p.marg_len);
+                    p.marg_ring[(size_t)marg_pos * cpad + ch] = (ct_ec);
+                    marg_pos++; if (marg_pos >= marg_len) marg_pos = 0;
+                    marg_val = marg_sum / ((double)marg_len);
                 }
                 {   // dt.update(pt_qpsk): 400-symbol delay (:536, DSP.h:455-460)
-                    p.dt_ring[(size_t)dt_pos * p.cpad + ch] = pt_qpsk;
-                    dt_pos++; dt_pos %= p.dt_len;
+                    p.dt_ring[(size_t)dt_pos * cpad + ch] = pt_qpsk;
+                    dt_pos++; if (dt_pos >= dt_len) dt_pos = 0;
                     pt_qpsk = sy_dt_old;                                  // requested after the previous strobe
                 }
                 pt_qpsk = cmul(pt_qpsk, make_double2(cos(marg_val), sin(marg_val)));   // :537
                 {   // MSEcalc::Update (DSP.cpp:451-463)
-                    const size_t e = (size_t)mse_pos * p.cpad + ch;
+                    const size_t e = (size_t)mse_pos * cpad + ch;
                     const double ab = hypot(pt_qpsk.x, pt_qpsk.y);
                     pm_sum = pm_sum - sy_pm_old; pm_sum = pm_sum + fabs(ab); p.mse_pm[e] = fabs(ab);
-                    double mu = pm_sum / ((double)p.mse_len);
+                    double mu = pm_sum / ((double)mse_len);
                     if (mu < 0.000001) mu = 0.000001;
                     const double r2 = sqrt(2.0);
                     const double tre = (r2 * pt_qpsk.x) / mu, tim = (r2 * pt_qpsk.y) / mu;
                     const double tda = (fabs(tre) - 1.0), tdb = (fabs(tim) - 1.0);
                     const double v = (tda * tda) + (tdb * tdb);
                     ma_sum = ma_sum - sy_ma_old; ma_sum = ma_sum + fabs(v); p.mse_ma[e] = fabs(v);
-                    mse_pos++; mse_pos %= p.mse_len;
-                    mse = ma_sum / ((double)p.mse_len);
+                    mse_pos++; if (mse_pos >= mse_len) mse_pos = 0;
+                    mse = ma_sum / ((double)mse_len);
                 }
                 // operands of the next strobe pair (slots written >= 400 symbols ago)
-                sy_marg_old = p.marg_ring[(size_t)marg_pos * p.cpad + ch];
-                sy_pm_old = p.mse_pm[(size_t)mse_pos * p.cpad + ch];
-                sy_ma_old = p.mse_ma[(size_t)mse_pos * p.cpad + ch];
-                sy_dt_old = p.dt_ring[(size_t)((dt_pos + 1) % p.dt_len) * p.cpad + ch];
-                if (mse < p.signalthreshold) {                            // :565
+                sy_marg_old = p.marg_ring[(size_t)marg_pos * cpad + ch];
+                sy_pm_old = p.mse_pm[(size_t)mse_pos * cpad + ch];
+                sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
+                { int r = dt_pos + 1; if (r >= dt_len) r = 0; sy_dt_old = p.dt_ring[(size_t)r * cpad + ch]; }
+                if (mse < thr) {                                          // :565
                     push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.y * 127.0 + 128.0));
                     push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.x * 127.0 + 128.0));
                     if (soft_pending >= 32) {                             // :583-592
-                        if (!p.sql || mse < p.signalthreshold || lastmse < p.signalthreshold) soft_count += soft_pending;
+                        if (!p.sql || mse < thr || lastmse < thr) soft_count += soft_pending;
                         soft_pending = 0;
                     }
                 }
             }
         }
         sig2_last = sig2;                                                 // :596
-        osc_next_frame(m2); osc_next_frame(mc); osc_next_frame(st); osc_next_frame(sr);   // :600-603
-        { const int t = osc_index(m2.ptr); c2_re = p.cos_t[t]; c2_im = p.sin_t[t]; }
-        { const int t = osc_index(st.ptr); cs_re = p.cos_t[t]; cs_im = p.sin_t[t]; }
-        { const int t = osc_index(mc.ptr); cc_re = p.cos_t[t]; cc_im = p.sin_t[t]; }
+        {   // this sample's mixed value enters the FIR ring (:453-456); finish the next output
+            const double cre = c2_re * dval, cim = c2_im * dval;
+            s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
+            s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
+            nfre += c_taps[54] * cre; nfim += c_taps[54] * cim;
+            fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
+        }
+        osc_next_frame(m2); osc_next_frame(st); osc_next_frame(sr);       // :600-603 (mixer_center advanced above)
+        {
+            const int t = osc_index(m2.ptr);
+            if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
+        }
+        { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
         cur_pcm = nxt_pcm; cur_agc_old = nxt_agc_old; cur_e1_old = nxt_e1_old; cur_e2_old = nxt_e2_old;
+        fre = nfre; fim = nfim;
     }
 
     // ---------------- store state
@@ -335,17 +398,21 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
     LI(I_SIG_TRUE) = sig_true; LI(I_SIG_FALSE) = sig_false;
     for (int k = 0; k < OQ_NT1; k++) {
-        p.fir_re[(size_t)k * p.cpad + ch] = s_re[k][lane];
-        p.fir_im[(size_t)k * p.cpad + ch] = s_im[k][lane];
+        p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
+        p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
     }
 }
 
 int oqpsk_segment_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s)
 {
     const int grid = (p.n_channels + OQ_THREADS - 1) / OQ_THREADS;
-    oqpsk_segment_kernel<<<grid, OQ_THREADS, 0, s>>>(p, a, d_pcm, stride);
+    const size_t smem = (size_t)2 * OQ_FIRROWS * OQ_THREADS * sizeof(double);
+    JB_CUDA(cudaFuncSetAttribute(oqpsk_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    oqpsk_segment_kernel<<<grid, OQ_THREADS, smem, s>>>(p, a, d_pcm, stride);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
 
+#undef LD
+#undef LI
 } // namespace jb
