@@ -344,6 +344,8 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         p.res_b1 = 0;
         st_freq = s->fb / 2;                                                  // :159
     }
+    if ((p.agc_len % 32) || (p.ebno_len % 32) || p.agc_len < 96 || p.ebno_len < 96) {
+        set_error("unsupported sample rate: the AGC / EbNo window lengths must be multiples of 32 samples"); delete b; return JAERO_E_ARG; }
     p.ntaps = (int)taps.size();
     p.soft_cap = std::max(4096, (int)(2 * s->fb) + 64);
     if (demod_set_taps(taps.data(), p.ntaps)) { delete b; return JAERO_E_CUDA; }
@@ -480,6 +482,20 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
     if (stride < n || n > 0x7fffffff) { set_error("jaero_batch_write_device: bad stride / length"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(b->device));
     const DemodParams &p = b->p;
+    if ((((uintptr_t)d_pcm) & 15) || (stride & 7)) {
+        // the kernels stage PCM rows with 16-byte bulk copies: re-pitch unaligned caller buffers on the device
+        const size_t C = p.n_channels, pitch = (n + 7) & ~(size_t)7;
+        if (d_pcm == b->d_stage) { set_error("internal: staging buffer misaligned"); return JAERO_E_STATE; }
+        if (C * pitch > b->stage_cap) {
+            JB_CUDA(cudaStreamSynchronize(b->stream));
+            cudaFree(b->d_stage); b->d_stage = 0;
+            JB_CUDA(cudaMalloc(&b->d_stage, C * pitch * sizeof(int16_t)));
+            b->stage_cap = C * pitch;
+        }
+        JB_CUDA(cudaMemcpy2DAsync(b->d_stage, pitch * sizeof(int16_t), d_pcm, stride * sizeof(int16_t), n * sizeof(int16_t), C,
+                                  cudaMemcpyDeviceToDevice, b->stream));
+        d_pcm = b->d_stage; stride = pitch;
+    }
     const int N = p.bbnfft, trig_every = p.cpu_reduce ? N : N / 4;
     SegmentArgs a;
     memset(&a, 0, sizeof a);

@@ -30,6 +30,13 @@ static const int OQ_THREADS = 32;
 static const int OQ_NT1 = 56;             // 55 taps + 1 (FIR ring, DSP.cpp:277)
 static const int OQ_FIRROWS = 2 * OQ_NT1; // every entry is stored twice so any 55-entry window is contiguous
 static const int OQ_EBNO_TAIL = 256;      // samples before the end of a launch over which the EbNo read-out is evaluated
+static const int OQ_T = 32;               // tile length (samples) of the staged HBM streams; one 256 B ring row per lane
+static const int OQ_PROW = 80;            // bytes per channel row of a PCM tile in shared memory (64 B payload + pad)
+// shared memory map (bytes)
+static const int OQ_SM_FIR = 2 * OQ_FIRROWS * OQ_THREADS * 8;          // FIR windows re/im
+static const int OQ_SM_RING = OQ_T * OQ_THREADS * 8;                   // one ring tile [T][32] doubles
+static const int OQ_SM_PCM = OQ_THREADS * OQ_PROW;                     // one PCM tile
+static const int OQ_SM_TOTAL = OQ_SM_FIR + 6 * OQ_SM_RING + 2 * OQ_SM_PCM + 64;
 
 #define LD(idx) p.D[(size_t)(idx) * cpad + ch]
 #define LI(idx) p.I[(size_t)(idx) * cpad + ch]
@@ -61,13 +68,23 @@ __device__ __forceinline__ void fir54(const double *__restrict__ wre, const doub
 __global__ void __launch_bounds__(OQ_THREADS)
 oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
 {
-    extern __shared__ double oq_smem[];
-    double *s_re = oq_smem;                                   // [OQ_FIRROWS][32]
-    double *s_im = oq_smem + OQ_FIRROWS * OQ_THREADS;
+    extern __shared__ __align__(128) unsigned char oq_smem_raw[];
+    double *s_re = reinterpret_cast<double *>(oq_smem_raw);   // [OQ_FIRROWS][32]
+    double *s_im = s_re + OQ_FIRROWS * OQ_THREADS;
+    double *t_agc = reinterpret_cast<double *>(oq_smem_raw + OQ_SM_FIR);          // [2][T][32]
+    double *t_e1 = t_agc + 2 * OQ_T * OQ_THREADS;
+    double *t_e2 = t_e1 + 2 * OQ_T * OQ_THREADS;
+    unsigned char *t_pcm = oq_smem_raw + OQ_SM_FIR + 6 * OQ_SM_RING;              // [2][32][OQ_PROW]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(t_pcm + 2 * OQ_SM_PCM);   // ring[2], pcm[2]
     const int lane = threadIdx.x;
-    const int ch = blockIdx.x * OQ_THREADS + lane;
-    if (ch >= p.n_channels) return;       // no block-level barriers below
+    const int ch_raw = blockIdx.x * OQ_THREADS + lane;
+    const bool live = ch_raw < p.n_channels;
+    const int ch = ch_raw;                                    // dead lanes run on their (allocated) pad column with zero input
+    const int nlive = min(OQ_THREADS, p.n_channels - (int)blockIdx.x * OQ_THREADS);
     const size_t cpad = p.cpad;
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
 
     // ---------------- load state
     Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
@@ -119,25 +136,19 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 LI(I_EMPTYING) = 4;                                       // CoarseFreqEstimate::bigchange (coarsefreqestimate.cpp:84-88)
                 LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
                 double2 *rowz = p.bb + (size_t)ch * p.bbnfft;             // :667 bbcycbuff[j]=0
-                for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);
+                if (live) for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);
             }
         } else countdown = 4;
         if (mse > p.signalthreshold) sig_false++; else sig_true++;       // :674-675
     }
 
-    // ---------------- lock-step ring cursors (pointer + position), advanced by one row per sample
+    // ---------------- lock-step positions
     const int agc_len = p.agc_len, eb_len = p.ebno_len;
-    int agc_pos = (int)(a.sample0 % agc_len);
-    int eb_pos = (int)(a.sample0 % eb_len);
-    int fir_pos = (int)(a.sample0 % OQ_NT1);                  // next FIR slot to write
+    long long S = a.sample0;                                  // samples fully processed so far: drives every sample-rate ring
+    int fir_pos = (int)(S % OQ_NT1);                          // next FIR slot to write
     int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
     const bool ebno_on = p.report_ebno != 0;
     const int16_t *row = pcm + (size_t)ch * stride;
-    double *agc_p = p.agc_ring + (size_t)agc_pos * cpad + ch;
-    double *agc_base = p.agc_ring + ch, *agc_end = p.agc_ring + (size_t)agc_len * cpad + ch;
-    double *e1_p = ebno_on ? p.ebno_e1 + (size_t)eb_pos * cpad + ch : nullptr;
-    double *e2_p = ebno_on ? p.ebno_e2 + (size_t)eb_pos * cpad + ch : nullptr;
-    const size_t eb_span = (size_t)eb_len * cpad;
     double2 *bb_row = p.bb + (size_t)ch * p.bbnfft;
     const int bbn = p.bbnfft;
     const bool cpu_reduce = p.cpu_reduce != 0;
@@ -148,15 +159,78 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     const int marg_len = p.marg_len, dt_len = p.dt_len, mse_len = p.mse_len;
     const int eb_from = a.i1 - OQ_EBNO_TAIL;
+    const long long S_end = S + (a.i1 - a.i0) - (a.stop_after_a ? 1 : 0);   // value of S when this launch returns
 
-    // ---- software-pipelined operands. The SM issues a warp's instructions in order: a load only stalls the warp
-    // when its result is used, so everything whose address is known early (lock-step ring slots, the next PCM sample,
-    // the NCO table entries of the already-advanced phases, the symbol-rate ring slots of the next strobe) is requested
-    // one iteration ahead and consumed from registers: one DRAM round trip per sample instead of a chain of them.
-    int cur_pcm = row[a.i0];
-    double cur_agc_old = *agc_p;
-    double cur_e1_old = ebno_on ? *e1_p : 0.0;
-    double cur_e2_old = ebno_on ? *e2_p : 0.0;
+    // ---------------- HBM streams staged through shared memory by the bulk-copy (TMA) engine.
+    // The three sample-rate rings (AGC, EbNo E and E2: [slot][channel], 256 B per slot for this warp's 32 channels) and the
+    // PCM rows are moved in tiles of 32 samples: lane r copies ring row r / its own PCM row with cp.async.bulk, completion
+    // is signalled on an mbarrier, two buffers per stream, the next tile is in flight while the current one is consumed and
+    // updated in place; finished ring tiles go back to HBM with bulk stores. The per-sample loop therefore never waits on
+    // DRAM: its ring/PCM operands are shared-memory reads.
+    auto ring_rows = [&](long long tile, double *&g_agc, double *&g_e1, double *&g_e2) {
+        const long long s0 = tile * OQ_T;
+        g_agc = p.agc_ring + ((size_t)(s0 % agc_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
+        if (ebno_on) {
+            g_e1 = p.ebno_e1 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
+            g_e2 = p.ebno_e2 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
+        }
+    };
+    const unsigned ring_tx = (ebno_on ? 3u : 1u) * OQ_SM_RING;
+    auto ring_load = [&](long long tile) {                    // all lanes call; lane r moves row r of the tile
+        const int b = (int)(tile & 1);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(&bars[b], ring_tx);
+        __syncwarp();
+        double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
+        ring_rows(tile, g_agc, g_e1, g_e2);
+        bulk_g2s(t_agc + (b * OQ_T + lane) * OQ_THREADS, g_agc, OQ_THREADS * 8, &bars[b]);
+        if (ebno_on) {
+            bulk_g2s(t_e1 + (b * OQ_T + lane) * OQ_THREADS, g_e1, OQ_THREADS * 8, &bars[b]);
+            bulk_g2s(t_e2 + (b * OQ_T + lane) * OQ_THREADS, g_e2, OQ_THREADS * 8, &bars[b]);
+        }
+    };
+    auto ring_store = [&](long long tile) {                   // write the (in-place updated) tile back to HBM
+        const int b = (int)(tile & 1);
+        fence_proxy_async();
+        __syncwarp();
+        double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
+        ring_rows(tile, g_agc, g_e1, g_e2);
+        bulk_s2g(g_agc, t_agc + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+        if (ebno_on) {
+            bulk_s2g(g_e1, t_e1 + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+            bulk_s2g(g_e2, t_e2 + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+        }
+        bulk_commit();
+    };
+    // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
+    auto pcm_bytes = [&](int tile) -> unsigned {
+        long long left = (long long)stride - (long long)tile * OQ_T;
+        if (left > OQ_T) left = OQ_T;
+        return left > 0 ? (unsigned)(left * 2) : 0u;
+    };
+    auto pcm_load = [&](int tile) {
+        const int b = tile & 1;
+        const unsigned nb = pcm_bytes(tile);
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
+        __syncwarp();
+        if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
+    };
+    unsigned phases = 0u;                                     // expected parity per barrier (bit b: ring b, bit 2+b: pcm b)
+#define OQ_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
+    long long rt = S / OQ_T;                                  // current ring tile
+    int pt = a.i0 / OQ_T;                                     // current PCM tile
+    bool ring_next_issued = false, pcm_next_issued = false;
+    ring_load(rt);
+    pcm_load(pt);
+    if ((rt + 1) * OQ_T < S_end) { ring_load(rt + 1); ring_next_issued = true; }
+    if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+    OQ_WAIT((int)(rt & 1));
+    OQ_WAIT(2 + (pt & 1));
+    bool ring_dirty = false;
+
+    // ---- table / symbol-rate operands requested ahead of use (the SM issues in order: a load stalls the warp only when
+    // its result is consumed)
     double c2_re, c2_im, cs_re, cs_im, cc_re, cc_im;
     { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
     { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
@@ -166,6 +240,8 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     double sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
     double2 sy_dt_old;
     { int r = dt_pos + 1; if (r >= dt_len) r = 0; sy_dt_old = p.dt_ring[(size_t)r * cpad + ch]; }
+    int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
+    bool pk_valid = false;
 
     // FIR output of the first sample of this launch: the 55 entries older than the slot about to be written
     // (DSP.cpp:292-304: the output excludes the sample just stored). The window that ends at logical slot q starts at
@@ -177,25 +253,32 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     }
 
     for (int i = a.i0; i < a.i1; i++) {
-        const double dval = ((double)cur_pcm) / 32768.0;                  // :390
-        // requests for the next iteration (slots this iteration does not write)
-        int nxt_pcm = cur_pcm;
-        double nxt_agc_old = 0, nxt_e1_old = 0, nxt_e2_old = 0;
-        double *agc_n = agc_p + cpad; if (agc_n >= agc_end) agc_n = agc_base;
-        if (i + 1 < a.i1) {
-            nxt_pcm = row[i + 1];
-            nxt_agc_old = *agc_n;
-            if (ebno_on) {
-                const bool wrap = (eb_pos + 1 >= eb_len);
-                nxt_e1_old = wrap ? *(e1_p + cpad - eb_span) : *(e1_p + cpad);
-                nxt_e2_old = wrap ? *(e2_p + cpad - eb_span) : *(e2_p + cpad);
-            }
+        // ---- PCM sample from the staged tile
+        const int po = i & (OQ_T - 1);
+        if ((i >> 5) != pt) {                                 // entered the next PCM tile (warp-uniform)
+            pt = i >> 5;
+            OQ_WAIT(2 + (pt & 1));
+            pcm_next_issued = false;
+            if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+            pk_valid = false;
         }
+        if (!pk_valid || (po & 7) == 0) {
+            pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + (po >> 3) * 16);
+            pk_valid = true;
+        }
+        int cur_pcm;
+        {
+            const int k = po & 7;
+            const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
+            cur_pcm = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+            if (!live) cur_pcm = 0;
+        }
+        const double dval = ((double)cur_pcm) / 32768.0;                  // :390
 
         // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
         if (!(i == a.i0 && a.skip_a_first)) {
             if (coarse_counter >= Fs || !cpu_reduce) {
-                bb_row[bb_pos] = make_double2(cc_re * dval, cc_im * dval);
+                if (live) bb_row[bb_pos] = make_double2(cc_re * dval, cc_im * dval);
                 bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
             }
         }
@@ -220,10 +303,12 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         const double sre = fre, sim = fim;
         const double dabval = sqrt(sre * sre + sim * sim);                // :461
 
+        const int ro = (int)(S & (OQ_T - 1));
+        const int rslot = (((int)(rt & 1)) * OQ_T + ro) * OQ_THREADS + lane;   // this sample's slot in the staged ring tiles
         if (ebno_on) {                                                    // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
             const double sq = dabval * dabval;
-            eb_sum2 = eb_sum2 - cur_e2_old; eb_sum2 = eb_sum2 + fabs(sq); *e2_p = fabs(sq);
-            eb_sum1 = eb_sum1 - cur_e1_old; eb_sum1 = eb_sum1 + fabs(dabval); *e1_p = fabs(dabval);
+            eb_sum2 = eb_sum2 - t_e2[rslot]; eb_sum2 = eb_sum2 + fabs(sq); t_e2[rslot] = fabs(sq);
+            eb_sum1 = eb_sum1 - t_e1[rslot]; eb_sum1 = eb_sum1 + fabs(dabval); t_e1[rslot] = fabs(dabval);
             // The smoothed read-out EbNo <- 0.8 EbNo + 0.2 tebno forgets its past by 0.8^k: evaluating it over the last
             // 256 samples of a launch reproduces the value a per-sample evaluation has at the end of the launch to
             // below 1e-24 relative, without a log10 and three divisions on every sample. Observable only (DSP.h:250).
@@ -240,15 +325,13 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 if (tebno < 0.0) tebno = 0;
                 eb_ebno = eb_ebno * 0.8 + 0.2 * tebno;
             }
-            e1_p += cpad; e2_p += cpad; eb_pos++;
-            if (eb_pos >= eb_len) { eb_pos = 0; e1_p -= eb_span; e2_p -= eb_span; }
         }
 
         {   // AGC::Update (DSP.cpp:370-379)
-            agc_sum = agc_sum - cur_agc_old;
+            agc_sum = agc_sum - t_agc[rslot];
             agc_sum = agc_sum + fabs(dabval);
-            *agc_p = fabs(dabval);
-            agc_p = agc_n;
+            t_agc[rslot] = fabs(dabval);
+            ring_dirty = true;
             agc_val = 1.414213562 / fmax(agc_sum / ((double)agc_len), 0.000001);
             agc_val = fmax(agc_val, 0.000001);
         }
@@ -347,7 +430,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 sy_pm_old = p.mse_pm[(size_t)mse_pos * cpad + ch];
                 sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
                 { int r = dt_pos + 1; if (r >= dt_len) r = 0; sy_dt_old = p.dt_ring[(size_t)r * cpad + ch]; }
-                if (mse < thr) {                                          // :565
+                if (live && mse < thr) {                                  // :565
                     push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.y * 127.0 + 128.0));
                     push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.x * 127.0 + 128.0));
                     if (soft_pending >= 32) {                             // :583-592
@@ -371,9 +454,28 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
             if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
         }
         { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
-        cur_pcm = nxt_pcm; cur_agc_old = nxt_agc_old; cur_e1_old = nxt_e1_old; cur_e2_old = nxt_e2_old;
         fre = nfre; fim = nfim;
+        // ---- ring tile bookkeeping (warp-uniform)
+        S++;
+        if ((S & (OQ_T - 1)) == 0) {
+            ring_store(rt);                                   // the finished tile goes back to HBM
+            ring_dirty = false;
+            rt++;
+            if (S < S_end) {
+                OQ_WAIT((int)(rt & 1));                       // next tile (requested a tile ago)
+                ring_next_issued = false;
+                if ((rt + 1) * OQ_T < S_end) {
+                    bulk_wait_read_all();                     // the buffer being refilled must have been read out by its store
+                    ring_load(rt + 1); ring_next_issued = true;
+                }
+            }
+        }
     }
+    // ---------------- drain the staging pipeline
+    if (ring_dirty) ring_store(rt);
+    if (ring_next_issued) OQ_WAIT((int)((rt + 1) & 1));
+    if (pcm_next_issued) OQ_WAIT(2 + ((pt + 1) & 1));
+    bulk_wait_all();
 
     // ---------------- store state
     LD(D_M2_PTR) = m2.ptr; LD(D_M2_STEP) = m2.step; LD(D_M2_FREQ) = m2.freq; LD(D_M2_LAST) = m2.last;
@@ -406,7 +508,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
 int oqpsk_segment_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s)
 {
     const int grid = (p.n_channels + OQ_THREADS - 1) / OQ_THREADS;
-    const size_t smem = (size_t)2 * OQ_FIRROWS * OQ_THREADS * sizeof(double);
+    const size_t smem = (size_t)OQ_SM_TOTAL;
     JB_CUDA(cudaFuncSetAttribute(oqpsk_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     oqpsk_segment_kernel<<<grid, OQ_THREADS, smem, s>>>(p, a, d_pcm, stride);
     JB_CUDA(cudaGetLastError());
