@@ -7,6 +7,7 @@
 #include "viterbi.cuh"
 #include "demod.cuh"
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -400,7 +401,10 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         c.is8400 = (s->fb == 8400);
         std::vector<double2> tw(c.nfft);
         for (int k = 0; k < c.nfft; k++) { const double a = -2.0 * M_PI * (double)k / (double)c.nfft; tw[k] = make_double2(cos(a), sin(a)); }
-        c.group = std::min(n_channels, 512);
+        // channels per pass group: the two work buffers of a group (2 x group x nfft x 16 B) (larger groups amortise launch tails; measured best at >= 512 on B200)
+        int grp = 1024;
+        if (const char *e = getenv("JAERO_CFE_GROUP")) grp = std::max(1, atoi(e));
+        c.group = std::min(n_channels, grp);
         if (batch_alloc(b, &c.tw, (size_t)c.nfft) || batch_alloc(b, &c.work_a, (size_t)c.group * c.nfft) ||
             batch_alloc(b, &c.work_b, (size_t)c.group * c.nfft) || batch_alloc(b, &c.y, (size_t)n_channels * c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
         JB_CUDA(cudaMemcpyAsync(c.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, b->stream));

@@ -14,8 +14,8 @@
 //   P3  column IFFT (over k1) -> square -> column FFT (over r) + twiddle           B    -> A
 //   P4  row FFT (over c) -> |.| -> 10log10 -> smoothing into y (fft-shifted)       A    -> y
 //   P5  fold search + emit gate (one warp per channel)
-// Each pass moves 16-row / 16-column tiles (256 B segments) through shared memory; the radix-2
-// butterflies of 16 independent n<=128-point FFTs run in one CTA. FFT rounding differs from the
+// Each pass moves 16-row / 16-column tiles (256 B segments) through shared memory; the 16 independent
+// n<=128-point FFTs of a tile run as Stockham radix-8/4 passes with the butterflies in registers. FFT rounding differs from the
 // CPU oracle's radix-2 (different factorisation) at the 1e-13 level; the bin decision is integer.
 #include "demod_device.cuh"
 
@@ -25,29 +25,89 @@ static const int TILE = 16;
 static const int MAXN = 128;
 static const int CFE_THREADS = 256;
 
-// in-place radix-2 DIT on TILE independent length-n sequences held bit-reversed in s[f][.]
-// tw = W_N^k table, tw_stride = N/n.  inverse -> conjugated twiddles (unnormalised).
-__device__ __forceinline__ void tile_fft(double2 (*s)[MAXN + 1], int n, int logn, const double2 *__restrict__ tw, int tw_stride, bool inverse)
+// ---- TILE independent length-n FFTs (n = 32, 64 or 128) held in natural order in s[f][.], natural order out.
+// Stockham autosort with radix-8 / radix-4 butterflies kept in registers: 128 = 8*4*4, 64 = 8*8, 32 = 8*4, i.e. two or three
+// passes over shared memory instead of log2(n) radix-2 passes. Every pass is "all threads read their inputs, barrier,
+// compute + write, barrier" so it runs in place. tw = W_N^k table (N = big transform), tw_stride = N/n.
+__device__ __forceinline__ double2 c_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 c_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <bool INV> __device__ __forceinline__ double2 c_rot(double2 a)      // multiply by -i (forward) / +i (inverse)
+{ return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }
+
+template <bool INV> __device__ __forceinline__ void dft4(double2 &a0, double2 &a1, double2 &a2, double2 &a3)
 {
-    const int nb = n >> 1;                       // butterflies per sequence
-    for (int st = 0; st < logn; st++) {
-        const int half = 1 << st, len = half << 1;
-        const int wstep = tw_stride * (n / len);
-        for (int b = threadIdx.x; b < TILE * nb; b += CFE_THREADS) {
-            const int f = b / nb, q = b - f * nb;
-            const int grp = q >> st, j = q & (half - 1);
-            const int i0 = grp * len + j, i1 = i0 + half;
-            double2 w = tw[j * wstep];
-            if (inverse) w.y = -w.y;
-            const double2 x1 = s[f][i1], x0 = s[f][i0];
-            const double2 t = make_double2(x1.x * w.x - x1.y * w.y, x1.x * w.y + x1.y * w.x);
-            s[f][i0] = make_double2(x0.x + t.x, x0.y + t.y);
-            s[f][i1] = make_double2(x0.x - t.x, x0.y - t.y);
+    const double2 t0 = c_add(a0, a2), t1 = c_sub(a0, a2), t2 = c_add(a1, a3), t3 = c_rot<INV>(c_sub(a1, a3));
+    a0 = c_add(t0, t2); a1 = c_add(t1, t3); a2 = c_sub(t0, t2); a3 = c_sub(t1, t3);
+}
+template <bool INV> __device__ __forceinline__ void dft8(double2 *v)
+{
+    // even / odd split: X[k] = E[k] + W8^k O[k], X[k+4] = E[k] - W8^k O[k]
+    double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4<INV>(e0, e1, e2, e3);
+    dft4<INV>(o0, o1, o2, o3);
+    const double h = 0.70710678118654752440;
+    // W8^1 = (1 -/+ i)/sqrt2, W8^2 = -/+ i, W8^3 = (-1 -/+ i)/sqrt2   (upper sign: forward)
+    const double2 w1 = INV ? make_double2(h, h) : make_double2(h, -h);
+    const double2 w3 = INV ? make_double2(-h, h) : make_double2(-h, -h);
+    o1 = c_mul(o1, w1); o2 = c_rot<INV>(o2); o3 = c_mul(o3, w3);
+    v[0] = c_add(e0, o0); v[4] = c_sub(e0, o0);
+    v[1] = c_add(e1, o1); v[5] = c_sub(e1, o1);
+    v[2] = c_add(e2, o2); v[6] = c_sub(e2, o2);
+    v[3] = c_add(e3, o3); v[7] = c_sub(e3, o3);
+}
+
+template <bool INV, int R>
+__device__ __forceinline__ void stockham_pass(double2 (*s)[MAXN + 1], int n, int Ns, const double2 *__restrict__ tw, int tw_stride)
+{
+    constexpr int PER = 8 / R;                       // butterflies per thread per round (8 complex values in registers)
+    const int nb = n / R;                            // butterflies per sequence
+    const int total = TILE * nb;
+    const int wmul = tw_stride * (n / (Ns * R));     // table step of exp(-2 pi i /(Ns R))
+    for (int base = 0; base < total; base += CFE_THREADS * PER) {
+        double2 v[8];
+        int ff[PER], jj[PER];
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int b = base + threadIdx.x + q * CFE_THREADS;
+            ff[q] = -1;
+            if (b < total) {
+                const int f = b / nb, j = b - f * nb;
+                ff[q] = f; jj[q] = j;
+#pragma unroll
+                for (int t = 0; t < R; t++) v[q * R + t] = s[f][j + t * nb];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (ff[q] >= 0) {
+                const int j = jj[q], k = j % Ns;
+#pragma unroll
+                for (int t = 1; t < R; t++) {
+                    double2 w = tw[(t * k * wmul)];
+                    if (INV) w.y = -w.y;
+                    v[q * R + t] = c_mul(v[q * R + t], w);
+                }
+                if (R == 8) dft8<INV>(&v[q * R]);
+                else dft4<INV>(v[q * R + 0], v[q * R + 1], v[q * R + 2], v[q * R + 3]);
+                const int ob = (j / Ns) * Ns * R + k;
+#pragma unroll
+                for (int t = 0; t < R; t++) s[ff[q]][ob + t * Ns] = v[q * R + t];
+            }
         }
         __syncthreads();
     }
 }
-__device__ __forceinline__ int bitrev(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
+
+template <bool INV>
+__device__ __forceinline__ void tile_fft(double2 (*s)[MAXN + 1], int n, const double2 *__restrict__ tw, int tw_stride)
+{
+    stockham_pass<INV, 8>(s, n, 1, tw, tw_stride);
+    if (n == 128) { stockham_pass<INV, 4>(s, n, 8, tw, tw_stride); stockham_pass<INV, 4>(s, n, 32, tw, tw_stride); }
+    else if (n == 64) stockham_pass<INV, 8>(s, n, 8, tw, tw_stride);
+    else stockham_pass<INV, 4>(s, n, 8, tw, tw_stride);          // n == 32
+}
 
 // P1 / P3: column pass. grid = (n2/TILE, channels)
 template <bool FUSED_INV_SQUARE>
@@ -58,7 +118,6 @@ cfe_col_kernel(CfePlan pl, const double2 *__restrict__ src, double2 *__restrict_
     const int ch = blockIdx.y;
     const int c0 = blockIdx.x * TILE;
     const int n1 = pl.n1, n2 = pl.n2, N = pl.nfft;
-    const int l1 = 31 - __clz(n1);
     const double2 *in = src + (size_t)(ch0 + ch) * src_pitch;
     double2 *out = dst + (size_t)ch * N;
     // load column tile: element (r, c0+cc) of the n1 x n2 matrix, n = n2*r + c  (rot linearises the ring:
@@ -67,29 +126,21 @@ cfe_col_kernel(CfePlan pl, const double2 *__restrict__ src, double2 *__restrict_
         const int r = e / TILE, cc = e - r * TILE;
         int n = n2 * r + c0 + cc;
         if (!FUSED_INV_SQUARE) { n += rot; if (n >= N) n -= N; }
-        s[cc][bitrev(r, l1)] = in[n];
+        s[cc][r] = in[n];
     }
     __syncthreads();
     if (FUSED_INV_SQUARE) {
         // column IFFT over k1 -> x'[n2*r+c]; square; then forward again
-        tile_fft(s, n1, l1, pl.tw, N / n1, true);
-        // square in natural order, then re-store bit-reversed for the forward transform
-        double2 v[(MAXN * TILE) / CFE_THREADS];
-        int cnt = 0;
-        for (int e = threadIdx.x; e < n1 * TILE; e += CFE_THREADS, cnt++) {
+        tile_fft<true>(s, n1, pl.tw, N / n1);
+        // square in place (natural order in, natural order out of the Stockham passes)
+        for (int e = threadIdx.x; e < n1 * TILE; e += CFE_THREADS) {
             const int cc = e / n1, r = e - cc * n1;
             const double2 x = s[cc][r];
-            v[cnt] = make_double2(x.x * x.x - x.y * x.y, x.x * x.y + x.y * x.x);   // in[i]*in[i] (:103)
-        }
-        __syncthreads();
-        cnt = 0;
-        for (int e = threadIdx.x; e < n1 * TILE; e += CFE_THREADS, cnt++) {
-            const int cc = e / n1, r = e - cc * n1;
-            s[cc][bitrev(r, l1)] = v[cnt];
+            s[cc][r] = make_double2(x.x * x.x - x.y * x.y, x.x * x.y + x.y * x.x);   // in[i]*in[i] (:103)
         }
         __syncthreads();
     }
-    tile_fft(s, n1, l1, pl.tw, N / n1, false);
+    tile_fft<false>(s, n1, pl.tw, N / n1);
     // twiddle W_N^{c*k1} and store A[k1][c]
     for (int e = threadIdx.x; e < n1 * TILE; e += CFE_THREADS) {
         const int k1 = e / TILE, cc = e - k1 * TILE;
@@ -108,34 +159,25 @@ cfe_row_mask_kernel(CfePlan pl, const double2 *__restrict__ src, double2 *__rest
     const int ch = blockIdx.y;
     const int r0 = blockIdx.x * TILE;
     const int n1 = pl.n1, n2 = pl.n2, N = pl.nfft;
-    const int l2 = 31 - __clz(n2);
     const double2 *in = src + (size_t)ch * N;
     double2 *out = dst + (size_t)ch * N;
     for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS) {
         const int rr = e / n2, c = e - rr * n2;
-        s[rr][bitrev(c, l2)] = in[(size_t)(r0 + rr) * n2 + c];
+        s[rr][c] = in[(size_t)(r0 + rr) * n2 + c];
     }
     __syncthreads();
-    tile_fft(s, n2, l2, pl.tw, N / n2, false);
-    // X[k1 + n1*k2] sits at s[k1-r0][k2]; mask (:99-100), then re-store bit-reversed for the inverse
-    double2 v[(MAXN * TILE) / CFE_THREADS];
-    int cnt = 0;
-    for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS, cnt++) {
+    tile_fft<false>(s, n2, pl.tw, N / n2);
+    // X[k1 + n1*k2] sits at s[k1-r0][k2]; mask (:99-100) in place
+    for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS) {
         const int rr = e / n2, k2 = e - rr * n2;
         const int k = (r0 + rr) + n1 * k2;
         double2 x = s[rr][k2];
         if (!pl.is8400) { if (k >= pl.startbin && k <= pl.stopbin) x = make_double2(0.0, 0.0); }
         else { const double w = pl.window[k]; x = make_double2(x.x * w, x.y * w); }
-        v[cnt] = x;
+        s[rr][k2] = x;
     }
     __syncthreads();
-    cnt = 0;
-    for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS, cnt++) {
-        const int rr = e / n2, k2 = e - rr * n2;
-        s[rr][bitrev(k2, l2)] = v[cnt];
-    }
-    __syncthreads();
-    tile_fft(s, n2, l2, pl.tw, N / n2, true);
+    tile_fft<true>(s, n2, pl.tw, N / n2);
     for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS) {
         const int rr = e / n2, c = e - rr * n2;
         const int k1 = r0 + rr;
@@ -154,16 +196,15 @@ cfe_row_logmag_kernel(CfePlan pl, DemodParams p, const double2 *__restrict__ src
     const int ch = blockIdx.y;
     const int r0 = blockIdx.x * TILE;
     const int n1 = pl.n1, n2 = pl.n2, N = pl.nfft;
-    const int l2 = 31 - __clz(n2);
     const double2 *in = src + (size_t)ch * N;
     double *y = pl.y + (size_t)(ch0 + ch) * N;
     const bool bigchange = p.I[(size_t)I_ZERO_BB * p.cpad + ch0 + ch] != 0;     // y[i]=20 pending (coarsefreqestimate.cpp:87)
     for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS) {
         const int rr = e / n2, c = e - rr * n2;
-        s[rr][bitrev(c, l2)] = in[(size_t)(r0 + rr) * n2 + c];
+        s[rr][c] = in[(size_t)(r0 + rr) * n2 + c];
     }
     __syncthreads();
-    tile_fft(s, n2, l2, pl.tw, N / n2, false);
+    tile_fft<false>(s, n2, pl.tw, N / n2);
     // Y[k1 + n1*k2]; fftshift (:105): shifted index i = (k + N/2) % N = k1 + n1*((k2 + n2/2) % n2)
     for (int e = threadIdx.x; e < n2 * TILE; e += CFE_THREADS) {
         const int k2 = e / TILE, rr = e - k2 * TILE;         // rr fastest -> 16 consecutive i per k2
