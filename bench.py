@@ -185,11 +185,11 @@ def main():
     a = parse()
     import torch
     from jaero_b200 import shard
-    rank, local, world = shard.init_from_env()
-    n_gpus = max(a.gpus, world)
     cores = usable_cores()
-
     if a.impl == "reference":
+        # CPU arm: rank 0 alone measures and prints; the other ranks exit without joining any process group
+        rank = int(os.environ.get("RANK", "0"))
+        n_gpus = max(a.gpus, int(os.environ.get("WORLD_SIZE", "1")))
         if rank != 0:
             return 0
         envs = base_envelopes(16, 7)
@@ -213,6 +213,8 @@ def main():
         print(json.dumps(line))
         return 0
 
+    rank, local, world = shard.init_from_env()
+    n_gpus = max(a.gpus, world)
     import jaero_b200
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")

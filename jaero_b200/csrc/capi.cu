@@ -6,7 +6,9 @@
 #include "common.cuh"
 #include "viterbi.cuh"
 #include "demod.cuh"
+#include "prefilter.cuh"
 #include <cstring>
+#include <complex>
 #include <cstdlib>
 #include <new>
 #include <vector>
@@ -168,22 +170,23 @@ std::vector<double> rrc_taps(double alpha, int firsize, double samplerate, doubl
     return pts;
 }
 
-// Delay<T>::update interpolation weight (JAERO/DSP.h:357-374) for every ring position; the kernels keep
-// the delay line as a shift register, which is only equivalent if the weight does not depend on the
-// ring position (true for every delay the reference configures) — verified here.
-bool delay_weight(double fractdelay, int *k_out, double *w_out)
+// Delay<T>::update interpolation weight (JAERO/DSP.h:357-374) for every ring position. The kernels keep the delay line
+// as a shift register; the weight the reference derives from (buffptr - fractdelay) can differ in the last bit between
+// ring positions, so it is tabulated per position and indexed by the lock-step sample count.
+bool delay_weights(double fractdelay, int *k_out, double *w_out /*[4]*/)
 {
     const int size = (int)std::ceil(fractdelay) + 1;
-    double w0 = 0;
+    if (size > 4 || size < 2) return false;
     for (int bp = 0; bp < size; bp++) {
         double dptr = ((double)bp) - fractdelay;
         while (std::floor(dptr) < 0) dptr += ((double)size);
         const int iptr = (int)std::floor(dptr);
-        const double w = dptr - ((double)iptr);
-        if (bp == 0) w0 = w; else if (w != w0) return false;
+        w_out[bp] = dptr - ((double)iptr);
+        // the shift-register form needs the read position to be "ceil(fd) samples ago" at every ring position
+        int expect = bp - (int)std::ceil(fractdelay); while (expect < 0) expect += size;
+        if (iptr != expect) return false;
     }
     *k_out = (int)std::ceil(fractdelay);
-    *w_out = w0;
     return true;
 }
 
@@ -206,6 +209,8 @@ struct jaero_batch {
     long long samples;          // samples fully processed
     int bb_pos, coarse_counter;
     int16_t *d_stage; size_t stage_cap;
+    // 8400 bps pre-filter (K6)
+    bool pre_on; PreParams pre; FirStream fir; int fir_fill; long long fir_blocks; double2 *d_x; size_t x_cap;
     int16_t *h_soft_stage;      // pinned
     int *h_ints; double *h_dbls;   // pinned mirrors of I / D
     long long launches;
@@ -292,7 +297,6 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     if (s->kind != JAERO_KIND_OQPSK && s->kind != JAERO_KIND_MSK) { set_error("jaero_batch_create: unknown kind"); return JAERO_E_ARG; }
     if (s->Fs <= 0 || s->fb <= 0 || s->coarsefreqest_fft_power < 10 || s->coarsefreqest_fft_power > 14) {
         set_error("jaero_batch_create: Fs/fb must be positive and coarsefreqest_fft_power in 10..14"); return JAERO_E_ARG; }
-    if (s->kind == JAERO_KIND_OQPSK && s->fb == 8400) { set_error("jaero_batch_create: the 8400 bps FFT pre-filter path is not implemented yet"); return JAERO_E_ARG; }
     int ndev = 0;
     JB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("jaero_batch_create: no such CUDA device"); return JAERO_E_CUDA; }
@@ -301,6 +305,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     if (!b) { set_error("out of host memory"); return JAERO_E_ARG; }
     b->set = *s; b->device = device; b->samples = 0; b->bb_pos = 0; b->coarse_counter = 0;
     b->d_stage = 0; b->stage_cap = 0; b->launches = 0;
+    b->pre_on = false; b->fir_fill = 0; b->fir_blocks = 0; b->d_x = 0; b->x_cap = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     b->own_stream = b->stream; b->profiling = false; b->prof_samples = 0;
     DemodParams &p = b->p;
@@ -312,16 +317,22 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     std::vector<double> taps;
     double st_freq;
     if (s->kind == JAERO_KIND_OQPSK) {
-        taps = rrc_taps(1.0, 55, s->Fs, s->fb / 2);                           // oqpskdemodulator.cpp:209-211
+        taps = (s->fb == 8400) ? rrc_taps(0.6, 55, s->Fs, s->fb / 2) : rrc_taps(1.0, 55, s->Fs, s->fb / 2);   // oqpskdemodulator.cpp:209-211
         p.agc_len = (int)round(4 * s->Fs);                                    // :197 AGC(4,Fs)
         p.ebno_len = 2 * 48000;                                               // :42 (built in the ctor with Fs=48000)
         p.marg_len = 800; p.dt_len = 401; p.mse_len = 400;                    // :44-45,53
         const double T = s->Fs / (s->fb / 2);                                 // :221
-        if (!delay_weight(T / 4.0, &p.k41, &p.w41) || !delay_weight(T / 8.0, &p.k8, &p.w8) || p.k41 > 3 || p.k8 > 3) {
+        if (!delay_weights(T / 4.0, &p.k41, p.w41v) || !delay_weights(T / 8.0, &p.k8, p.w8v) || p.k41 > 3 || p.k8 > 3) {
             set_error("unsupported fractional delay for this Fs/fb"); delete b; return JAERO_E_ARG; }
-        p.res_b0 = 0.00032714218939589035; p.res_b1 = 0; p.res_b2 = 0.00032714218939589035;   // :256-261
-        p.res_a1 = -0.39005299948210803; p.res_a2 = 0.99934571562120822;
-        p.ee = 0.4;                                                           // :263
+        if (s->fb == 8400) {                                                  // :243-250 (the 10 Hz set, assigned last, wins)
+            p.res_b0 = 0.0012845857864470789; p.res_b1 = 0; p.res_b2 = -0.0012845857864470789;
+            p.res_a1 = -0.90681461999279889; p.res_a2 = 0.99743082842710584;
+            p.ee = 0.65;
+        } else {
+            p.res_b0 = 0.00032714218939589035; p.res_b1 = 0; p.res_b2 = 0.00032714218939589035;   // :256-261
+            p.res_a1 = -0.39005299948210803; p.res_a2 = 0.99934571562120822;
+            p.ee = 0.4;                                                       // :263
+        }
         p.lf_b0 = 0.0010275610653672064; p.lf_b1 = 0.0020551221307344128; p.lf_b2 = 0.0010275610653672064;   // :95-100
         p.lf_a1 = -1.9207386815577139; p.lf_a2 = 0.92509247310306331;
         st_freq = s->fb;                                                      // :270
@@ -408,7 +419,52 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         if (batch_alloc(b, &c.tw, (size_t)c.nfft) || batch_alloc(b, &c.work_a, (size_t)c.group * c.nfft) ||
             batch_alloc(b, &c.work_b, (size_t)c.group * c.nfft) || batch_alloc(b, &c.y, (size_t)n_channels * c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
         JB_CUDA(cudaMemcpyAsync(c.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
+        if (c.is8400) {                                                       // raised-cosine window (coarsefreqestimate.cpp:62-74)
+            std::vector<double> win(c.nfft, 0.0);
+            win[0] = 1;
+            for (int i = 1; i <= c.startbin; i++) {
+                double val = cos(M_PI_2 * ((double)i) / ((double)c.startbin)); val *= val;
+                if ((c.nfft - i) < 0) break;
+                if (i >= c.nfft) break;
+                win[c.nfft - i] = val; win[i] = val;
+            }
+            if (batch_alloc(b, &c.window, (size_t)c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+            JB_CUDA(cudaMemcpyAsync(c.window, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        }
         JB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    if (s->kind == JAERO_KIND_OQPSK && s->fb == 8400) {
+        // K6: 2049-tap RRC (alpha 0.6) applied by streaming FFT convolution, nfft 4096 (oqpskdemodulator.cpp:280-283)
+        b->pre_on = true;
+        std::vector<double> kern = rrc_taps(0.6, 2048, s->Fs, s->fb / 2);
+        const int NF = 4096;
+        std::vector<std::complex<double>> H(NF, 0.0), tw(NF);
+        for (size_t i = 0; i < kern.size(); i++) H[i] = kern[i];
+        for (int k = 0; k < NF; k++) { const double a = -2.0 * M_PI * (double)k / (double)NF; tw[k] = std::complex<double>(cos(a), sin(a)); }
+        {   // host radix-2 FFT of the kernel
+            int bits = 12;
+            for (int i = 0; i < NF; i++) { int r = 0; for (int q = 0; q < bits; q++) if (i & (1 << q)) r |= 1 << (bits - 1 - q); if (r > i) std::swap(H[i], H[r]); }
+            for (int len = 2; len <= NF; len <<= 1)
+                for (int i = 0; i < NF; i += len)
+                    for (int k = 0; k < len / 2; k++) { auto w = tw[k * (NF / len)]; auto u = H[i + k], v = H[i + k + len / 2] * w; H[i + k] = u + v; H[i + k + len / 2] = u - v; }
+        }
+        FirStream &f = b->fir; memset(&f, 0, sizeof f);
+        PreParams &q = b->pre; memset(&q, 0, sizeof q);
+        int rc2 = 0;
+        rc2 |= batch_alloc(b, &f.H, (size_t)NF); rc2 |= batch_alloc(b, &f.tw, (size_t)NF);
+        rc2 |= batch_alloc(b, &f.hist, (size_t)n_channels * FIR_L); rc2 |= batch_alloc(b, &f.inblk, (size_t)n_channels * FIR_L);
+        rc2 |= batch_alloc(b, &f.outblk, (size_t)n_channels * FIR_L);
+        rc2 |= batch_alloc(b, &q.osc, (size_t)4 * cp);
+        rc2 |= batch_alloc(b, &p.m2_freq_sum, (size_t)cp);
+        if (rc2) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+        JB_CUDA(cudaMemcpyAsync(f.H, H.data(), NF * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaMemcpyAsync(f.tw, tw.data(), NF * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
+        // mixer_fir_pre.SetFreq(freq_center,Fs) is only done in the ctor, with the ctor's 8000 Hz (oqpskdemodulator.cpp:21,115)
+        std::vector<double> osc(4 * cp, 0.0);
+        for (size_t c2 = 0; c2 < cp; c2++) { osc[1 * cp + c2] = (8000.0) * ((double)jb::WTSIZE) / ((double)((float)48000)); osc[2 * cp + c2] = 8000.0; }
+        JB_CUDA(cudaMemcpyAsync(q.osc, osc.data(), osc.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        q.n_channels = n_channels; q.cpad = p.cpad; q.sin_t = p.sin_t; q.cos_t = p.cos_t;
     }
     // per-channel initial state
     {
@@ -435,7 +491,7 @@ void jaero_batch_destroy(jaero_batch *b)
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     for (void *q : b->allocs) cudaFree(q);
-    cudaFree(b->d_stage);
+    cudaFree(b->d_stage); cudaFree(b->d_x);
     cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage);
     for (auto &e : b->ev_seg) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : b->ev_cfe) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -500,6 +556,33 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
                                   cudaMemcpyDeviceToDevice, b->stream));
         d_pcm = b->d_stage; stride = pitch;
     }
+    if (b->pre_on) {
+        // K6 over the whole call first (oqpskdemodulator.cpp:343-381), then the per-sample loop consumes its output
+        const size_t C = p.n_channels, xs = (n + 7) & ~(size_t)7;
+        if (C * xs > b->x_cap) {
+            JB_CUDA(cudaStreamSynchronize(b->stream));
+            cudaFree(b->d_x); b->d_x = 0;
+            JB_CUDA(cudaMalloc(&b->d_x, C * xs * sizeof(double2)));
+            b->x_cap = C * xs;
+        }
+        b->pre.x = b->d_x; b->pre.xstride = xs;
+        b->p.xpre = b->d_x; b->p.xstride = xs;
+        if (pre_down_launch(b->pre, d_pcm, stride, (int)n, b->stream)) return JAERO_E_CUDA;
+        b->launches++;
+        int i = 0;
+        while (i < (int)n) {
+            const int room = FIR_L - b->fir_fill;
+            const int take = std::min(room, (int)n - i);
+            if (fir_exchange_up_launch(b->pre, b->fir, i, i + take, b->fir_fill, b->stream)) return JAERO_E_CUDA;
+            b->launches++;
+            b->fir_fill += take; i += take;
+            if (b->fir_fill == FIR_L) {
+                if (fir_block_launch(b->fir, p.n_channels, b->fir_blocks == 0 ? 1 : 0, b->stream)) return JAERO_E_CUDA;
+                b->launches++;
+                b->fir_fill = 0; b->fir_blocks++;
+            }
+        }
+    }
     const int N = p.bbnfft, trig_every = p.cpu_reduce ? N : N / 4;
     SegmentArgs a;
     memset(&a, 0, sizeof a);
@@ -541,6 +624,10 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
     if (launch(seg_start, (int)n, false, seg_bb, seg_cc)) return JAERO_E_CUDA;
     b->samples += ((int)n - seg_start);
     b->bb_pos = bb; b->coarse_counter = cc;
+    if (b->pre_on) {                                               // :608 mixer_fir_pre.SetFreq(mixer2_freq_sum/i)
+        if (pre_finish_launch(b->pre, p.m2_freq_sum, (int)n, p.Fs, b->stream)) return JAERO_E_CUDA;
+        b->launches++;
+    }
     return JAERO_OK;
 }
 

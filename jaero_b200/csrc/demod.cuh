@@ -60,8 +60,8 @@ struct DemodParams {
     double correctionfactor;          // MSK
     double res_a1, res_a2, res_b0, res_b1, res_b2;   // st_iir_resonator (a0 = 1)
     double lf_a1, lf_a2, lf_b0, lf_b1, lf_b2;        // ct_iir_loopfilter
-    double w41, w8;                   // Delay<> interpolation weights (ceil(fd)-fd as the reference computes it)
-    int k41, k8;                      // ceil(fd) for T/4 and T/8
+    double w41v[4], w8v[4];           // Delay<> interpolation weight at each ring position (DSP.h:357-374 computes it from buffptr)
+    int k41, k8;                      // ceil(fd) for T/4 and T/8; ring sizes are k+1
     int soft_cap;                     // per-channel soft-bit ring capacity (shorts)
     // device pointers
     double *D; int *I;
@@ -75,6 +75,9 @@ struct DemodParams {
     int16_t *soft;                    // [ch][soft_cap]
     const double *sin_t, *cos_t;      // the reference's 19999-entry tables (DSP.cpp:19-20), built on the host
     double *cfe_est_out;              // [ch] value CoarseFreqEstimate would emit this epoch
+    const double2 *xpre;              // 8400 bps: K6 output of the current call [ch][xstride] (null otherwise)
+    size_t xstride;
+    double *m2_freq_sum;              // 8400 bps: running mixer2_freq_sum of the current call [cpad]
 };
 
 // Uniform (lock-step) positions the host tracks and passes per launch.

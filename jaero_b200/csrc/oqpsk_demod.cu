@@ -36,7 +36,10 @@ static const int OQ_PROW = 80;            // bytes per channel row of a PCM tile
 static const int OQ_SM_FIR = 2 * OQ_FIRROWS * OQ_THREADS * 8;          // FIR windows re/im
 static const int OQ_SM_RING = OQ_T * OQ_THREADS * 8;                   // one ring tile [T][32] doubles
 static const int OQ_SM_PCM = OQ_THREADS * OQ_PROW;                     // one PCM tile
+static const int OQ_XROW = 32 * 16 + 16;    // bytes per channel row of a pre-filtered-sample tile (32 double2 + pad)
+static const int OQ_SM_X = OQ_THREADS * OQ_XROW;
 static const int OQ_SM_TOTAL = OQ_SM_FIR + 6 * OQ_SM_RING + 2 * OQ_SM_PCM + 64;
+static const int OQ_SM_TOTAL_PRE = OQ_SM_TOTAL + 2 * OQ_SM_X;
 
 #define LD(idx) p.D[(size_t)(idx) * cpad + ch]
 #define LI(idx) p.I[(size_t)(idx) * cpad + ch]
@@ -65,8 +68,12 @@ __device__ __forceinline__ void fir54(const double *__restrict__ wre, const doub
     ore = sre; oim = sim;
 }
 
+// PRE = true: the 8400 bps variant (oqpskdemodulator.cpp:436-448): no FIR in the loop, the sample entering the loop is
+// mixer2.CIS * cval_prefiltered[i] (K6 output, staged like the PCM rows), and mixer2's frequency is summed per sample.
+template <bool PRE>
 __global__ void __launch_bounds__(OQ_THREADS)
-oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
+oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride,
+                     const double2 *__restrict__ xpre, size_t xstride, double *__restrict__ m2_freq_sum)
 {
     extern __shared__ __align__(128) unsigned char oq_smem_raw[];
     double *s_re = reinterpret_cast<double *>(oq_smem_raw);   // [OQ_FIRROWS][32]
@@ -75,14 +82,15 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     double *t_e1 = t_agc + 2 * OQ_T * OQ_THREADS;
     double *t_e2 = t_e1 + 2 * OQ_T * OQ_THREADS;
     unsigned char *t_pcm = oq_smem_raw + OQ_SM_FIR + 6 * OQ_SM_RING;              // [2][32][OQ_PROW]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(t_pcm + 2 * OQ_SM_PCM);   // ring[2], pcm[2]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(t_pcm + 2 * OQ_SM_PCM);   // ring[2], pcm[2], x[2]
+    unsigned char *t_x = oq_smem_raw + OQ_SM_TOTAL;                               // [2][32][OQ_XROW] (PRE only)
     const int lane = threadIdx.x;
     const int ch_raw = blockIdx.x * OQ_THREADS + lane;
     const bool live = ch_raw < p.n_channels;
     const int ch = ch_raw;                                    // dead lanes run on their (allocated) pad column with zero input
     const int nlive = min(OQ_THREADS, p.n_channels - (int)blockIdx.x * OQ_THREADS);
     const size_t cpad = p.cpad;
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); }
+    if (lane == 0) { for (int k = 0; k < 6; k++) mbar_init(&bars[k], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
 
@@ -154,7 +162,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     const bool cpu_reduce = p.cpu_reduce != 0;
     const double Fs = p.Fs, fbr = p.fb, thr = p.signalthreshold, ee = p.ee;
     const double res_a1 = p.res_a1, res_a2 = p.res_a2, res_b0 = p.res_b0, res_b1 = p.res_b1, res_b2 = p.res_b2;
-    const double w41 = p.w41, w8 = p.w8;
+    int p41 = (int)(S % (p.k41 + 1)), p8 = (int)(S % (p.k8 + 1));   // Delay<> ring positions (lock-step)
     const int k41 = p.k41, k8 = p.k8;
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     const int marg_len = p.marg_len, dt_len = p.dt_len, mse_len = p.mse_len;
@@ -215,6 +223,14 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
         __syncwarp();
         if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
+        if (PRE) {
+            long long left = (long long)xstride - (long long)tile * OQ_T;
+            if (left > OQ_T) left = OQ_T;
+            const unsigned xb = left > 0 ? (unsigned)(left * 16) : 0u;
+            if (lane == 0) mbar_expect_tx(&bars[4 + b], xb * (unsigned)nlive);
+            __syncwarp();
+            if (live && xb) bulk_g2s(t_x + b * OQ_SM_X + lane * OQ_XROW, xpre + (size_t)ch * xstride + (size_t)tile * OQ_T, xb, &bars[4 + b]);
+        }
     };
     unsigned phases = 0u;                                     // expected parity per barrier (bit b: ring b, bit 2+b: pcm b)
 #define OQ_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
@@ -227,6 +243,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
     OQ_WAIT((int)(rt & 1));
     OQ_WAIT(2 + (pt & 1));
+    if (PRE) OQ_WAIT(4 + (pt & 1));
     bool ring_dirty = false;
 
     // ---- table / symbol-rate operands requested ahead of use (the SM issues in order: a load stalls the warp only when
@@ -246,11 +263,12 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     // FIR output of the first sample of this launch: the 55 entries older than the slot about to be written
     // (DSP.cpp:292-304: the output excludes the sample just stored). The window that ends at logical slot q starts at
     // row q+2 of the doubled buffer.
-    double fre, fim;
-    {
+    double fre = 0, fim = 0;
+    if (!PRE) {
         int newest = fir_pos - 1; if (newest < 0) newest += OQ_NT1;
         fir55(s_re + (newest + 2) * OQ_THREADS + lane, s_im + (newest + 2) * OQ_THREADS + lane, fre, fim);
     }
+    double m2sum = PRE ? (a.new_write ? 0.0 : m2_freq_sum[ch]) : 0.0;     // mixer2_freq_sum (:385,447)
 
     for (int i = a.i0; i < a.i1; i++) {
         // ---- PCM sample from the staged tile
@@ -258,6 +276,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         if ((i >> 5) != pt) {                                 // entered the next PCM tile (warp-uniform)
             pt = i >> 5;
             OQ_WAIT(2 + (pt & 1));
+            if (PRE) OQ_WAIT(4 + (pt & 1));
             pcm_next_issued = false;
             if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
             pk_valid = false;
@@ -297,8 +316,16 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         // dependency chain the scheduler interleaves with the serial loop arithmetic below.
         // The 54 older terms are summed first (same order as DSP.cpp:296-303), the newest term is appended once the mixed
         // sample is available.
-        double nfre, nfim;
-        fir54(s_re + (fir_pos + 2) * OQ_THREADS + lane, s_im + (fir_pos + 2) * OQ_THREADS + lane, nfre, nfim);
+        double nfre = 0, nfim = 0;
+        if (!PRE) fir54(s_re + (fir_pos + 2) * OQ_THREADS + lane, s_im + (fir_pos + 2) * OQ_THREADS + lane, nfre, nfim);
+        if (PRE) {
+            // sig2 = mixer2.WTCISValue()*cval_prefiltered[i] (:440); mixer2_freq_sum+=mixer2.GetFreqHz() (:447)
+            double2 xv = *reinterpret_cast<const double2 *>(t_x + (pt & 1) * OQ_SM_X + lane * OQ_XROW + po * 16);
+            if (!live) xv = make_double2(0.0, 0.0);
+            const double2 sg = cmul(make_double2(c2_re, c2_im), xv);
+            fre = sg.x; fim = sg.y;
+            m2sum += m2.freq;
+        }
 
         const double sre = fre, sim = fim;
         const double dabval = sqrt(sre * sre + sim * sim);                // :461
@@ -345,6 +372,9 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         dly_s0 = ab2;
         // Delay(T/4): older = x[n-k41], newer = x[n-k41+1]  (DSP.h:357-374)
         double st_d1out, st_d2out;
+        const double w41 = p.w41v[p41], w8 = p.w8v[p8];
+        p41++; if (p41 > k41) p41 = 0;
+        p8++; if (p8 > k8) p8 = 0;
         {
             const double older = (k41 == 3) ? d41_2 : (k41 == 2 ? d41_1 : d41_0);
             const double newer = (k41 == 3) ? d41_1 : (k41 == 2 ? d41_0 : st_diff);
@@ -441,7 +471,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
             }
         }
         sig2_last = sig2;                                                 // :596
-        {   // this sample's mixed value enters the FIR ring (:453-456); finish the next output
+        if (!PRE) {   // this sample's mixed value enters the FIR ring (:453-456); finish the next output
             const double cre = c2_re * dval, cim = c2_im * dval;
             s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
             s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
@@ -474,7 +504,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     // ---------------- drain the staging pipeline
     if (ring_dirty) ring_store(rt);
     if (ring_next_issued) OQ_WAIT((int)((rt + 1) & 1));
-    if (pcm_next_issued) OQ_WAIT(2 + ((pt + 1) & 1));
+    if (pcm_next_issued) { OQ_WAIT(2 + ((pt + 1) & 1)); if (PRE) OQ_WAIT(4 + ((pt + 1) & 1)); }
     bulk_wait_all();
 
     // ---------------- store state
@@ -495,6 +525,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     LD(D_MARG_SUM) = marg_sum; LD(D_MARG_VAL) = marg_val;
     LD(D_MSE_PM_SUM) = pm_sum; LD(D_MSE_MA_SUM) = ma_sum; LD(D_MSE) = mse;
     LD(D_LASTMSE) = lastmse;
+    if (PRE) m2_freq_sum[ch] = m2sum;
     LI(I_YUI) = yui; LI(I_COUNTDOWN) = countdown; LI(I_COUNTDOWN2) = countdown2; LI(I_SIG2L_INIT) = sig2l_init;
     LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
     LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
@@ -508,9 +539,15 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
 int oqpsk_segment_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s)
 {
     const int grid = (p.n_channels + OQ_THREADS - 1) / OQ_THREADS;
-    const size_t smem = (size_t)OQ_SM_TOTAL;
-    JB_CUDA(cudaFuncSetAttribute(oqpsk_segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    oqpsk_segment_kernel<<<grid, OQ_THREADS, smem, s>>>(p, a, d_pcm, stride);
+    if (p.xpre) {
+        const size_t smem = (size_t)OQ_SM_TOTAL_PRE;
+        JB_CUDA(cudaFuncSetAttribute(oqpsk_segment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        oqpsk_segment_kernel<true><<<grid, OQ_THREADS, smem, s>>>(p, a, d_pcm, stride, p.xpre, p.xstride, p.m2_freq_sum);
+    } else {
+        const size_t smem = (size_t)OQ_SM_TOTAL;
+        JB_CUDA(cudaFuncSetAttribute(oqpsk_segment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        oqpsk_segment_kernel<false><<<grid, OQ_THREADS, smem, s>>>(p, a, d_pcm, stride, nullptr, 0, nullptr);
+    }
     JB_CUDA(cudaGetLastError());
     return 0;
 }

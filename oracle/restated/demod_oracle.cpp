@@ -131,6 +131,13 @@ OqpskDemodOracle::OqpskDemodOracle(const DemodSettings &st) : s(st)
     ct_iir_loopfilter.a[0] = 1; ct_iir_loopfilter.a[1] = -1.9207386815577139; ct_iir_loopfilter.a[2] = 0.92509247310306331;
     ct_iir_loopfilter.init();
     st_osc.SetFreq(s.fb, (int)s.Fs); st_osc_ref.SetFreq(s.fb, (int)s.Fs);                       // :270-271
+    {   // :280-283 (kernel of the 8400 pre-filter; built for every rate, used only at 8400) and ctor :115
+        std::vector<double> pts = (s.fb == 8400) ? rrc_design(0.6, 2048, s.Fs, s.fb / 2) : rrc_design(1.0, 2048, s.Fs, s.fb / 2);
+        QVector<double> qp((int)pts.size());
+        for (size_t i = 0; i < pts.size(); i++) qp[(int)i] = pts[i];
+        fir_pre.SetKernel(qp, 4096);
+        mixer_fir_pre.SetFreq(8000, 48000);               // ctor freq_center=8000, Fs=48000; setSettings never touches it
+    }
     coarseCounter = 0;
     sig2_last_init = false; sig2_last = 0; pt_d = 0; yui = 0; countdown2 = 5; countdown = 4;
     n_sig_true = n_sig_false = 0; nsamples = 0;
@@ -140,6 +147,23 @@ void OqpskDemodOracle::writeData(const int16_t *ptr, long len)
 {
     if (!len) return;
     double lastmse = mse;                                                                       // :339
+    std::vector<cpx> cval_prefiltered;                                                          // :343-381
+    if (s.fb == 8400) {
+        cval_prefiltered.resize(len);
+        double savedphase = mixer_fir_pre.GetPhaseDeg();
+        for (long i = 0; i < len; i++) {
+            double dval = ((double)(ptr[i])) / 32768.0;
+            cval_prefiltered[i] = mixer_fir_pre.WTCISValue() * dval;
+            mixer_fir_pre.WTnextFrame();
+        }
+        fir_pre.update(cval_prefiltered.data(), (int)len);
+        mixer_fir_pre.SetPhaseDeg(savedphase);
+        for (long i = 0; i < len; i++) {
+            cval_prefiltered[i] *= mixer_fir_pre.WTCISValue_conj();
+            mixer_fir_pre.WTnextFrame();
+        }
+    }
+    double mixer2_freq_sum = 0;                                                                 // :385
     for (long i = 0; i < len; i++) {
         double dval = ((double)(ptr[i])) / 32768.0;                                             // :390
         if ((coarseCounter >= s.Fs || !s.cpuReduce)) {                                          // :410-429
@@ -154,8 +178,14 @@ void OqpskDemodOracle::writeData(const int16_t *ptr, long len)
             }
         }
         coarseCounter++;
-        cpx cval = mixer2.WTCISValue() * dval;                                                  // :453
-        cpx sig2 = cpx(fir_re.FIRUpdateAndProcess(cval.real()), fir_im.FIRUpdateAndProcess(cval.imag()));   // :456
+        cpx sig2;
+        if (s.fb == 8400) {                                                                     // :436-448
+            sig2 = mixer2.WTCISValue() * cval_prefiltered[i];
+            mixer2_freq_sum += mixer2.GetFreqHz();
+        } else {
+            cpx cval = mixer2.WTCISValue() * dval;                                              // :453
+            sig2 = cpx(fir_re.FIRUpdateAndProcess(cval.real()), fir_im.FIRUpdateAndProcess(cval.imag()));   // :456
+        }
         double dabval = std::sqrt(sig2.real() * sig2.real() + sig2.imag() * sig2.imag());       // :461
         ebno.Update(dabval);                                                                    // :463
         sig2 *= agc.Update(dabval);                                                             // :466
@@ -201,11 +231,11 @@ void OqpskDemodOracle::writeData(const int16_t *ptr, long len)
                 pt_qpsk *= cpx(cos(marg.Val), sin(marg.Val));
                 mse = msecalc.Update(pt_qpsk);                                                  // :563
                 if (mse < s.signalthreshold) {                                                  // :565
-                    int ibit = qRound(0.75 * pt_qpsk.imag() * 127.0 + 128.0);
+                    int ibit = jor::qRound(0.75 * pt_qpsk.imag() * 127.0 + 128.0);
                     if (ibit > 255) ibit = 255;
                     if (ibit < 0) ibit = 0;
                     RxDataBits.push_back((short)(unsigned char)ibit);
-                    ibit = qRound(0.75 * pt_qpsk.real() * 127.0 + 128.0);
+                    ibit = jor::qRound(0.75 * pt_qpsk.real() * 127.0 + 128.0);
                     if (ibit > 255) ibit = 255;
                     if (ibit < 0) ibit = 0;
                     RxDataBits.push_back((short)(unsigned char)ibit);
@@ -221,11 +251,12 @@ void OqpskDemodOracle::writeData(const int16_t *ptr, long len)
         mixer2.WTnextFrame(); mixer_center.WTnextFrame(); st_osc.WTnextFrame(); st_osc_ref.WTnextFrame();   // :600-603
         nsamples++;
     }
+    mixer_fir_pre.SetFreq(mixer2_freq_sum / ((double)len));                                     // :608
 }
 
 void OqpskDemodOracle::FreqOffsetEstimateSlot(double est)
 {
-    // :634-638 only touches the 8400 pre-filter mixer (not restated here)
+    if ((mse > s.signalthreshold) || (!dcd)) mixer_fir_pre.SetFreq(mixer_center.GetFreqHz() + est, (int)s.Fs);   // :634-638
     if ((mse < s.signalthreshold) && (!dcd)) {                                                  // :642-650
         if (countdown2 > 0) countdown2--;
         else mixer2.SetFreq(mixer_center.GetFreqHz() + est);
@@ -334,13 +365,13 @@ void MskDemodOracle::writeData(const int16_t *ptr, long len)
             double tdb = (fabs((pt_msk).imag() * 0.75) - 1.0);
             mse = msema.Update((tda * tda) + (tdb * tdb));
             double imagin = diffdecode.UpdateSoft(pt_msk.imag());                               // :451-469
-            int ibit = qRound((imagin) * 127.0 + 128.0);
+            int ibit = jor::qRound((imagin) * 127.0 + 128.0);
             if (ibit > 255) ibit = 255;
             if (ibit < 0) ibit = 0;
             RxDataBits.push_back((short)(unsigned char)ibit);
             double real = diffdecode.UpdateSoft(pt_msk.real());
             real = -real;
-            ibit = qRound((real) * 127.0 + 128.0);
+            ibit = jor::qRound((real) * 127.0 + 128.0);
             if (ibit > 255) ibit = 255;
             if (ibit < 0) ibit = 0;
             RxDataBits.push_back((short)(unsigned char)ibit);

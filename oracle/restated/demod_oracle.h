@@ -3,6 +3,7 @@
 #ifndef JAERO_DEMOD_ORACLE_H
 #define JAERO_DEMOD_ORACLE_H
 #include "dsp_oracle.h"
+#include "jfft.h"      // restated JFastFir (oracle/jfft_restated.cpp) for the 8400 bps pre-filter
 
 namespace jor {
 
@@ -32,10 +33,11 @@ struct OqpskDemodOracle                                // oqpskdemodulator.cpp
     // function-local statics of the reference, made per-instance (oqpskdemodulator.cpp:487,496,498,641,652)
     bool sig2_last_init; cpx sig2_last, pt_d; int yui, countdown2, countdown;
     std::vector<short> RxDataBits;
+    JFastFir fir_pre; WaveTable mixer_fir_pre;         // 8400 bps pre-filter (:112-115,280-283)
     // observables
     std::vector<short> soft_out; std::vector<double> cfe_log; long n_sig_true, n_sig_false; long nsamples;
     explicit OqpskDemodOracle(const DemodSettings &);
-    void writeData(const int16_t *pcm, long n);        // :334-627 (fb != 8400 branch)
+    void writeData(const int16_t *pcm, long n);        // :334-627
     void FreqOffsetEstimateSlot(double est);           // :629-677
     void DCDstatSlot(bool d) { dcd = d; }
 };

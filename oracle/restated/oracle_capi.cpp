@@ -56,7 +56,7 @@ void jor_free(void *hv) { OrHandle *h = (OrHandle *)hv; delete h->oq; delete h->
 int jor_rrc_design(double alpha, int firsize, double Fs, double symbol_freq, double *out, int cap)
 { std::vector<double> p = rrc_design(alpha, firsize, Fs, symbol_freq); int n = (int)p.size(); for (int i = 0; i < n && i < cap; i++) out[i] = p[i]; return n; }
 void jor_trig_tables(double *s, double *c) { for (int i = 0; i < WTSIZE; i++) { s[i] = trig().SinWT[i]; c[i] = trig().CosWT[i]; } }
-int jor_qround(double d) { return qRound(d); }
+int jor_qround(double d) { return jor::qRound(d); }
 void jor_fft(int n, int inverse, const double *in_ri, double *out_ri)
 { std::vector<cpx> x(n); for (int i = 0; i < n; i++) x[i] = cpx(in_ri[2 * i], in_ri[2 * i + 1]); fft_pow2(x.data(), n, inverse != 0);
   for (int i = 0; i < n; i++) { out_ri[2 * i] = x[i].real(); out_ri[2 * i + 1] = x[i].imag(); } }

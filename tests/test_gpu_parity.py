@@ -130,7 +130,7 @@ def _assert_parity(soft_g, st_g, soft_o, st_o):
     assert st_g["n_sig_true"] == st_o["n_sig_true"] and st_g["n_sig_false"] == st_o["n_sig_false"]
 
 
-@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "msk_600"])
+@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600"])
 def test_demod_parity_on_reference_recordings(golden, name):
     case = golden[name]
     pcm = load_excerpt(case["excerpt"])
@@ -246,7 +246,7 @@ def test_error_behaviour():
     with pytest.raises(jb.JaeroError, match="overflow"):
         b.read_softbits()
     with pytest.raises(jb.JaeroError):
-        jb.DemodBatch("oqpsk", 2, fb=8400)                         # pre-filter path not implemented: refuses, no fallback
+        jb.DemodBatch("oqpsk", 2, fb=10500, Fs=44100)              # unsupported rate: refuses, no fallback
     with pytest.raises(jb.JaeroError):
         jb.DemodBatch("msk", 0, fb=600)
     b.close()

@@ -104,7 +104,7 @@ def _run_restated(case, pcm):
     return d.take_soft(), d.state(), d.take_cfe_log()
 
 
-@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "msk_600"])
+@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600"])
 def test_restated_oracle_matches_reference_golden(golden, name):
     """The restatement reproduces the verbatim reference bit for bit on the recordings (soft bits, coarse
     estimates, loop state) — golden values were produced by oracle/_ref (tools/make_golden_outputs.py)."""

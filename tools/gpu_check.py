@@ -152,6 +152,8 @@ if __name__ == "__main__":
         ok &= check_viterbi()
     if "oqpsk" in which:
         ok &= check_demod("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
+    if "oqpsk8400" in which:
+        ok &= check_demod("oqpsk", "oqpsk_8400", dict(fb=8400, freq_center=8000, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
     if "msk" in which:
         ok &= check_demod("msk", "msk_600", dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True))
     if "pchannel" in which:
