@@ -14,6 +14,10 @@ STATE_FIELDS = ["mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtp
                 "ebno", "marg", "cfe_est", "n_sig_true", "n_sig_false", "center_wtptr", "st_ref_wtptr"]
 
 
+BURST_STATE_FIELDS = ["mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse",
+                      "ebno", "vol_gain", "rotator_freq", "n_sig_true", "n_sig_false", "cntr", "startstop"]
+
+
 def available():
     return os.path.exists(_SO)
 
@@ -25,6 +29,9 @@ def lib():
         vp, d, i, l = ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_long
         for name in ("jref_oqpsk_new", "jref_msk_new"):
             f = getattr(L, name); f.restype = vp; f.argtypes = [d, d, d, d, i, d, i, i, i]
+        for name in ("jref_burst_msk_new", "jref_burst_oqpsk_new"):
+            f = getattr(L, name); f.restype = vp; f.argtypes = [d, d, d, d, d]
+        L.jref_ebno_log_take.restype = l; L.jref_ebno_log_take.argtypes = [vp, vp, l]
         L.jref_write.argtypes = [vp, vp, l]
         L.jref_set_dcd.argtypes = [vp, i]
         L.jref_soft_count.restype = l; L.jref_soft_count.argtypes = [vp]
@@ -66,8 +73,12 @@ class RefDemod:
     def __init__(self, kind, fb, Fs=48000.0, freq_center=8000.0, lockingbw=10500.0, fft_power=14,
                  signalthreshold=0.65, afc=False, sql=False, cpureduce=False):
         L = lib()
-        new = L.jref_oqpsk_new if kind == "oqpsk" else L.jref_msk_new
-        self.h = new(fb, Fs, freq_center, lockingbw, fft_power, signalthreshold, int(afc), int(sql), int(cpureduce))
+        if kind in ("burst_msk", "burst_oqpsk"):
+            new = L.jref_burst_msk_new if kind == "burst_msk" else L.jref_burst_oqpsk_new
+            self.h = new(fb, Fs, freq_center, lockingbw, signalthreshold)
+        else:
+            new = L.jref_oqpsk_new if kind == "oqpsk" else L.jref_msk_new
+            self.h = new(fb, Fs, freq_center, lockingbw, fft_power, signalthreshold, int(afc), int(sql), int(cpureduce))
         self.kind = kind
 
     def write(self, pcm):
@@ -89,10 +100,16 @@ class RefDemod:
         n = lib().jref_cfe_log_take(self.h, _p(out), len(out))
         return out[:n].copy()
 
+    def take_ebno_log(self):
+        out = np.zeros(4096, dtype=np.float64)
+        n = lib().jref_ebno_log_take(self.h, _p(out), len(out))
+        return out[:n].copy()
+
     def state(self):
         o = np.zeros(16, dtype=np.float64)
         n = lib().jref_state(self.h, _p(o))
-        return dict(zip(STATE_FIELDS, o[:n]))
+        fields = STATE_FIELDS if not self.kind.startswith("burst") else BURST_STATE_FIELDS
+        return dict(zip(fields, o[:n]))
 
     def close(self):
         if self.h:

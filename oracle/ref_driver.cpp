@@ -22,6 +22,8 @@
 #include "coarsefreqestimate.h"
 #include "mskdemodulator.h"
 #include "oqpskdemodulator.h"
+#include "burstmskdemodulator.h"
+#include "burstoqpskdemodulator.h"
 #include "fftwrapper.h"
 #include "fftrwrapper.h"
 #include "jconvolutionalcodec.h"
@@ -39,9 +41,12 @@ void operator delete[](void *p, std::size_t) noexcept { free(p); }
 
 struct RefHandle
 {
-    int kind;                       // 0 = OQPSK, 1 = MSK
+    int kind;                       // 0 = OQPSK, 1 = MSK, 2 = burst MSK, 3 = burst OQPSK
     OqpskDemodulator *oq;
     MskDemodulator *msk;
+    BurstMskDemodulator *bmsk;
+    BurstOqpskDemodulator *boq;
+    std::vector<double> ebno_log;   // EbNoMeasurmentSignal values (burst modes emit one per burst)
     std::vector<short> soft;        // concatenated processDemodulatedSoftBits payloads
     std::vector<int> emit_sizes;    // size of each emit
     std::vector<double> cfe_log;    // every FreqOffsetEstimate value, in order
@@ -62,6 +67,13 @@ static RefHandle *find(const void *p) { auto it = g_handles.find(p); return it =
     void C::WarningTextSignal(const QString &) {}
 NOP_SIGNALS(OqpskDemodulator)
 NOP_SIGNALS(MskDemodulator)
+NOP_SIGNALS(BurstMskDemodulator)
+NOP_SIGNALS(BurstOqpskDemodulator)
+void BurstMskDemodulator::SymbolPhase(double) {}
+void BurstMskDemodulator::RxData(QByteArray &) {}
+void BurstMskDemodulator::BBOverlapedBuffer(const QVector<cpx_type> &) {}
+void BurstOqpskDemodulator::BBOverlapedBuffer(const QVector<cpx_type> &) {}
+void BurstOqpskDemodulator::writeDataSignal(const char *, qint64) {}
 void MskDemodulator::SymbolPhase(double) {}
 void MskDemodulator::RxData(const QByteArray &) {}
 
@@ -76,12 +88,14 @@ void CoarseFreqEstimate::FreqOffsetEstimate(double f)
 }
 #define OBS_SIGNALS(C) \
     void C::MSESignal(double m) { RefHandle *h = find(this); if (h) h->last_mse_signal = m; } \
-    void C::EbNoMeasurmentSignal(double e) { RefHandle *h = find(this); if (h) h->last_ebno_signal = e; } \
+    void C::EbNoMeasurmentSignal(double e) { RefHandle *h = find(this); if (h) { h->last_ebno_signal = e; h->ebno_log.push_back(e); } } \
     void C::SignalStatus(bool s) { RefHandle *h = find(this); if (h) { if (s) h->n_signal_true++; else h->n_signal_false++; } } \
     void C::processDemodulatedSoftBits(const QVector<short> &v) \
     { RefHandle *h = find(this); if (!h) return; h->emit_sizes.push_back(v.size()); for (int i = 0; i < v.size(); i++) h->soft.push_back(v[i]); }
 OBS_SIGNALS(OqpskDemodulator)
 OBS_SIGNALS(MskDemodulator)
+OBS_SIGNALS(BurstMskDemodulator)
+OBS_SIGNALS(BurstOqpskDemodulator)
 
 extern "C" {
 
@@ -120,16 +134,53 @@ void *jref_msk_new(double fb, double Fs, double freq_center, double lockingbw, i
     h->msk->start();
     return h;
 }
+// burst demodulators (burstmskdemodulator.cpp / burstoqpskdemodulator.cpp), settings as mainwindow.cpp:876-899
+void *jref_burst_msk_new(double fb, double Fs, double freq_center, double lockingbw, double signalthreshold)
+{
+    RefHandle *h = new RefHandle();
+    h->kind = 2;
+    h->bmsk = new BurstMskDemodulator(0);
+    g_handles[h->bmsk] = h;
+    BurstMskDemodulator::Settings s;
+    s.fb = fb; s.Fs = Fs; s.freq_center = freq_center; s.lockingbw = lockingbw; s.signalthreshold = signalthreshold;
+    h->bmsk->setSettings(s);
+    h->bmsk->start();
+    return h;
+}
+void *jref_burst_oqpsk_new(double fb, double Fs, double freq_center, double lockingbw, double signalthreshold)
+{
+    RefHandle *h = new RefHandle();
+    h->kind = 3;
+    h->boq = new BurstOqpskDemodulator(0);
+    g_handles[h->boq] = h;
+    BurstOqpskDemodulator::Settings s;
+    s.fb = fb; s.Fs = Fs; s.freq_center = freq_center; s.lockingbw = lockingbw; s.signalthreshold = signalthreshold;
+    h->boq->setSettings(s);
+    h->boq->start();
+    return h;
+}
 void jref_write(void *hv, const int16_t *pcm, long n)
 {
     RefHandle *h = (RefHandle *)hv;
     if (h->kind == 0) h->oq->writeData((const char *)pcm, (qint64)n * 2);
-    else h->msk->writeData((const char *)pcm, (qint64)n * 2);
+    else if (h->kind == 1) h->msk->writeData((const char *)pcm, (qint64)n * 2);
+    else if (h->kind == 2) h->bmsk->writeData((const char *)pcm, (qint64)n * 2);
+    else h->boq->writeData((const char *)pcm, (qint64)n * 2);
 }
 void jref_set_dcd(void *hv, int dcd)
 {
     RefHandle *h = (RefHandle *)hv;
-    if (h->kind == 0) h->oq->DCDstatSlot(dcd != 0); else h->msk->DCDstatSlot(dcd != 0);
+    if (h->kind == 0) h->oq->DCDstatSlot(dcd != 0);
+    else if (h->kind == 1) h->msk->DCDstatSlot(dcd != 0);
+    else if (h->kind == 2) h->bmsk->DCDstatSlot(dcd != 0);
+}
+long jref_ebno_log_take(void *hv, double *out, long cap)
+{
+    RefHandle *h = (RefHandle *)hv;
+    long n = (long)h->ebno_log.size(); if (n > cap) n = cap;
+    memcpy(out, h->ebno_log.data(), n * sizeof(double));
+    h->ebno_log.clear();
+    return n;
 }
 long jref_soft_count(void *hv) { return (long)((RefHandle *)hv)->soft.size(); }
 long jref_soft_take(void *hv, short *out, long cap)
@@ -163,20 +214,36 @@ int jref_state(void *hv, double *o)
         o[7] = d->ebnomeasure->EbNo; o[8] = d->marg->Val; o[9] = d->coarsefreqestimate->freq_offset_est;
         o[10] = (double)h->n_signal_true; o[11] = (double)h->n_signal_false;
         o[12] = d->mixer_center.WTptr; o[13] = d->st_osc_ref.WTptr;
-    } else {
+    } else if (h->kind == 1) {
         MskDemodulator *d = h->msk;
         o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer_center.freq;
         o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr; o[5] = d->agc->AGCVal; o[6] = d->mse;
         o[7] = d->ebnomeasure->EbNo; o[8] = d->marg->Val; o[9] = d->coarsefreqestimate->freq_offset_est;
         o[10] = (double)h->n_signal_true; o[11] = (double)h->n_signal_false;
         o[12] = d->mixer_center.WTptr; o[13] = 0;
+    } else if (h->kind == 2) {
+        // burst layout: 8 = vol_gain, 9 = rotator_freq, 12 = cntr, 13 = startstop
+        BurstMskDemodulator *d = h->bmsk;
+        o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer_center.freq;
+        o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr; o[5] = d->agc->AGCVal; o[6] = d->mse;
+        o[7] = d->ebnomeasure->EbNo; o[8] = d->vol_gain; o[9] = d->rotator_freq;
+        o[10] = (double)h->n_signal_true; o[11] = (double)h->n_signal_false;
+        o[12] = (double)d->cntr; o[13] = (double)d->startstop;
+    } else {
+        BurstOqpskDemodulator *d = h->boq;
+        o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer2.freq;
+        o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr; o[5] = d->agc->AGCVal; o[6] = d->mse;
+        o[7] = d->ebnomeasure->EbNo; o[8] = d->vol_gain; o[9] = d->rotator_freq;
+        o[10] = (double)h->n_signal_true; o[11] = (double)h->n_signal_false;
+        o[12] = (double)d->cntr; o[13] = (double)d->startstop;
     }
     return 14;
 }
 void jref_free(void *hv)
 {
     RefHandle *h = (RefHandle *)hv;
-    if (h->kind == 0) { g_handles.erase(h->oq); delete h->oq; } else { g_handles.erase(h->msk); delete h->msk; }
+    if (h->kind == 0) { g_handles.erase(h->oq); delete h->oq; } else if (h->kind == 1) { g_handles.erase(h->msk); delete h->msk; }
+    else if (h->kind == 2) { g_handles.erase(h->bmsk); delete h->bmsk; } else { g_handles.erase(h->boq); delete h->boq; }
     delete h;
 }
 

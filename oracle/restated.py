@@ -13,6 +13,10 @@ STATE_FIELDS = ["mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtp
                 "ebno", "marg", "cfe_est", "n_sig_true", "n_sig_false", "center_wtptr", "st_ref_wtptr"]
 
 
+BURST_STATE_FIELDS = ["mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse",
+                      "ebno", "vol_gain", "rotator_freq", "n_sig_true", "n_sig_false", "cntr", "startstop"]
+
+
 def available():
     return os.path.exists(_SO)
 
@@ -23,6 +27,8 @@ def lib():
         L = ctypes.CDLL(_SO)
         vp, d, i, l = ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_long
         L.jor_demod_new.restype = vp; L.jor_demod_new.argtypes = [i, d, d, d, d, i, d, i, i, i]
+        L.jor_burst_msk_new.restype = vp; L.jor_burst_msk_new.argtypes = [d, d, d, d, d]
+        L.jor_aux_take.restype = l; L.jor_aux_take.argtypes = [vp, i, vp, l]
         L.jor_write.argtypes = [vp, vp, l]; L.jor_set_dcd.argtypes = [vp, i]
         L.jor_soft_count.restype = l; L.jor_soft_count.argtypes = [vp]
         L.jor_soft_take.restype = l; L.jor_soft_take.argtypes = [vp, vp, l]
@@ -57,8 +63,11 @@ class OracleDemod:
     def __init__(self, kind, fb, Fs=48000.0, freq_center=8000.0, lockingbw=10500.0, fft_power=14,
                  signalthreshold=0.65, afc=False, sql=False, cpureduce=False):
         self.kind = kind
-        self.h = lib().jor_demod_new(0 if kind == "oqpsk" else 1, fb, Fs, freq_center, lockingbw, fft_power,
-                                     signalthreshold, int(afc), int(sql), int(cpureduce))
+        if kind == "burst_msk":
+            self.h = lib().jor_burst_msk_new(fb, Fs, freq_center, lockingbw, signalthreshold)
+        else:
+            self.h = lib().jor_demod_new(0 if kind == "oqpsk" else 1, fb, Fs, freq_center, lockingbw, fft_power,
+                                         signalthreshold, int(afc), int(sql), int(cpureduce))
 
     def write(self, pcm):
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
@@ -79,10 +88,16 @@ class OracleDemod:
         n = lib().jor_cfe_log_take(self.h, _p(out), len(out))
         return out[:n].copy()
 
+    def take_aux(self, which):
+        out = np.zeros(1 << 14, dtype=np.float64)
+        n = lib().jor_aux_take(self.h, which, _p(out), len(out))
+        return out[:n].copy()
+
     def state(self):
         o = np.zeros(16, dtype=np.float64)
         n = lib().jor_state(self.h, _p(o))
-        return dict(zip(STATE_FIELDS, o[:n]))
+        fields = BURST_STATE_FIELDS if self.kind.startswith("burst") else STATE_FIELDS
+        return dict(zip(fields, o[:n]))
 
     def close(self):
         if self.h:
