@@ -173,6 +173,29 @@ int jaero_pchannel_discard_sus(jaero_pchannel *p);
 int jaero_pchannel_get_stats(jaero_pchannel *p, int32_t *dcd, int64_t *su_total, int64_t *su_ok);
 int64_t jaero_pchannel_launch_count(const jaero_pchannel *p);
 
+/* ---- burst MSK demodulator (600 / 1200 bps R/T-channel bursts) ----
+ * Replaces BurstMskDemodulator (JAERO/burstmskdemodulator.h:49-215): ctor + setSettings (burstmskdemodulator.cpp:11-323),
+ * writeData (:371-754), DCDstatSlot (:757), and its processDemodulatedSoftBits / SignalStatus / EbNoMeasurmentSignal
+ * signals. Soft-bit streams carry the reference's -1 "start of burst" marker. */
+typedef struct jaero_burst jaero_burst;
+typedef struct jaero_burst_status {
+    double mixer2_freq, mixer2_wtptr, center_freq, st_freq, st_wtptr, agc, mse, ebno, vol_gain, rotator_freq;
+    double n_sig_true, n_sig_false;   /* SignalStatus(true/false) emits */
+    double cntr, startstop;
+    double last_burst_ebno;           /* value of the most recent EbNoMeasurmentSignal */
+    double n_ebno_emits;
+} jaero_burst_status;
+/* settings->kind is ignored; fb 600 or 1200, Fs 48000; freq_center / lockingbw / signalthreshold as BurstMskDemodulator::Settings */
+int jaero_burst_msk_create(const jaero_settings *settings, int n_channels, int device_ordinal, jaero_burst **out);
+void jaero_burst_destroy(jaero_burst *b);
+int jaero_burst_write(jaero_burst *b, const int16_t *pcm, size_t n_samples, size_t channel_stride);          /* HOST pcm */
+int jaero_burst_write_device(jaero_burst *b, const int16_t *d_pcm, size_t n_samples, size_t channel_stride);
+int jaero_burst_read_softbits(jaero_burst *b, int16_t *out, size_t cap_per_channel, int32_t *counts);
+int jaero_burst_set_dcd(jaero_burst *b, int channel, int dcd);
+int jaero_burst_get_status_all(jaero_burst *b, jaero_burst_status *out);
+int jaero_burst_sync(jaero_burst *b);
+int64_t jaero_burst_launch_count(const jaero_burst *b);
+
 #ifdef __cplusplus
 }
 #endif

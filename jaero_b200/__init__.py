@@ -44,7 +44,10 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_viterbi_reset", "jaero_viterbi_sync", "jaero_viterbi_launch_count",
            "jaero_pchannel_create", "jaero_pchannel_destroy", "jaero_pchannel_process_batch",
            "jaero_pchannel_process_softbits", "jaero_pchannel_tick", "jaero_pchannel_read_sus",
-           "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count"]
+           "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count",
+           "jaero_burst_msk_create", "jaero_burst_destroy", "jaero_burst_write", "jaero_burst_write_device",
+           "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
+           "jaero_burst_launch_count"]
 
 
 def lib():
@@ -88,6 +91,14 @@ def lib():
         L.jaero_pchannel_discard_sus.argtypes = [vp]
         L.jaero_pchannel_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_pchannel_launch_count.argtypes = [vp]; L.jaero_pchannel_launch_count.restype = ctypes.c_int64
+        L.jaero_burst_msk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
+        L.jaero_burst_destroy.argtypes = [vp]; L.jaero_burst_destroy.restype = None
+        L.jaero_burst_write.argtypes = [vp, vp, sz, sz]; L.jaero_burst_write_device.argtypes = [vp, vp, sz, sz]
+        L.jaero_burst_read_softbits.argtypes = [vp, vp, sz, vp]
+        L.jaero_burst_set_dcd.argtypes = [vp, i, i]
+        L.jaero_burst_get_status_all.argtypes = [vp, vp]
+        L.jaero_burst_sync.argtypes = [vp]
+        L.jaero_burst_launch_count.argtypes = [vp]; L.jaero_burst_launch_count.restype = ctypes.c_int64
         _lib = L
     return _lib
 
@@ -287,6 +298,63 @@ class PChannelBatch:
     def close(self):
         if self.h:
             lib().jaero_pchannel_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BurstStatus(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in
+                ("mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse", "ebno", "vol_gain",
+                 "rotator_freq", "n_sig_true", "n_sig_false", "cntr", "startstop", "last_burst_ebno", "n_ebno_emits")]
+
+
+class BurstMskBatch:
+    """n_channels independent burst MSK demodulators (BurstMskDemodulator, 600 / 1200 bps R/T channels)."""
+
+    def __init__(self, n_channels, fb=1200.0, Fs=48000.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6, device=0):
+        if n_channels <= 0:
+            raise JaeroError("n_channels must be positive")
+        s = Settings(KIND_MSK, 13, freq_center, lockingbw, fb, Fs, signalthreshold, 1, 0, 0, 1)
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        self.soft_cap = max(4096, int(2 * fb) + 64)
+        _check(lib().jaero_burst_msk_create(ctypes.byref(s), n_channels, device, ctypes.byref(self.h)))
+
+    def write(self, pcm):
+        pcm = np.asarray(pcm)
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n
+        if not pcm.flags.c_contiguous:
+            pcm = np.ascontiguousarray(pcm)
+        _check(lib().jaero_burst_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2))
+
+    def read_softbits(self):
+        out = np.zeros((self.n, self.soft_cap), dtype=np.int16)
+        counts = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_burst_read_softbits(self.h, _p(out), self.soft_cap, _p(counts)))
+        return [out[c, :counts[c]].copy() for c in range(self.n)]
+
+    def set_dcd(self, dcd, channel=-1):
+        _check(lib().jaero_burst_set_dcd(self.h, channel, int(dcd)))
+
+    def status(self):
+        arr = (BurstStatus * self.n)()
+        _check(lib().jaero_burst_get_status_all(self.h, ctypes.cast(arr, ctypes.c_void_p)))
+        return [{f[0]: getattr(arr[c], f[0]) for f in BurstStatus._fields_} for c in range(self.n)]
+
+    def sync(self):
+        _check(lib().jaero_burst_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().jaero_burst_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().jaero_burst_destroy(self.h); self.h = None
 
     def __del__(self):
         try:

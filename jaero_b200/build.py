@@ -17,6 +17,7 @@ UNITS = [
     ("cfe.cu", []),
     ("pchannel.cu", []),
     ("prefilter.cu", ["-fmad=false"]),
+    ("burst.cu", ["-fmad=false"]),
     ("demod_kernels.cu", ["-fmad=false"]),
 ]
 

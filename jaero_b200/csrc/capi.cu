@@ -932,3 +932,321 @@ int jaero_pchannel_get_stats(jaero_pchannel *p, int32_t *dcd, int64_t *su_total,
 }
 
 } // extern "C"
+
+// ====================================================================== burst MSK demodulator
+#include "burst.cuh"
+namespace jb { int burst_trident_fft_launch(const BurstParams &p, const int *d_ev_list, int n_events, double2 *wa, double2 *wb, const double2 *tw, cudaStream_t s); }
+
+struct jaero_burst {
+    int device; cudaStream_t stream;
+    BurstParams p; HilbertStream hil;
+    std::vector<void *> allocs;
+    long long samples; int hil_fill; long long hil_blocks;
+    int16_t *d_stage; size_t stage_cap;
+    double2 *tw32k, *wa, *wb; int *d_ev_list; int ev_round;
+    int *h_ints; double *h_dbls; int16_t *h_soft;
+    std::vector<int> h_ev;
+    long long launches;
+};
+
+namespace {
+template <class T> int bu_alloc(jaero_burst *b, T **ptr, size_t count)
+{
+    int r = dev_alloc_zero(ptr, count, b->stream);
+    if (r == 0) b->allocs.push_back((void *)*ptr);
+    return r;
+}
+bool delay_w1(double fd, int *k, double *w)          // Delay<T> weight at ring position 0 (DSP.h:357-374); integer delays -> 0
+{
+    const int size = (int)std::ceil(fd) + 1;
+    double w0 = 0;
+    for (int bp = 0; bp < size; bp++) {
+        double dptr = ((double)bp) - fd;
+        while (std::floor(dptr) < 0) dptr += ((double)size);
+        const double ww = dptr - std::floor(dptr);
+        if (bp == 0) w0 = ww; else if (ww != w0) return false;
+    }
+    *k = (int)std::ceil(fd); *w = w0;
+    return true;
+}
+__global__ void burst_init_kernel(BurstParams p, double freq_center, double st_freq)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.cpad) return;
+    auto D = [&](int i) -> double & { return p.BD[(size_t)i * p.cpad + ch]; };
+    auto I = [&](int i) -> int & { return p.BI[(size_t)i * p.cpad + ch]; };
+    const double sr = (double)((float)((int)p.Fs));
+    D(BD_M2_FREQ) = freq_center; D(BD_M2_STEP) = (freq_center) * ((double)jb::WTSIZE) / sr;
+    D(BD_MC_FREQ) = freq_center; D(BD_MC_STEP) = (freq_center) * ((double)jb::WTSIZE) / sr;
+    D(BD_ST_FREQ) = st_freq; D(BD_ST_STEP) = (st_freq) * ((double)jb::WTSIZE) / sr;
+    D(BD_SH_FREQ) = st_freq; D(BD_SH_STEP) = (st_freq) * ((double)jb::WTSIZE) / sr;
+    D(BD_MSE) = 10.0;                                    // burstmskdemodulator.cpp:195
+    D(BD_ROT_RE) = 1.0; D(BD_SAV_RE) = 1.0;              // rotator=1, symboltone_averotator=1 (:201-202); symboltone_rotator stays 0
+    D(BD_DIFF_LAST) = -1.0;
+    I(BI_PD_CNTDOWN) = 2 * p.pd_len; I(BI_PD_MAXPOSCNT) = -1;    // PeakDetector::setSettings (DSP.h:502-513)
+    I(BI_STARTSTOP) = -1;                                // ctor :69
+}
+__global__ void burst_soft_reset_kernel(BurstParams p)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels) return;
+    int &count = p.BI[(size_t)BI_SOFT_COUNT * p.cpad + ch];
+    const int pending = p.BI[(size_t)BI_SOFT_PENDING * p.cpad + ch];
+    int16_t *ring = p.soft + (size_t)ch * p.soft_cap;
+    for (int k = 0; k < pending; k++) ring[k] = ring[count + k];
+    count = 0;
+}
+__global__ void burst_set_int_kernel(BurstParams p, int idx, int channel, int value)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels) return;
+    if (channel < 0 || channel == ch) p.BI[(size_t)idx * p.cpad + ch] = value;
+}
+} // namespace
+
+extern "C" {
+
+int jaero_burst_msk_create(const jaero_settings *s, int n_channels, int device, jaero_burst **out)
+{
+    if (!s || !out || n_channels <= 0) { set_error("jaero_burst_msk_create: bad argument"); return JAERO_E_ARG; }
+    if (s->Fs != 48000 || (s->fb != 600 && s->fb != 1200)) { set_error("jaero_burst_msk_create: burst MSK runs at Fs=48000 with fb 600 or 1200"); return JAERO_E_ARG; }
+    int ndev = 0;
+    JB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("jaero_burst_msk_create: no such CUDA device"); return JAERO_E_CUDA; }
+    JB_CUDA(cudaSetDevice(device));
+    jaero_burst *b = new (std::nothrow) jaero_burst();
+    if (!b) { set_error("out of host memory"); return JAERO_E_ARG; }
+    b->device = device; b->samples = 0; b->hil_fill = 0; b->hil_blocks = 0; b->d_stage = 0; b->stage_cap = 0; b->launches = 0;
+    JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    BurstParams &p = b->p;
+    memset(&p, 0, sizeof p);
+    p.n_channels = n_channels; p.cpad = (n_channels + 31) & ~31;
+    p.Fs = s->Fs; p.fb = s->fb; p.lockingbw = s->lockingbw; p.signalthreshold = s->signalthreshold; p.afc = 1;   // ctor: afc=true (:15)
+    double fc = s->freq_center;
+    if (fc > ((p.Fs / 2.0) - (p.lockingbw / 2.0))) fc = ((p.Fs / 2.0) - (p.lockingbw / 2.0));
+    p.sps = (int)(p.Fs / p.fb);
+    const double SPS = (double)p.sps;
+    p.ntaps = 2 * p.sps;
+    if (p.ntaps > MAX_TAPS) { set_error("burst MSK: matched filter too long"); delete b; return JAERO_E_ARG; }
+    std::vector<double> taps(p.ntaps);
+    for (int i = 0; i < p.ntaps; i++) taps[i] = sin(M_PI * i / (2.0 * SPS)) / (2.0 * SPS);      // :173-177
+    if (burst_set_taps(taps.data(), p.ntaps)) { delete b; return JAERO_E_CUDA; }
+    p.agc_len = (int)round(1 * p.Fs);
+    auto qround = [](double d) { return d >= 0.0 ? int(d + 0.5) : int(d - double(int(d - 1)) + 0.5) + int(d - 1); };
+    if (p.fb >= 1200) {                                           // :205-256
+        p.btma_len = qround(126.0 * SPS); p.mav1_len = (int)(SPS * 126); p.btdiff_len = (int)std::ceil(SPS * 126) + 1;
+        p.pd_len = (int)(SPS * 126.0 / 2.0); p.pd_threshold = 0.1;
+        p.tri_sz = qround(200.0 * SPS); p.d1_len = ((int)289 * p.sps) + 20 + 1; p.d2_len = (int)(qround(72 + 120.0) * SPS) + 1;
+        p.size_base = 126; p.size_top = 74; p.start_processing = 120; p.end_rotation = (int)((120 + 37) * SPS);
+        p.res_a1 = -1.993312819378528; p.res_a2 = 0.999476538254407; p.res_b0 = 2.617308727964618e-04; p.res_b1 = 0; p.res_b2 = -2.617308727964618e-04;
+        p.ee = 0.025;
+    } else {                                                      // :257-311
+        p.btma_len = qround(150.0 * SPS); p.mav1_len = (int)(SPS * 150); p.btdiff_len = (int)std::ceil(SPS * 150) + 1;
+        p.pd_len = (int)(SPS * 150.0 / 2.0); p.pd_threshold = 0.2;
+        p.tri_sz = qround(224 * SPS); p.d1_len = ((int)397 * p.sps) + 20 + 1; p.d2_len = qround((72 + 150.0) * SPS) + 1;
+        p.size_base = 150; p.size_top = 74; p.start_processing = 150; p.end_rotation = (int)((150 + 56) * SPS);
+        p.res_a1 = -1.991228154418550; p.res_a2 = 0.997385427096603; p.res_b0 = 0.001307286451699; p.res_b1 = 0; p.res_b2 = -0.001307286451699;
+        p.ee = 0.015;
+    }
+    p.startstopstart = (int)(SPS * 500);
+    p.btd1_len = (int)std::ceil(1.0 * SPS) + 1;
+    int kk;
+    if (!delay_w1(1.0 * SPS, &kk, &p.btd1_w) || !delay_w1(SPS * (p.fb >= 1200 ? 126 : 150), &kk, &p.btdiff_w) ||
+        !delay_w1(SPS / 2, &p.a1_k, &p.a1_w) || !delay_w1(SPS / 2.0, &p.d8_k, &p.d8_w)) { set_error("burst MSK: unsupported delay"); delete b; return JAERO_E_ARG; }
+    p.eb_len = (int)(0.15 * p.Fs); p.agc2_len = (int)round((SPS * 128.0 / p.Fs) * p.Fs); p.ds_len = p.sps + 1; p.msema_len = 75;
+    p.soft_cap = std::max(4096, (int)(2 * p.fb) + 64);
+    const size_t cp = p.cpad, C = n_channels;
+    int rc = 0;
+    rc |= bu_alloc(b, &p.BD, (size_t)BD_COUNT * cp); rc |= bu_alloc(b, &p.BI, (size_t)BI_COUNT * cp);
+    rc |= bu_alloc(b, &p.agc_ring, (size_t)p.agc_len * cp); rc |= bu_alloc(b, &p.d1_ring, (size_t)p.d1_len * cp);
+    rc |= bu_alloc(b, &p.d2_ring, (size_t)p.d2_len * cp); rc |= bu_alloc(b, &p.btd1_ring, (size_t)p.btd1_len * cp);
+    rc |= bu_alloc(b, &p.btma_ring, (size_t)p.btma_len * cp); rc |= bu_alloc(b, &p.mav1_ring, (size_t)p.mav1_len * cp);
+    rc |= bu_alloc(b, &p.btdiff_ring, (size_t)p.btdiff_len * cp);
+    rc |= bu_alloc(b, &p.pd1_ring, (size_t)(2 * p.pd_len + 1) * cp); rc |= bu_alloc(b, &p.pd2_ring, (size_t)(p.pd_len + 1) * cp);
+    rc |= bu_alloc(b, &p.pd3_ring, (size_t)(2 * p.pd_len + 1) * cp);
+    rc |= bu_alloc(b, &p.a1_ring, (size_t)(p.a1_k + 1) * cp); rc |= bu_alloc(b, &p.eb1_ring, (size_t)p.eb_len * cp);
+    rc |= bu_alloc(b, &p.eb2_ring, (size_t)p.eb_len * cp); rc |= bu_alloc(b, &p.agc2_ring, (size_t)p.agc2_len * cp);
+    rc |= bu_alloc(b, &p.d8_ring, (size_t)(p.d8_k + 1) * cp); rc |= bu_alloc(b, &p.msema_ring, (size_t)p.msema_len * cp);
+    rc |= bu_alloc(b, &p.fir_re, (size_t)(p.ntaps + 1) * cp); rc |= bu_alloc(b, &p.fir_im, (size_t)(p.ntaps + 1) * cp);
+    rc |= bu_alloc(b, &p.ds_ring, (size_t)p.ds_len * cp);
+    rc |= bu_alloc(b, &p.tri, C * BURST_MAXEV * p.tri_sz); rc |= bu_alloc(b, &p.ev_sample, C * BURST_MAXEV);
+    rc |= bu_alloc(b, &p.ev_result, C * BURST_MAXEV * 8);
+    p.astride = BURST_CHUNK;
+    rc |= bu_alloc(b, &p.analytic, C * p.astride); rc |= bu_alloc(b, &p.vtd, C * p.astride);
+    rc |= bu_alloc(b, &p.soft, C * p.soft_cap);
+    // Hilbert filter: QJHilbertFilter::setSize(2048) (DSP.cpp:759-789), streaming FFT convolution nfft 8192
+    HilbertStream &h = b->hil; memset(&h, 0, sizeof h);
+    h.K = 2048; h.nfft = 8192; h.L = h.nfft - h.K + 1;
+    rc |= bu_alloc(b, &h.H, (size_t)h.nfft); rc |= bu_alloc(b, &h.tw, (size_t)h.nfft);
+    rc |= bu_alloc(b, &h.hist, C * (h.K - 1)); rc |= bu_alloc(b, &h.inblk, C * h.L); rc |= bu_alloc(b, &h.outblk, C * h.L);
+    b->ev_round = 128;
+    rc |= bu_alloc(b, &b->tw32k, (size_t)TRI_N); rc |= bu_alloc(b, &b->wa, (size_t)2 * b->ev_round * TRI_N); rc |= bu_alloc(b, &b->wb, (size_t)2 * b->ev_round * TRI_N);
+    rc |= bu_alloc(b, &b->d_ev_list, (size_t)2 * C * BURST_MAXEV);
+    if (rc) { jaero_burst_destroy(b); return JAERO_E_CUDA; }
+    {
+        std::vector<double> sn(jb::WTSIZE), cs(jb::WTSIZE);
+        for (int i = 0; i < jb::WTSIZE; i++) sn[i] = (sin(2 * M_PI * ((double)i) / jb::WTSIZE));
+        for (int i = 0; i < jb::WTSIZE; i++) cs[i] = (sin(M_PI_2 + 2 * M_PI * ((double)i) / jb::WTSIZE));
+        double *ds, *dc;
+        if (bu_alloc(b, &ds, (size_t)jb::WTSIZE) || bu_alloc(b, &dc, (size_t)jb::WTSIZE)) { jaero_burst_destroy(b); return JAERO_E_CUDA; }
+        JB_CUDA(cudaMemcpyAsync(ds, sn.data(), sn.size() * 8, cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaMemcpyAsync(dc, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, b->stream));
+        p.sin_t = ds; p.cos_t = dc;
+        // Hilbert kernel and its spectrum (host radix-2), twiddle tables
+        const int NF = h.nfft;
+        std::vector<std::complex<double>> Hk(NF, 0.0), tw(NF), tw32(TRI_N);
+        const int N = 2048;
+        for (int i = 0; i < N; i++) {
+            if (i == N / 2) Hk[i] = std::complex<double>(-1, 0);
+            else if ((i % 2) == 0) Hk[i] = 0;
+            else Hk[i] = std::complex<double>(0, (2.0 / ((double)N)) / (std::tan(M_PI * (((double)i) / ((double)N) - 0.5))));
+        }
+        for (int k = 0; k < NF; k++) { const double a = -2.0 * M_PI * (double)k / (double)NF; tw[k] = std::complex<double>(cos(a), sin(a)); }
+        for (int k = 0; k < TRI_N; k++) { const double a = -2.0 * M_PI * (double)k / (double)TRI_N; tw32[k] = std::complex<double>(cos(a), sin(a)); }
+        {
+            int bits = 13;
+            for (int i = 0; i < NF; i++) { int r = 0; for (int q = 0; q < bits; q++) if (i & (1 << q)) r |= 1 << (bits - 1 - q); if (r > i) std::swap(Hk[i], Hk[r]); }
+            for (int len = 2; len <= NF; len <<= 1)
+                for (int i = 0; i < NF; i += len)
+                    for (int k = 0; k < len / 2; k++) { auto w = tw[k * (NF / len)]; auto u = Hk[i + k], v = Hk[i + k + len / 2] * w; Hk[i + k] = u + v; Hk[i + k + len / 2] = u - v; }
+        }
+        JB_CUDA(cudaMemcpyAsync(h.H, Hk.data(), NF * 16, cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaMemcpyAsync(h.tw, tw.data(), NF * 16, cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaMemcpyAsync(b->tw32k, tw32.data(), (size_t)TRI_N * 16, cudaMemcpyHostToDevice, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    burst_init_kernel<<<(p.cpad + 127) / 128, 128, 0, b->stream>>>(p, fc, p.fb / 2.0);
+    JB_CUDA(cudaGetLastError());
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)BI_COUNT * cp * sizeof(int)));
+    JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)BD_COUNT * cp * sizeof(double)));
+    JB_CUDA(cudaMallocHost(&b->h_soft, C * p.soft_cap * sizeof(int16_t)));
+    *out = b;
+    return JAERO_OK;
+}
+void jaero_burst_destroy(jaero_burst *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaStreamSynchronize(b->stream);
+    for (void *q : b->allocs) cudaFree(q);
+    cudaFree(b->d_stage);
+    cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft);
+    cudaStreamDestroy(b->stream);
+    delete b;
+}
+int64_t jaero_burst_launch_count(const jaero_burst *b) { return b ? b->launches : 0; }
+int jaero_burst_sync(jaero_burst *b)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    return JAERO_OK;
+}
+int jaero_burst_write_device(jaero_burst *b, const int16_t *d_pcm, size_t n, size_t stride)
+{
+    if (!b || !d_pcm) { set_error("jaero_burst_write_device: null argument"); return JAERO_E_ARG; }
+    if (n == 0) return JAERO_OK;
+    if (stride < n || n > 0x7fffffff) { set_error("jaero_burst_write_device: bad stride / length"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const BurstParams &p = b->p;
+    const size_t cp = p.cpad;
+    for (size_t c0 = 0; c0 < n; c0 += BURST_CHUNK) {
+        const int m = (int)std::min((size_t)BURST_CHUNK, n - c0);
+        // Hilbert transform of this chunk (JFastFir::update: per-sample exchange + block transforms)
+        int i = 0;
+        while (i < m) {
+            const int take = std::min(b->hil.L - b->hil_fill, m - i);
+            if (hilbert_exchange_launch(b->hil, p, d_pcm, stride, (int)c0, i, i + take, b->hil_fill, b->stream)) return JAERO_E_CUDA;
+            b->launches++;
+            b->hil_fill += take; i += take;
+            if (b->hil_fill == b->hil.L) {
+                if (hilbert_block_launch(b->hil, p.n_channels, b->hil_blocks == 0 ? 1 : 0, b->stream)) return JAERO_E_CUDA;
+                b->launches++; b->hil_fill = 0; b->hil_blocks++;
+            }
+        }
+        if (burst_front_launch(p, b->samples, m, b->stream)) return JAERO_E_CUDA;
+        b->launches++;
+        // trident events of this chunk
+        JB_CUDA(cudaMemcpyAsync(b->h_ints, p.BI + (size_t)BI_NEV * cp, cp * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        b->h_ev.clear();
+        for (int ch = 0; ch < p.n_channels; ch++) for (int e = 0; e < b->h_ints[ch]; e++) { b->h_ev.push_back(ch); b->h_ev.push_back(e); }
+        const int nevt = (int)b->h_ev.size() / 2;
+        if (nevt) JB_CUDA(cudaMemcpyAsync(b->d_ev_list, b->h_ev.data(), b->h_ev.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+        for (int e0 = 0; e0 < nevt; e0 += b->ev_round) {
+            const int cnt = std::min(b->ev_round, nevt - e0);
+            if (burst_trident_fft_launch(p, b->d_ev_list + 2 * e0, cnt, b->wa, b->wb, b->tw32k, b->stream)) return JAERO_E_CUDA;
+            b->launches += 2;
+        }
+        if (burst_back_launch(p, m, b->stream)) return JAERO_E_CUDA;
+        b->launches++;
+        b->samples += m;
+    }
+    return JAERO_OK;
+}
+int jaero_burst_write(jaero_burst *b, const int16_t *pcm, size_t n, size_t stride)
+{
+    if (!b || !pcm) { set_error("jaero_burst_write: null argument"); return JAERO_E_ARG; }
+    if (n == 0) return JAERO_OK;
+    if (stride < n) { set_error("jaero_burst_write: channel_stride < n_samples"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t C = b->p.n_channels, pitch = (n + 7) & ~(size_t)7;
+    if (C * pitch > b->stage_cap) {
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_stage); b->d_stage = 0;
+        JB_CUDA(cudaMalloc(&b->d_stage, C * pitch * sizeof(int16_t)));
+        b->stage_cap = C * pitch;
+    }
+    JB_CUDA(cudaMemcpy2DAsync(b->d_stage, pitch * 2, pcm, stride * 2, n * 2, C, cudaMemcpyHostToDevice, b->stream));
+    return jaero_burst_write_device(b, b->d_stage, n, pitch);
+}
+int jaero_burst_read_softbits(jaero_burst *b, int16_t *out, size_t cap, int32_t *counts)
+{
+    if (!b || !out || !counts) { set_error("jaero_burst_read_softbits: null argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const BurstParams &p = b->p; const size_t cp = p.cpad;
+    JB_CUDA(cudaMemcpyAsync(b->h_ints, p.BI, (size_t)BI_COUNT * cp * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    const int *cnt = b->h_ints + (size_t)BI_SOFT_COUNT * cp, *ovf = b->h_ints + (size_t)BI_SOFT_OVERFLOW * cp;
+    int maxc = 0; bool overflow = false;
+    for (int ch = 0; ch < p.n_channels; ch++) { maxc = std::max(maxc, cnt[ch]); overflow |= ovf[ch] != 0 || (size_t)cnt[ch] > cap; }
+    if (overflow) { set_error("soft-bit ring overflow: drain more often or pass a larger buffer"); return JAERO_E_OVERFLOW; }
+    if (maxc) {
+        JB_CUDA(cudaMemcpy2DAsync(b->h_soft, (size_t)p.soft_cap * 2, p.soft, (size_t)p.soft_cap * 2, (size_t)maxc * 2, p.n_channels, cudaMemcpyDeviceToHost, b->stream));
+        JB_CUDA(cudaStreamSynchronize(b->stream));
+    }
+    for (int ch = 0; ch < p.n_channels; ch++) { counts[ch] = cnt[ch]; if (cnt[ch]) memcpy(out + (size_t)ch * cap, b->h_soft + (size_t)ch * p.soft_cap, (size_t)cnt[ch] * 2); }
+    burst_soft_reset_kernel<<<(p.n_channels + 127) / 128, 128, 0, b->stream>>>(p);
+    JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_burst_set_dcd(jaero_burst *b, int channel, int dcd)
+{
+    if (!b || channel >= b->p.n_channels) { set_error("jaero_burst_set_dcd: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    burst_set_int_kernel<<<(b->p.n_channels + 127) / 128, 128, 0, b->stream>>>(b->p, BI_DCD, channel, dcd ? 1 : 0);
+    JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_burst_get_status_all(jaero_burst *b, jaero_burst_status *out)
+{
+    if (!b || !out) { set_error("null argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(b->device));
+    const size_t cp = b->p.cpad;
+    JB_CUDA(cudaMemcpyAsync(b->h_dbls, b->p.BD, (size_t)BD_COUNT * cp * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    JB_CUDA(cudaMemcpyAsync(b->h_ints, b->p.BI, (size_t)BI_COUNT * cp * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    for (int ch = 0; ch < b->p.n_channels; ch++) {
+        auto D = [&](int i) { return b->h_dbls[(size_t)i * cp + ch]; };
+        auto I = [&](int i) { return b->h_ints[(size_t)i * cp + ch]; };
+        jaero_burst_status &s = out[ch];
+        s.mixer2_freq = D(BD_M2_FREQ); s.mixer2_wtptr = D(BD_M2_PTR); s.center_freq = D(BD_MC_FREQ); s.st_freq = D(BD_ST_FREQ); s.st_wtptr = D(BD_ST_PTR);
+        s.agc = D(BD_AGC_VAL); s.mse = D(BD_MSE); s.ebno = D(BD_EB_EBNO); s.vol_gain = D(BD_VOL_GAIN); s.rotator_freq = D(BD_ROT_FREQ);
+        s.n_sig_true = I(BI_SIG_TRUE); s.n_sig_false = I(BI_SIG_FALSE); s.cntr = I(BI_CNTR); s.startstop = I(BI_STARTSTOP);
+        s.last_burst_ebno = D(BD_LAST_EBNO_EMIT); s.n_ebno_emits = I(BI_EBNO_EMITS);
+    }
+    return JAERO_OK;
+}
+
+} // extern "C"

@@ -237,6 +237,41 @@ def test_pchannel_frame_layer_bit_exact(golden):
         b.close(); pc.close()
 
 
+@pytest.mark.parametrize("name", ["burst_msk_1200_a", "burst_msk_1200_b"])
+def test_burst_msk_parity_on_reference_recordings(golden, name):
+    """BASELINE cfg 4 source material: Hilbert FFT-FIR, burst detector, trident FFT acquisition, preamble-aided tail.
+    Soft bits (incl. the -1 start-of-burst markers) identical after hard decision; gain / carrier from the acquisition FFTs
+    within 1e-6."""
+    jb = _import()
+    case = golden[name]
+    pcm = load_excerpt(name)
+    pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 3 // 5).astype(np.int16), np.roll(pcm, 12345)])
+    b = jb.BurstMskBatch(3, **case["kw"])
+    acc = [[] for _ in range(3)]
+    for a in range(0, pcm2.shape[1], case["chunk"]):
+        b.write(pcm2[:, a:a + case["chunk"]])
+        for c, s in enumerate(b.read_softbits()):
+            acc[c].append(s)
+    st = b.status()
+    b.close()
+    for c in range(3):
+        o = restated.OracleDemod("burst_msk", **case["kw"])
+        for a in range(0, pcm2.shape[1], case["chunk"]):
+            o.write(pcm2[c, a:a + case["chunk"]])
+        so = o.take_soft(); sg = np.concatenate(acc[c]); os_ = o.state()
+        assert len(so) == len(sg)
+        assert np.array_equal(so < 0, sg < 0) and np.array_equal(so >= 128, sg >= 128)
+        assert np.abs(so.astype(int) - sg.astype(int)).max(initial=0) <= 1
+        for k in ("mixer2_freq", "vol_gain", "mse", "agc", "st_wtptr", "rotator_freq"):
+            assert abs(st[c][k] - os_[k]) <= STATE_TOL * max(abs(os_[k]), 1e-9), k
+        for k in ("n_sig_true", "n_sig_false", "cntr", "startstop"):
+            assert st[c][k] == os_[k], k
+        eb = o.take_aux(0)
+        assert st[c]["n_ebno_emits"] == len(eb) and (len(eb) == 0 or abs(st[c]["last_burst_ebno"] - eb[-1]) < 1e-6)
+    assert len(np.concatenate(acc[0])) == case["n_soft"]          # golden from the verbatim reference build
+    assert int((np.concatenate(acc[0]) < 0).sum()) >= 2
+
+
 def test_error_behaviour():
     jb = _import()
     b = jb.DemodBatch("oqpsk", 2, fb=10500, freq_center=5760)

@@ -145,6 +145,43 @@ def check_pchannel():
     return ok
 
 
+def check_burst():
+    ok = True
+    for name in ("burst_msk_1200_a", "burst_msk_1200_b"):
+        pcm = np.load(os.path.join(ROOT, "tests", "golden", name + "_excerpt.npz"))["pcm"]
+        pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 3 // 5).astype(np.int16), np.roll(pcm, 12345)])
+        kw = dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)
+        b = jaero_b200.BurstMskBatch(3, **kw)
+        acc = [[] for _ in range(3)]
+        t = time.time()
+        for a in range(0, pcm2.shape[1], 4800):
+            b.write(pcm2[:, a:a + 4800])
+            for c, s_ in enumerate(b.read_softbits()):
+                acc[c].append(s_)
+        tg = time.time() - t
+        st = b.status()
+        for c in range(3):
+            o = restated.OracleDemod("burst_msk", **kw)
+            for a in range(0, pcm2.shape[1], 4800):
+                o.write(pcm2[c, a:a + 4800])
+            so = o.take_soft(); sg = np.concatenate(acc[c]); os_ = o.state()
+            n = min(len(so), len(sg))
+            same_len = len(so) == len(sg)
+            hard = same_len and np.array_equal(so >= 128, sg >= 128) and np.array_equal(so < 0, sg < 0)
+            maxd = int(np.abs(so[:n].astype(int) - sg[:n].astype(int)).max()) if n else -1
+            keys = ["mixer2_freq", "vol_gain", "mse", "n_sig_true", "n_sig_false", "cntr", "startstop", "agc", "st_wtptr", "rotator_freq"]
+            rel = {k: abs(st[c][k] - os_[k]) / max(abs(os_[k]), 1e-9) for k in keys}
+            worst = max(rel, key=rel.get)
+            eb = o.take_aux(0)
+            print(f"burst {name} ch{c}: soft {len(sg)}/{len(so)} markers {int((sg<0).sum())}/{int((so<0).sum())} hard_same={hard} max|d|={maxd} worst {worst} rel={rel[worst]:.2e} "
+                  f"f={st[c]['mixer2_freq']:.3f}/{os_['mixer2_freq']:.3f} gain={st[c]['vol_gain']:.6f}/{os_['vol_gain']:.6f} ebno_last={st[c]['last_burst_ebno']:.4f}/{eb[-1] if len(eb) else float('nan'):.4f} emits={st[c]['n_ebno_emits']:.0f}/{len(eb)}")
+            ok &= hard and rel[worst] < 1e-6
+        print("gpu wall %.2fs launches=%d" % (tg, b.launches))
+        b.close()
+    print("BURST", "PASS" if ok else "FAIL")
+    return ok
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["viterbi", "oqpsk", "msk", "pchannel"]
     ok = True
@@ -156,6 +193,8 @@ if __name__ == "__main__":
         ok &= check_demod("oqpsk", "oqpsk_8400", dict(fb=8400, freq_center=8000, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
     if "msk" in which:
         ok &= check_demod("msk", "msk_600", dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True))
+    if "burst" in which:
+        ok &= check_burst()
     if "pchannel" in which:
         ok &= check_pchannel()
     print("ALL", "PASS" if ok else "FAIL")
