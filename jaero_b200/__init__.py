@@ -45,7 +45,7 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_pchannel_create", "jaero_pchannel_destroy", "jaero_pchannel_process_batch",
            "jaero_pchannel_process_softbits", "jaero_pchannel_tick", "jaero_pchannel_read_sus",
            "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count",
-           "jaero_burst_msk_create", "jaero_burst_destroy", "jaero_burst_write", "jaero_burst_write_device",
+           "jaero_burst_msk_create", "jaero_burst_oqpsk_create", "jaero_burst_destroy", "jaero_burst_write", "jaero_burst_write_device",
            "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
            "jaero_burst_launch_count"]
 
@@ -92,6 +92,7 @@ def lib():
         L.jaero_pchannel_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_pchannel_launch_count.argtypes = [vp]; L.jaero_pchannel_launch_count.restype = ctypes.c_int64
         L.jaero_burst_msk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
+        L.jaero_burst_oqpsk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_destroy.argtypes = [vp]; L.jaero_burst_destroy.restype = None
         L.jaero_burst_write.argtypes = [vp, vp, sz, sz]; L.jaero_burst_write_device.argtypes = [vp, vp, sz, sz]
         L.jaero_burst_read_softbits.argtypes = [vp, vp, sz, vp]
@@ -361,3 +362,16 @@ class BurstMskBatch:
             self.close()
         except Exception:
             pass
+
+
+class BurstOqpskBatch(BurstMskBatch):
+    """n_channels independent burst OQPSK demodulators (BurstOqpskDemodulator, 10500 bps bursts)."""
+
+    def __init__(self, n_channels, fb=10500.0, Fs=48000.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6, sql=False, device=0):
+        if n_channels <= 0:
+            raise JaeroError("n_channels must be positive")
+        s = Settings(KIND_OQPSK, 13, freq_center, lockingbw, fb, Fs, signalthreshold, 1, int(bool(sql)), 0, 1)
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        self.soft_cap = max(4096, int(2 * fb) + 64)
+        _check(lib().jaero_burst_oqpsk_create(ctypes.byref(s), n_channels, device, ctypes.byref(self.h)))

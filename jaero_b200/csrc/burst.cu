@@ -228,7 +228,8 @@ burst_front_kernel(BurstParams p, long long sample0, int n)
             int io = btd1_pos - (p.btd1_len - 1); if (io < 0) io += p.btd1_len;
             int in_ = io + 1; if (in_ >= p.btd1_len) in_ = 0;
             const double2 older = p.btd1_ring[(size_t)io * cp + ch], newer = p.btd1_ring[(size_t)in_ * cp + ch];
-            dly = make_double2(p.btd1_w * newer.x + (1.0 - p.btd1_w) * older.x, p.btd1_w * newer.y + (1.0 - p.btd1_w) * older.y);
+            const double w = p.btd1_wv[btd1_pos];
+            dly = make_double2(w * newer.x + (1.0 - w) * older.x, w * newer.y + (1.0 - w) * older.y);
             btd1_pos++; if (btd1_pos >= p.btd1_len) btd1_pos = 0;
         }
         const double2 prod = b_mul(cval, make_double2(dly.x, -dly.y));     // cval*std::conj(...)
@@ -254,7 +255,8 @@ burst_front_kernel(BurstParams p, long long sample0, int n)
             int io = btdiff_pos - (p.btdiff_len - 1); if (io < 0) io += p.btdiff_len;
             int in_ = io + 1; if (in_ >= p.btdiff_len) in_ = 0;
             const double older = p.btdiff_ring[(size_t)io * cp + ch], newer = p.btdiff_ring[(size_t)in_ * cp + ch];
-            fastarm -= (p.btdiff_w * newer + (1.0 - p.btdiff_w) * older);
+            const double w = p.btdiff_wv[btdiff_pos];
+            fastarm -= (w * newer + (1.0 - w) * older);
             btdiff_pos++; if (btdiff_pos >= p.btdiff_len) btdiff_pos = 0;
         }
         if (fastarm < 0) fastarm = 0;
@@ -314,7 +316,7 @@ trident_fft_kernel(BurstParams p, const int *__restrict__ ev_list, int n_events,
     const int ch = ev_list[2 * e], ev = ev_list[2 * e + 1];
     const int slot = p.ev_sample[(size_t)ch * BURST_MAXEV + ev] >> 24;
     const double *buf = p.tri + ((size_t)ch * BURST_MAXEV + slot) * p.tri_sz;
-    const int nb = (int)rint(p.size_base * (double)p.sps), nt = (int)rint(p.size_top * (double)p.sps);
+    const int nb = p.tri_nb, nt = p.tri_nt;
     const int off = which ? nb : 0, cnt = which ? nt : nb;
     double2 *a = wa + (size_t)blockIdx.x * TRI_N, *b = wb + (size_t)blockIdx.x * TRI_N;
     for (int j = threadIdx.x; j < TRI_N; j += blockDim.x)
@@ -378,6 +380,55 @@ trident_peaks_kernel(BurstParams p, const int *__restrict__ ev_list, int n_event
         double *r = p.ev_result + ((size_t)ch * BURST_MAXEV + ev) * 8;
         r[0] = (double)minvalbin; r[1] = minval; r[2] = (double)maxtoppos; r[3] = (double)maxtopposhigh;
         r[4] = atan2(base[minvalbin].y, base[minvalbin].x);              // std::arg(out_base[minvalbin])
+    }
+}
+
+// burst OQPSK: three-peak "trident" on |top|-|base| plus the strongest base bin (burstoqpskdemodulator.cpp:416-465)
+__global__ void __launch_bounds__(1024)
+trident_peaks_oqpsk_kernel(BurstParams p, const int *__restrict__ ev_list, int n_events, const double2 *__restrict__ wb, double2 *__restrict__ wa)
+{
+    __shared__ double s_val[1024];
+    __shared__ int s_idx[1024];
+    const int e = blockIdx.x;
+    if (e >= n_events) return;
+    const int ch = ev_list[2 * e], ev = ev_list[2 * e + 1];
+    const double2 *base = wb + (size_t)(2 * e) * TRI_N, *top = wb + (size_t)(2 * e + 1) * TRI_N;
+    double *diff = reinterpret_cast<double *>(wa + (size_t)(2 * e) * TRI_N);      // scratch: the FFT input buffer is free now
+    const int half = TRI_N / 2;
+    const double hzperbin = p.Fs / ((double)TRI_N);
+    const int bps = (int)rint((0.25 * p.fb) / hzperbin);
+    auto argmax_first = [&](double v, int idx) -> int {
+        s_val[threadIdx.x] = v; s_idx[threadIdx.x] = idx;
+        __syncthreads();
+        for (int st = 512; st > 0; st >>= 1) {
+            if (threadIdx.x < st) {
+                const double ov = s_val[threadIdx.x + st]; const int oi = s_idx[threadIdx.x + st];
+                if (oi != 0x7fffffff && (s_idx[threadIdx.x] == 0x7fffffff || ov > s_val[threadIdx.x] || (ov == s_val[threadIdx.x] && oi < s_idx[threadIdx.x]))) { s_val[threadIdx.x] = ov; s_idx[threadIdx.x] = oi; }
+            }
+            __syncthreads();
+        }
+        const int r = s_idx[0];
+        __syncthreads();
+        return r;
+    };
+    for (int k = threadIdx.x; k < half; k += blockDim.x) diff[k] = (hypot(top[k].x, top[k].y) - hypot(base[k].x, base[k].y));
+    __syncthreads();
+    // maxval over i in [firstbin, lstbin): starts at (testval(firstbin), firstbin), strict '>' -> first maximum
+    const int firstbin = bps, lstbin = half - bps;
+    double tv = 0.0; int ti = 0x7fffffff;
+    for (int k = firstbin + threadIdx.x; k < lstbin; k += blockDim.x) {
+        const double t = diff[k - bps] + diff[k + bps] - diff[k];
+        if (ti == 0x7fffffff || t > tv) { tv = t; ti = k; }
+    }
+    int maxvalbin = argmax_first(tv, ti); if (maxvalbin == 0x7fffffff) maxvalbin = firstbin;
+    const double maxval = diff[maxvalbin - bps] + diff[maxvalbin + bps] - diff[maxvalbin];
+    double bv = 0.0; int bi = 0x7fffffff;
+    for (int k = threadIdx.x; k < half; k += blockDim.x) { const double m = hypot(base[k].x, base[k].y); if (bi == 0x7fffffff || m > bv) { bv = m; bi = k; } }
+    int minvalbin = argmax_first(bv, bi); if (minvalbin == 0x7fffffff) minvalbin = 0;
+    if (threadIdx.x == 0) {
+        double *r = p.ev_result + ((size_t)ch * BURST_MAXEV + ev) * 8;
+        r[0] = (double)minvalbin; r[1] = hypot(base[minvalbin].x, base[minvalbin].y); r[2] = (double)maxvalbin; r[3] = maxval;
+        r[4] = atan2(base[minvalbin].y, base[minvalbin].x);
     }
 }
 
@@ -479,7 +530,8 @@ burst_back_kernel(BurstParams p, int n)
                     p.a1_ring[(size_t)a1_pos * cp + ch] = spt.x;
                     int io = a1_pos - p.a1_k; if (io < 0) io += a1_len;
                     int in_ = io + 1; if (in_ >= a1_len) in_ = 0;
-                    a1out = (p.a1_w * p.a1_ring[(size_t)in_ * cp + ch] + (1.0 - p.a1_w) * p.a1_ring[(size_t)io * cp + ch]);
+                    const double w = p.a1_wv[a1_pos];
+                    a1out = (w * p.a1_ring[(size_t)in_ * cp + ch] + (1.0 - w) * p.a1_ring[(size_t)io * cp + ch]);
                     a1_pos++; if (a1_pos >= a1_len) a1_pos = 0;
                 }
                 spt = make_double2(spt.x, a1out);
@@ -588,6 +640,235 @@ burst_back_kernel(BurstParams p, int n)
     BI(BI_SIG_TRUE) = sig_true; BI(BI_SIG_FALSE) = sig_false; BI(BI_EBNO_EMITS) = ebno_emits;
 }
 
+// ------------------------------------------------------------------------------------------------ burst OQPSK tail
+// BurstOqpskDemodulator::writeDataSlot after the trident check (burstoqpskdemodulator.cpp:508-733). Unlike the MSK burst
+// tail this one runs on every sample, so all its sample-rate rings advance in lock-step.
+__global__ void __launch_bounds__(32)
+burst_oqpsk_back_kernel(BurstParams p, long long sample0, int n, int new_write)
+{
+    extern __shared__ double bsm[];
+    const int lane = threadIdx.x;
+    const int ch = blockIdx.x * 32 + lane;
+    if (ch >= p.n_channels) return;
+    const size_t cp = p.cpad;
+    const int nt1 = p.ntaps + 1;
+    double *s_re = bsm, *s_im = bsm + (size_t)nt1 * 32;
+    for (int k = 0; k < nt1; k++) { s_re[k * 32 + lane] = p.fir_re[(size_t)k * cp + ch]; s_im[k * 32 + lane] = p.fir_im[(size_t)k * cp + ch]; }
+    Osc m2 = {BD(BD_M2_PTR), BD(BD_M2_STEP), BD(BD_M2_FREQ), BD(BD_M2_LAST)};
+    Osc st = {BD(BD_ST_PTR), BD(BD_ST_STEP), BD(BD_ST_FREQ), BD(BD_ST_LAST)};
+    Osc sr = {BD(BD_SR_PTR), BD(BD_SR_STEP), BD(BD_SR_FREQ), BD(BD_SR_LAST)};
+    Osc sq = {BD(BD_SH_PTR), BD(BD_SH_STEP), BD(BD_SH_FREQ), BD(BD_SH_LAST)};      // st_osc_quarter
+    double vol_gain = BD(BD_VOL_GAIN), mse = BD(BD_MSE), msema_sum = BD(BD_MSEMA_SUM), rot_freq = BD(BD_ROT_FREQ);
+    double2 rot = make_double2(BD(BD_ROT_RE), BD(BD_ROT_IM)), strot = make_double2(BD(BD_STR_RE), BD(BD_STR_IM)), savrot = make_double2(BD(BD_SAV_RE), BD(BD_SAV_IM));
+    double eb_sum1 = BD(BD_EB_SUM1), eb_sum2 = BD(BD_EB_SUM2), eb_ebno = BD(BD_EB_EBNO), agc2_sum = BD(BD_AGC2_SUM), agc2_val = BD(BD_AGC2_VAL);
+    Biquad res = {BD(BD_RES_X1), BD(BD_RES_X2), BD(BD_RES_Y1), BD(BD_RES_Y2)};
+    double dly_s0 = BD(BD_DLY_S0), d41_0 = BD(BD_DLY41_0), d41_1 = BD(BD_DLY41_1), d41_2 = BD(BD_DLY41_2);
+    double d42_0 = BD(BD_DLY42_0), d42_1 = BD(BD_DLY42_1), d42_2 = BD(BD_DLY42_2), d8_0 = BD(BD_DLY8_0), d8_1 = BD(BD_DLY8_1), d8_2 = BD(BD_DLY8_2);
+    double2 sig2_last = make_double2(BD(BD_SIG2L_RE), BD(BD_SIG2L_IM)), pt_d = make_double2(BD(BD_PTD_RE), BD(BD_PTD_IM));
+    double lastmse = BD(BD_LASTMSE), last_ebno_emit = BD(BD_LAST_EBNO_EMIT);
+    if (new_write) lastmse = mse;                                         // :317
+    int cntr = BI(BI_CNTR), startstop = BI(BI_STARTSTOP), yui = BI(BI_YUI), insertpreamble = BI(BI_INSERTPREAMBLE);
+    int a1_pos = BI(BI_A1_POS), msema_pos = BI(BI_MSEMA_POS);
+    int soft_count = BI(BI_SOFT_COUNT), soft_pending = BI(BI_SOFT_PENDING), soft_overflow = BI(BI_SOFT_OVERFLOW);
+    int sig_true = BI(BI_SIG_TRUE), sig_false = BI(BI_SIG_FALSE), ebno_emits = BI(BI_EBNO_EMITS);
+    const int nev = BI(BI_NEV);
+    int next_ev = 0;
+    int next_ev_sample = nev > 0 ? (p.ev_sample[(size_t)ch * BURST_MAXEV] & 0xffffff) : -1;
+    const double *vtd = p.vtd + (size_t)ch * p.astride;
+    const double SPS = p.spsd;
+    int fir_pos = (int)(sample0 % nt1), eb_pos = (int)(sample0 % p.eb_len), agc2_pos = (int)(sample0 % p.agc2_len);
+    const int a1_len = p.a1_k + 1;
+    int p41 = (int)(sample0 % (p.k41 + 1)), p8 = (int)(sample0 % (p.k8 + 1));
+    auto push = [&](int v) {
+        const int pos = soft_count + soft_pending;
+        if (pos < p.soft_cap) { p.soft[(size_t)ch * p.soft_cap + pos] = (int16_t)v; soft_pending++; } else soft_overflow = 1;
+    };
+    for (int i = 0; i < n; i++) {
+        if (i == next_ev_sample) {                                        // trident test outcome (:466-504)
+            const double *r = p.ev_result + ((size_t)ch * BURST_MAXEV + next_ev) * 8;
+            const double minvalbin = r[0], minval = r[1], maxvalbin = r[2], maxval = r[3];
+            const double hzperbin = p.Fs / ((double)TRI_N);
+            if ((maxval > 500.0) && (fabs((((double)(maxvalbin - minvalbin))) * hzperbin) < 20.0)) {
+                const double carrierphase = r[4] - (M_PI / 4.0);
+                osc_set_freq(m2, hzperbin * minvalbin, p.Fs);
+                osc_set_phase_deg(m2, (180.0 / M_PI) * carrierphase);
+                vol_gain = 1.4142 * 500.0 / minval;
+                osc_set_freq(st, sr.freq, p.Fs);
+                osc_set_phase_deg(st, 0); osc_set_phase_deg(sr, 0);
+                res.x1 = res.x2 = res.y1 = res.y2 = 0;
+                startstop = p.startstopstart; cntr = 0; rot = make_double2(1.0, 0.0); insertpreamble = 1; rot_freq = 0;
+                savrot = make_double2(1.0, 0.0);
+                sig_true++;
+                mse = 0;
+                for (int k = 0; k < p.msema_len; k++) p.msema_ring[(size_t)k * cp + ch] = 0.0;
+                msema_pos = 0; msema_sum = 0;
+            }
+            next_ev++;
+            next_ev_sample = next_ev < nev ? (p.ev_sample[(size_t)ch * BURST_MAXEV + next_ev] & 0xffffff) : -1;
+        }
+        // mix + RRC (:509-512)
+        const int t2 = osc_index(m2.ptr);
+        const double gv = (vol_gain * vtd[i]);
+        const double cre = p.cos_t[t2] * gv, cim = p.sin_t[t2] * gv;
+        s_re[fir_pos * 32 + lane] = cre; s_im[fir_pos * 32 + lane] = cim;
+        fir_pos++; if (fir_pos >= nt1) fir_pos = 0;
+        double sre = 0, sim = 0;
+        { int tp = fir_pos; for (int k = 0; k < p.ntaps; k++) { sre += c_btaps[k] * s_re[tp * 32 + lane]; sim += c_btaps[k] * s_im[tp * 32 + lane]; tp++; if (tp >= nt1) tp = 0; } }
+        double2 sig2 = make_double2(sre, sim);
+        if (startstop > 0) { startstop--; if (cntr < 1000000) cntr++; if (mse < 0.75) startstop = p.startstopstart; }   // :515-524
+        if (startstop == 0) { startstop--; sig_false++; }                 // :525-529
+        if ((cntr > ((256 - 10) * SPS)) && insertpreamble) { push(-1); insertpreamble = 0; }   // :531-535
+        if ((cntr > SPS * (128 + 10)) && (cntr < ((256 - 10) * SPS))) {  // :538-558
+            const double progress = (((double)cntr) - (SPS * (128 + 10))) / (((256 - 10) * SPS) - (SPS * (128 + 10)));
+            double2 spt = cmul(cmul(sig2, strot), make_double2(0.0, 1.0));
+            const double er = tanh(spt.y) * (spt.x);
+            const double ang = (1.0 * er) * 0.01;
+            strot = cmul(strot, make_double2(cos(ang), sin(ang)));
+            savrot = make_double2(savrot.x * 0.95 + 0.05 * strot.x, savrot.y * 0.95 + 0.05 * strot.y);
+            double a1out;
+            {
+                p.a1_ring[(size_t)a1_pos * cp + ch] = spt.x;
+                int io = a1_pos - p.a1_k; if (io < 0) io += a1_len;
+                int in_ = io + 1; if (in_ >= a1_len) in_ = 0;
+                const double w = p.a1_wv[a1_pos];
+                a1out = (w * p.a1_ring[(size_t)in_ * cp + ch] + (1.0 - w) * p.a1_ring[(size_t)io * cp + ch]);
+                a1_pos++; if (a1_pos >= a1_len) a1_pos = 0;
+            }
+            spt = make_double2(spt.x, a1out);
+            const int tq = osc_index(sq.ptr);
+            const double2 q = cmul(make_double2(p.cos_t[tq], p.sin_t[tq]), make_double2(spt.x, -spt.y));
+            double st_err = atan2(q.y, q.x);
+            st_err *= 1.5 * (1.0 - progress * progress);
+            osc_advance_fraction_of_wave(sq, -(1.0 / (2.0 * M_PI)) * st_err * 0.1);
+            osc_set_phase_deg(st, ((360.0 * sq.ptr / ((double)WTSIZE))) * 4.0 + (360.0 * p.ee));
+        }
+        sig2 = cmul(sig2, savrot);                                        // :562-565
+        rot = cmul(rot, make_double2(cos(rot_freq), sin(rot_freq)));
+        sig2 = cmul(sig2, rot);
+        const double sig2abs = hypot(sig2.x, sig2.y);
+        {   // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
+            const size_t e = (size_t)eb_pos * cp + ch;
+            const double sq2 = sig2abs * sig2abs;
+            eb_sum2 = eb_sum2 - p.eb2_ring[e]; eb_sum2 = eb_sum2 + fabs(sq2); p.eb2_ring[e] = fabs(sq2);
+            eb_sum1 = eb_sum1 - p.eb1_ring[e]; eb_sum1 = eb_sum1 + fabs(sig2abs); p.eb1_ring[e] = fabs(sig2abs);
+            eb_pos++; if (eb_pos >= p.eb_len) eb_pos = 0;
+            const double e2val = eb_sum2 / ((double)p.eb_len), mean = eb_sum1 / ((double)p.eb_len);
+            const double mean_sq = mean * mean;
+            double var = (e2val) - (mean * mean);
+            var -= (0.024709 * mean_sq);
+            double mvr = (((p.Fs * mean_sq / (2.0 * p.fb * var))) * 0.13743);
+            if (mvr < 0.000000001) mvr = 0.000000001;
+            double tebno = 10.0 * log10(mvr);
+            if (isnan(tebno)) tebno = 50;
+            if (tebno > 50.0) tebno = 50;
+            if (tebno < 0.0) tebno = 0;
+            eb_ebno = eb_ebno * 0.8 + 0.2 * tebno;
+        }
+        if (fabs(cntr - ((128.0 + 128.0 + 128.0) * SPS)) < 0.5) { last_ebno_emit = eb_ebno; ebno_emits++; }   // :573
+        {   // sig2*=agc2->Update(sig2abs) (:576)
+            const size_t e = (size_t)agc2_pos * cp + ch;
+            agc2_sum = agc2_sum - p.agc2_ring[e]; agc2_sum = agc2_sum + fabs(sig2abs); p.agc2_ring[e] = fabs(sig2abs);
+            agc2_pos++; if (agc2_pos >= p.agc2_len) agc2_pos = 0;
+            agc2_val = 1.414213562 / fmax(agc2_sum / ((double)p.agc2_len), 0.000001);
+            agc2_val = fmax(agc2_val, 0.000001);
+            sig2 = make_double2(sig2.x * agc2_val, sig2.y * agc2_val);
+        }
+        const double abval = hypot(sig2.x, sig2.y);
+        if (abval > 2.84) { const double g = (2.84 / abval); sig2 = make_double2(g * sig2.x, g * sig2.y); }
+        // symbol timing (:583-603)
+        const double ab2 = abval * abval;
+        const double st_diff = (0.0 * ab2 + (1.0 - 0.0) * dly_s0) - (ab2);
+        dly_s0 = ab2;
+        double st_d1out, st_d2out;
+        const double w41 = p.w41v[p41], w8 = p.w8v[p8];
+        p41++; if (p41 > p.k41) p41 = 0;
+        p8++; if (p8 > p.k8) p8 = 0;
+        { const double older = (p.k41 == 3) ? d41_2 : (p.k41 == 2 ? d41_1 : d41_0), newer = (p.k41 == 3) ? d41_1 : (p.k41 == 2 ? d41_0 : st_diff);
+          st_d1out = (w41 * newer + (1.0 - w41) * older); d41_2 = d41_1; d41_1 = d41_0; d41_0 = st_diff; }
+        { const double older = (p.k41 == 3) ? d42_2 : (p.k41 == 2 ? d42_1 : d42_0), newer = (p.k41 == 3) ? d42_1 : (p.k41 == 2 ? d42_0 : st_d1out);
+          st_d2out = (w41 * newer + (1.0 - w41) * older); d42_2 = d42_1; d42_1 = d42_0; d42_0 = st_d1out; }
+        double st_eta = (st_d2out - st_diff) * st_d1out;
+        const double resy = biquad_update(res, st_eta, p.res_a1, p.res_a2, p.res_b0, p.res_b1, p.res_b2);
+        if (cntr > SPS * (128 + 128)) st_eta = resy;
+        double d8out;
+        { const double older = (p.k8 == 3) ? d8_2 : (p.k8 == 2 ? d8_1 : d8_0), newer = (p.k8 == 3) ? d8_1 : (p.k8 == 2 ? d8_0 : st_eta);
+          d8out = (w8 * newer + (1.0 - w8) * older); d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta; }
+        const int ts = osc_index(st.ptr);
+        const double2 st_out = cmul(make_double2(p.cos_t[ts], p.sin_t[ts]), make_double2(st_eta, -d8out));
+        const double st_angle_error = atan2(st_out.y, st_out.x);
+        if (cntr > SPS * (128 + 64)) {
+            osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, p.Fs);
+            osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0);
+        }
+        if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), p.Fs);
+        if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), p.Fs);
+        double frac;
+        if (osc_have_passed_point(st, p.ee, frac)) {                      // :606
+            const double pt_last = frac, pt_this = 1.0 - pt_last;
+            const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
+            const double twospeed = -4.0 * ((fmod(((360.0 * sq.ptr / ((double)WTSIZE))) * 2.0 + (360.0 * p.ee * 0.5), 360.0) / 360.0) - (0.34046 + 0.4111 * p.ee));
+            bool even = true;
+            if (twospeed < 0) even = false;
+            yui++; yui %= 2;
+            if (cntr < ((128 + 128) * SPS)) { if ((even && yui == 1) || (!even && yui == 0)) { yui++; yui %= 2; } }
+            if (!yui) pt_d = pt;
+            else {
+                const double2 pt_qpsk = make_double2(pt.x, pt_d.y);
+                const double ct_xt = tanh(pt.y) * pt.x;
+                const double ct_xt_d = tanh(pt_d.x) * pt_d.y;
+                double ct_ec = ct_xt_d - ct_xt;
+                if (ct_ec > M_PI) ct_ec = M_PI;
+                if (ct_ec < -M_PI) ct_ec = -M_PI;
+                if (ct_ec > M_PI_2) ct_ec = M_PI_2;
+                if (ct_ec < -M_PI_2) ct_ec = -M_PI_2;
+                if (cntr > ((128 + 10) * SPS)) {                          // :641-645
+                    const double ang = (1.0 * ct_ec) * 0.1;
+                    rot = cmul(rot, make_double2(cos(ang), sin(ang)));
+                    rot_freq = rot_freq + ct_ec * 0.0001;
+                }
+                if (cntr > ((128 + 10) * SPS)) {                          // :684-689 msema MA(128)
+                    const double tda = (fabs(pt_qpsk.x) - 1.0), tdb = (fabs(pt_qpsk.y) - 1.0);
+                    const double vv = (tda * tda) + (tdb * tdb);
+                    const size_t e = (size_t)msema_pos * cp + ch;
+                    msema_sum = msema_sum - p.msema_ring[e]; msema_sum = msema_sum + fabs(vv); p.msema_ring[e] = fabs(vv);
+                    msema_pos++; if (msema_pos >= p.msema_len) msema_pos = 0;
+                    mse = msema_sum / ((double)p.msema_len);
+                }
+                if (startstop > 0) {                                      // :692-722
+                    int ibit = q_round(0.75 * pt_qpsk.y * 127.0 + 128.0); if (ibit > 255) ibit = 255; if (ibit < 0) ibit = 0;
+                    push(ibit);
+                    ibit = q_round(0.75 * pt_qpsk.x * 127.0 + 128.0); if (ibit > 255) ibit = 255; if (ibit < 0) ibit = 0;
+                    push(ibit);
+                    if (soft_pending >= 32) {
+                        if (!p.sql || mse < p.signalthreshold || lastmse < p.signalthreshold) soft_count += soft_pending;
+                        soft_pending = 0;
+                    }
+                }
+            }
+        }
+        sig2_last = sig2;                                                 // :727
+        osc_next_frame(m2); osc_next_frame(st); osc_next_frame(sr); osc_next_frame(sq);
+    }
+    for (int k = 0; k < nt1; k++) { p.fir_re[(size_t)k * cp + ch] = s_re[k * 32 + lane]; p.fir_im[(size_t)k * cp + ch] = s_im[k * 32 + lane]; }
+    BD(BD_M2_PTR) = m2.ptr; BD(BD_M2_STEP) = m2.step; BD(BD_M2_FREQ) = m2.freq; BD(BD_M2_LAST) = m2.last;
+    BD(BD_ST_PTR) = st.ptr; BD(BD_ST_STEP) = st.step; BD(BD_ST_FREQ) = st.freq; BD(BD_ST_LAST) = st.last;
+    BD(BD_SR_PTR) = sr.ptr; BD(BD_SR_STEP) = sr.step; BD(BD_SR_FREQ) = sr.freq; BD(BD_SR_LAST) = sr.last;
+    BD(BD_SH_PTR) = sq.ptr; BD(BD_SH_STEP) = sq.step; BD(BD_SH_FREQ) = sq.freq; BD(BD_SH_LAST) = sq.last;
+    BD(BD_MC_FREQ) = m2.freq;
+    BD(BD_VOL_GAIN) = vol_gain; BD(BD_MSE) = mse; BD(BD_MSEMA_SUM) = msema_sum; BD(BD_ROT_FREQ) = rot_freq;
+    BD(BD_ROT_RE) = rot.x; BD(BD_ROT_IM) = rot.y; BD(BD_STR_RE) = strot.x; BD(BD_STR_IM) = strot.y; BD(BD_SAV_RE) = savrot.x; BD(BD_SAV_IM) = savrot.y;
+    BD(BD_EB_SUM1) = eb_sum1; BD(BD_EB_SUM2) = eb_sum2; BD(BD_EB_EBNO) = eb_ebno; BD(BD_AGC2_SUM) = agc2_sum; BD(BD_AGC2_VAL) = agc2_val;
+    BD(BD_RES_X1) = res.x1; BD(BD_RES_X2) = res.x2; BD(BD_RES_Y1) = res.y1; BD(BD_RES_Y2) = res.y2;
+    BD(BD_DLY_S0) = dly_s0; BD(BD_DLY41_0) = d41_0; BD(BD_DLY41_1) = d41_1; BD(BD_DLY41_2) = d41_2;
+    BD(BD_DLY42_0) = d42_0; BD(BD_DLY42_1) = d42_1; BD(BD_DLY42_2) = d42_2; BD(BD_DLY8_0) = d8_0; BD(BD_DLY8_1) = d8_1; BD(BD_DLY8_2) = d8_2;
+    BD(BD_SIG2L_RE) = sig2_last.x; BD(BD_SIG2L_IM) = sig2_last.y; BD(BD_PTD_RE) = pt_d.x; BD(BD_PTD_IM) = pt_d.y;
+    BD(BD_LASTMSE) = lastmse; BD(BD_LAST_EBNO_EMIT) = last_ebno_emit;
+    BI(BI_CNTR) = cntr; BI(BI_STARTSTOP) = startstop; BI(BI_YUI) = yui; BI(BI_INSERTPREAMBLE) = insertpreamble;
+    BI(BI_A1_POS) = a1_pos; BI(BI_MSEMA_POS) = msema_pos;
+    BI(BI_SOFT_COUNT) = soft_count; BI(BI_SOFT_PENDING) = soft_pending; BI(BI_SOFT_OVERFLOW) = soft_overflow;
+    BI(BI_SIG_TRUE) = sig_true; BI(BI_SIG_FALSE) = sig_false; BI(BI_EBNO_EMITS) = ebno_emits;
+}
+
 // ------------------------------------------------------------------------------------------------ launches
 int hilbert_exchange_launch(const HilbertStream &h, const BurstParams &p, const int16_t *pcm, size_t stride, int pcm0, int i0, int i1, int fill0, cudaStream_t s)
 {
@@ -613,13 +894,19 @@ int burst_trident_fft_launch(const BurstParams &p, const int *d_ev_list, int n_e
 {
     trident_fft_kernel<<<2 * n_events, 1024, 0, s>>>(p, d_ev_list, n_events, wa, wb, tw);
     JB_CUDA(cudaGetLastError());
-    trident_peaks_kernel<<<n_events, 1024, 0, s>>>(p, d_ev_list, n_events, wb);
+    if (p.kind == 1) trident_peaks_oqpsk_kernel<<<n_events, 1024, 0, s>>>(p, d_ev_list, n_events, wb, wa);
+    else trident_peaks_kernel<<<n_events, 1024, 0, s>>>(p, d_ev_list, n_events, wb);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
-int burst_back_launch(const BurstParams &p, int n, cudaStream_t s)
+int burst_back_launch(const BurstParams &p, long long sample0, int n, int new_write, cudaStream_t s)
 {
     const size_t smem = (size_t)2 * (p.ntaps + 1) * 32 * sizeof(double);
+    if (p.kind == 1) {
+        burst_oqpsk_back_kernel<<<(p.n_channels + 31) / 32, 32, smem, s>>>(p, sample0, n, new_write);
+        JB_CUDA(cudaGetLastError());
+        return 0;
+    }
     JB_CUDA(cudaFuncSetAttribute(burst_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     burst_back_kernel<<<(p.n_channels + 31) / 32, 32, smem, s>>>(p, n);
     JB_CUDA(cudaGetLastError());

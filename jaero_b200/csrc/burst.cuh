@@ -23,17 +23,28 @@ enum BDIdx {
     BD_VOL_GAIN, BD_MSE, BD_MSEMA_SUM, BD_ROT_RE, BD_ROT_IM, BD_ROT_FREQ, BD_STR_RE, BD_STR_IM, BD_SAV_RE, BD_SAV_IM,
     BD_EB_SUM1, BD_EB_SUM2, BD_EB_EBNO, BD_AGC2_SUM, BD_AGC2_VAL, BD_RES_X1, BD_RES_X2, BD_RES_Y1, BD_RES_Y2, BD_DIFF_LAST,
     BD_LAST_EBNO_EMIT,
+    // burst OQPSK only
+    BD_SR_PTR, BD_SR_STEP, BD_SR_FREQ, BD_SR_LAST,           // st_osc_ref (BD_SH_* holds st_osc_quarter)
+    BD_DLY_S0, BD_DLY41_0, BD_DLY41_1, BD_DLY41_2, BD_DLY42_0, BD_DLY42_1, BD_DLY42_2, BD_DLY8_0, BD_DLY8_1, BD_DLY8_2,
+    BD_SIG2L_RE, BD_SIG2L_IM, BD_PTD_RE, BD_PTD_IM, BD_LASTMSE,
     BD_COUNT
 };
 enum BIIdx {
     BI_PD_CNTDOWN, BI_PD_MAXPOSCNT, BI_TRI_PTR, BI_TRI_SLOT, BI_NEV, BI_CNTR, BI_STARTSTOP, BI_DCD,
     BI_FIR_POS, BI_A1_POS, BI_EB_POS, BI_AGC2_POS, BI_DS_POS, BI_D8_POS, BI_MSEMA_POS,
     BI_SOFT_COUNT, BI_SOFT_PENDING, BI_SOFT_OVERFLOW, BI_SIG_TRUE, BI_SIG_FALSE, BI_EBNO_EMITS,
+    BI_YUI, BI_INSERTPREAMBLE,
     BI_COUNT
 };
 
 struct BurstParams {
+    int kind;                              // 0 = burst MSK, 1 = burst OQPSK
     int n_channels, cpad, sps, ntaps;
+    double spsd;                           // SamplesPerSymbol as the reference holds it (9.142857... for OQPSK)
+    int tri_nb, tri_nt;                    // samples of the base / top trident sections
+    int sql;
+    double w41v[4], w8v[4]; int k41, k8;   // OQPSK timing delays (T/4, T/8): weight per ring position
+    const double *btd1_wv, *btdiff_wv, *a1_wv;   // Delay<> interpolation weight per ring position
     double Fs, fb, lockingbw, signalthreshold, ee;
     int afc;
     int agc_len, d1_len, d2_len, btd1_len, btma_len, mav1_len, btdiff_len, pd_len, tri_sz;      // ring sizes (entries)
@@ -63,6 +74,6 @@ int hilbert_exchange_launch(const HilbertStream &h, const BurstParams &p, const 
 int hilbert_block_launch(const HilbertStream &h, int n_channels, int first_block, cudaStream_t s);
 int burst_front_launch(const BurstParams &p, long long sample0, int n, cudaStream_t s);
 int burst_trident_launch(const BurstParams &p, double2 *work_a, double2 *work_b, const double2 *tw16k, double *absbuf, cudaStream_t s, long long *launches);
-int burst_back_launch(const BurstParams &p, int n, cudaStream_t s);
+int burst_back_launch(const BurstParams &p, long long sample0, int n, int new_write, cudaStream_t s);
 
 } // namespace jb

@@ -969,6 +969,22 @@ bool delay_w1(double fd, int *k, double *w)          // Delay<T> weight at ring 
     *k = (int)std::ceil(fd); *w = w0;
     return true;
 }
+// Delay<T> weight at every ring position (DSP.h:357-374); the ring read position must be "ceil(fd) samples ago"
+bool delay_table(double fd, std::vector<double> &w, int *k)
+{
+    const int size = (int)std::ceil(fd) + 1;
+    w.assign(size, 0.0);
+    for (int bp = 0; bp < size; bp++) {
+        double dptr = ((double)bp) - fd;
+        while (std::floor(dptr) < 0) dptr += ((double)size);
+        const int iptr = (int)std::floor(dptr);
+        w[bp] = dptr - ((double)iptr);
+        int expect = bp - (int)std::ceil(fd); while (expect < 0) expect += size;
+        if (iptr != expect) return false;
+    }
+    *k = (int)std::ceil(fd);
+    return true;
+}
 __global__ void burst_init_kernel(BurstParams p, double freq_center, double st_freq)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -983,6 +999,12 @@ __global__ void burst_init_kernel(BurstParams p, double freq_center, double st_f
     D(BD_MSE) = 10.0;                                    // burstmskdemodulator.cpp:195
     D(BD_ROT_RE) = 1.0; D(BD_SAV_RE) = 1.0;              // rotator=1, symboltone_averotator=1 (:201-202); symboltone_rotator stays 0
     D(BD_DIFF_LAST) = -1.0;
+    if (p.kind == 1) {                                   // burst OQPSK ctor (burstoqpskdemodulator.cpp:4-133)
+        D(BD_MSE) = 100.0; D(BD_VOL_GAIN) = 1.0; D(BD_STR_RE) = 1.0;     // symboltone_rotator=1, never reset
+        D(BD_ST_FREQ) = 10500.0; D(BD_ST_STEP) = (10500.0) * ((double)jb::WTSIZE) / sr;
+        D(BD_SR_FREQ) = 10500.0; D(BD_SR_STEP) = (10500.0) * ((double)jb::WTSIZE) / sr;
+        D(BD_SH_FREQ) = 10500.0 / 4.0; D(BD_SH_STEP) = (10500.0 / 4.0) * ((double)jb::WTSIZE) / sr;
+    }
     I(BI_PD_CNTDOWN) = 2 * p.pd_len; I(BI_PD_MAXPOSCNT) = -1;    // PeakDetector::setSettings (DSP.h:502-513)
     I(BI_STARTSTOP) = -1;                                // ctor :69
 }
@@ -1006,10 +1028,11 @@ __global__ void burst_set_int_kernel(BurstParams p, int idx, int channel, int va
 
 extern "C" {
 
-int jaero_burst_msk_create(const jaero_settings *s, int n_channels, int device, jaero_burst **out)
+static int burst_create(const jaero_settings *s, int n_channels, int device, int kind, jaero_burst **out)
 {
-    if (!s || !out || n_channels <= 0) { set_error("jaero_burst_msk_create: bad argument"); return JAERO_E_ARG; }
-    if (s->Fs != 48000 || (s->fb != 600 && s->fb != 1200)) { set_error("jaero_burst_msk_create: burst MSK runs at Fs=48000 with fb 600 or 1200"); return JAERO_E_ARG; }
+    if (!s || !out || n_channels <= 0) { set_error("jaero_burst_create: bad argument"); return JAERO_E_ARG; }
+    if (kind == 0 && (s->Fs != 48000 || (s->fb != 600 && s->fb != 1200))) { set_error("jaero_burst_msk_create: burst MSK runs at Fs=48000 with fb 600 or 1200"); return JAERO_E_ARG; }
+    if (kind == 1 && (s->Fs != 48000 || s->fb != 10500)) { set_error("jaero_burst_oqpsk_create: burst OQPSK runs at Fs=48000, fb=10500"); return JAERO_E_ARG; }
     int ndev = 0;
     JB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("jaero_burst_msk_create: no such CUDA device"); return JAERO_E_CUDA; }
@@ -1020,40 +1043,65 @@ int jaero_burst_msk_create(const jaero_settings *s, int n_channels, int device, 
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     BurstParams &p = b->p;
     memset(&p, 0, sizeof p);
+    p.kind = kind; p.sql = s->sql;
     p.n_channels = n_channels; p.cpad = (n_channels + 31) & ~31;
     p.Fs = s->Fs; p.fb = s->fb; p.lockingbw = s->lockingbw; p.signalthreshold = s->signalthreshold; p.afc = 1;   // ctor: afc=true (:15)
     double fc = s->freq_center;
     if (fc > ((p.Fs / 2.0) - (p.lockingbw / 2.0))) fc = ((p.Fs / 2.0) - (p.lockingbw / 2.0));
     p.sps = (int)(p.Fs / p.fb);
-    const double SPS = (double)p.sps;
-    p.ntaps = 2 * p.sps;
-    if (p.ntaps > MAX_TAPS) { set_error("burst MSK: matched filter too long"); delete b; return JAERO_E_ARG; }
-    std::vector<double> taps(p.ntaps);
-    for (int i = 0; i < p.ntaps; i++) taps[i] = sin(M_PI * i / (2.0 * SPS)) / (2.0 * SPS);      // :173-177
+    const double SPS = kind == 1 ? 2.0 * p.Fs / p.fb : (double)p.sps;            // burstoqpskdemodulator.cpp:219
+    p.spsd = SPS;
+    std::vector<double> taps;
+    if (kind == 1) { p.sps = (int)SPS; p.ntaps = 55; taps = rrc_taps(1.0, 55, 48000, 10500 / 2.0); }    // ctor :38-46
+    else {
+        p.ntaps = 2 * p.sps;
+        if (p.ntaps > MAX_TAPS) { set_error("burst MSK: matched filter too long"); delete b; return JAERO_E_ARG; }
+        taps.resize(p.ntaps);
+        for (int i = 0; i < p.ntaps; i++) taps[i] = sin(M_PI * i / (2.0 * SPS)) / (2.0 * SPS);      // :173-177
+    }
     if (burst_set_taps(taps.data(), p.ntaps)) { delete b; return JAERO_E_CUDA; }
     p.agc_len = (int)round(1 * p.Fs);
     auto qround = [](double d) { return d >= 0.0 ? int(d + 0.5) : int(d - double(int(d - 1)) + 0.5) + int(d - 1); };
-    if (p.fb >= 1200) {                                           // :205-256
+    double btdiff_fd = 0;
+    if (kind == 1) {                                              // burstoqpskdemodulator.cpp:202-277
+        p.btma_len = qround(128.0 * SPS); p.mav1_len = (int)(SPS * 128); btdiff_fd = SPS * 128; p.btdiff_len = (int)std::ceil(btdiff_fd) + 1;
+        p.pd_len = (int)(SPS * 128.0 / 2.0); p.pd_threshold = 0.2;
+        p.tri_sz = qround((256.0 + 16.0 + 16.0) * SPS); p.d1_len = (int)(SPS * 128.0 * 2.5 - 190) + 1; p.d2_len = p.tri_sz + 1;
+        p.tri_nb = p.tri_nt = qround(128.0 * SPS);
+        p.res_b0 = 0.0048847995518126464; p.res_b1 = 0; p.res_b2 = -0.0048847995518126464;       // ctor :69-75 (75 Hz)
+        p.res_a1 = -0.3882746897971619; p.res_a2 = 0.99023040089637471;
+        p.ee = 0.4;
+    } else if (p.fb >= 1200) {                                           // :205-256
         p.btma_len = qround(126.0 * SPS); p.mav1_len = (int)(SPS * 126); p.btdiff_len = (int)std::ceil(SPS * 126) + 1;
         p.pd_len = (int)(SPS * 126.0 / 2.0); p.pd_threshold = 0.1;
         p.tri_sz = qround(200.0 * SPS); p.d1_len = ((int)289 * p.sps) + 20 + 1; p.d2_len = (int)(qround(72 + 120.0) * SPS) + 1;
         p.size_base = 126; p.size_top = 74; p.start_processing = 120; p.end_rotation = (int)((120 + 37) * SPS);
         p.res_a1 = -1.993312819378528; p.res_a2 = 0.999476538254407; p.res_b0 = 2.617308727964618e-04; p.res_b1 = 0; p.res_b2 = -2.617308727964618e-04;
-        p.ee = 0.025;
+        p.ee = 0.025; btdiff_fd = SPS * 126;
     } else {                                                      // :257-311
         p.btma_len = qround(150.0 * SPS); p.mav1_len = (int)(SPS * 150); p.btdiff_len = (int)std::ceil(SPS * 150) + 1;
         p.pd_len = (int)(SPS * 150.0 / 2.0); p.pd_threshold = 0.2;
         p.tri_sz = qround(224 * SPS); p.d1_len = ((int)397 * p.sps) + 20 + 1; p.d2_len = qround((72 + 150.0) * SPS) + 1;
         p.size_base = 150; p.size_top = 74; p.start_processing = 150; p.end_rotation = (int)((150 + 56) * SPS);
         p.res_a1 = -1.991228154418550; p.res_a2 = 0.997385427096603; p.res_b0 = 0.001307286451699; p.res_b1 = 0; p.res_b2 = -0.001307286451699;
-        p.ee = 0.015;
+        p.ee = 0.015; btdiff_fd = SPS * 150;
     }
-    p.startstopstart = (int)(SPS * 500);
+    if (kind == 0) { p.tri_nb = (int)rint(p.size_base * SPS); p.tri_nt = (int)rint(p.size_top * SPS); }
+    p.startstopstart = kind == 1 ? (int)(SPS * (1050)) : (int)(SPS * 500);
     p.btd1_len = (int)std::ceil(1.0 * SPS) + 1;
     int kk;
-    if (!delay_w1(1.0 * SPS, &kk, &p.btd1_w) || !delay_w1(SPS * (p.fb >= 1200 ? 126 : 150), &kk, &p.btdiff_w) ||
-        !delay_w1(SPS / 2, &p.a1_k, &p.a1_w) || !delay_w1(SPS / 2.0, &p.d8_k, &p.d8_w)) { set_error("burst MSK: unsupported delay"); delete b; return JAERO_E_ARG; }
-    p.eb_len = (int)(0.15 * p.Fs); p.agc2_len = (int)round((SPS * 128.0 / p.Fs) * p.Fs); p.ds_len = p.sps + 1; p.msema_len = 75;
+    std::vector<double> w_btd1, w_btdiff, w_a1, w_tmp;
+    if (!delay_table(1.0 * SPS, w_btd1, &kk) || !delay_table(btdiff_fd, w_btdiff, &kk) || !delay_table(SPS / 2.0, w_a1, &p.a1_k)) {
+        set_error("burst: unsupported delay"); delete b; return JAERO_E_ARG; }
+    if (kind == 0) {
+        if (!delay_w1(SPS / 2.0, &p.d8_k, &p.d8_w)) { set_error("burst MSK: unsupported delay"); delete b; return JAERO_E_ARG; }
+        p.eb_len = (int)(0.15 * p.Fs); p.agc2_len = (int)round((SPS * 128.0 / p.Fs) * p.Fs); p.ds_len = p.sps + 1; p.msema_len = 75;
+    } else {
+        const double sps0 = 2.0 * 48000 / 10500;                  // ctor :48-52
+        if (!delay_weights(sps0 / 4.0, &p.k41, p.w41v) || !delay_weights(sps0 / 8.0, &p.k8, p.w8v)) { set_error("burst OQPSK: unsupported delay"); delete b; return JAERO_E_ARG; }
+        p.d8_k = 1; p.ds_len = 1;
+        p.eb_len = (int)(SPS * (256.0)); p.agc2_len = (int)round((SPS * 64.0 / p.Fs) * p.Fs); p.msema_len = 128;
+    }
     p.soft_cap = std::max(4096, (int)(2 * p.fb) + 64);
     const size_t cp = p.cpad, C = n_channels;
     int rc = 0;
@@ -1074,6 +1122,17 @@ int jaero_burst_msk_create(const jaero_settings *s, int n_channels, int device, 
     p.astride = BURST_CHUNK;
     rc |= bu_alloc(b, &p.analytic, C * p.astride); rc |= bu_alloc(b, &p.vtd, C * p.astride);
     rc |= bu_alloc(b, &p.soft, C * p.soft_cap);
+    {
+        double *d1 = 0, *d2 = 0, *d3 = 0;
+        rc |= bu_alloc(b, &d1, w_btd1.size()); rc |= bu_alloc(b, &d2, w_btdiff.size()); rc |= bu_alloc(b, &d3, w_a1.size());
+        if (!rc) {
+            JB_CUDA(cudaMemcpyAsync(d1, w_btd1.data(), w_btd1.size() * 8, cudaMemcpyHostToDevice, b->stream));
+            JB_CUDA(cudaMemcpyAsync(d2, w_btdiff.data(), w_btdiff.size() * 8, cudaMemcpyHostToDevice, b->stream));
+            JB_CUDA(cudaMemcpyAsync(d3, w_a1.data(), w_a1.size() * 8, cudaMemcpyHostToDevice, b->stream));
+            JB_CUDA(cudaStreamSynchronize(b->stream));
+        }
+        p.btd1_wv = d1; p.btdiff_wv = d2; p.a1_wv = d3;
+    }
     // Hilbert filter: QJHilbertFilter::setSize(2048) (DSP.cpp:759-789), streaming FFT convolution nfft 8192
     HilbertStream &h = b->hil; memset(&h, 0, sizeof h);
     h.K = 2048; h.nfft = 8192; h.L = h.nfft - h.K + 1;
@@ -1124,6 +1183,8 @@ int jaero_burst_msk_create(const jaero_settings *s, int n_channels, int device, 
     *out = b;
     return JAERO_OK;
 }
+int jaero_burst_msk_create(const jaero_settings *s, int n_channels, int device, jaero_burst **out) { return burst_create(s, n_channels, device, 0, out); }
+int jaero_burst_oqpsk_create(const jaero_settings *s, int n_channels, int device, jaero_burst **out) { return burst_create(s, n_channels, device, 1, out); }
 void jaero_burst_destroy(jaero_burst *b)
 {
     if (!b) return;
@@ -1151,6 +1212,7 @@ int jaero_burst_write_device(jaero_burst *b, const int16_t *d_pcm, size_t n, siz
     JB_CUDA(cudaSetDevice(b->device));
     const BurstParams &p = b->p;
     const size_t cp = p.cpad;
+    int new_write = 1;
     for (size_t c0 = 0; c0 < n; c0 += BURST_CHUNK) {
         const int m = (int)std::min((size_t)BURST_CHUNK, n - c0);
         // Hilbert transform of this chunk (JFastFir::update: per-sample exchange + block transforms)
@@ -1179,7 +1241,8 @@ int jaero_burst_write_device(jaero_burst *b, const int16_t *d_pcm, size_t n, siz
             if (burst_trident_fft_launch(p, b->d_ev_list + 2 * e0, cnt, b->wa, b->wb, b->tw32k, b->stream)) return JAERO_E_CUDA;
             b->launches += 2;
         }
-        if (burst_back_launch(p, m, b->stream)) return JAERO_E_CUDA;
+        if (burst_back_launch(p, b->samples, m, new_write, b->stream)) return JAERO_E_CUDA;
+        new_write = 0;
         b->launches++;
         b->samples += m;
     }

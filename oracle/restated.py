@@ -28,6 +28,7 @@ def lib():
         vp, d, i, l = ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_long
         L.jor_demod_new.restype = vp; L.jor_demod_new.argtypes = [i, d, d, d, d, i, d, i, i, i]
         L.jor_burst_msk_new.restype = vp; L.jor_burst_msk_new.argtypes = [d, d, d, d, d]
+        L.jor_burst_oqpsk_new.restype = vp; L.jor_burst_oqpsk_new.argtypes = [d, d, d, d, d]
         L.jor_aux_take.restype = l; L.jor_aux_take.argtypes = [vp, i, vp, l]
         L.jor_write.argtypes = [vp, vp, l]; L.jor_set_dcd.argtypes = [vp, i]
         L.jor_soft_count.restype = l; L.jor_soft_count.argtypes = [vp]
@@ -65,6 +66,8 @@ class OracleDemod:
         self.kind = kind
         if kind == "burst_msk":
             self.h = lib().jor_burst_msk_new(fb, Fs, freq_center, lockingbw, signalthreshold)
+        elif kind == "burst_oqpsk":
+            self.h = lib().jor_burst_oqpsk_new(fb, Fs, freq_center, lockingbw, signalthreshold)
         else:
             self.h = lib().jor_demod_new(0 if kind == "oqpsk" else 1, fb, Fs, freq_center, lockingbw, fft_power,
                                          signalthreshold, int(afc), int(sql), int(cpureduce))

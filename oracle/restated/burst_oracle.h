@@ -69,4 +69,27 @@ struct BurstMskOracle                                    // burstmskdemodulator.
     void CenterFreqChangedSlot(double f);              // :326-343
 };
 } // namespace jor
+
+namespace jor {
+struct BurstOqpskOracle                                  // burstoqpskdemodulator.cpp
+{
+    double Fs, fb, lockingbw, freq_center, signalthreshold, SamplesPerSymbol, ee;
+    bool sql;
+    WaveTable mixer2, st_osc, st_osc_ref, st_osc_quarter;
+    FIR fir_re, fir_im; AGC agc, agc2; EbNoMeasure ebno; MovingAverage msema, mav1;
+    JFastFir hfir;
+    Delay<cpx> bt_d1; Delay<double> bt_ma_diff, a1, delays, delayt41, delayt42, delayt8; CMovingAverage bt_ma1; PeakDetector pdet;
+    DelayThing<cpx> d1; DelayThing<double> d2;
+    std::vector<double> tridentbuffer; int tridentbuffer_ptr, tridentbuffer_sz;
+    IIR st_iir_resonator;
+    double mse, vol_gain, rotator_freq, carrier_rotation_est;
+    cpx symboltone_averotator, symboltone_rotator, rotator, pt_d, sig2_last;
+    int cntr, startstop, startstopstart, yui; bool insertpreamble;
+    std::vector<short> RxDataBits;
+    std::vector<short> soft_out; std::vector<double> ebno_log; long n_sig_true, n_sig_false;
+    std::vector<double> trident_log;                   // per trident test: minvalbin, minval, maxvalbin, maxval, accepted
+    BurstOqpskOracle(double fb, double Fs, double freq_center, double lockingbw, double signalthreshold);
+    void writeData(const int16_t *pcm, long n);        // writeDataSlot :315-737 (mono)
+};
+} // namespace jor
 #endif

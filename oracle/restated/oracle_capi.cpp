@@ -5,7 +5,7 @@
 #include <cstring>
 using namespace jor;
 
-struct OrHandle { int kind; OqpskDemodOracle *oq; MskDemodOracle *msk; BurstMskOracle *bmsk; };
+struct OrHandle { int kind; OqpskDemodOracle *oq; MskDemodOracle *msk; BurstMskOracle *bmsk; BurstOqpskOracle *boq; };
 
 extern "C" {
 void *jor_demod_new(int kind, double fb, double Fs, double freq_center, double lockingbw, int fft_power,
@@ -13,23 +13,25 @@ void *jor_demod_new(int kind, double fb, double Fs, double freq_center, double l
 {
     DemodSettings s; s.coarsefreqest_fft_power = fft_power; s.freq_center = freq_center; s.lockingbw = lockingbw;
     s.fb = fb; s.Fs = Fs; s.signalthreshold = signalthreshold; s.afc = afc; s.sql = sql; s.cpuReduce = cpureduce;
-    OrHandle *h = new OrHandle(); h->kind = kind; h->oq = 0; h->msk = 0; h->bmsk = 0;
+    OrHandle *h = new OrHandle(); h->kind = kind; h->oq = 0; h->msk = 0; h->bmsk = 0; h->boq = 0;
     if (kind == 0) h->oq = new OqpskDemodOracle(s); else h->msk = new MskDemodOracle(s);
     return h;
 }
 void *jor_burst_msk_new(double fb, double Fs, double freq_center, double lockingbw, double signalthreshold)
-{ OrHandle *h = new OrHandle(); h->kind = 2; h->oq = 0; h->msk = 0; h->bmsk = new BurstMskOracle(fb, Fs, freq_center, lockingbw, signalthreshold); return h; }
+{ OrHandle *h = new OrHandle(); h->kind = 2; h->oq = 0; h->msk = 0; h->boq = 0; h->bmsk = new BurstMskOracle(fb, Fs, freq_center, lockingbw, signalthreshold); return h; }
+void *jor_burst_oqpsk_new(double fb, double Fs, double freq_center, double lockingbw, double signalthreshold)
+{ OrHandle *h = new OrHandle(); h->kind = 3; h->oq = 0; h->msk = 0; h->bmsk = 0; h->boq = new BurstOqpskOracle(fb, Fs, freq_center, lockingbw, signalthreshold); return h; }
 void jor_write(void *hv, const int16_t *pcm, long n)
-{ OrHandle *h = (OrHandle *)hv; if (h->kind == 0) h->oq->writeData(pcm, n); else if (h->kind == 1) h->msk->writeData(pcm, n); else h->bmsk->writeData(pcm, n); }
+{ OrHandle *h = (OrHandle *)hv; if (h->kind == 0) h->oq->writeData(pcm, n); else if (h->kind == 1) h->msk->writeData(pcm, n); else if (h->kind == 2) h->bmsk->writeData(pcm, n); else h->boq->writeData(pcm, n); }
 void jor_set_dcd(void *hv, int d)
-{ OrHandle *h = (OrHandle *)hv; if (h->kind == 0) h->oq->DCDstatSlot(d != 0); else if (h->kind == 1) h->msk->DCDstatSlot(d != 0); else h->bmsk->dcd = (d != 0); }
-static std::vector<short> &soft_of(OrHandle *h) { return h->kind == 0 ? h->oq->soft_out : (h->kind == 1 ? h->msk->soft_out : h->bmsk->soft_out); }
+{ OrHandle *h = (OrHandle *)hv; if (h->kind == 0) h->oq->DCDstatSlot(d != 0); else if (h->kind == 1) h->msk->DCDstatSlot(d != 0); else if (h->kind == 2) h->bmsk->dcd = (d != 0); }
+static std::vector<short> &soft_of(OrHandle *h) { return h->kind == 0 ? h->oq->soft_out : (h->kind == 1 ? h->msk->soft_out : (h->kind == 2 ? h->bmsk->soft_out : h->boq->soft_out)); }
 long jor_soft_count(void *hv)
 { OrHandle *h = (OrHandle *)hv; return (long)soft_of(h).size(); }
 long jor_aux_take(void *hv, int which, double *out, long cap)     // burst: 0 = EbNo per burst, 1 = trident log (5 values per test)
 {
-    OrHandle *h = (OrHandle *)hv; if (h->kind != 2) return 0;
-    std::vector<double> &v = which == 0 ? h->bmsk->ebno_log : h->bmsk->trident_log;
+    OrHandle *h = (OrHandle *)hv; if (h->kind < 2) return 0;
+    std::vector<double> &v = h->kind == 2 ? (which == 0 ? h->bmsk->ebno_log : h->bmsk->trident_log) : (which == 0 ? h->boq->ebno_log : h->boq->trident_log);
     long n = (long)v.size(); if (n > cap) n = cap;
     memcpy(out, v.data(), n * sizeof(double)); v.erase(v.begin(), v.begin() + n); return n;
 }
@@ -41,7 +43,7 @@ long jor_soft_take(void *hv, short *out, long cap)
 }
 long jor_cfe_log_take(void *hv, double *out, long cap)
 {
-    OrHandle *h = (OrHandle *)hv; if (h->kind == 2) return 0;
+    OrHandle *h = (OrHandle *)hv; if (h->kind >= 2) return 0;
     std::vector<double> &v = h->kind == 0 ? h->oq->cfe_log : h->msk->cfe_log;
     long n = (long)v.size(); if (n > cap) n = cap;
     memcpy(out, v.data(), n * sizeof(double)); v.erase(v.begin(), v.begin() + n); return n;
@@ -55,6 +57,11 @@ int jor_state(void *hv, double *o)
         o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer_center.freq; o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr;
         o[5] = d->agc.AGCVal; o[6] = d->mse; o[7] = d->ebno.EbNo; o[8] = d->marg.Val; o[9] = d->cfe.freq_offset_est;
         o[10] = (double)d->n_sig_true; o[11] = (double)d->n_sig_false; o[12] = d->mixer_center.WTptr; o[13] = d->st_osc_ref.WTptr;
+    } else if (h->kind == 3) {
+        BurstOqpskOracle *d = h->boq;
+        o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer2.freq; o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr;
+        o[5] = d->agc.AGCVal; o[6] = d->mse; o[7] = d->ebno.EbNo; o[8] = d->vol_gain; o[9] = d->rotator_freq;
+        o[10] = (double)d->n_sig_true; o[11] = (double)d->n_sig_false; o[12] = (double)d->cntr; o[13] = (double)d->startstop;
     } else if (h->kind == 2) {
         BurstMskOracle *d = h->bmsk;      // same layout as jref_state for burst kinds
         o[0] = d->mixer2.freq; o[1] = d->mixer2.WTptr; o[2] = d->mixer_center.freq; o[3] = d->st_osc.freq; o[4] = d->st_osc.WTptr;
@@ -68,7 +75,7 @@ int jor_state(void *hv, double *o)
     }
     return 14;
 }
-void jor_free(void *hv) { OrHandle *h = (OrHandle *)hv; delete h->oq; delete h->msk; delete h->bmsk; delete h; }
+void jor_free(void *hv) { OrHandle *h = (OrHandle *)hv; delete h->oq; delete h->msk; delete h->bmsk; delete h->boq; delete h; }
 
 int jor_rrc_design(double alpha, int firsize, double Fs, double symbol_freq, double *out, int cap)
 { std::vector<double> p = rrc_design(alpha, firsize, Fs, symbol_freq); int n = (int)p.size(); for (int i = 0; i < n && i < cap; i++) out[i] = p[i]; return n; }

@@ -145,13 +145,15 @@ def check_pchannel():
     return ok
 
 
-def check_burst():
+def check_burst(names=("burst_msk_1200_a", "burst_msk_1200_b")):
     ok = True
-    for name in ("burst_msk_1200_a", "burst_msk_1200_b"):
+    for name in names:
         pcm = np.load(os.path.join(ROOT, "tests", "golden", name + "_excerpt.npz"))["pcm"]
         pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 3 // 5).astype(np.int16), np.roll(pcm, 12345)])
-        kw = dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)
-        b = jaero_b200.BurstMskBatch(3, **kw)
+        oq = name.startswith("burst_oqpsk")
+        okind = "burst_oqpsk" if oq else "burst_msk"
+        kw = dict(fb=10500.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6) if oq else dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)
+        b = (jaero_b200.BurstOqpskBatch if oq else jaero_b200.BurstMskBatch)(3, **kw)
         acc = [[] for _ in range(3)]
         t = time.time()
         for a in range(0, pcm2.shape[1], 4800):
@@ -161,7 +163,7 @@ def check_burst():
         tg = time.time() - t
         st = b.status()
         for c in range(3):
-            o = restated.OracleDemod("burst_msk", **kw)
+            o = restated.OracleDemod(okind, **kw)
             for a in range(0, pcm2.shape[1], 4800):
                 o.write(pcm2[c, a:a + 4800])
             so = o.take_soft(); sg = np.concatenate(acc[c]); os_ = o.state()
@@ -189,6 +191,8 @@ if __name__ == "__main__":
         ok &= check_viterbi()
     if "oqpsk" in which:
         ok &= check_demod("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
+    if "burst_oqpsk" in which:
+        ok &= check_burst(("burst_oqpsk_10500",))
     if "oqpsk8400" in which:
         ok &= check_demod("oqpsk", "oqpsk_8400", dict(fb=8400, freq_center=8000, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
     if "msk" in which:
