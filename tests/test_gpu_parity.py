@@ -255,16 +255,16 @@ def test_pchannel_frame_layer_bit_exact(golden):
         b.close(); pc.close()
 
 
-@pytest.mark.parametrize("name", ["burst_msk_1200_a", "burst_msk_1200_b"])
-def test_burst_msk_parity_on_reference_recordings(golden, name):
-    """BASELINE cfg 4 source material: Hilbert FFT-FIR, burst detector, trident FFT acquisition, preamble-aided tail.
-    Soft bits (incl. the -1 start-of-burst markers) identical after hard decision; gain / carrier from the acquisition FFTs
-    within 1e-6."""
+@pytest.mark.parametrize("name", ["burst_msk_1200_a", "burst_msk_1200_b", "burst_oqpsk_10500"])
+def test_burst_parity_on_reference_recordings(golden, name):
+    """BASELINE cfg 4 source material (burst MSK 1200) and the 10.5k burst OQPSK recording: Hilbert FFT-FIR, burst
+    detector, trident FFT acquisition, preamble-aided tail. Soft bits (incl. the -1 start-of-burst markers) identical
+    after hard decision and within 1 LSB; gain / carrier from the acquisition FFTs within 1e-6."""
     jb = _import()
     case = golden[name]
     pcm = load_excerpt(name)
     pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 3 // 5).astype(np.int16), np.roll(pcm, 12345)])
-    b = jb.BurstMskBatch(3, **case["kw"])
+    b = (jb.BurstOqpskBatch if case["kind"] == "burst_oqpsk" else jb.BurstMskBatch)(3, **case["kw"])
     acc = [[] for _ in range(3)]
     for a in range(0, pcm2.shape[1], case["chunk"]):
         b.write(pcm2[:, a:a + case["chunk"]])
@@ -273,7 +273,7 @@ def test_burst_msk_parity_on_reference_recordings(golden, name):
     st = b.status()
     b.close()
     for c in range(3):
-        o = restated.OracleDemod("burst_msk", **case["kw"])
+        o = restated.OracleDemod(case["kind"], **case["kw"])
         for a in range(0, pcm2.shape[1], case["chunk"]):
             o.write(pcm2[c, a:a + case["chunk"]])
         so = o.take_soft(); sg = np.concatenate(acc[c]); os_ = o.state()

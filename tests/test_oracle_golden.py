@@ -95,8 +95,8 @@ def test_dsp_primitive_semantics():
 
 
 def _run_restated(case, pcm):
-    if case["kind"] == "burst_msk":
-        d = restated.OracleDemod("burst_msk", **case["kw"])
+    if case["kind"].startswith("burst"):
+        d = restated.OracleDemod(case["kind"], **case["kw"])
         for a in range(0, len(pcm), case["chunk"]):
             d.write(pcm[a:a + case["chunk"]])
         return d.take_soft(), d.state(), np.zeros(0)
@@ -109,7 +109,8 @@ def _run_restated(case, pcm):
     return d.take_soft(), d.state(), d.take_cfe_log()
 
 
-@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600", "burst_msk_1200_a", "burst_msk_1200_b"])
+@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600", "burst_msk_1200_a", "burst_msk_1200_b",
+                                  "burst_oqpsk_10500"])
 def test_restated_oracle_matches_reference_golden(golden, name):
     """The restatement reproduces the verbatim reference bit for bit on the recordings (soft bits, coarse
     estimates, loop state) — golden values were produced by oracle/_ref (tools/make_golden_outputs.py)."""
@@ -117,7 +118,7 @@ def test_restated_oracle_matches_reference_golden(golden, name):
     soft, state, cfe = _run_restated(case, load_excerpt(case["excerpt"]))
     assert len(soft) == case["n_soft"]
     assert hashlib.sha256(soft.astype("<i2").tobytes()).hexdigest() == case["soft_sha256"]
-    if case["kind"] != "burst_msk":
+    if not case["kind"].startswith("burst"):
         assert hashlib.sha256(np.asarray(cfe, dtype="<f8").tobytes()).hexdigest() == case["cfe_log_sha256"]
     else:
         assert int((soft < 0).sum()) >= 2                      # burst start markers (-1) survive

@@ -23,6 +23,7 @@ CASES = {
     "oqpsk_8400": dict(kind="oqpsk", nosu=True, kw=dict(fb=8400, freq_center=8000, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)),
     "burst_msk_1200_a": dict(kind="burst_msk", nosu=True, kw=dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)),
     "burst_msk_1200_b": dict(kind="burst_msk", nosu=True, kw=dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)),
+    "burst_oqpsk_10500": dict(kind="burst_oqpsk", nosu=True, kw=dict(fb=10500.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6)),
     "msk_600": dict(kind="msk", kw=dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True)),
 }
 
