@@ -216,6 +216,7 @@ struct jaero_batch {
     long long launches;
     cudaStream_t own_stream;
     bool profiling;
+    bool use_pipe;              // 10500 bps: warp-specialised segment kernel (JAERO_OQPSK_PIPE=0 selects the single-warp one, for A/B profiling)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_seg, ev_cfe;
     double prof_samples;
 };
@@ -308,6 +309,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     b->pre_on = false; b->fir_fill = 0; b->fir_blocks = 0; b->d_x = 0; b->x_cap = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     b->own_stream = b->stream; b->profiling = false; b->prof_samples = 0;
+    { const char *e = getenv("JAERO_OQPSK_PIPE"); b->use_pipe = !(e && e[0] == '0'); }
     DemodParams &p = b->p;
     memset(&p, 0, sizeof p);
     p.kind = s->kind; p.n_channels = n_channels; p.cpad = (n_channels + 31) & ~31;
@@ -593,7 +595,8 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         a.apply_cfe = resume ? 1 : 0; a.bb_pos = bb0; a.coarse_counter = cc0;
         cudaEvent_t e0 = 0, e1 = 0;
         if (b->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
-        int r = (p.kind == JAERO_KIND_OQPSK) ? oqpsk_segment_launch(p, a, d_pcm, stride, b->stream)
+        int r = (p.kind == JAERO_KIND_OQPSK) ? ((b->use_pipe && !p.xpre) ? oqpsk_pipe_launch(p, a, d_pcm, stride, b->stream)
+                                                                          : oqpsk_segment_launch(p, a, d_pcm, stride, b->stream))
                                              : msk_segment_launch(p, a, d_pcm, stride, b->stream);
         if (b->profiling) { cudaEventRecord(e1, b->stream); b->ev_seg.push_back({e0, e1}); b->prof_samples += (i1 - i0 - (stop_after_a ? 1 : 0)); }
         b->launches++;

@@ -1,0 +1,564 @@
+// K1a (10500 bps) — warp-specialised OQPSK demodulator segment kernel.
+//
+// Same arithmetic, statement for statement, as oqpsk_segment_kernel<false> (oqpsk_demod.cu), i.e. as
+// OqpskDemodulator::writeData (JAERO/oqpskdemodulator.cpp:334-627). What changes is who executes it: the per-sample
+// recursion of one channel is a feedback loop (carrier NCO -> FIR -> AGC -> timing -> strobe -> carrier NCO), so a
+// single thread per channel is bound by the length of its dependent instruction chain (~1500 instructions per sample),
+// not by HBM. The chain is cut where the reference's own structure allows it:
+//
+//   * the FIR output of sample n excludes the sample written at n (DSP.cpp:292-304), so everything from the FIR to the
+//     timing-error detector's input (FIR, EbNo, AGC, clip, T/4 delays, resonator, T/8 delay) is FEED-FORWARD from the
+//     mixed samples up to n-1;
+//   * the symbol-rate tail after the carrier update (bias rotate, 400-symbol delay, MSE, soft bits) feeds nothing back
+//     inside a call.
+//
+// Four warps of one CTA each own a slice of the per-sample work of the same 32 channels (lane = channel in every warp)
+// and hand their results to the next warp through shared memory, ordered by named barriers (bar.arrive / bar.sync on
+// alternating ids, one producer warp + one consumer warp per barrier):
+//
+//   warp F  PCM tile, coarse-estimator ring write (mixer_center), 55-tap FIR of the mixed samples        -> sig2raw
+//   warp E  EbNo + AGC running sums (TMA-staged ring tiles), AGC gain, clip, timing feed-forward chain     -> sig2, st_eta, d8out
+//   warp C  symbol-timing PLL (arg, NCO nudges), strobe interpolation, carrier error + loop filter, NCOs,
+//           mixes the NEXT input sample and puts it into the FIR window                                     -> cval, (pt_qpsk, ct_ec)
+//   warp S  marg MA(800), 400-symbol delay, bias rotate, MSE, soft bits
+//
+// While C works on sample n, E and F already work on sample n+1 and S on sample n (or n-1): the time per sample drops
+// from the sum of the four slices to (about) the longest one.
+#include "demod_device.cuh"
+
+namespace jb {
+
+static const int PP_THREADS = 128;
+// shared memory map (bytes): FIR windows | ring tiles x6 | PCM tiles x2 | mbarriers | hand-off slots
+static const int PP_SM_HAND = 2 * 12 * 32 * 8;     // [2 slots][12 doubles][32 lanes]
+static const int PP_SM_TOTAL = OQ_SM_TOTAL + PP_SM_HAND;
+// named barriers (0 is __syncthreads)
+enum { BAR_X = 1, BAR_Y = 3, BAR_Z = 5, BAR_W = 7, BAR_V = 9 };
+
+__device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+#define LD(idx) p.D[(size_t)(idx) * cpad + ch]
+#define LI(idx) p.I[(size_t)(idx) * cpad + ch]
+
+__global__ void __launch_bounds__(PP_THREADS)
+oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
+{
+    extern __shared__ __align__(128) unsigned char pp_smem_raw[];
+    double *s_re = reinterpret_cast<double *>(pp_smem_raw);   // [OQ_FIRROWS][32]
+    double *s_im = s_re + OQ_FIRROWS * OQ_THREADS;
+    double *t_agc = reinterpret_cast<double *>(pp_smem_raw + OQ_SM_FIR);          // [2][T][32]
+    double *t_e1 = t_agc + 2 * OQ_T * OQ_THREADS;
+    double *t_e2 = t_e1 + 2 * OQ_T * OQ_THREADS;
+    unsigned char *t_pcm = pp_smem_raw + OQ_SM_FIR + 6 * OQ_SM_RING;              // [2][32][OQ_PROW]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(t_pcm + 2 * OQ_SM_PCM);   // ring[2], pcm[2]
+    double *hand = reinterpret_cast<double *>(pp_smem_raw + OQ_SM_TOTAL);          // [2][12][32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ch_raw = blockIdx.x * OQ_THREADS + lane;
+    const bool live = ch_raw < p.n_channels;
+    const int ch = ch_raw;                                    // dead lanes run on their (allocated) pad column with zero input
+    const int nlive = min(OQ_THREADS, p.n_channels - (int)blockIdx.x * OQ_THREADS);
+    const size_t cpad = p.cpad;
+    if (threadIdx.x == 0) { for (int k = 0; k < 4; k++) mbar_init(&bars[k], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+
+    const int nB = (a.i1 - a.i0) - (a.stop_after_a ? 1 : 0);             // samples whose loop body runs in this launch
+    const long long S0 = a.sample0;
+    const double Fs = p.Fs;
+    const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
+    // hand-off slot layout: slot s, field f -> hand[(s * 12 + f) * 32 + lane]
+    //   f 0,1: sig2raw (F->E)   f 2..5: sig2.x, sig2.y, st_eta, d8out (E->C)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (C->S)
+#define HAND(s, f) hand[((s) * 12 + (f)) * 32 + lane]
+
+    // ======================================================================================= warp C: feedback loops
+    if (warp == 2) {
+        Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
+        Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
+        Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
+        Biquad lf = {LD(D_LF_X1), LD(D_LF_X2), LD(D_LF_Y1), LD(D_LF_Y2)};
+        double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
+        double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
+        int yui = LI(I_YUI), sig2l_init = LI(I_SIG2L_INIT);
+        // ---- FreqOffsetEstimateSlot (oqpskdemodulator.cpp:629-677), re-entrant in the reference: it runs after the ring
+        // write and before the mixer of the same sample.
+        if (a.apply_cfe) {
+            Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+            const double mse = LD(D_MSE);
+            const int dcd = LI(I_DCD);
+            int countdown = LI(I_COUNTDOWN), countdown2 = LI(I_COUNTDOWN2);
+            const double est = p.cfe_est_out[ch];
+            if ((mse < p.signalthreshold) && (!dcd)) {                        // :642-650
+                if (countdown2 > 0) countdown2--;
+                else osc_set_freq(m2, mc.freq + est, p.Fs);
+            } else countdown2 = 5;
+            if ((mse > p.signalthreshold) && (fabs(m2.freq - (mc.freq + est)) > 3.0))    // :653-657
+                osc_set_freq(m2, mc.freq + est, p.Fs);
+            if ((p.afc) && (mse < p.signalthreshold) && (fabs(m2.freq - mc.freq) > 3.0)) {   // :658-669
+                if (countdown > 0) countdown--;
+                else {
+                    osc_set_freq(mc, m2.freq, p.Fs);
+                    if (mc.freq < p.lockingbw / 2.0) osc_set_freq(mc, p.lockingbw / 2.0, p.Fs);
+                    if (mc.freq > (p.Fs / 2.0 - p.lockingbw / 2.0)) osc_set_freq(mc, p.Fs / 2.0 - p.lockingbw / 2.0, p.Fs);
+                    LI(I_EMPTYING) = 4;                                       // CoarseFreqEstimate::bigchange (coarsefreqestimate.cpp:84-88)
+                    LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
+                    double2 *rowz = p.bb + (size_t)ch * p.bbnfft;             // :667 bbcycbuff[j]=0
+                    if (live) for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);
+                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp F reloads mixer_center after the barrier
+                }
+            } else countdown = 4;
+            if (mse > p.signalthreshold) LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;   // :674-675
+            LI(I_COUNTDOWN) = countdown; LI(I_COUNTDOWN2) = countdown2;
+        }
+        __syncthreads();                                       // (1) slot done, FIR window resident
+        if (nB > 0) {
+            const int16_t *row = pcm + (size_t)ch * stride;
+            auto ldpk = [&](int blk) -> int4 {
+                if (live && (size_t)blk * 8 < stride) return __ldg(reinterpret_cast<const int4 *>(row + (size_t)blk * 8));
+                return make_int4(0, 0, 0, 0);
+            };
+            int blk = a.i0 >> 3;
+            int4 pk = ldpk(blk), pk_next = ldpk(blk + 1);
+            auto dval_at = [&](int ii) -> double {             // ((double)*ptr)/32768.0 (:390); ii advances by one per call
+                if ((ii >> 3) != blk) { blk = ii >> 3; pk = pk_next; pk_next = ldpk(blk + 1); }
+                const int k = ii & 7;
+                const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
+                const int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+                return ((double)v) / 32768.0;
+            };
+            double c2_re, c2_im, cs_re, cs_im;
+            { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
+            { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+            int fir_pos = (int)(S0 % OQ_NT1);                  // slot of the sample being mixed
+            {   // cval of the first sample (:453)
+                const double dval = dval_at(a.i0);
+                const double cre = c2_re * dval, cim = c2_im * dval;
+                s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
+                s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
+                fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
+                __threadfence_block();
+                nb_arrive(BAR_X + 0);                          // X_0
+            }
+            const double ee = p.ee, fbr = p.fb;
+            for (int j = 0; j < nB; j++) {
+                const int sl = j & 1;
+                // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
+                const int m2_spec = osc_next_index(m2);
+                const double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
+                const double dnext = (j + 1 < nB) ? dval_at(a.i0 + j + 1) : 0.0;
+                nb_sync(BAR_Y + sl);                           // Y_j: sig2, st_eta, d8out of this sample
+                double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
+                const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
+                const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
+                const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
+                osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
+                osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0); // :482
+                if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);
+                if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), Fs);
+                if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
+                double frac;
+                double sy_flag = 0.0, sy_x = 0.0, sy_y = 0.0, sy_ec = 0.0;
+                if (osc_have_passed_point(st, ee, frac)) {                        // :488
+                    const double pt_last = frac, pt_this = 1.0 - pt_last;
+                    const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
+                    yui ^= 1;                                                     // yui++; yui%=2;
+                    if (!yui) pt_d = pt;
+                    else {
+                        const double2 pt_qpsk = make_double2(pt.x, pt_d.y);       // :503
+                        const double ct_xt = tanh(pt.y) * pt.x;
+                        const double ct_xt_d = tanh(pt_d.x) * pt_d.y;
+                        double ct_ec = ct_xt_d - ct_xt;
+                        if (ct_ec > M_PI) ct_ec = M_PI;
+                        if (ct_ec < -M_PI) ct_ec = -M_PI;
+                        if (fbr > 8400) {                                         // :518-525
+                            ct_ec = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
+                            if (ct_ec > M_PI_2) ct_ec = M_PI_2;
+                            if (ct_ec < -M_PI_2) ct_ec = -M_PI_2;
+                            osc_increase_phase_deg(m2, 1.0 * ct_ec);
+                            osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, Fs);
+                        } else {                                                  // :526-532
+                            osc_increase_phase_deg(m2, 1.0 * ct_ec);
+                            const double lfo = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
+                            osc_set_freq(m2, (0.5 * 0.01 * lfo) + m2.freq, Fs);
+                        }
+                        sy_flag = 1.0; sy_x = pt_qpsk.x; sy_y = pt_qpsk.y; sy_ec = ct_ec;
+                    }
+                }
+                sig2_last = sig2;                                                 // :596
+                osc_next_frame(m2); osc_next_frame(st); osc_next_frame(sr);       // :600-603 (mixer_center lives in warp F)
+                {
+                    const int t = osc_index(m2.ptr);
+                    if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
+                }
+                if (j + 1 < nB) {   // the next sample's mixed value enters the FIR ring (:453-456)
+                    const double cre = c2_re * dnext, cim = c2_im * dnext;
+                    s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
+                    s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
+                    fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
+                    __threadfence_block();
+                    nb_arrive(BAR_X + ((j + 1) & 1));          // X_{j+1}
+                }
+                { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+                // symbol hand-off to warp S (slot reuse is gated by V)
+                if (j >= 2) nb_sync(BAR_V + sl);               // V_{j-2}: S has read slot sl
+                HAND(sl, 6) = sy_x; HAND(sl, 7) = sy_y; HAND(sl, 8) = sy_ec; HAND(sl, 9) = sy_flag;
+                __threadfence_block();
+                nb_arrive(BAR_W + sl);                         // W_j
+            }
+            // drain: S still owes the V arrivals of the last two slots
+            if (nB >= 2) nb_sync(BAR_V + (nB & 1));            // V_{nB-2}
+            nb_sync(BAR_V + ((nB - 1) & 1));                   // V_{nB-1}
+        }
+        LD(D_M2_PTR) = m2.ptr; LD(D_M2_STEP) = m2.step; LD(D_M2_FREQ) = m2.freq; LD(D_M2_LAST) = m2.last;
+        LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
+        LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
+        LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
+        LD(D_SIG2L_RE) = sig2_last.x; LD(D_SIG2L_IM) = sig2_last.y;
+        LD(D_PTD_RE) = pt_d.x; LD(D_PTD_IM) = pt_d.y;
+        LI(I_YUI) = yui; LI(I_SIG2L_INIT) = sig2l_init;
+    }
+    // ======================================================================================= warp S: symbol-rate tail
+    else if (warp == 3) {
+        double marg_sum = LD(D_MARG_SUM), marg_val = LD(D_MARG_VAL);
+        double pm_sum = LD(D_MSE_PM_SUM), ma_sum = LD(D_MSE_MA_SUM), mse = LD(D_MSE);
+        double lastmse = LD(D_LASTMSE);
+        int marg_pos = LI(I_MARG_POS), dt_pos = LI(I_DT_POS), mse_pos = LI(I_MSE_POS);
+        int soft_count = LI(I_SOFT_COUNT), soft_pending = LI(I_SOFT_PENDING), soft_overflow = LI(I_SOFT_OVERFLOW);
+        if (a.new_write) lastmse = mse;                                       // oqpskdemodulator.cpp:339
+        const int marg_len = p.marg_len, dt_len = p.dt_len, mse_len = p.mse_len;
+        const double thr = p.signalthreshold;
+        double sy_marg_old = p.marg_ring[(size_t)marg_pos * cpad + ch];
+        double sy_pm_old = p.mse_pm[(size_t)mse_pos * cpad + ch];
+        double sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
+        double2 sy_dt_old;
+        { int r = dt_pos + 1; if (r >= dt_len) r = 0; sy_dt_old = p.dt_ring[(size_t)r * cpad + ch]; }
+        __syncthreads();                                       // (1)
+        for (int j = 0; j < nB; j++) {
+            const int sl = j & 1;
+            nb_sync(BAR_W + sl);                               // W_j
+            const double fx = HAND(sl, 6), fy = HAND(sl, 7), fec = HAND(sl, 8), fl = HAND(sl, 9);
+            __threadfence_block();
+            nb_arrive(BAR_V + sl);                             // V_j: slot read
+            if (fl != 0.0) {
+                double2 pt_qpsk = make_double2(fx, fy);
+                const double ct_ec = fec;
+                {   // marg->UpdateSigned(ct_ec)  MA(800)  (:535, DSP.cpp:418-426)
+                    marg_sum = marg_sum - sy_marg_old;
+                    marg_sum = marg_sum + (ct_ec);
+                    p.marg_ring[(size_t)marg_pos * cpad + ch] = (ct_ec);
+                    marg_pos++; if (marg_pos >= marg_len) marg_pos = 0;
+                    marg_val = marg_sum / ((double)marg_len);
+                }
+                {   // dt.update(pt_qpsk): 400-symbol delay (:536, DSP.h:455-460)
+                    p.dt_ring[(size_t)dt_pos * cpad + ch] = pt_qpsk;
+                    dt_pos++; if (dt_pos >= dt_len) dt_pos = 0;
+                    pt_qpsk = sy_dt_old;                                  // requested after the previous strobe
+                }
+                pt_qpsk = cmul(pt_qpsk, make_double2(cos(marg_val), sin(marg_val)));   // :537
+                {   // MSEcalc::Update (DSP.cpp:451-463)
+                    const size_t e = (size_t)mse_pos * cpad + ch;
+                    const double ab = hypot(pt_qpsk.x, pt_qpsk.y);
+                    pm_sum = pm_sum - sy_pm_old; pm_sum = pm_sum + fabs(ab); p.mse_pm[e] = fabs(ab);
+                    double mu = pm_sum / ((double)mse_len);
+                    if (mu < 0.000001) mu = 0.000001;
+                    const double r2 = sqrt(2.0);
+                    const double tre = (r2 * pt_qpsk.x) / mu, tim = (r2 * pt_qpsk.y) / mu;
+                    const double tda = (fabs(tre) - 1.0), tdb = (fabs(tim) - 1.0);
+                    const double v = (tda * tda) + (tdb * tdb);
+                    ma_sum = ma_sum - sy_ma_old; ma_sum = ma_sum + fabs(v); p.mse_ma[e] = fabs(v);
+                    mse_pos++; if (mse_pos >= mse_len) mse_pos = 0;
+                    mse = ma_sum / ((double)mse_len);
+                }
+                // operands of the next strobe pair (slots written >= 400 symbols ago)
+                sy_marg_old = p.marg_ring[(size_t)marg_pos * cpad + ch];
+                sy_pm_old = p.mse_pm[(size_t)mse_pos * cpad + ch];
+                sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
+                { int r = dt_pos + 1; if (r >= dt_len) r = 0; sy_dt_old = p.dt_ring[(size_t)r * cpad + ch]; }
+                if (live && mse < thr) {                                  // :565
+                    push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.y * 127.0 + 128.0));
+                    push_soft(p, ch, soft_count, soft_pending, soft_overflow, q_round(0.75 * pt_qpsk.x * 127.0 + 128.0));
+                    if (soft_pending >= 32) {                             // :583-592
+                        if (!p.sql || mse < thr || lastmse < thr) soft_count += soft_pending;
+                        soft_pending = 0;
+                    }
+                }
+            }
+        }
+        LD(D_MARG_SUM) = marg_sum; LD(D_MARG_VAL) = marg_val;
+        LD(D_MSE_PM_SUM) = pm_sum; LD(D_MSE_MA_SUM) = ma_sum; LD(D_MSE) = mse;
+        LD(D_LASTMSE) = lastmse;
+        LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
+        LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
+    }
+    // ======================================================================================= warp E: envelope chain
+    else if (warp == 1) {
+        double agc_sum = LD(D_AGC_SUM), agc_val = LD(D_AGC_VAL);
+        double eb_sum1 = LD(D_EB_SUM1), eb_sum2 = LD(D_EB_SUM2), eb_ebno = LD(D_EB_EBNO);
+        double dly_s0 = LD(D_DLY_S0);
+        double d41_0 = LD(D_DLY41_0), d41_1 = LD(D_DLY41_1), d41_2 = LD(D_DLY41_2);
+        double d42_0 = LD(D_DLY42_0), d42_1 = LD(D_DLY42_1), d42_2 = LD(D_DLY42_2);
+        double d8_0 = LD(D_DLY8_0), d8_1 = LD(D_DLY8_1), d8_2 = LD(D_DLY8_2);
+        Biquad res = {LD(D_RES_X1), LD(D_RES_X2), LD(D_RES_Y1), LD(D_RES_Y2)};
+        const int agc_len = p.agc_len, eb_len = p.ebno_len;
+        const bool ebno_on = p.report_ebno != 0;
+        const double fbr = p.fb;
+        const double res_a1 = p.res_a1, res_a2 = p.res_a2, res_b0 = p.res_b0, res_b1 = p.res_b1, res_b2 = p.res_b2;
+        long long S = S0;
+        int p41 = (int)(S % (p.k41 + 1)), p8 = (int)(S % (p.k8 + 1));   // Delay<> ring positions (lock-step)
+        const int k41 = p.k41, k8 = p.k8;
+        const long long S_end = S + nB;
+        const int eb_from_j = (a.i1 - a.i0) - OQ_EBNO_TAIL;       // same read-out window as oqpsk_segment_kernel
+        __syncthreads();                                       // (1)
+        if (nB > 0) {
+            auto ring_rows = [&](long long tile, double *&g_agc, double *&g_e1, double *&g_e2) {
+                const long long s0 = tile * OQ_T;
+                g_agc = p.agc_ring + ((size_t)(s0 % agc_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
+                if (ebno_on) {
+                    g_e1 = p.ebno_e1 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
+                    g_e2 = p.ebno_e2 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
+                }
+            };
+            const unsigned ring_tx = (ebno_on ? 3u : 1u) * OQ_SM_RING;
+            auto ring_load = [&](long long tile) {                    // all lanes call; lane r moves row r of the tile
+                const int b = (int)(tile & 1);
+                fence_proxy_async();
+                if (lane == 0) mbar_expect_tx(&bars[b], ring_tx);
+                __syncwarp();
+                double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
+                ring_rows(tile, g_agc, g_e1, g_e2);
+                bulk_g2s(t_agc + (b * OQ_T + lane) * OQ_THREADS, g_agc, OQ_THREADS * 8, &bars[b]);
+                if (ebno_on) {
+                    bulk_g2s(t_e1 + (b * OQ_T + lane) * OQ_THREADS, g_e1, OQ_THREADS * 8, &bars[b]);
+                    bulk_g2s(t_e2 + (b * OQ_T + lane) * OQ_THREADS, g_e2, OQ_THREADS * 8, &bars[b]);
+                }
+            };
+            auto ring_store = [&](long long tile) {                   // write the (in-place updated) tile back to HBM
+                const int b = (int)(tile & 1);
+                fence_proxy_async();
+                __syncwarp();
+                double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
+                ring_rows(tile, g_agc, g_e1, g_e2);
+                bulk_s2g(g_agc, t_agc + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+                if (ebno_on) {
+                    bulk_s2g(g_e1, t_e1 + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+                    bulk_s2g(g_e2, t_e2 + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+                }
+                bulk_commit();
+            };
+            unsigned phases = 0u;
+#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
+            long long rt = S / OQ_T;                                  // current ring tile
+            bool ring_next_issued = false, ring_dirty = false;
+            ring_load(rt);
+            if ((rt + 1) * OQ_T < S_end) { ring_load(rt + 1); ring_next_issued = true; }
+            PP_WAIT((int)(rt & 1));
+            for (int j = 0; j < nB; j++) {
+                const int sl = j & 1;
+                const int ro = (int)(S & (OQ_T - 1));
+                const int rslot = (((int)(rt & 1)) * OQ_T + ro) * OQ_THREADS + lane;   // this sample's slot in the staged ring tiles
+                const double w41 = p.w41v[p41], w8 = p.w8v[p8];
+                p41++; if (p41 > k41) p41 = 0;
+                p8++; if (p8 > k8) p8 = 0;
+                nb_sync(BAR_Z + sl);                           // Z_j: FIR output of this sample
+                const double sre = HAND(sl, 0), sim = HAND(sl, 1);
+                const double dabval = sqrt(sre * sre + sim * sim);                // :461
+                if (ebno_on) {                                                    // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
+                    const double sq = dabval * dabval;
+                    eb_sum2 = eb_sum2 - t_e2[rslot]; eb_sum2 = eb_sum2 + fabs(sq); t_e2[rslot] = fabs(sq);
+                    eb_sum1 = eb_sum1 - t_e1[rslot]; eb_sum1 = eb_sum1 + fabs(dabval); t_e1[rslot] = fabs(dabval);
+                    // read-out over the last OQ_EBNO_TAIL samples of the launch only (see oqpsk_demod.cu)
+                    if (j >= eb_from_j) {
+                        const double e2val = eb_sum2 / ((double)eb_len), mean = eb_sum1 / ((double)eb_len);
+                        const double mean_sq = mean * mean;
+                        double var = (e2val) - (mean * mean);
+                        var -= (0.024709 * mean_sq);
+                        double mvr = (((Fs * mean_sq / (2.0 * fbr * var))) * 0.13743);
+                        if (mvr < 0.000000001) mvr = 0.000000001;
+                        double tebno = 10.0 * log10(mvr);
+                        if (isnan(tebno)) tebno = 50;
+                        if (tebno > 50.0) tebno = 50;
+                        if (tebno < 0.0) tebno = 0;
+                        eb_ebno = eb_ebno * 0.8 + 0.2 * tebno;
+                    }
+                }
+                {   // AGC::Update (DSP.cpp:370-379)
+                    agc_sum = agc_sum - t_agc[rslot];
+                    agc_sum = agc_sum + fabs(dabval);
+                    t_agc[rslot] = fabs(dabval);
+                    ring_dirty = true;
+                    agc_val = 1.414213562 / fmax(agc_sum / ((double)agc_len), 0.000001);
+                    agc_val = fmax(agc_val, 0.000001);
+                }
+                double2 sig2 = make_double2(sre * agc_val, sim * agc_val);        // :466
+                const double abval = hypot(sig2.x, sig2.y);                       // :469 std::abs
+                if (abval > 2.84) { const double g = (2.84 / abval); sig2 = make_double2(g * sig2.x, g * sig2.y); }   // :470
+                // ---- symbol timing, feed-forward part (:473-477)
+                const double ab2 = abval * abval;
+                const double st_diff = (0.0 * ab2 + (1.0 - 0.0) * dly_s0) - (ab2);    // Delay(1): weighting 0 -> x[n-1]
+                dly_s0 = ab2;
+                double st_d1out, st_d2out;
+                {
+                    const double older = (k41 == 3) ? d41_2 : (k41 == 2 ? d41_1 : d41_0);
+                    const double newer = (k41 == 3) ? d41_1 : (k41 == 2 ? d41_0 : st_diff);
+                    st_d1out = (w41 * newer + (1.0 - w41) * older);
+                    d41_2 = d41_1; d41_1 = d41_0; d41_0 = st_diff;
+                }
+                {
+                    const double older = (k41 == 3) ? d42_2 : (k41 == 2 ? d42_1 : d42_0);
+                    const double newer = (k41 == 3) ? d42_1 : (k41 == 2 ? d42_0 : st_d1out);
+                    st_d2out = (w41 * newer + (1.0 - w41) * older);
+                    d42_2 = d42_1; d42_1 = d42_0; d42_0 = st_d1out;
+                }
+                double st_eta = (st_d2out - st_diff) * st_d1out;
+                st_eta = biquad_update(res, st_eta, res_a1, res_a2, res_b0, res_b1, res_b2);
+                double d8out;
+                {
+                    const double older = (k8 == 3) ? d8_2 : (k8 == 2 ? d8_1 : d8_0);
+                    const double newer = (k8 == 3) ? d8_1 : (k8 == 2 ? d8_0 : st_eta);
+                    d8out = (w8 * newer + (1.0 - w8) * older);
+                    d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta;
+                }
+                // slot sl's E->C fields were last read by C(j-2), which precedes X_{j-1} -> Z_j: free
+                HAND(sl, 2) = sig2.x; HAND(sl, 3) = sig2.y; HAND(sl, 4) = st_eta; HAND(sl, 5) = d8out;
+                __threadfence_block();
+                nb_arrive(BAR_Y + sl);                         // Y_j
+                // ---- ring tile bookkeeping (warp-uniform)
+                S++;
+                if ((S & (OQ_T - 1)) == 0) {
+                    ring_store(rt);                                   // the finished tile goes back to HBM
+                    ring_dirty = false;
+                    rt++;
+                    if (S < S_end) {
+                        PP_WAIT((int)(rt & 1));                       // next tile (requested a tile ago)
+                        ring_next_issued = false;
+                        if ((rt + 1) * OQ_T < S_end) {
+                            bulk_wait_read_all();                     // the buffer being refilled must have been read out by its store
+                            ring_load(rt + 1); ring_next_issued = true;
+                        }
+                    }
+                }
+            }
+            if (ring_dirty) ring_store(rt);
+            if (ring_next_issued) PP_WAIT((int)((rt + 1) & 1));
+            bulk_wait_all();
+        }
+        LD(D_AGC_SUM) = agc_sum; LD(D_AGC_VAL) = agc_val;
+        LD(D_EB_SUM1) = eb_sum1; LD(D_EB_SUM2) = eb_sum2; LD(D_EB_EBNO) = eb_ebno;
+        LD(D_DLY_S0) = dly_s0;
+        LD(D_DLY41_0) = d41_0; LD(D_DLY41_1) = d41_1; LD(D_DLY41_2) = d41_2;
+        LD(D_DLY42_0) = d42_0; LD(D_DLY42_1) = d42_1; LD(D_DLY42_2) = d42_2;
+        LD(D_DLY8_0) = d8_0; LD(D_DLY8_1) = d8_1; LD(D_DLY8_2) = d8_2;
+        LD(D_RES_X1) = res.x1; LD(D_RES_X2) = res.x2; LD(D_RES_Y1) = res.y1; LD(D_RES_Y2) = res.y2;
+    }
+    // ======================================================================================= warp F: input + matched filter
+    else {
+        for (int k = 0; k < OQ_NT1; k++) {
+            const double vr = p.fir_re[(size_t)k * cpad + ch], vi = p.fir_im[(size_t)k * cpad + ch];
+            s_re[k * OQ_THREADS + lane] = vr; s_re[(k + OQ_NT1) * OQ_THREADS + lane] = vr;
+            s_im[k * OQ_THREADS + lane] = vi; s_im[(k + OQ_NT1) * OQ_THREADS + lane] = vi;
+        }
+        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
+        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
+        const int16_t *row = pcm + (size_t)ch * stride;
+        double2 *bb_row = p.bb + (size_t)ch * p.bbnfft;
+        const int bbn = p.bbnfft;
+        const bool cpu_reduce = p.cpu_reduce != 0;
+        auto pcm_bytes = [&](int tile) -> unsigned {
+            long long left = (long long)stride - (long long)tile * OQ_T;
+            if (left > OQ_T) left = OQ_T;
+            return left > 0 ? (unsigned)(left * 2) : 0u;
+        };
+        auto pcm_load = [&](int tile) {
+            const int b = tile & 1;
+            const unsigned nb = pcm_bytes(tile);
+            fence_proxy_async();
+            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
+            __syncwarp();
+            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
+        };
+        unsigned phases = 0u;
+        int pt = a.i0 / OQ_T;                                     // current PCM tile
+        bool pcm_next_issued = false;
+        pcm_load(pt);
+        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+        PP_WAIT(2 + (pt & 1));
+        double cc_re, cc_im;
+        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
+        bool pk_valid = false;
+        // 54 older terms of the first output: window ending at the slot of sample i0-1 ... the tail slot is that of i0-1
+        int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);             // slot of the newest sample entering output j (cval[i0+j-1])
+        double nfre = 0, nfim = 0;
+        if (nB > 0) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+        for (int i = a.i0; i < a.i1; i++) {
+            const int j = i - a.i0;
+            // ---- PCM sample from the staged tile
+            const int po = i & (OQ_T - 1);
+            if ((i >> 5) != pt) {                                 // entered the next PCM tile (warp-uniform)
+                pt = i >> 5;
+                PP_WAIT(2 + (pt & 1));
+                pcm_next_issued = false;
+                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+                pk_valid = false;
+            }
+            if (!pk_valid || (po & 7) == 0) {
+                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + (po >> 3) * 16);
+                pk_valid = true;
+            }
+            int cur_pcm;
+            {
+                const int k = po & 7;
+                const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
+                cur_pcm = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+                if (!live) cur_pcm = 0;
+            }
+            const double dval = ((double)cur_pcm) / 32768.0;                  // :390
+            // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
+            if (!(i == a.i0 && a.skip_a_first)) {
+                if (coarse_counter >= Fs || !cpu_reduce) {
+                    if (live) bb_row[bb_pos] = make_double2(cc_re * dval, cc_im * dval);
+                    bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
+                }
+            }
+            if (i == a.i1 - 1 && a.stop_after_a) break;
+            coarse_counter++;                                                 // :431
+            osc_next_frame(mc);                                               // :601
+            { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+            // ---- matched filter output of this sample (:456): 54 older terms were summed ahead, the newest term follows
+            // as soon as warp C has mixed sample i-1
+            if (j > 0) nb_sync(BAR_X + ((j - 1) & 1));        // X_{j-1}
+            nfre += c_taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += c_taps[54] * s_im[tail * OQ_THREADS + lane];
+            const int sl = j & 1;
+            // slot sl's F->E fields were read by E(j-2) before Y_{j-2} -> C(j-2) -> X_{j-1}: free
+            HAND(sl, 0) = nfre; HAND(sl, 1) = nfim;
+            __threadfence_block();
+            nb_arrive(BAR_Z + sl);                             // Z_j
+            tail++; if (tail >= OQ_NT1) tail = 0;
+            if (j + 1 < nB) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+        }
+        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
+        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp C
+        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
+    }
+    __syncthreads();                                           // (2) every warp is done with the FIR window
+    for (int k = warp; k < OQ_NT1; k += 4) {
+        p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
+        p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
+    }
+#undef PP_WAIT
+#undef HAND
+}
+
+int oqpsk_pipe_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s)
+{
+    const int grid = (p.n_channels + OQ_THREADS - 1) / OQ_THREADS;
+    const size_t smem = (size_t)PP_SM_TOTAL;
+    JB_CUDA(cudaFuncSetAttribute(oqpsk_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    oqpsk_pipe_kernel<<<grid, PP_THREADS, smem, s>>>(p, a, d_pcm, stride);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+#undef LD
+#undef LI
+} // namespace jb
