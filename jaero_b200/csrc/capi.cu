@@ -216,6 +216,8 @@ struct jaero_batch {
     long long launches;
     cudaStream_t own_stream;
     bool profiling;
+    // asynchronous coarse estimator (see jaero_batch_write_device)
+    bool async_cfe; cudaStream_t cfe_stream; cudaEvent_t ev_seg_done, ev_cfe_done[2]; int cfe_count; int bb_phys;
     bool use_pipe;              // 10500 bps: warp-specialised segment kernel (JAERO_OQPSK_PIPE=0 selects the single-warp one, for A/B profiling)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_seg, ev_cfe;
     double prof_samples;
@@ -285,8 +287,8 @@ __global__ void center_freq_kernel(DemodParams p, int channel, double freq_cente
     if (p.afc) set_m2(D(D_MC_FREQ));
     if ((D(D_M2_FREQ) - D(D_MC_FREQ)) > (p.lockingbw / 2.0)) set_m2(D(D_MC_FREQ) + (p.lockingbw / 2.0));
     if ((D(D_M2_FREQ) - D(D_MC_FREQ)) < (-p.lockingbw / 2.0)) set_m2(D(D_MC_FREQ) - (p.lockingbw / 2.0));
-    double2 *row = p.bb + (size_t)ch * p.bbnfft;
-    for (int j = 0; j < p.bbnfft; j++) row[j] = make_double2(0.0, 0.0);
+    double2 *row = p.bb + (size_t)ch * p.bb_len;
+    for (int j = 0; j < p.bb_len; j++) row[j] = make_double2(0.0, 0.0);
 }
 } // namespace
 
@@ -310,6 +312,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     b->own_stream = b->stream; b->profiling = false; b->prof_samples = 0;
     { const char *e = getenv("JAERO_OQPSK_PIPE"); b->use_pipe = !(e && e[0] == '0'); }
+    b->async_cfe = false; b->cfe_stream = 0; b->ev_seg_done = 0; b->ev_cfe_done[0] = b->ev_cfe_done[1] = 0; b->cfe_count = 0; b->bb_phys = 0;
     DemodParams &p = b->p;
     memset(&p, 0, sizeof p);
     p.kind = s->kind; p.n_channels = n_channels; p.cpad = (n_channels + 31) & ~31;
@@ -372,7 +375,29 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     if (p.report_ebno) { rc |= batch_alloc(b, &p.ebno_e1, (size_t)p.ebno_len * cp); rc |= batch_alloc(b, &p.ebno_e2, (size_t)p.ebno_len * cp); }
     rc |= batch_alloc(b, &p.fir_re, (size_t)(p.ntaps + 1) * cp);
     rc |= batch_alloc(b, &p.fir_im, (size_t)(p.ntaps + 1) * cp);
-    rc |= batch_alloc(b, &p.bb, (size_t)n_channels * p.bbnfft);
+    {
+        // The coarse estimate of a trigger is only consumed by channels that are unlocked, have no carrier detect or are about
+        // to re-centre (FreqOffsetEstimateSlot, oqpskdemodulator.cpp:629-677), so in steady state the estimator kernels can run
+        // on a second stream while the next segment is demodulated. Conditions: the warp-specialised 10500 bps kernel, the
+        // non-cpuReduce schedule, and a segment grid that is fully resident (a waiting CTA must never keep the estimator's
+        // CTAs from being scheduled). OFF unless JAERO_ASYNC_CFE=1: measured on B200 (4096 channels) the estimator's FP64 work,
+        // when it shares SMs with the latency-bound segment warps, slows both kernels by 3-4x (FP64 pipe contention).
+        cudaDeviceProp prop;
+        JB_CUDA(cudaGetDeviceProperties(&prop, device));
+        const char *e = getenv("JAERO_ASYNC_CFE");
+        const int grid = (n_channels + 31) / 32;
+        b->async_cfe = (e && e[0] == '1') && s->kind == JAERO_KIND_OQPSK && s->fb != 8400 && !s->cpu_reduce && b->use_pipe &&
+                       grid <= prop.multiProcessorCount;
+        p.bb_len = b->async_cfe ? p.bbnfft + p.bbnfft / 4 : p.bbnfft;
+        if (b->async_cfe) {
+            JB_CUDA(cudaStreamCreateWithFlags(&b->cfe_stream, cudaStreamNonBlocking));
+            JB_CUDA(cudaEventCreateWithFlags(&b->ev_seg_done, cudaEventDisableTiming));
+            JB_CUDA(cudaEventCreateWithFlags(&b->ev_cfe_done[0], cudaEventDisableTiming));
+            JB_CUDA(cudaEventCreateWithFlags(&b->ev_cfe_done[1], cudaEventDisableTiming));
+        }
+        rc |= batch_alloc(b, &p.cfe_flag, (size_t)1);
+    }
+    rc |= batch_alloc(b, &p.bb, (size_t)n_channels * p.bb_len);
     rc |= batch_alloc(b, &p.marg_ring, (size_t)p.marg_len * cp);
     rc |= batch_alloc(b, &p.mse_pm, (size_t)p.mse_len * cp);
     rc |= batch_alloc(b, &p.mse_ma, (size_t)p.mse_len * cp);
@@ -418,6 +443,10 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         int grp = 1024;
         if (const char *e = getenv("JAERO_CFE_GROUP")) grp = std::max(1, atoi(e));
         c.group = std::min(n_channels, grp);
+        if (c.nfft == 16384) {
+            const char *e = getenv("JAERO_CFE_CLUSTER");
+            if (!(e && e[0] == '0')) c.clusters = cfe_cluster_capacity();
+        }
         if (batch_alloc(b, &c.tw, (size_t)c.nfft) || batch_alloc(b, &c.work_a, (size_t)c.group * c.nfft) ||
             batch_alloc(b, &c.work_b, (size_t)c.group * c.nfft) || batch_alloc(b, &c.y, (size_t)n_channels * c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
         JB_CUDA(cudaMemcpyAsync(c.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
@@ -492,6 +521,9 @@ void jaero_batch_destroy(jaero_batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
+    if (b->cfe_stream) { cudaStreamSynchronize(b->cfe_stream); cudaStreamDestroy(b->cfe_stream); }
+    if (b->ev_seg_done) cudaEventDestroy(b->ev_seg_done);
+    for (int k = 0; k < 2; k++) if (b->ev_cfe_done[k]) cudaEventDestroy(b->ev_cfe_done[k]);
     for (void *q : b->allocs) cudaFree(q);
     cudaFree(b->d_stage); cudaFree(b->d_x);
     cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage);
@@ -593,6 +625,7 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
     auto launch = [&](int i0, int i1, bool stop_after_a, int bb0, int cc0) -> int {
         a.sample0 = b->samples; a.i0 = i0; a.i1 = i1; a.skip_a_first = resume ? 1 : 0; a.stop_after_a = stop_after_a ? 1 : 0;
         a.apply_cfe = resume ? 1 : 0; a.bb_pos = bb0; a.coarse_counter = cc0;
+        a.cfe_wait = (resume && b->async_cfe) ? b->cfe_count : 0;
         cudaEvent_t e0 = 0, e1 = 0;
         if (b->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
         int r = (p.kind == JAERO_KIND_OQPSK) ? ((b->use_pipe && !p.xpre) ? oqpsk_pipe_launch(p, a, d_pcm, stride, b->stream)
@@ -603,30 +636,50 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         a.new_write = 0;
         return r;
     };
-    int bb = b->bb_pos, cc = b->coarse_counter;
-    int seg_bb = bb, seg_cc = cc;                                  // counters at the start of the open segment
+    int bb = b->bb_pos, cc = b->coarse_counter, bbp = b->bb_phys;  // bb: bbcycbuff_ptr of the reference; bbp: slot in our ring
+    int seg_bb = bbp, seg_cc = cc;                                 // counters at the start of the open segment
+    bool cfe_in_flight = false;
     for (int i = 0; i < (int)n; i++) {
         // A(i): ring write + trigger test (oqpskdemodulator.cpp:410-429) — lock-step for the whole batch
         bool trigger = false;
         if (cc >= p.Fs || !p.cpu_reduce) {
             bb++; if (bb >= N) bb = 0;
+            bbp++; if (bbp >= p.bb_len) bbp = 0;
             if (bb % trig_every == 0) trigger = true;
         }
         if (trigger) {
             if (launch(seg_start, i + 1, true, seg_bb, seg_cc)) return JAERO_E_CUDA;
             b->samples += (i - seg_start);                         // samples whose B part has run
             cudaEvent_t c0 = 0, c1 = 0;
-            if (b->profiling) { cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventRecord(c0, b->stream); }
-            if (cfe_run(b->cfe, p, bb, b->stream, &b->launches)) return JAERO_E_CUDA;
-            if (b->profiling) { cudaEventRecord(c1, b->stream); b->ev_cfe.push_back({c0, c1}); }
+            int oldest = bbp + (p.bb_len - N); if (oldest >= p.bb_len) oldest -= p.bb_len;
+            cudaStream_t cs = b->async_cfe ? b->cfe_stream : b->stream;
+            if (b->async_cfe) {
+                JB_CUDA(cudaEventRecord(b->ev_seg_done, b->stream));
+                JB_CUDA(cudaStreamWaitEvent(cs, b->ev_seg_done, 0));
+            }
+            if (b->profiling) { cudaEventCreate(&c0); cudaEventCreate(&c1); cudaEventRecord(c0, cs); }
+            if (b->cfe.clusters > 0 ? cfe_cluster_run(b->cfe, p, oldest, std::min(b->cfe.clusters, p.n_channels), cs, &b->launches)
+                                    : cfe_run(b->cfe, p, oldest, cs, &b->launches)) return JAERO_E_CUDA;
+            if (b->profiling) { cudaEventRecord(c1, cs); b->ev_cfe.push_back({c0, c1}); }
+            if (b->async_cfe) {
+                b->cfe_count++;
+                if (cfe_mark_launch(p.cfe_flag, b->cfe_count, cs)) return JAERO_E_CUDA;
+                b->launches++;
+                JB_CUDA(cudaEventRecord(b->ev_cfe_done[b->cfe_count & 1], cs));
+                // the segment after the next one overwrites the quarter this estimate reads first: order the NEXT segment
+                // behind the PREVIOUS estimate (a no-op in steady state)
+                if (cfe_in_flight) JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_cfe_done[(b->cfe_count - 1) & 1], 0));
+                cfe_in_flight = true;
+            }
             cc = 0;                                                // :426
-            seg_start = i; resume = true; seg_bb = bb; seg_cc = 0;
+            seg_start = i; resume = true; seg_bb = bbp; seg_cc = 0;
         }
         cc++;                                                      // :431
     }
     if (launch(seg_start, (int)n, false, seg_bb, seg_cc)) return JAERO_E_CUDA;
     b->samples += ((int)n - seg_start);
-    b->bb_pos = bb; b->coarse_counter = cc;
+    b->bb_pos = bb; b->coarse_counter = cc; b->bb_phys = bbp;
+    if (cfe_in_flight) JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_cfe_done[b->cfe_count & 1], 0));   // join: a call leaves nothing in flight
     if (b->pre_on) {                                               // :608 mixer_fir_pre.SetFreq(mixer2_freq_sum/i)
         if (pre_finish_launch(b->pre, p.m2_freq_sum, (int)n, p.Fs, b->stream)) return JAERO_E_CUDA;
         b->launches++;

@@ -18,6 +18,8 @@
 // n<=128-point FFTs of a tile run as Stockham radix-8/4 passes with the butterflies in registers. FFT rounding differs from the
 // CPU oracle's radix-2 (different factorisation) at the 1e-13 level; the bin decision is integer.
 #include "demod_device.cuh"
+#include <cooperative_groups.h>
+#include <cstring>
 
 namespace jb {
 
@@ -112,7 +114,7 @@ __device__ __forceinline__ void tile_fft(double2 (*s)[MAXN + 1], int n, const do
 // P1 / P3: column pass. grid = (n2/TILE, channels)
 template <bool FUSED_INV_SQUARE>
 __global__ void __launch_bounds__(CFE_THREADS)
-cfe_col_kernel(CfePlan pl, const double2 *__restrict__ src, double2 *__restrict__ dst, size_t src_pitch, int rot, int ch0)
+cfe_col_kernel(CfePlan pl, const double2 *__restrict__ src, double2 *__restrict__ dst, size_t src_pitch, int rot, int ring_len, int ch0)
 {
     __shared__ double2 s[TILE][MAXN + 1];
     const int ch = blockIdx.y;
@@ -125,7 +127,7 @@ cfe_col_kernel(CfePlan pl, const double2 *__restrict__ src, double2 *__restrict_
     for (int e = threadIdx.x; e < n1 * TILE; e += CFE_THREADS) {
         const int r = e / TILE, cc = e - r * TILE;
         int n = n2 * r + c0 + cc;
-        if (!FUSED_INV_SQUARE) { n += rot; if (n >= N) n -= N; }
+        if (!FUSED_INV_SQUARE) { n += rot; if (n >= ring_len) n -= ring_len; }
         s[cc][r] = in[n];
     }
     __syncthreads();
@@ -253,15 +255,241 @@ cfe_search_kernel(CfePlan pl, DemodParams p)
     }
 }
 
-int cfe_run(const CfePlan &pl, const DemodParams &p, int bb_pos, cudaStream_t s, long long *launches)
+// ================================================================================================ cluster-resident estimator
+// nfft = 16384 (both OQPSK modes). One thread-block cluster of 4 CTAs owns one channel at a time and keeps the whole
+// 128 x 128 working matrix (256 KB of complex doubles) in the distributed shared memory of its four SMs through all three
+// transforms: CTA q holds 32 columns (column passes) or 32 rows (row passes); the three layout changes are pulls from
+// the peers' shared memory (DSMEM) with the four-step twiddle folded into the pull. HBM traffic per channel falls to the
+// ring read (256 KB, bulk-copied one channel ahead) plus the read-modify-write of y (2 x 128 KB), from eight 256 KB
+// matrix passes before.
+namespace cgx = cooperative_groups;
+
+static const int CC_CL = 4, CC_T = 512, CC_SEQ = 32, CC_RS = 145;             // cluster size, threads, sequences per CTA, row stride
+static const int CC_BUF = CC_SEQ * CC_RS * 16;                                // one working buffer (bytes)
+static const int CC_SM_L = 128 * 32 * 16;                                     // staged ring columns [r][cc]
+static const int CC_SM_TOTAL = 2 * CC_BUF + CC_SM_L + 2 * 128 * 16 + 64;
+
+__device__ __forceinline__ int cc_ph(int e) { return e + (e >> 3); }          // padded position inside a 128-point sequence
+
+// 32 x FFT-128 in place (same factorisation and arithmetic as tile_fft for n = 128: Stockham radix 8, 4, 4). Warp w owns
+// sequences w and w+16 through all three passes, so the passes are ordered by __syncwarp() only: each pass reads its
+// butterflies' inputs into registers, __syncwarp, writes the outputs back into the same rows. `last` receives
+// (sequence, position, value) of the final pass and normally stores it back (mask / square are fused there).
+template <bool INV, class Store>
+__device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 *__restrict__ tws, Store last)
+{
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    {   // radix 8, Ns = 1: lanes 0-15 -> sequence w, lanes 16-31 -> sequence w+16
+        double2 *row = buf + (w + (l & 16)) * CC_RS;
+        const int j = l & 15;
+        double2 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = row[cc_ph(j + 16 * t)];
+        __syncwarp();
+        dft8<INV>(v);
+#pragma unroll
+        for (int t = 0; t < 8; t++) row[cc_ph(8 * j + t)] = v[t];
+        __syncwarp();
+    }
+    double2 *r0 = buf + w * CC_RS, *r1 = buf + (w + 16) * CC_RS;
+    auto radix4 = [&](double2 &v0, double2 &v1, double2 &v2, double2 &v3, int k, int wm) {
+        double2 w1 = tws[(k * wm) & 127], w2 = tws[(2 * k * wm) & 127], w3 = tws[(3 * k * wm) & 127];
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        v1 = c_mul(v1, w1); v2 = c_mul(v2, w2); v3 = c_mul(v3, w3);
+        dft4<INV>(v0, v1, v2, v3);
+    };
+    {   // radix 4, Ns = 8 (both sequences, j = lane)
+        double2 a0 = r0[cc_ph(l)], a1 = r0[cc_ph(l + 32)], a2 = r0[cc_ph(l + 64)], a3 = r0[cc_ph(l + 96)];
+        double2 b0 = r1[cc_ph(l)], b1 = r1[cc_ph(l + 32)], b2 = r1[cc_ph(l + 64)], b3 = r1[cc_ph(l + 96)];
+        __syncwarp();
+        const int k = l & 7, ob = (l >> 3) * 32 + k;
+        radix4(a0, a1, a2, a3, k, 4); radix4(b0, b1, b2, b3, k, 4);
+        r0[cc_ph(ob)] = a0; r0[cc_ph(ob + 8)] = a1; r0[cc_ph(ob + 16)] = a2; r0[cc_ph(ob + 24)] = a3;
+        r1[cc_ph(ob)] = b0; r1[cc_ph(ob + 8)] = b1; r1[cc_ph(ob + 16)] = b2; r1[cc_ph(ob + 24)] = b3;
+        __syncwarp();
+    }
+    {   // radix 4, Ns = 32
+        double2 a0 = r0[cc_ph(l)], a1 = r0[cc_ph(l + 32)], a2 = r0[cc_ph(l + 64)], a3 = r0[cc_ph(l + 96)];
+        double2 b0 = r1[cc_ph(l)], b1 = r1[cc_ph(l + 32)], b2 = r1[cc_ph(l + 64)], b3 = r1[cc_ph(l + 96)];
+        __syncwarp();
+        radix4(a0, a1, a2, a3, l, 1); radix4(b0, b1, b2, b3, l, 1);
+        last(w, l, a0); last(w, l + 32, a1); last(w, l + 64, a2); last(w, l + 96, a3);
+        last(w + 16, l, b0); last(w + 16, l + 32, b1); last(w + 16, l + 64, b2); last(w + 16, l + 96, b3);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(CC_T)
+cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
+{
+    extern __shared__ __align__(128) unsigned char cc_smem[];
+    double2 *bufA = reinterpret_cast<double2 *>(cc_smem);
+    double2 *bufB = reinterpret_cast<double2 *>(cc_smem + CC_BUF);
+    double2 *bufL = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF);
+    double2 *tws = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF + CC_SM_L);
+    double2 *twl = tws + 128;                                                 // W_N^b, b < 128
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cc_smem + 2 * CC_BUF + CC_SM_L + 2 * 128 * 16);
+    cgx::cluster_group cluster = cgx::this_cluster();
+    const int q = (int)cluster.block_rank();
+    const int n_clusters = gridDim.x / CC_CL, cid = blockIdx.x / CC_CL;
+    const int N = 16384, ring_len = p.bb_len;
+    const double2 *__restrict__ twN = pl.tw;
+    if (threadIdx.x < 128) { tws[threadIdx.x] = twN[threadIdx.x * (N / 128)]; twl[threadIdx.x] = twN[threadIdx.x]; }
+    // four-step twiddle W_N^m, m = c*k1 < 16384, from the two shared tables: W_N^m = W_128^(m>>7) * W_N^(m&127)
+    auto twid = [&](int m) -> double2 { return c_mul(tws[m >> 7], twl[m & 127]); };
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    // peers' buffers
+    const double2 *rA[CC_CL], *rB[CC_CL];
+#pragma unroll
+    for (int s = 0; s < CC_CL; s++) { rA[s] = cluster.map_shared_rank(bufA, s); rB[s] = cluster.map_shared_rank(bufB, s); }
+
+    auto stage = [&](int ch) {             // bulk-copy this CTA's 32 columns of the linearised ring: 128 runs of 512 B
+        fence_proxy_async();
+        if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)CC_SM_L);
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            int n = oldest + 128 * threadIdx.x + 32 * q;
+            if (n >= ring_len) n -= ring_len;
+            if (n >= ring_len) n -= ring_len;
+            bulk_g2s(bufL + threadIdx.x * 32, p.bb + (size_t)ch * ring_len + n, 512u, bar);
+        }
+    };
+    unsigned parity = 0;
+    bool arrived = false;
+    if (cid < p.n_channels) stage(cid);
+    cluster.sync();                        // every CTA of the cluster is resident before the first remote access
+    for (int ch = cid; ch < p.n_channels; ch += n_clusters) {
+        mbar_wait(bar, parity); parity ^= 1u;
+        if (arrived) { cluster.barrier_wait(); arrived = false; }   // the peers have pulled the previous channel's P3 result out of A
+        // ---- columns of the ring -> A[cc][r]
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * i, r = e >> 5, cc = e & 31;
+            bufA[cc * CC_RS + cc_ph(r)] = bufL[r * 32 + cc];
+        }
+        __syncthreads();
+        if (ch + n_clusters < p.n_channels) stage(ch + n_clusters);
+        // ---- P1: column FFT over r, in place                                         A[cc][k1]
+        cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+        cluster.sync();
+        // rows k1 = 32q+kk, all c: B[kk][c] = A_src[cc][k1] * W_N^{c k1}
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;     // kk fastest: contiguous remote reads
+            const int c = 32 * s + cc, k1 = 32 * q + kk;
+            const double2 x = rA[s][cc * CC_RS + cc_ph(k1)];
+            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, twid(c * k1));
+        }
+        __syncthreads();
+        // ---- P2: row FFT over c -> mask (:99-100) -> row IFFT, in place               B[kk][c]
+        cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) {
+            const int k = (32 * q + f) + 128 * e;          // X[k1 + n1*k2]
+            if (!pl.is8400) { if (k >= pl.startbin && k <= pl.stopbin) v = make_double2(0.0, 0.0); }
+            else { const double w = pl.window[k]; v = make_double2(v.x * w, v.y * w); }
+            bufB[f * CC_RS + cc_ph(e)] = v;
+        });
+        cc_fft<true>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
+        cluster.sync();                    // every peer has finished reading A (it passed the pull above before its own P2)
+        // columns c = 32q+cc, all k1: A[cc][k1] = B_src[kk][c] * conj(W_N^{c k1})
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * (i & 1), cc = e & 31, kk = e >> 5, s = i >> 1;     // cc fastest: contiguous remote reads
+            const int c = 32 * q + cc, k1 = 32 * s + kk;
+            const double2 x = rB[s][kk * CC_RS + cc_ph(c)];
+            double2 w = twid(c * k1); w.y = -w.y;
+            bufA[cc * CC_RS + cc_ph(k1)] = c_mul(x, w);
+        }
+        __syncthreads();
+        // ---- P3: column IFFT over k1 -> square (:103) -> column FFT over r, in place  A[cc][k1]
+        cc_fft<true>(bufA, tws, [&](int f, int e, double2 v) {
+            bufA[f * CC_RS + cc_ph(e)] = make_double2(v.x * v.x - v.y * v.y, v.x * v.y + v.y * v.x);
+        });
+        cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+        cluster.sync();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;     // kk fastest: contiguous remote reads
+            const int c = 32 * s + cc, k1 = 32 * q + kk;
+            const double2 x = rA[s][cc * CC_RS + cc_ph(k1)];
+            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, twid(c * k1));
+        }
+        cluster.barrier_arrive();          // split barrier: this CTA is done reading its peers' A (waited on before A is refilled)
+        arrived = true;
+        __syncthreads();
+        // ---- P4: row FFT over c -> |.| -> 10 log10 -> smoothing into y (:105-108)      B
+        {
+            double *y = pl.y + (size_t)ch * N;
+            const bool bigchange = p.I[(size_t)I_ZERO_BB * p.cpad + ch] != 0;     // y[i]=20 pending (coarsefreqestimate.cpp:87)
+            double yo[8];                                                         // requested before the transform, consumed after it
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int e = threadIdx.x + CC_T * i, kk = e & 31, k2 = e >> 5;
+                yo[i] = bigchange ? 20.0 : y[(32 * q + kk) + 128 * ((k2 + 64) & 127)];
+            }
+            cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int e = threadIdx.x + CC_T * i, kk = e & 31, k2 = e >> 5;
+                const int i_sh = (32 * q + kk) + 128 * ((k2 + 64) & 127);         // fftshift (:105)
+                const double2 x = bufB[kk * CC_RS + cc_ph(k2)];
+                // 10*log10(max(|x|,1)) = 5*log10(max(|x|^2,1))
+                y[i_sh] = yo[i] * 0.9 + 0.1 * 5 * log10(fmax(x.x * x.x + x.y * x.y, 1.0));   // :108
+            }
+        }
+        __syncthreads();
+    }
+    if (arrived) cluster.barrier_wait();
+    cluster.sync();                        // no CTA leaves while a peer may still read its shared memory
+}
+
+int cfe_cluster_run(const CfePlan &pl, const DemodParams &p, int oldest, int n_clusters, cudaStream_t s, long long *launches)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(n_clusters * CC_CL)); cfg.blockDim = dim3(CC_T); cfg.dynamicSmemBytes = CC_SM_TOTAL; cfg.stream = s;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CC_CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    JB_CUDA(cudaLaunchKernelEx(&cfg, cfe_cluster_kernel, pl, p, oldest));
+    cfe_search_kernel<<<(p.n_channels + 3) / 4, 128, 0, s>>>(pl, p);
+    JB_CUDA(cudaGetLastError());
+    *launches += 2;
+    return 0;
+}
+// number of clusters that can be co-resident (0: the device cannot run the cluster kernel)
+int cfe_cluster_capacity()
+{
+    if (cudaFuncSetAttribute(cfe_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CC_SM_TOTAL) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(CC_CL * 64); cfg.blockDim = dim3(CC_T); cfg.dynamicSmemBytes = CC_SM_TOTAL;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CC_CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, cfe_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+__global__ void cfe_mark_kernel(int *flag, int value) { __threadfence(); atomicExch(flag, value); }
+int cfe_mark_launch(int *flag, int value, cudaStream_t s)
+{
+    cfe_mark_kernel<<<1, 1, 0, s>>>(flag, value);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// `oldest` = ring index of the oldest sample (the linearisation origin, oqpskdemodulator.cpp:418-424)
+int cfe_run(const CfePlan &pl, const DemodParams &p, int oldest, cudaStream_t s, long long *launches)
 {
     const int C = p.n_channels;
     for (int ch0 = 0; ch0 < C; ch0 += pl.group) {
         const int g = (C - ch0 < pl.group) ? C - ch0 : pl.group;
         dim3 gc(pl.n2 / TILE, g), gr(pl.n1 / TILE, g);
-        cfe_col_kernel<false><<<gc, CFE_THREADS, 0, s>>>(pl, p.bb, pl.work_a, (size_t)pl.nfft, bb_pos, ch0);
+        cfe_col_kernel<false><<<gc, CFE_THREADS, 0, s>>>(pl, p.bb, pl.work_a, (size_t)p.bb_len, oldest, p.bb_len, ch0);
         cfe_row_mask_kernel<<<gr, CFE_THREADS, 0, s>>>(pl, pl.work_a, pl.work_b);
-        cfe_col_kernel<true><<<gc, CFE_THREADS, 0, s>>>(pl, pl.work_b, pl.work_a, (size_t)pl.nfft, 0, 0);
+        cfe_col_kernel<true><<<gc, CFE_THREADS, 0, s>>>(pl, pl.work_b, pl.work_a, (size_t)pl.nfft, 0, pl.nfft, 0);
         cfe_row_logmag_kernel<<<gr, CFE_THREADS, 0, s>>>(pl, p, pl.work_a, ch0);
         *launches += 4;
     }

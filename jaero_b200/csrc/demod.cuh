@@ -55,6 +55,9 @@ struct DemodParams {
     int afc, sql, cpu_reduce, report_ebno;
     int ntaps;                        // 55 (OQPSK) / 2*SPS (MSK)
     int agc_len, ebno_len, bbnfft;
+    int bb_len;                       // entries per row of the coarse-estimator ring: nfft, or 5*nfft/4 when the estimator runs
+                                      // concurrently with the next segment (the extra quarter is the one being written)
+    int *cfe_flag;                    // device counter: coarse estimates completed (asynchronous estimator only)
     int marg_len, dt_len, mse_len;    // 800/401/400 (OQPSK) ; SPS / SPS/2+1 / 600 (MSK)
     int sps;                          // MSK: int(Fs/fb)
     double correctionfactor;          // MSK
@@ -67,7 +70,7 @@ struct DemodParams {
     double *D; int *I;
     double *agc_ring, *ebno_e1, *ebno_e2;
     double *fir_re, *fir_im;          // [(ntaps+1)][cpad]
-    double2 *bb;                      // [ch][bbnfft]   (channel-major: rows feed the FFT directly)
+    double2 *bb;                      // [ch][bb_len]   (channel-major: rows feed the FFT directly)
     double *marg_ring, *mse_pm, *mse_ma;
     double2 *dt_ring;
     double2 *dsmpl_ring;              // MSK delayedsmpl [(sps+1)][cpad]
@@ -89,6 +92,8 @@ struct SegmentArgs {
     int apply_cfe;                    // run FreqOffsetEstimateSlot(cfe_est_out[ch]) before anything else
     int bb_pos, coarse_counter;       // bbcycbuff_ptr, coarseCounter at entry
     int new_write;                    // first launch of a writeData call: latch lastmse
+    int cfe_wait;                     // >0: the estimate consumed by apply_cfe is produced concurrently; a channel that needs
+                                      // it waits until *cfe_flag >= cfe_wait
 };
 
 int demod_set_taps(const double *taps, int n);
@@ -104,8 +109,12 @@ struct CfePlan {
     double2 *work_a, *work_b;   // [group][nfft]
     double *y;          // [ch][nfft]  smoothed log spectrum (fft-shifted order, as the reference keeps it)
     double *window;     // 8400 only
+    int clusters;       // >0: nfft 16384 runs in the cluster-resident kernel with this many co-resident clusters
     int group;          // channels per pass group (sized so the work buffers stay L2-resident)
 };
-int cfe_run(const CfePlan &plan, const DemodParams &p, int bb_pos, cudaStream_t s, long long *launches);
+int cfe_run(const CfePlan &plan, const DemodParams &p, int oldest, cudaStream_t s, long long *launches);
+int cfe_mark_launch(int *flag, int value, cudaStream_t s);
+int cfe_cluster_run(const CfePlan &plan, const DemodParams &p, int oldest, int n_clusters, cudaStream_t s, long long *launches);
+int cfe_cluster_capacity();
 
 } // namespace jb

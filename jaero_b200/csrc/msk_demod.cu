@@ -70,8 +70,8 @@ msk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__re
                 if (mc.freq < p.lockingbw / 2.0) osc_set_freq(mc, p.lockingbw / 2.0, p.Fs);
                 if (mc.freq > (p.Fs / 2.0 - p.lockingbw / 2.0)) osc_set_freq(mc, p.Fs / 2.0 - p.lockingbw / 2.0, p.Fs);
                 LI(I_EMPTYING) = 4; LI(I_ZERO_BB) = 1;                                   // bigchange()
-                double2 *rowz = p.bb + (size_t)ch * p.bbnfft;
-                for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);    // :507
+                double2 *rowz = p.bb + (size_t)ch * p.bb_len;
+                for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);    // :507
             }
         } else countdown = 4;
         if (mse > p.signalthreshold) sig_false++; else sig_true++;                       // :516-517
@@ -91,8 +91,8 @@ msk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__re
         if (!(i == a.i0 && a.skip_a_first)) {                                            // :350-367
             if (coarse_counter >= p.Fs || !p.cpu_reduce) {
                 const int t = osc_index(mc.ptr);
-                p.bb[(size_t)ch * p.bbnfft + bb_pos] = make_double2(p.cos_t[t] * dval, p.sin_t[t] * dval);
-                bb_pos++; if (bb_pos >= p.bbnfft) bb_pos = 0;
+                p.bb[(size_t)ch * p.bb_len + bb_pos] = make_double2(p.cos_t[t] * dval, p.sin_t[t] * dval);
+                bb_pos++; if (bb_pos >= p.bb_len) bb_pos = 0;
             }
         }
         if (i == a.i1 - 1 && a.stop_after_a) break;

@@ -143,8 +143,8 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
                 if (mc.freq > (p.Fs / 2.0 - p.lockingbw / 2.0)) osc_set_freq(mc, p.Fs / 2.0 - p.lockingbw / 2.0, p.Fs);
                 LI(I_EMPTYING) = 4;                                       // CoarseFreqEstimate::bigchange (coarsefreqestimate.cpp:84-88)
                 LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
-                double2 *rowz = p.bb + (size_t)ch * p.bbnfft;             // :667 bbcycbuff[j]=0
-                if (live) for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);
+                double2 *rowz = p.bb + (size_t)ch * p.bb_len;             // :667 bbcycbuff[j]=0
+                if (live) for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);
             }
         } else countdown = 4;
         if (mse > p.signalthreshold) sig_false++; else sig_true++;       // :674-675
@@ -157,8 +157,8 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
     const bool ebno_on = p.report_ebno != 0;
     const int16_t *row = pcm + (size_t)ch * stride;
-    double2 *bb_row = p.bb + (size_t)ch * p.bbnfft;
-    const int bbn = p.bbnfft;
+    double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
+    const int bbn = p.bb_len;
     const bool cpu_reduce = p.cpu_reduce != 0;
     const double Fs = p.Fs, fbr = p.fb, thr = p.signalthreshold, ee = p.ee;
     const double res_a1 = p.res_a1, res_a2 = p.res_a2, res_b0 = p.res_b0, res_b1 = p.res_b1, res_b2 = p.res_b2;

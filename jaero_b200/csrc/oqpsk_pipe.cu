@@ -86,7 +86,20 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             const double mse = LD(D_MSE);
             const int dcd = LI(I_DCD);
             int countdown = LI(I_COUNTDOWN), countdown2 = LI(I_COUNTDOWN2);
-            const double est = p.cfe_est_out[ch];
+            double est = 0.0;
+            if (a.cfe_wait > 0) {
+                // The estimator of this trigger runs concurrently (capi.cu). Its result only enters the arithmetic below when
+                // the channel is unlocked / has no carrier detect, and its state (y[], emptyingcountdown) is only touched by
+                // the AFC re-centre: channels in neither case proceed without it.
+                const bool recentre = (p.afc) && (mse < p.signalthreshold) && (fabs(m2.freq - mc.freq) > 3.0) && (countdown <= 0);
+                const bool need = (mse > p.signalthreshold) || (!dcd) || recentre;
+                if (__any_sync(0xffffffffu, need)) {
+                    const volatile int *flag = p.cfe_flag;
+                    while (*flag < a.cfe_wait) __nanosleep(256);
+                    __threadfence();
+                }
+                if (need) est = __ldcg(p.cfe_est_out + ch);
+            } else est = p.cfe_est_out[ch];
             if ((mse < p.signalthreshold) && (!dcd)) {                        // :642-650
                 if (countdown2 > 0) countdown2--;
                 else osc_set_freq(m2, mc.freq + est, p.Fs);
@@ -101,8 +114,8 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     if (mc.freq > (p.Fs / 2.0 - p.lockingbw / 2.0)) osc_set_freq(mc, p.Fs / 2.0 - p.lockingbw / 2.0, p.Fs);
                     LI(I_EMPTYING) = 4;                                       // CoarseFreqEstimate::bigchange (coarsefreqestimate.cpp:84-88)
                     LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
-                    double2 *rowz = p.bb + (size_t)ch * p.bbnfft;             // :667 bbcycbuff[j]=0
-                    if (live) for (int j = 0; j < p.bbnfft; j++) rowz[j] = make_double2(0.0, 0.0);
+                    double2 *rowz = p.bb + (size_t)ch * p.bb_len;             // :667 bbcycbuff[j]=0
+                    if (live) for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);
                     LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp F reloads mixer_center after the barrier
                 }
             } else countdown = 4;
@@ -460,8 +473,8 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
         int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
         const int16_t *row = pcm + (size_t)ch * stride;
-        double2 *bb_row = p.bb + (size_t)ch * p.bbnfft;
-        const int bbn = p.bbnfft;
+        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
+        const int bbn = p.bb_len;
         const bool cpu_reduce = p.cpu_reduce != 0;
         auto pcm_bytes = [&](int tile) -> unsigned {
             long long left = (long long)stride - (long long)tile * OQ_T;
