@@ -12,28 +12,29 @@
 //   * the symbol-rate tail after the carrier update (bias rotate, 400-symbol delay, MSE, soft bits) feeds nothing back
 //     inside a call.
 //
-// Four warps of one CTA each own a slice of the per-sample work of the same 32 channels (lane = channel in every warp)
+// Five warps of one CTA each own a slice of the per-sample work of the same 32 channels (lane = channel in every warp)
 // and hand their results to the next warp through shared memory, ordered by named barriers (bar.arrive / bar.sync on
 // alternating ids, one producer warp + one consumer warp per barrier):
 //
 //   warp F  PCM tile, coarse-estimator ring write (mixer_center), 55-tap FIR of the mixed samples        -> sig2raw
 //   warp E  EbNo + AGC running sums (TMA-staged ring tiles), AGC gain, clip, timing feed-forward chain     -> sig2, st_eta, d8out
-//   warp C  symbol-timing PLL (arg, NCO nudges), strobe interpolation, carrier error + loop filter, NCOs,
-//           mixes the NEXT input sample and puts it into the FIR window                                     -> cval, (pt_qpsk, ct_ec)
+//   warp T  symbol-timing PLL: arg of the timing-error phasor, st_osc nudges, strobe test                  -> (strobe, fraction)
+//   warp K  strobe interpolation, carrier error + loop filter, carrier NCO; mixes the NEXT input sample
+//           and puts it into the FIR window                                                                 -> cval, (pt_qpsk, ct_ec)
 //   warp S  marg MA(800), 400-symbol delay, bias rotate, MSE, soft bits
 //
-// While C works on sample n, E and F already work on sample n+1 and S on sample n (or n-1): the time per sample drops
-// from the sum of the four slices to (about) the longest one.
+// The only loop that remains serial is K(n-1) -> newest FIR tap -> E(n+1) -> T(n+1) -> K(n+1): it advances two samples per
+// turn, and K(n) runs inside it. F, S and the bulk of the FIR are off that loop entirely.
 #include "demod_device.cuh"
 
 namespace jb {
 
-static const int PP_THREADS = 128;
+static const int PP_THREADS = 160;
 // shared memory map (bytes): FIR windows | ring tiles x6 | PCM tiles x2 | mbarriers | hand-off slots
 static const int PP_SM_HAND = 2 * 12 * 32 * 8;     // [2 slots][12 doubles][32 lanes]
 static const int PP_SM_TOTAL = OQ_SM_TOTAL + PP_SM_HAND;
 // named barriers (0 is __syncthreads)
-enum { BAR_X = 1, BAR_Y = 3, BAR_Z = 5, BAR_W = 7, BAR_V = 9 };
+enum { BAR_X = 1, BAR_YT = 3, BAR_Z = 5, BAR_W = 7, BAR_V = 9, BAR_YK = 11, BAR_U = 13 };
 
 __device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -67,14 +68,13 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const double Fs = p.Fs;
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     // hand-off slot layout: slot s, field f -> hand[(s * 12 + f) * 32 + lane]
-    //   f 0,1: sig2raw (F->E)   f 2..5: sig2.x, sig2.y, st_eta, d8out (E->C)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (C->S)
+    //   f 0,1: sig2raw (F->E)   f 2,3: sig2 (E->K)   f 4,5: st_eta, d8out (E->T)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (K->S)
+    //   f 10,11: strobe flag, FractionOfSampleItPassesBy (T->K)
 #define HAND(s, f) hand[((s) * 12 + (f)) * 32 + lane]
 
-    // ======================================================================================= warp C: feedback loops
-    if (warp == 2) {
+    // ======================================================================================= warp K: carrier loop
+    if (warp == 3) {
         Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
-        Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
-        Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
         Biquad lf = {LD(D_LF_X1), LD(D_LF_X2), LD(D_LF_Y1), LD(D_LF_Y2)};
         double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
         double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
@@ -138,9 +138,8 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 const int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
                 return ((double)v) / 32768.0;
             };
-            double c2_re, c2_im, cs_re, cs_im;
+            double c2_re, c2_im;
             { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
-            { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
             int fir_pos = (int)(S0 % OQ_NT1);                  // slot of the sample being mixed
             {   // cval of the first sample (:453)
                 const double dval = dval_at(a.i0);
@@ -151,26 +150,20 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 __threadfence_block();
                 nb_arrive(BAR_X + 0);                          // X_0
             }
-            const double ee = p.ee, fbr = p.fb;
+            const double fbr = p.fb;
             for (int j = 0; j < nB; j++) {
                 const int sl = j & 1;
                 // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
                 const int m2_spec = osc_next_index(m2);
                 const double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
                 const double dnext = (j + 1 < nB) ? dval_at(a.i0 + j + 1) : 0.0;
-                nb_sync(BAR_Y + sl);                           // Y_j: sig2, st_eta, d8out of this sample
+                nb_sync(BAR_YK + sl);                          // sig2 of this sample (warp E)
                 double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
-                const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
-                const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
-                const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
-                osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
-                osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0); // :482
-                if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);
-                if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), Fs);
+                nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
+                const double strobe = HAND(sl, 10), frac = HAND(sl, 11);
                 if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
-                double frac;
                 double sy_flag = 0.0, sy_x = 0.0, sy_y = 0.0, sy_ec = 0.0;
-                if (osc_have_passed_point(st, ee, frac)) {                        // :488
+                if (strobe != 0.0) {                                              // :488
                     const double pt_last = frac, pt_this = 1.0 - pt_last;
                     const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
                     yui ^= 1;                                                     // yui++; yui%=2;
@@ -197,7 +190,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     }
                 }
                 sig2_last = sig2;                                                 // :596
-                osc_next_frame(m2); osc_next_frame(st); osc_next_frame(sr);       // :600-603 (mixer_center lives in warp F)
+                osc_next_frame(m2);                                               // :600 (st_osc / st_osc_ref live in warp T, mixer_center in warp F)
                 {
                     const int t = osc_index(m2.ptr);
                     if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
@@ -210,7 +203,6 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     __threadfence_block();
                     nb_arrive(BAR_X + ((j + 1) & 1));          // X_{j+1}
                 }
-                { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
                 // symbol hand-off to warp S (slot reuse is gated by V)
                 if (j >= 2) nb_sync(BAR_V + sl);               // V_{j-2}: S has read slot sl
                 HAND(sl, 6) = sy_x; HAND(sl, 7) = sy_y; HAND(sl, 8) = sy_ec; HAND(sl, 9) = sy_flag;
@@ -222,15 +214,13 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             nb_sync(BAR_V + ((nB - 1) & 1));                   // V_{nB-1}
         }
         LD(D_M2_PTR) = m2.ptr; LD(D_M2_STEP) = m2.step; LD(D_M2_FREQ) = m2.freq; LD(D_M2_LAST) = m2.last;
-        LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
-        LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
         LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
         LD(D_SIG2L_RE) = sig2_last.x; LD(D_SIG2L_IM) = sig2_last.y;
         LD(D_PTD_RE) = pt_d.x; LD(D_PTD_IM) = pt_d.y;
         LI(I_YUI) = yui; LI(I_SIG2L_INIT) = sig2l_init;
     }
     // ======================================================================================= warp S: symbol-rate tail
-    else if (warp == 3) {
+    else if (warp == 4) {
         double marg_sum = LD(D_MARG_SUM), marg_val = LD(D_MARG_VAL);
         double pm_sum = LD(D_MSE_PM_SUM), ma_sum = LD(D_MSE_MA_SUM), mse = LD(D_MSE);
         double lastmse = LD(D_LASTMSE);
@@ -239,6 +229,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         if (a.new_write) lastmse = mse;                                       // oqpskdemodulator.cpp:339
         const int marg_len = p.marg_len, dt_len = p.dt_len, mse_len = p.mse_len;
         const double thr = p.signalthreshold;
+        const double r_marg = 1.0 / ((double)marg_len), r_mse = 1.0 / ((double)mse_len);
         double sy_marg_old = p.marg_ring[(size_t)marg_pos * cpad + ch];
         double sy_pm_old = p.mse_pm[(size_t)mse_pos * cpad + ch];
         double sy_ma_old = p.mse_ma[(size_t)mse_pos * cpad + ch];
@@ -259,7 +250,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     marg_sum = marg_sum + (ct_ec);
                     p.marg_ring[(size_t)marg_pos * cpad + ch] = (ct_ec);
                     marg_pos++; if (marg_pos >= marg_len) marg_pos = 0;
-                    marg_val = marg_sum / ((double)marg_len);
+                    marg_val = div_exact(marg_sum, (double)marg_len, r_marg);
                 }
                 {   // dt.update(pt_qpsk): 400-symbol delay (:536, DSP.h:455-460)
                     p.dt_ring[(size_t)dt_pos * cpad + ch] = pt_qpsk;
@@ -271,7 +262,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     const size_t e = (size_t)mse_pos * cpad + ch;
                     const double ab = hypot(pt_qpsk.x, pt_qpsk.y);
                     pm_sum = pm_sum - sy_pm_old; pm_sum = pm_sum + fabs(ab); p.mse_pm[e] = fabs(ab);
-                    double mu = pm_sum / ((double)mse_len);
+                    double mu = div_exact(pm_sum, (double)mse_len, r_mse);
                     if (mu < 0.000001) mu = 0.000001;
                     const double r2 = sqrt(2.0);
                     const double tre = (r2 * pt_qpsk.x) / mu, tim = (r2 * pt_qpsk.y) / mu;
@@ -279,7 +270,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     const double v = (tda * tda) + (tdb * tdb);
                     ma_sum = ma_sum - sy_ma_old; ma_sum = ma_sum + fabs(v); p.mse_ma[e] = fabs(v);
                     mse_pos++; if (mse_pos >= mse_len) mse_pos = 0;
-                    mse = ma_sum / ((double)mse_len);
+                    mse = div_exact(ma_sum, (double)mse_len, r_mse);
                 }
                 // operands of the next strobe pair (slots written >= 400 symbols ago)
                 sy_marg_old = p.marg_ring[(size_t)marg_pos * cpad + ch];
@@ -302,6 +293,36 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
         LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
     }
+    // ======================================================================================= warp T: symbol-timing PLL
+    else if (warp == 2) {
+        Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
+        Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
+        __syncthreads();                                       // (1)
+        const double ee = p.ee;
+        double cs_re, cs_im;
+        { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+        for (int j = 0; j < nB; j++) {
+            const int sl = j & 1;
+            nb_sync(BAR_YT + sl);                              // st_eta, d8out of this sample (warp E)
+            const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
+            const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
+            const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
+            osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
+            osc_advance_fraction_of_wave(st, div_exact(-st_angle_error * 0.01, 360.0, 1.0 / 360.0)); // :482
+            if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);
+            if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), Fs);
+            double frac = 0.0;
+            const bool strobe = osc_have_passed_point(st, ee, frac);          // :488
+            // slot sl's T->K fields were read by K(j-2), which precedes X_{j-1} -> Z_j -> (E) -> this point: free
+            HAND(sl, 10) = strobe ? 1.0 : 0.0; HAND(sl, 11) = frac;
+            __threadfence_block();
+            nb_arrive(BAR_U + sl);
+            osc_next_frame(st); osc_next_frame(sr);                           // :602-603
+            { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+        }
+        LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
+        LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
+    }
     // ======================================================================================= warp E: envelope chain
     else if (warp == 1) {
         double agc_sum = LD(D_AGC_SUM), agc_val = LD(D_AGC_VAL);
@@ -313,7 +334,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         Biquad res = {LD(D_RES_X1), LD(D_RES_X2), LD(D_RES_Y1), LD(D_RES_Y2)};
         const int agc_len = p.agc_len, eb_len = p.ebno_len;
         const bool ebno_on = p.report_ebno != 0;
-        const double fbr = p.fb;
+        const double fbr = p.fb, r_agc = 1.0 / ((double)agc_len);
         const double res_a1 = p.res_a1, res_a2 = p.res_a2, res_b0 = p.res_b0, res_b1 = p.res_b1, res_b2 = p.res_b2;
         long long S = S0;
         int p41 = (int)(S % (p.k41 + 1)), p8 = (int)(S % (p.k8 + 1));   // Delay<> ring positions (lock-step)
@@ -398,7 +419,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     agc_sum = agc_sum + fabs(dabval);
                     t_agc[rslot] = fabs(dabval);
                     ring_dirty = true;
-                    agc_val = 1.414213562 / fmax(agc_sum / ((double)agc_len), 0.000001);
+                    agc_val = 1.414213562 / fmax(div_exact(agc_sum, (double)agc_len, r_agc), 0.000001);
                     agc_val = fmax(agc_val, 0.000001);
                 }
                 double2 sig2 = make_double2(sre * agc_val, sim * agc_val);        // :466
@@ -430,10 +451,11 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     d8out = (w8 * newer + (1.0 - w8) * older);
                     d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta;
                 }
-                // slot sl's E->C fields were last read by C(j-2), which precedes X_{j-1} -> Z_j: free
+                // slot sl's fields were last read by T(j-2) and K(j-2), which precede X_{j-1} -> Z_j: free
                 HAND(sl, 2) = sig2.x; HAND(sl, 3) = sig2.y; HAND(sl, 4) = st_eta; HAND(sl, 5) = d8out;
                 __threadfence_block();
-                nb_arrive(BAR_Y + sl);                         // Y_j
+                nb_arrive(BAR_YT + sl);                        // timing inputs -> warp T
+                nb_arrive(BAR_YK + sl);                        // sig2 -> warp K
                 // ---- ring tile bookkeeping (warp-uniform)
                 S++;
                 if ((S & (OQ_T - 1)) == 0) {
@@ -554,7 +576,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
-    for (int k = warp; k < OQ_NT1; k += 4) {
+    for (int k = warp; k < OQ_NT1; k += 5) {
         p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
         p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
     }
