@@ -267,7 +267,7 @@ namespace cgx = cooperative_groups;
 static const int CC_CL = 4, CC_T = 512, CC_SEQ = 32, CC_RS = 145;             // cluster size, threads, sequences per CTA, row stride
 static const int CC_BUF = CC_SEQ * CC_RS * 16;                                // one working buffer (bytes)
 static const int CC_SM_L = 128 * 32 * 16;                                     // staged ring columns [r][cc]
-static const int CC_SM_TOTAL = 2 * CC_BUF + CC_SM_L + 2 * 128 * 16 + 64;
+static const int CC_SM_TOTAL = 2 * CC_BUF + CC_SM_L + 128 * 16 + 64;
 
 __device__ __forceinline__ int cc_ph(int e) { return e + (e >> 3); }          // padded position inside a 128-point sequence
 
@@ -327,16 +327,16 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
     double2 *bufB = reinterpret_cast<double2 *>(cc_smem + CC_BUF);
     double2 *bufL = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF);
     double2 *tws = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF + CC_SM_L);
-    double2 *twl = tws + 128;                                                 // W_N^b, b < 128
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cc_smem + 2 * CC_BUF + CC_SM_L + 2 * 128 * 16);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cc_smem + 2 * CC_BUF + CC_SM_L + 128 * 16);
     cgx::cluster_group cluster = cgx::this_cluster();
     const int q = (int)cluster.block_rank();
     const int n_clusters = gridDim.x / CC_CL, cid = blockIdx.x / CC_CL;
     const int N = 16384, ring_len = p.bb_len;
     const double2 *__restrict__ twN = pl.tw;
-    if (threadIdx.x < 128) { tws[threadIdx.x] = twN[threadIdx.x * (N / 128)]; twl[threadIdx.x] = twN[threadIdx.x]; }
-    // four-step twiddle W_N^m, m = c*k1 < 16384, from the two shared tables: W_N^m = W_128^(m>>7) * W_N^(m&127)
-    auto twid = [&](int m) -> double2 { return c_mul(tws[m >> 7], twl[m & 127]); };
+    if (threadIdx.x < 128) tws[threadIdx.x] = twN[threadIdx.x * (N / 128)];
+    // The four-step twiddles W_N^(c*k1) are read from the same table the reference-order transforms use (a product of two
+    // smaller tables breaks the exact conjugate symmetry of the table and with it the estimator's tie-breaks on symmetric
+    // spectra). Their indices do not depend on the data, so the loads are issued ahead of the cluster barrier they follow.
     if (threadIdx.x == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -373,6 +373,12 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
         if (ch + n_clusters < p.n_channels) stage(ch + n_clusters);
         // ---- P1: column FFT over r, in place                                         A[cc][k1]
         cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+        double2 tw8[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;
+            tw8[i] = __ldg(&twN[((32 * s + cc) * (32 * q + kk)) & (N - 1)]);
+        }
         cluster.sync();
         // rows k1 = 32q+kk, all c: B[kk][c] = A_src[cc][k1] * W_N^{c k1}
 #pragma unroll
@@ -380,7 +386,7 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
             const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;     // kk fastest: contiguous remote reads
             const int c = 32 * s + cc, k1 = 32 * q + kk;
             const double2 x = rA[s][cc * CC_RS + cc_ph(k1)];
-            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, twid(c * k1));
+            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, tw8[i]);
         }
         __syncthreads();
         // ---- P2: row FFT over c -> mask (:99-100) -> row IFFT, in place               B[kk][c]
@@ -391,6 +397,11 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
             bufB[f * CC_RS + cc_ph(e)] = v;
         });
         cc_fft<true>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * (i & 1), cc = e & 31, kk = e >> 5, s = i >> 1;
+            tw8[i] = __ldg(&twN[((32 * q + cc) * (32 * s + kk)) & (N - 1)]);
+        }
         cluster.sync();                    // every peer has finished reading A (it passed the pull above before its own P2)
         // columns c = 32q+cc, all k1: A[cc][k1] = B_src[kk][c] * conj(W_N^{c k1})
 #pragma unroll
@@ -398,7 +409,7 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
             const int e = threadIdx.x + CC_T * (i & 1), cc = e & 31, kk = e >> 5, s = i >> 1;     // cc fastest: contiguous remote reads
             const int c = 32 * q + cc, k1 = 32 * s + kk;
             const double2 x = rB[s][kk * CC_RS + cc_ph(c)];
-            double2 w = twid(c * k1); w.y = -w.y;
+            double2 w = tw8[i]; w.y = -w.y;
             bufA[cc * CC_RS + cc_ph(k1)] = c_mul(x, w);
         }
         __syncthreads();
@@ -407,13 +418,18 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
             bufA[f * CC_RS + cc_ph(e)] = make_double2(v.x * v.x - v.y * v.y, v.x * v.y + v.y * v.x);
         });
         cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;
+            tw8[i] = __ldg(&twN[((32 * s + cc) * (32 * q + kk)) & (N - 1)]);
+        }
         cluster.sync();
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;     // kk fastest: contiguous remote reads
             const int c = 32 * s + cc, k1 = 32 * q + kk;
             const double2 x = rA[s][cc * CC_RS + cc_ph(k1)];
-            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, twid(c * k1));
+            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, tw8[i]);
         }
         cluster.barrier_arrive();          // split barrier: this CTA is done reading its peers' A (waited on before A is refilled)
         arrived = true;

@@ -16,9 +16,10 @@
 // and hand their results to the next warp through shared memory, ordered by named barriers (bar.arrive / bar.sync on
 // alternating ids, one producer warp + one consumer warp per barrier):
 //
-//   warp F  PCM tile, coarse-estimator ring write (mixer_center), 55-tap FIR of the mixed samples        -> sig2raw
+//   warp F  55-tap FIR of the mixed samples                                                                -> sig2raw
 //   warp E  EbNo + AGC running sums (TMA-staged ring tiles), AGC gain, clip, timing feed-forward chain     -> sig2, st_eta, d8out
-//   warp T  symbol-timing PLL: arg of the timing-error phasor, st_osc nudges, strobe test                  -> (strobe, fraction)
+//   warp T  input: PCM tiles (TMA), coarse-estimator ring write (mixer_center); symbol-timing PLL: arg of
+//           the timing-error phasor, st_osc nudges, strobe test                                            -> dval, (strobe, fraction)
 //   warp K  strobe interpolation, carrier error + loop filter, carrier NCO; mixes the NEXT input sample
 //           and puts it into the FIR window                                                                 -> cval, (pt_qpsk, ct_ec)
 //   warp S  marg MA(800), 400-symbol delay, bias rotate, MSE, soft bits
@@ -31,7 +32,8 @@ namespace jb {
 
 static const int PP_THREADS = 160;
 // shared memory map (bytes): FIR windows | ring tiles x6 | PCM tiles x2 | mbarriers | hand-off slots
-static const int PP_SM_HAND = 2 * 12 * 32 * 8;     // [2 slots][12 doubles][32 lanes]
+static const int PP_HF = 14;                        // doubles per lane in a hand-off slot
+static const int PP_SM_HAND = 2 * PP_HF * 32 * 8;  // [2 slots][PP_HF doubles][32 lanes]
 static const int PP_SM_TOTAL = OQ_SM_TOTAL + PP_SM_HAND;
 // named barriers (0 is __syncthreads)
 enum { BAR_X = 1, BAR_YT = 3, BAR_Z = 5, BAR_W = 7, BAR_V = 9, BAR_YK = 11, BAR_U = 13 };
@@ -62,6 +64,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const size_t cpad = p.cpad;
     if (threadIdx.x == 0) { for (int k = 0; k < 4; k++) mbar_init(&bars[k], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();                                           // (0) mbarriers usable
 
     const int nB = (a.i1 - a.i0) - (a.stop_after_a ? 1 : 0);             // samples whose loop body runs in this launch
     const long long S0 = a.sample0;
@@ -69,8 +72,8 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     // hand-off slot layout: slot s, field f -> hand[(s * 12 + f) * 32 + lane]
     //   f 0,1: sig2raw (F->E)   f 2,3: sig2 (E->K)   f 4,5: st_eta, d8out (E->T)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (K->S)
-    //   f 10,11: strobe flag, FractionOfSampleItPassesBy (T->K)
-#define HAND(s, f) hand[((s) * 12 + (f)) * 32 + lane]
+    //   f 10,11,12: strobe flag, FractionOfSampleItPassesBy, next input sample (T->K)   f 13 (slot 0): first input sample (T->K)
+#define HAND(s, f) hand[((s) * PP_HF + (f)) * 32 + lane]
 
     // ======================================================================================= warp K: carrier loop
     if (warp == 3) {
@@ -116,7 +119,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
                     double2 *rowz = p.bb + (size_t)ch * p.bb_len;             // :667 bbcycbuff[j]=0
                     if (live) for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);
-                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp F reloads mixer_center after the barrier
+                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp T reloads mixer_center after the barrier
                 }
             } else countdown = 4;
             if (mse > p.signalthreshold) LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;   // :674-675
@@ -124,25 +127,11 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         }
         __syncthreads();                                       // (1) slot done, FIR window resident
         if (nB > 0) {
-            const int16_t *row = pcm + (size_t)ch * stride;
-            auto ldpk = [&](int blk) -> int4 {
-                if (live && (size_t)blk * 8 < stride) return __ldg(reinterpret_cast<const int4 *>(row + (size_t)blk * 8));
-                return make_int4(0, 0, 0, 0);
-            };
-            int blk = a.i0 >> 3;
-            int4 pk = ldpk(blk), pk_next = ldpk(blk + 1);
-            auto dval_at = [&](int ii) -> double {             // ((double)*ptr)/32768.0 (:390); ii advances by one per call
-                if ((ii >> 3) != blk) { blk = ii >> 3; pk = pk_next; pk_next = ldpk(blk + 1); }
-                const int k = ii & 7;
-                const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
-                const int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
-                return ((double)v) / 32768.0;
-            };
             double c2_re, c2_im;
             { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
             int fir_pos = (int)(S0 % OQ_NT1);                  // slot of the sample being mixed
             {   // cval of the first sample (:453)
-                const double dval = dval_at(a.i0);
+                const double dval = HAND(0, 13);               // first input sample, decoded by warp T before barrier (1)
                 const double cre = c2_re * dval, cim = c2_im * dval;
                 s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
                 s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
@@ -156,11 +145,10 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
                 const int m2_spec = osc_next_index(m2);
                 const double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
-                const double dnext = (j + 1 < nB) ? dval_at(a.i0 + j + 1) : 0.0;
                 nb_sync(BAR_YK + sl);                          // sig2 of this sample (warp E)
                 double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
                 nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
-                const double strobe = HAND(sl, 10), frac = HAND(sl, 11);
+                const double strobe = HAND(sl, 10), frac = HAND(sl, 11), dnext = HAND(sl, 12);
                 if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
                 double sy_flag = 0.0, sy_x = 0.0, sy_y = 0.0, sy_ec = 0.0;
                 if (strobe != 0.0) {                                              // :488
@@ -293,16 +281,77 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
         LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
     }
-    // ======================================================================================= warp T: symbol-timing PLL
+    // ======================================================================================= warp T: input + symbol-timing PLL
     else if (warp == 2) {
         Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
         Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
-        __syncthreads();                                       // (1)
+        const int16_t *row = pcm + (size_t)ch * stride;
+        // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
+        auto pcm_bytes = [&](int tile) -> unsigned {
+            long long left = (long long)stride - (long long)tile * OQ_T;
+            if (left > OQ_T) left = OQ_T;
+            return left > 0 ? (unsigned)(left * 2) : 0u;
+        };
+        auto pcm_load = [&](int tile) {
+            const int b = tile & 1;
+            const unsigned nb = pcm_bytes(tile);
+            fence_proxy_async();
+            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
+            __syncwarp();
+            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
+        };
+        unsigned phases = 0u;
+#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
+        int pt = a.i0 / OQ_T;                                     // current PCM tile
+        bool pcm_next_issued = false;
+        pcm_load(pt);
+        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+        PP_WAIT(2 + (pt & 1));
+        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
+        int pk_blk = -1;
+        auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:390); ii advances by one per call
+            if ((ii >> 5) != pt) {                                // entered the next PCM tile (warp-uniform)
+                pt = ii >> 5;
+                PP_WAIT(2 + (pt & 1));
+                pcm_next_issued = false;
+                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+            }
+            if ((ii >> 3) != pk_blk) {
+                pk_blk = ii >> 3;
+                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
+            }
+            const int k = ii & 7;
+            const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
+            int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+            if (!live) v = 0;
+            return ((double)v) / 32768.0;
+        };
+        double dcur = dval_at(a.i0);
+        HAND(0, 13) = dcur;
+        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
+        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
+        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
+        const int bbn = p.bb_len;
+        const bool cpu_reduce = p.cpu_reduce != 0;
         const double ee = p.ee;
-        double cs_re, cs_im;
+        double cs_re, cs_im, cc_re, cc_im;
         { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
-        for (int j = 0; j < nB; j++) {
-            const int sl = j & 1;
+        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+        for (int i = a.i0; i < a.i1; i++) {
+            const int j = i - a.i0, sl = j & 1;
+            // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
+            if (!(i == a.i0 && a.skip_a_first)) {
+                if (coarse_counter >= Fs || !cpu_reduce) {
+                    if (live) bb_row[bb_pos] = make_double2(cc_re * dcur, cc_im * dcur);
+                    bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
+                }
+            }
+            if (i == a.i1 - 1 && a.stop_after_a) break;
+            coarse_counter++;                                                 // :431
+            osc_next_frame(mc);                                               // :601
+            { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+            const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
             nb_sync(BAR_YT + sl);                              // st_eta, d8out of this sample (warp E)
             const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
             const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
@@ -314,14 +363,17 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             double frac = 0.0;
             const bool strobe = osc_have_passed_point(st, ee, frac);          // :488
             // slot sl's T->K fields were read by K(j-2), which precedes X_{j-1} -> Z_j -> (E) -> this point: free
-            HAND(sl, 10) = strobe ? 1.0 : 0.0; HAND(sl, 11) = frac;
+            HAND(sl, 10) = strobe ? 1.0 : 0.0; HAND(sl, 11) = frac; HAND(sl, 12) = dnxt;
             __threadfence_block();
             nb_arrive(BAR_U + sl);
             osc_next_frame(st); osc_next_frame(sr);                           // :602-603
             { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+            dcur = dnxt;
         }
+        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
         LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
         LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
+        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
     // ======================================================================================= warp E: envelope chain
     else if (warp == 1) {
@@ -379,7 +431,6 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 bulk_commit();
             };
             unsigned phases = 0u;
-#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
             long long rt = S / OQ_T;                                  // current ring tile
             bool ring_next_issued = false, ring_dirty = false;
             ring_load(rt);
@@ -484,96 +535,31 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         LD(D_DLY8_0) = d8_0; LD(D_DLY8_1) = d8_1; LD(D_DLY8_2) = d8_2;
         LD(D_RES_X1) = res.x1; LD(D_RES_X2) = res.x2; LD(D_RES_Y1) = res.y1; LD(D_RES_Y2) = res.y2;
     }
-    // ======================================================================================= warp F: input + matched filter
+    // ======================================================================================= warp F: matched filter
     else {
         for (int k = 0; k < OQ_NT1; k++) {
             const double vr = p.fir_re[(size_t)k * cpad + ch], vi = p.fir_im[(size_t)k * cpad + ch];
             s_re[k * OQ_THREADS + lane] = vr; s_re[(k + OQ_NT1) * OQ_THREADS + lane] = vr;
             s_im[k * OQ_THREADS + lane] = vi; s_im[(k + OQ_NT1) * OQ_THREADS + lane] = vi;
         }
-        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
-        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
-        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
-        const int16_t *row = pcm + (size_t)ch * stride;
-        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
-        const int bbn = p.bb_len;
-        const bool cpu_reduce = p.cpu_reduce != 0;
-        auto pcm_bytes = [&](int tile) -> unsigned {
-            long long left = (long long)stride - (long long)tile * OQ_T;
-            if (left > OQ_T) left = OQ_T;
-            return left > 0 ? (unsigned)(left * 2) : 0u;
-        };
-        auto pcm_load = [&](int tile) {
-            const int b = tile & 1;
-            const unsigned nb = pcm_bytes(tile);
-            fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
-            __syncwarp();
-            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
-        };
-        unsigned phases = 0u;
-        int pt = a.i0 / OQ_T;                                     // current PCM tile
-        bool pcm_next_issued = false;
-        pcm_load(pt);
-        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-        PP_WAIT(2 + (pt & 1));
-        double cc_re, cc_im;
-        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
-        bool pk_valid = false;
-        // 54 older terms of the first output: window ending at the slot of sample i0-1 ... the tail slot is that of i0-1
-        int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);             // slot of the newest sample entering output j (cval[i0+j-1])
+        __syncthreads();                                       // (1)
+        // output j (:456) = sum over the 55 mixed samples older than sample i0+j; the newest of them (slot `tail`) is produced
+        // by warp K one sample earlier, the 54 older terms are summed ahead of that
+        int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);
         double nfre = 0, nfim = 0;
         if (nB > 0) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
-        for (int i = a.i0; i < a.i1; i++) {
-            const int j = i - a.i0;
-            // ---- PCM sample from the staged tile
-            const int po = i & (OQ_T - 1);
-            if ((i >> 5) != pt) {                                 // entered the next PCM tile (warp-uniform)
-                pt = i >> 5;
-                PP_WAIT(2 + (pt & 1));
-                pcm_next_issued = false;
-                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-                pk_valid = false;
-            }
-            if (!pk_valid || (po & 7) == 0) {
-                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + (po >> 3) * 16);
-                pk_valid = true;
-            }
-            int cur_pcm;
-            {
-                const int k = po & 7;
-                const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
-                cur_pcm = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
-                if (!live) cur_pcm = 0;
-            }
-            const double dval = ((double)cur_pcm) / 32768.0;                  // :390
-            // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
-            if (!(i == a.i0 && a.skip_a_first)) {
-                if (coarse_counter >= Fs || !cpu_reduce) {
-                    if (live) bb_row[bb_pos] = make_double2(cc_re * dval, cc_im * dval);
-                    bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
-                }
-            }
-            if (i == a.i1 - 1 && a.stop_after_a) break;
-            coarse_counter++;                                                 // :431
-            osc_next_frame(mc);                                               // :601
-            { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-            // ---- matched filter output of this sample (:456): 54 older terms were summed ahead, the newest term follows
-            // as soon as warp C has mixed sample i-1
+        for (int j = 0; j < nB; j++) {
             if (j > 0) nb_sync(BAR_X + ((j - 1) & 1));        // X_{j-1}
             nfre += c_taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += c_taps[54] * s_im[tail * OQ_THREADS + lane];
             const int sl = j & 1;
-            // slot sl's F->E fields were read by E(j-2) before Y_{j-2} -> C(j-2) -> X_{j-1}: free
+            // slot sl's F->E fields were read by E(j-2) before its Y arrivals -> K(j-2) -> X_{j-1}: free
             HAND(sl, 0) = nfre; HAND(sl, 1) = nfim;
             __threadfence_block();
             nb_arrive(BAR_Z + sl);                             // Z_j
             tail++; if (tail >= OQ_NT1) tail = 0;
             if (j + 1 < nB) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
         }
-        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
-        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp C
-        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
+        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp K
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
     for (int k = warp; k < OQ_NT1; k += 5) {
