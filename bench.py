@@ -296,7 +296,7 @@ def main():
 
     tot = shard.reduce_sum([float(su_tot.sum()), float(su_ok.sum()), float(dcd.sum())], device=dev)
 
-    # ---- roofline of the dominant kernel (oqpsk_segment_kernel), measured live with events around every launch
+    # ---- roofline of the dominant kernel (oqpsk_pipe_kernel), measured live with events around every launch
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -305,13 +305,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     seg_s = prof["segment_ms"] * 1e-3
     achieved = (ALG_BYTES_PER_SAMPLE * prof["samples"] * C) / seg_s / 1e9 if seg_s > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "oqpsk_segment_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "oqpsk_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
                 "avg_launch_ms": prof["segment_ms"] / max(1, prof["segment_launches"]), "launches": prof["segment_launches"],
                 "share_of_step": prof["segment_ms"] / (e0.elapsed_time(e1)), "cfe_share_of_step": prof["cfe_ms"] / (e0.elapsed_time(e1)),
-                "note": "serial fp64 recursion per channel: latency/FP64-issue bound, not HBM bound (see DESIGN.md)"}
+                "note": "per-channel fp64 feedback loop: bound by dependent-issue latency, not HBM (see DESIGN.md section 5)"}
 
     cpu_base = None
     if rank == 0 and not a.no_cpu_baseline:
