@@ -13,6 +13,7 @@
 // Integer/byte work throughout: bit-exact against the oracle. Known deviation, stated in DESIGN.md: CRC-driven
 // updates of datacdcountdown (aerol.cpp:1601-1608) are applied after stage 3, i.e. at the end of the call that
 // completed the frame, not in the middle of the bit loop.
+#include <cstdint>
 #include "common.cuh"
 #include "demod.cuh"
 #include "viterbi.cuh"
@@ -57,20 +58,36 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     const int16_t *bits = soft + (size_t)ch * soft_cap;
     const int block_len = pp.block_len;
     s.blocks_ready = 0;
+    // the soft-bit row is read 8 values (16 B) at a time, the next group requested while the current one is consumed
+    // (soft and soft_cap*2 are 16-byte multiples: cudaMalloc base, capacity rounded by the caller)
+    const bool vec_ok = ((((size_t)soft_cap * 2) & 15) == 0) && ((((uintptr_t)soft) & 15) == 0);
+    int4 grp = make_int4(0, 0, 0, 0), grp_next = make_int4(0, 0, 0, 0);
+    if (vec_ok && n > 0) { grp = *reinterpret_cast<const int4 *>(bits); if (n > 8) grp_next = *reinterpret_cast<const int4 *>(bits + 8); }
     for (int i = 0; i < n; i++) {
-        const int v = bits[i];
+        int v;
+        if (vec_ok) {
+            const int k = i & 7;
+            if (k == 0 && i > 0) { grp = grp_next; if (i + 8 < n) grp_next = *reinterpret_cast<const int4 *>(bits + i + 8); }
+            const int w = (k < 2) ? grp.x : (k < 4) ? grp.y : (k < 6) ? grp.z : grp.w;
+            v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+        } else v = bits[i];
         int bit = (((unsigned char)v) >= 128) ? 1 : 0;                       // aerol.cpp:1136-1139
         int soft_bit = (unsigned short)v;
         if (v < 0) continue;                                                 // burst marker: never in continuous modes
         int gotsync;
         if (pp.oqpsk) {                                                      // :1156-1233
             s.realimag++; s.realimag %= 2;
-            unsigned &sr = s.realimag ? s.sr_imag : s.sr_real;
-            int &inv = s.realimag ? s.inv_imag : s.inv_real;
-            if (s.cntr > pp.number_of_bits - 68 || s.cntr <= 0 || !s.datacd) {
-                gotsync = uw_invariant(sr, bit, inv);
-                if (!s.gotsync_last) { s.gotsync_last = gotsync; gotsync = 0; } else s.gotsync_last = 0;
-            } else { gotsync = 0; s.gotsync_last = 0; }
+            const bool search = (s.cntr > pp.number_of_bits - 68 || s.cntr <= 0 || !s.datacd);
+            int inv;
+            if (s.realimag) {                                                // explicit arms: the state stays in registers
+                if (search) gotsync = uw_invariant(s.sr_imag, bit, s.inv_imag);
+                inv = s.inv_imag;
+            } else {
+                if (search) gotsync = uw_invariant(s.sr_real, bit, s.inv_real);
+                inv = s.inv_real;
+            }
+            if (search) { if (!s.gotsync_last) { s.gotsync_last = gotsync; gotsync = 0; } else s.gotsync_last = 0; }
+            else { gotsync = 0; s.gotsync_last = 0; }
             if (inv) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
         } else gotsync = uw_exact(s.sr_plain, bit);                          // :1269-1272
 
@@ -107,7 +124,10 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
                 if (s.blocks_ready < PCHAN_QUEUE) {
                     const uint8_t *srcb = pp.blocks + ((size_t)ch * PCHAN_QUEUE + (s.blocks_ready - 1)) * block_len;
                     uint8_t *dstb = pp.blocks + ((size_t)ch * PCHAN_QUEUE + s.blocks_ready) * block_len;
-                    for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
+                    if ((block_len & 15) == 0) {
+                        const int4 *s4 = reinterpret_cast<const int4 *>(srcb); int4 *d4 = reinterpret_cast<int4 *>(dstb);
+                        for (int k = 0; k < block_len / 16; k++) d4[k] = s4[k];
+                    } else for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
                 }
             }
         }
