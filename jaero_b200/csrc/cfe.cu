@@ -20,6 +20,8 @@
 #include "demod_device.cuh"
 #include <cooperative_groups.h>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 
 namespace jb {
 
@@ -256,31 +258,31 @@ cfe_search_kernel(CfePlan pl, DemodParams p)
 }
 
 // ================================================================================================ cluster-resident estimator
-// nfft = 16384 (both OQPSK modes). One thread-block cluster of 4 CTAs owns one channel at a time and keeps the whole
-// 128 x 128 working matrix (256 KB of complex doubles) in the distributed shared memory of its four SMs through all three
-// transforms: CTA q holds 32 columns (column passes) or 32 rows (row passes); the three layout changes are pulls from
-// the peers' shared memory (DSMEM) with the four-step twiddle folded into the pull. HBM traffic per channel falls to the
-// ring read (256 KB, bulk-copied one channel ahead) plus the read-modify-write of y (2 x 128 KB), from eight 256 KB
-// matrix passes before.
+// nfft = 16384 (both OQPSK modes). One thread-block cluster of 8 CTAs owns one channel at a time and keeps the whole
+// 128 x 128 working matrix (256 KB of complex doubles) in the distributed shared memory of its CTAs through all three
+// transforms: CTA q holds 16 columns (column passes) or 16 rows (row passes); the three layout changes are pulls from
+// the peers' shared memory (DSMEM) with the four-step twiddle folded into the pull. A CTA needs 74 KB of shared memory
+// and 256 threads, so three clusters' CTAs share an SM and three channels are in flight per SM: one channel's barrier /
+// pull latency is covered by the others' butterflies. HBM traffic per channel falls to the ring read (256 KB) plus the
+// read-modify-write of y (2 x 128 KB), from eight 256 KB matrix passes before.
 namespace cgx = cooperative_groups;
 
-static const int CC_CL = 4, CC_T = 512, CC_SEQ = 32, CC_RS = 145;             // cluster size, threads, sequences per CTA, row stride
+static const int CC_CL = 8, CC_T = 256, CC_SEQ = 16, CC_RS = 143;             // cluster size, threads, sequences per CTA, row stride
 static const int CC_BUF = CC_SEQ * CC_RS * 16;                                // one working buffer (bytes)
-static const int CC_SM_L = 128 * 32 * 16;                                     // staged ring columns [r][cc]
-static const int CC_SM_TOTAL = 2 * CC_BUF + CC_SM_L + 128 * 16 + 64;
+static const int CC_SM_TOTAL = 2 * CC_BUF + 128 * 16;
 
 __device__ __forceinline__ int cc_ph(int e) { return e + (e >> 3); }          // padded position inside a 128-point sequence
 
-// 32 x FFT-128 in place (same factorisation and arithmetic as tile_fft for n = 128: Stockham radix 8, 4, 4). Warp w owns
-// sequences w and w+16 through all three passes, so the passes are ordered by __syncwarp() only: each pass reads its
+// 16 x FFT-128 in place (same factorisation and arithmetic as tile_fft for n = 128: Stockham radix 8, 4, 4). Warp w owns
+// sequences w and w+8 through all three passes, so the passes are ordered by __syncwarp() only: each pass reads its
 // butterflies' inputs into registers, __syncwarp, writes the outputs back into the same rows. `last` receives
 // (sequence, position, value) of the final pass and normally stores it back (mask / square are fused there).
 template <bool INV, class Store>
 __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 *__restrict__ tws, Store last)
 {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    {   // radix 8, Ns = 1: lanes 0-15 -> sequence w, lanes 16-31 -> sequence w+16
-        double2 *row = buf + (w + (l & 16)) * CC_RS;
+    {   // radix 8, Ns = 1: lanes 0-15 -> sequence w, lanes 16-31 -> sequence w+8
+        double2 *row = buf + (w + ((l & 16) >> 1)) * CC_RS;
         const int j = l & 15;
         double2 v[8];
 #pragma unroll
@@ -291,7 +293,7 @@ __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 
         for (int t = 0; t < 8; t++) row[cc_ph(8 * j + t)] = v[t];
         __syncwarp();
     }
-    double2 *r0 = buf + w * CC_RS, *r1 = buf + (w + 16) * CC_RS;
+    double2 *r0 = buf + w * CC_RS, *r1 = buf + (w + 8) * CC_RS;
     auto radix4 = [&](double2 &v0, double2 &v1, double2 &v2, double2 &v3, int k, int wm) {
         double2 w1 = tws[(k * wm) & 127], w2 = tws[(2 * k * wm) & 127], w3 = tws[(3 * k * wm) & 127];
         if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
@@ -314,20 +316,18 @@ __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 
         __syncwarp();
         radix4(a0, a1, a2, a3, l, 1); radix4(b0, b1, b2, b3, l, 1);
         last(w, l, a0); last(w, l + 32, a1); last(w, l + 64, a2); last(w, l + 96, a3);
-        last(w + 16, l, b0); last(w + 16, l + 32, b1); last(w + 16, l + 64, b2); last(w + 16, l + 96, b3);
+        last(w + 8, l, b0); last(w + 8, l + 32, b1); last(w + 8, l + 64, b2); last(w + 8, l + 96, b3);
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(CC_T)
+__global__ void __launch_bounds__(CC_T, 2)
 cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
 {
     extern __shared__ __align__(128) unsigned char cc_smem[];
     double2 *bufA = reinterpret_cast<double2 *>(cc_smem);
     double2 *bufB = reinterpret_cast<double2 *>(cc_smem + CC_BUF);
-    double2 *bufL = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF);
-    double2 *tws = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF + CC_SM_L);
-    unsigned long long *bar = reinterpret_cast<unsigned long long *>(cc_smem + 2 * CC_BUF + CC_SM_L + 128 * 16);
+    double2 *tws = reinterpret_cast<double2 *>(cc_smem + 2 * CC_BUF);
     cgx::cluster_group cluster = cgx::this_cluster();
     const int q = (int)cluster.block_rank();
     const int n_clusters = gridDim.x / CC_CL, cid = blockIdx.x / CC_CL;
@@ -337,80 +337,76 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
     // The four-step twiddles W_N^(c*k1) are read from the same table the reference-order transforms use (a product of two
     // smaller tables breaks the exact conjugate symmetry of the table and with it the estimator's tie-breaks on symmetric
     // spectra). Their indices do not depend on the data, so the loads are issued ahead of the cluster barrier they follow.
-    if (threadIdx.x == 0) mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     // peers' buffers
     const double2 *rA[CC_CL], *rB[CC_CL];
 #pragma unroll
     for (int s = 0; s < CC_CL; s++) { rA[s] = cluster.map_shared_rank(bufA, s); rB[s] = cluster.map_shared_rank(bufB, s); }
-
-    auto stage = [&](int ch) {             // bulk-copy this CTA's 32 columns of the linearised ring: 128 runs of 512 B
-        fence_proxy_async();
-        if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)CC_SM_L);
-        __syncthreads();
-        if (threadIdx.x < 128) {
-            int n = oldest + 128 * threadIdx.x + 32 * q;
-            if (n >= ring_len) n -= ring_len;
-            if (n >= ring_len) n -= ring_len;
-            bulk_g2s(bufL + threadIdx.x * 32, p.bb + (size_t)ch * ring_len + n, 512u, bar);
-        }
-    };
-    unsigned parity = 0;
     bool arrived = false;
-    if (cid < p.n_channels) stage(cid);
     cluster.sync();                        // every CTA of the cluster is resident before the first remote access
     for (int ch = cid; ch < p.n_channels; ch += n_clusters) {
-        mbar_wait(bar, parity); parity ^= 1u;
-        if (arrived) { cluster.barrier_wait(); arrived = false; }   // the peers have pulled the previous channel's P3 result out of A
-        // ---- columns of the ring -> A[cc][r]
+        // ---- this CTA's 16 columns of the linearised ring (oqpskdemodulator.cpp:418-424) -> A[cc][r]: 256 B runs per r
+        double2 colv[8];
+        {
+            const double2 *ring = p.bb + (size_t)ch * ring_len;
+            const int cc = threadIdx.x & 15, r0i = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * i, r = e >> 5, cc = e & 31;
-            bufA[cc * CC_RS + cc_ph(r)] = bufL[r * 32 + cc];
+            for (int i = 0; i < 8; i++) {
+                int n = oldest + 128 * (r0i + 16 * i) + 16 * q + cc;
+                if (n >= ring_len) n -= ring_len;
+                if (n >= ring_len) n -= ring_len;
+                colv[i] = ring[n];
+            }
+        }
+        if (arrived) { cluster.barrier_wait(); arrived = false; }   // the peers have pulled the previous channel's P3 result out of A
+        {
+            const int cc = threadIdx.x & 15, r0i = threadIdx.x >> 4;
+#pragma unroll
+            for (int i = 0; i < 8; i++) bufA[cc * CC_RS + cc_ph(r0i + 16 * i)] = colv[i];
         }
         __syncthreads();
-        if (ch + n_clusters < p.n_channels) stage(ch + n_clusters);
         // ---- P1: column FFT over r, in place                                         A[cc][k1]
         cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
         double2 tw8[8];
+        {
+            const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;
-            tw8[i] = __ldg(&twN[((32 * s + cc) * (32 * q + kk)) & (N - 1)]);
+            for (int s = 0; s < 8; s++) tw8[s] = __ldg(&twN[((16 * s + cc) * (16 * q + kk)) & (N - 1)]);
         }
         cluster.sync();
-        // rows k1 = 32q+kk, all c: B[kk][c] = A_src[cc][k1] * W_N^{c k1}
+        // rows k1 = 16q+kk, all c: B[kk][c] = A_src[cc][k1] * W_N^{c k1}   (kk fastest: contiguous remote reads)
+        {
+            const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;     // kk fastest: contiguous remote reads
-            const int c = 32 * s + cc, k1 = 32 * q + kk;
-            const double2 x = rA[s][cc * CC_RS + cc_ph(k1)];
-            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, tw8[i]);
+            for (int s = 0; s < 8; s++) {
+                const double2 x = rA[s][cc * CC_RS + cc_ph(16 * q + kk)];
+                bufB[kk * CC_RS + cc_ph(16 * s + cc)] = c_mul(x, tw8[s]);
+            }
         }
         __syncthreads();
         // ---- P2: row FFT over c -> mask (:99-100) -> row IFFT, in place               B[kk][c]
         cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) {
-            const int k = (32 * q + f) + 128 * e;          // X[k1 + n1*k2]
+            const int k = (16 * q + f) + 128 * e;          // X[k1 + n1*k2]
             if (!pl.is8400) { if (k >= pl.startbin && k <= pl.stopbin) v = make_double2(0.0, 0.0); }
             else { const double w = pl.window[k]; v = make_double2(v.x * w, v.y * w); }
             bufB[f * CC_RS + cc_ph(e)] = v;
         });
         cc_fft<true>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
+        {
+            const int cc = threadIdx.x & 15, kk = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * (i & 1), cc = e & 31, kk = e >> 5, s = i >> 1;
-            tw8[i] = __ldg(&twN[((32 * q + cc) * (32 * s + kk)) & (N - 1)]);
+            for (int s = 0; s < 8; s++) tw8[s] = __ldg(&twN[((16 * q + cc) * (16 * s + kk)) & (N - 1)]);
         }
         cluster.sync();                    // every peer has finished reading A (it passed the pull above before its own P2)
-        // columns c = 32q+cc, all k1: A[cc][k1] = B_src[kk][c] * conj(W_N^{c k1})
+        // columns c = 16q+cc, all k1: A[cc][k1] = B_src[kk][c] * conj(W_N^{c k1})   (cc fastest: contiguous remote reads)
+        {
+            const int cc = threadIdx.x & 15, kk = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * (i & 1), cc = e & 31, kk = e >> 5, s = i >> 1;     // cc fastest: contiguous remote reads
-            const int c = 32 * q + cc, k1 = 32 * s + kk;
-            const double2 x = rB[s][kk * CC_RS + cc_ph(c)];
-            double2 w = tw8[i]; w.y = -w.y;
-            bufA[cc * CC_RS + cc_ph(k1)] = c_mul(x, w);
+            for (int s = 0; s < 8; s++) {
+                const double2 x = rB[s][kk * CC_RS + cc_ph(16 * q + cc)];
+                double2 w = tw8[s]; w.y = -w.y;
+                bufA[cc * CC_RS + cc_ph(16 * s + kk)] = c_mul(x, w);
+            }
         }
         __syncthreads();
         // ---- P3: column IFFT over k1 -> square (:103) -> column FFT over r, in place  A[cc][k1]
@@ -418,18 +414,19 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
             bufA[f * CC_RS + cc_ph(e)] = make_double2(v.x * v.x - v.y * v.y, v.x * v.y + v.y * v.x);
         });
         cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+        {
+            const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;
-            tw8[i] = __ldg(&twN[((32 * s + cc) * (32 * q + kk)) & (N - 1)]);
+            for (int s = 0; s < 8; s++) tw8[s] = __ldg(&twN[((16 * s + cc) * (16 * q + kk)) & (N - 1)]);
         }
         cluster.sync();
+        {
+            const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int e = threadIdx.x + CC_T * (i & 1), kk = e & 31, cc = e >> 5, s = i >> 1;     // kk fastest: contiguous remote reads
-            const int c = 32 * s + cc, k1 = 32 * q + kk;
-            const double2 x = rA[s][cc * CC_RS + cc_ph(k1)];
-            bufB[kk * CC_RS + cc_ph(c)] = c_mul(x, tw8[i]);
+            for (int s = 0; s < 8; s++) {
+                const double2 x = rA[s][cc * CC_RS + cc_ph(16 * q + kk)];
+                bufB[kk * CC_RS + cc_ph(16 * s + cc)] = c_mul(x, tw8[s]);
+            }
         }
         cluster.barrier_arrive();          // split barrier: this CTA is done reading its peers' A (waited on before A is refilled)
         arrived = true;
@@ -438,18 +435,16 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
         {
             double *y = pl.y + (size_t)ch * N;
             const bool bigchange = p.I[(size_t)I_ZERO_BB * p.cpad + ch] != 0;     // y[i]=20 pending (coarsefreqestimate.cpp:87)
+            const int kk = threadIdx.x & 15, k2b = threadIdx.x >> 4;
             double yo[8];                                                         // requested before the transform, consumed after it
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int e = threadIdx.x + CC_T * i, kk = e & 31, k2 = e >> 5;
-                yo[i] = bigchange ? 20.0 : y[(32 * q + kk) + 128 * ((k2 + 64) & 127)];
-            }
+            for (int i = 0; i < 8; i++) yo[i] = bigchange ? 20.0 : y[(16 * q + kk) + 128 * ((k2b + 16 * i + 64) & 127)];
             cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int e = threadIdx.x + CC_T * i, kk = e & 31, k2 = e >> 5;
-                const int i_sh = (32 * q + kk) + 128 * ((k2 + 64) & 127);         // fftshift (:105)
+                const int k2 = k2b + 16 * i;
+                const int i_sh = (16 * q + kk) + 128 * ((k2 + 64) & 127);         // fftshift (:105)
                 const double2 x = bufB[kk * CC_RS + cc_ph(k2)];
                 // 10*log10(max(|x|,1)) = 5*log10(max(|x|^2,1))
                 y[i_sh] = yo[i] * 0.9 + 0.1 * 5 * log10(fmax(x.x * x.x + x.y * x.y, 1.0));   // :108
@@ -485,6 +480,7 @@ int cfe_cluster_capacity()
     cfg.attrs = &at; cfg.numAttrs = 1;
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, cfe_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (getenv("JAERO_DEBUG")) fprintf(stderr, "[jaero_b200] estimator clusters co-resident: %d x %d CTAs\n", n, CC_CL);
     return n;
 }
 
