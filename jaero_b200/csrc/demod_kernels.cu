@@ -3,3 +3,4 @@
 #include "oqpsk_demod.cu"
 #include "oqpsk_pipe.cu"
 #include "msk_demod.cu"
+#include "msk_pipe.cu"
