@@ -170,3 +170,41 @@ class OraclePChannel:
     def close(self):
         if self.h:
             lib().jor_pchan_free(self.h); self.h = None
+
+
+class OracleRTChannel:
+    """Restated burst branch of AeroL::Decode + RTChannelDeleaveFECScram: soft bits (with -1 markers) -> R / T packets."""
+
+    def __init__(self, fb):
+        L = lib()
+        L.jor_rt_new.restype = ctypes.c_void_p; L.jor_rt_new.argtypes = [ctypes.c_int]
+        L.jor_rt_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.jor_rt_update_dcd.argtypes = [ctypes.c_void_p]
+        L.jor_rt_packet_count.restype = ctypes.c_long; L.jor_rt_packet_count.argtypes = [ctypes.c_void_p]
+        L.jor_rt_trials.restype = ctypes.c_long; L.jor_rt_trials.argtypes = [ctypes.c_void_p]
+        L.jor_rt_packet.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.jor_rt_free.argtypes = [ctypes.c_void_p]
+        self.h = L.jor_rt_new(int(fb))
+
+    def process(self, soft, vector_semantics=False):
+        soft = np.ascontiguousarray(soft, dtype=np.int16)
+        lib().jor_rt_process(self.h, _p(soft), len(soft), int(vector_semantics))
+
+    def update_dcd(self):
+        lib().jor_rt_update_dcd(self.h)
+
+    @property
+    def trials(self):
+        return lib().jor_rt_trials(self.h)
+
+    def packets(self):
+        out = []
+        for k in range(lib().jor_rt_packet_count(self.h)):
+            t = ctypes.c_int(); ns = ctypes.c_int(); bi = ctypes.c_long(); buf = np.zeros(1024, dtype=np.uint8)
+            n = lib().jor_rt_packet(self.h, k, ctypes.byref(t), ctypes.byref(ns), ctypes.byref(bi), _p(buf), 1024)
+            out.append(dict(type=t.value, nsus=ns.value, bit_index=bi.value, bytes=buf[:n].copy()))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().jor_rt_free(self.h); self.h = None

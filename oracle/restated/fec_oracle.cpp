@@ -192,3 +192,231 @@ void PChannelOracle::process(const short *bits, int n)
         if (cntr + 1 == TotalNumberOfBits) { scr_pos = 0; cntr = -1; }   // :2013-2016
     }
 }
+
+
+// ====================================================================================== R/T burst channel
+namespace {
+enum { RT_OK_R = 3, RT_OK_T = 5, RT_BAD = 0, RT_TEST_FAILED = 32, RT_NOTHING = 8, RT_FULL = 16 };
+const uint32_t RT_UW = 0xE15AE893u;                            // aerol.cpp:947,959-963
+// AeroLcrc16::calcusingbitsandcheck (aerol.h:287-313)
+bool crc_bits_check(const int *bits, int numberofbits)
+{
+    uint16_t crc_rec = 0;
+    for (int i = numberofbits - 1; i >= numberofbits - 16; i--) { crc_rec <<= 1; crc_rec |= (uint16_t)bits[i]; }
+    numberofbits -= 16;
+    uint16_t crc = 0xFFFF;
+    for (int i = 0; i < numberofbits; i++) {
+        const int crc_bit = crc & 1;
+        crc >>= 1;
+        if (crc_bit ^ bits[i]) crc = crc ^ 0x8408;
+    }
+    crc = (uint16_t)~crc;
+    return crc_rec == crc;
+}
+// PreambleDetectorPhaseInvariant::Update (aerol.cpp:781-804) on a 32-bit shift register
+int uw_invariant_tol(uint32_t &sr, int bit, bool &inverted, int tol)
+{
+    sr = (sr << 1) | (uint32_t)bit;
+    const int xorsum = __builtin_popcount(sr ^ RT_UW);
+    if (xorsum >= (32 - tol)) { inverted = true; return 1; }
+    if (xorsum <= tol) { inverted = false; return 1; }
+    return 0;
+}
+}
+
+RTChannelOracle::RTChannelOracle(int fb)
+{
+    ifb = fb;
+    useingOQPSK = (fb == 10500 || fb == 8400);
+    NumberOfBits = (fb == 10500) ? 4992 : (fb == 8400 ? 4096 : 1152);                 // aerol.cpp:1012-1050
+    TotalNumberOfBits = useingOQPSK ? ifb : ifb * 3;                                    // :1062-1070
+    sr_imag = sr_real = sr_msk = 0; inv_imag = inv_real = inv_msk = false;
+    realimag = 0; gotsync_last = 0;
+    cntr = 1000000000; muw = 0; datacd = false; datacdcountdown = 0;
+    block.assign(64 * 95, 0); blockptr = 0; lastpacketstate = RT_NOTHING; targetSUSize = targetBlocks = numberofsus = 0;
+    correct_convolutional_polynomial_t poly[2] = {109, 79};
+    conv = correct_convolutional_create(2, 7, poly);
+    {   // AeroLScrambler (aerol.h:397-437)
+        int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
+        scr.resize(5000);
+        for (int a = 0; a < 5000; a++) {
+            const int v = st[0] ^ st[14];
+            scr[a] = v;
+            for (int i = 14; i > 0; i--) st[i] = st[i - 1];
+            st[0] = v;
+        }
+    }
+    n_bad = n_trials = bits_seen = 0;
+}
+RTChannelOracle::~RTChannelOracle() { correct_convolutional_destroy(conv); }
+
+int RTChannelOracle::resetblockptr()                           // aerol.h:590-601
+{
+    blockptr = 0;
+    if (lastpacketstate == RT_TEST_FAILED) { lastpacketstate = RT_NOTHING; return RT_BAD; }
+    lastpacketstate = RT_NOTHING;
+    return RT_NOTHING;
+}
+
+static void rt_decode(RTChannelOracle &o, const std::vector<uint8_t> &del, int nsoft)
+{
+    // JConvolutionalCodec::Decode_soft (jconvolutionalcodec.cpp:98-125) + scrambler.reset/update
+    std::vector<uint8_t> dec(nsoft / 2 / 8 + 8, 0);
+    correct_convolutional_decode_soft(o.conv, del.data(), (size_t)nsoft, dec.data());
+    const int dbits = nsoft / 2;
+    o.deconvol.assign(dbits, 0);
+    for (int i = 0; i < dbits; i++) o.deconvol[i] = (dec[i >> 3] >> (7 - (i & 7))) & 1;
+    for (int i = 0; i < dbits; i++) o.deconvol[i] ^= o.scr[i];
+    o.n_trials++;
+}
+static void rt_pack(RTChannelOracle &o)                        // packintobytes (aerol.h:602-628)
+{
+    o.infofield.clear();
+    int charptr = 0; uint8_t ch = 0;
+    for (size_t h = 0; h < o.deconvol.size(); h++) {
+        ch |= (uint8_t)(o.deconvol[h] * 128);
+        charptr++; charptr %= 8;
+        if (charptr == 0) { o.infofield.push_back(ch); ch = 0; } else ch >>= 1;
+    }
+}
+
+int RTChannelOracle::rt_update(int bit)                        // aerol.h:786-877
+{
+    if (blockptr >= (int)block.size()) return RT_FULL;
+    block[blockptr] = bit; blockptr++;
+    if (((blockptr - (64 * 5)) % (64 * 3)) == 0) {
+        const int cols = blockptr / 64;
+        std::vector<uint8_t> del((size_t)blockptr);
+        { int k = 0; for (int j = 0; j < cols; j++) for (int i = 0; i < 64; i++) del[k++] = (uint8_t)block[((i * 27) % 64) * cols + j]; }   // deinterleave_ba
+        rt_decode(*this, del, blockptr);
+        if (blockptr == (64 * 5)) {
+            if (!crc_bits_check(deconvol.data(), 8 * 19)) { lastpacketstate = RT_TEST_FAILED; return RT_TEST_FAILED; }
+            rt_pack(*this);
+            blockptr = (int)block.size();
+            lastpacketstate = RT_OK_R;
+            return RT_OK_R;
+        }
+        if (!crc_bits_check(deconvol.data(), 8 * 6)) {
+            if (blockptr >= (int)block.size()) { lastpacketstate = RT_BAD; return RT_BAD; }
+            lastpacketstate = RT_TEST_FAILED; return RT_TEST_FAILED;
+        }
+        numberofsus = 1 + (blockptr - (64 * 5)) / (64 * 3);
+        for (int i = 0; i < numberofsus; i++) {
+            if (!crc_bits_check(deconvol.data() + (8 * 6) + (8 * 12) * i, 8 * 12)) {
+                if (blockptr >= (int)block.size()) { lastpacketstate = RT_BAD; return RT_BAD; }
+                lastpacketstate = RT_TEST_FAILED; return RT_TEST_FAILED;
+            }
+        }
+        rt_pack(*this);
+        if (!infofield.empty()) infofield.pop_back();          // chop(1)
+        blockptr = (int)block.size();
+        lastpacketstate = RT_OK_T;
+        return RT_OK_T;
+    }
+    return RT_NOTHING;
+}
+
+int RTChannelOracle::rt_updateMSK(int bit)                     // aerol.h:631-783
+{
+    if (blockptr >= (int)block.size()) return RT_FULL;
+    block[blockptr] = bit; blockptr++;
+    int ok = 0;
+    bool cont = false;
+    if ((((blockptr - (64 * 5)) % (64 * 3)) == 0) && (blockptr / 64 == 5 || blockptr / 64 == targetBlocks || blockptr / 64 == 11 || blockptr / 64 == 50)) cont = true;
+    if (cont) {
+        const int blocks = blockptr / 64;
+        std::vector<uint8_t> del((size_t)blockptr);
+        {   // deinterleaveMSK_ba (aerol.cpp:673-714): 5 columns first, then groups of 3
+            int k = 0;
+            for (int j = 0; j < 5; j++) for (int i = 0; i < 64; i++) del[k++] = (uint8_t)block[((i * 27) % 64) * 5 + j];
+            int procblocks = 5;
+            while (k < blocks * 64) {
+                for (int j = 0; j < 3; j++) for (int i = 0; i < 64; i++) del[k++] = (uint8_t)block[(64 * procblocks) + (((i * 27) % 64) * 3 + j)];
+                procblocks += 3;
+            }
+        }
+        rt_decode(*this, del, blockptr);
+        if (blockptr == (64 * 5)) {
+            targetSUSize = 0; targetBlocks = 0;
+            if (crc_bits_check(deconvol.data(), 8 * 19)) {
+                rt_pack(*this);
+                blockptr = (int)block.size();
+                lastpacketstate = RT_OK_R;
+                return RT_OK_R;
+            }
+            return RT_NOTHING;
+        }
+        if (!crc_bits_check(deconvol.data(), 8 * 6)) { lastpacketstate = RT_BAD; return RT_BAD; }
+        if (blockptr / 64 == 11) {
+            const int *isu = deconvol.data() + (8 * 6) + (8 * 12) * 1;
+            int bin = 2;
+            bin += ((isu[0] * 1) + (isu[1] * 2) + (isu[2] * 4) + (isu[3] * 8) + (isu[4] * 16) + (isu[5] * 32));
+            targetSUSize = bin;
+            if (targetSUSize >= 16) targetSUSize = (int)floor(targetSUSize / 2) + 1;
+            targetBlocks = ((targetSUSize + 1) * 3) + 2;
+            return RT_NOTHING;
+        }
+        if (blockptr / 64 == targetBlocks) {
+            for (int i = 0; i < targetSUSize - 3; i++) if (crc_bits_check(deconvol.data() + (8 * 6) + (8 * 12) * i, 8 * 12)) ok++;
+            if (ok <= targetSUSize) {
+                rt_pack(*this);
+                if (!infofield.empty()) infofield.pop_back();
+                numberofsus = targetSUSize;
+                blockptr = (int)block.size();
+                lastpacketstate = RT_OK_T;
+                return RT_OK_T;
+            }
+        }
+        return RT_NOTHING;
+    }
+    return RT_NOTHING;
+}
+
+void RTChannelOracle::process(const short *bits, int n, bool vector_semantics)
+{
+    for (int i = 0; i < n; i++) {
+        bits_seen++;
+        int bit = (((uint8_t)bits[i]) >= 128) ? 1 : 0;          // aerol.cpp:1136-1139
+        int soft_bit = (uint16_t)bits[i];
+        if (bits[i] < 0) { muw = 0; continue; }                 // :1146-1151 start-of-burst marker
+        if (muw < 100000) muw++;
+        int gotsync = 0;
+        if (useingOQPSK) {                                      // :1156-1233
+            realimag++; realimag %= 2;
+            uint32_t &sr = realimag ? sr_imag : sr_real;
+            bool &inv = realimag ? inv_imag : inv_real;
+            if (cntr > NumberOfBits - 68 || cntr <= 0 || !datacd) {
+                gotsync = uw_invariant_tol(sr, bit, inv, 4);
+                if (!gotsync_last) { gotsync_last = gotsync; gotsync = 0; } else gotsync_last = 0;
+            } else { gotsync = 0; gotsync_last = 0; }
+            if (gotsync) { if (ifb == 10500 && (labs(muw - 80) > 150)) gotsync = 0; }   // :1193-1200
+            if (inv) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
+        } else {                                                // :1236-1266
+            const bool inverted = inv_msk;
+            gotsync = uw_invariant_tol(sr_msk, bit, inv_msk, 4);
+            if (muw > 250 && gotsync) { if (inverted != inv_msk) inv_msk = inverted; gotsync = 0; }
+            if (inv_msk) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
+        }
+        if (cntr < 1000000000) cntr++;
+        if (cntr < 16) {                                        // :1275-1300: no header on R/T channels
+            if (cntr == 0) { cntr = 16; if (resetblockptr() == RT_BAD) n_bad++; }
+        }
+        if (cntr >= 16) {                                       // :1327-1345
+            const int result = useingOQPSK ? rt_update(soft_bit) : rt_updateMSK(soft_bit);
+            if (result == RT_OK_R) { RTPacket pk; pk.type = 1; pk.nsus = 0; pk.bit_index = bits_seen; pk.bytes.assign(infofield.begin(), infofield.begin() + 19); packets.push_back(pk); }
+            else if (result == RT_OK_T) { RTPacket pk; pk.type = 2; pk.nsus = numberofsus; pk.bit_index = bits_seen; pk.bytes = infofield; packets.push_back(pk); }
+        }
+        if (gotsync) { cntr = -1; datacd = true; datacdcountdown = 12; }   // :1990-2011
+        if (cntr + 1 == TotalNumberOfBits) {                    // :2013-2029
+            cntr = 1000000000; datacd = false; datacdcountdown = 0;
+            if (vector_semantics) return;
+        }
+    }
+}
+
+void RTChannelOracle::updateDCD()                              // aerol.cpp:1109-1122
+{
+    if (datacdcountdown > 0) datacdcountdown -= 3;
+    else { if (datacdcountdown < 0) datacdcountdown = 0; }
+    if (datacd && !datacdcountdown) datacd = false;
+}

@@ -53,5 +53,33 @@ struct PChannelOracle
     void updateDCD();                              // AeroL::updateDCD (aerol.cpp:1109-1122), 1 s tick
     void lostSignal();                             // AeroL::LostSignal (aerol.h:925-931)
 };
-uint16_t oracle_crc16(const uint8_t *bytes, int n);   // AeroLcrc16::calcusingbytes (aerol.h:334-362)
+uint16_t oracle_crc16(const uint8_t *bytes, int n);
+
+// ---- burst (R/T channel) branch of AeroL::Decode (JAERO/aerol.cpp:1124-1350, :1985-2031) with
+// RTChannelDeleaveFECScram (JAERO/aerol.h:554-895), minus all text output / ACARS parsing.
+struct RTPacket { int type; int nsus; long bit_index; std::vector<uint8_t> bytes; };   // type 1 = R packet (19 bytes), 2 = T packet (6+12n)
+struct RTChannelOracle
+{
+    int ifb; bool useingOQPSK; int NumberOfBits, TotalNumberOfBits;
+    uint32_t sr_imag, sr_real, sr_msk; bool inv_imag, inv_real, inv_msk;   // PreambleDetectorPhaseInvariant x3, tollerence 4
+    int realimag, gotsync_last;
+    long cntr, muw; bool datacd; int datacdcountdown;
+    // RTChannelDeleaveFECScram
+    std::vector<int> block; int blockptr; int lastpacketstate; int targetSUSize, targetBlocks, numberofsus;
+    correct_convolutional *conv;
+    std::vector<int> scr;
+    std::vector<int> deconvol;
+    std::vector<uint8_t> infofield;
+    // outputs
+    std::vector<RTPacket> packets; long n_bad, n_trials, bits_seen;
+    explicit RTChannelOracle(int fb);
+    ~RTChannelOracle();
+    // one call per processDemodulatedSoftBits emit when vector_semantics (the reference returns from Decode() in the middle
+    // of a vector when the burst time-out fires, aerol.cpp:2018-2027); otherwise the stream is processed without drops
+    void process(const short *soft, int n, bool vector_semantics);
+    void updateDCD();
+    int rt_update(int soft_bit);        // RTChannelDeleaveFECScram::update (OQPSK)
+    int rt_updateMSK(int soft_bit);     // RTChannelDeleaveFECScram::updateMSK
+    int resetblockptr();
+};   // AeroLcrc16::calcusingbytes (aerol.h:334-362)
 #endif

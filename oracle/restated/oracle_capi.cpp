@@ -124,5 +124,23 @@ long jor_pchan_su_take(void *p, uint8_t *bytes12, int *crc_ok, long *frame, long
     o->sus.erase(o->sus.begin(), o->sus.begin() + n); return n;
 }
 void jor_pchan_free(void *p) { delete (PChannelOracle *)p; }
+// ---- R/T burst channel
+void *jor_rt_new(int fb) { return new RTChannelOracle(fb); }
+void jor_rt_process(void *p, const short *soft, int n, int vector_semantics) { ((RTChannelOracle *)p)->process(soft, n, vector_semantics != 0); }
+void jor_rt_update_dcd(void *p) { ((RTChannelOracle *)p)->updateDCD(); }
+long jor_rt_packet_count(void *p) { return (long)((RTChannelOracle *)p)->packets.size(); }
+long jor_rt_trials(void *p) { return ((RTChannelOracle *)p)->n_trials; }
+// packet k: returns length, fills type / nsus / bit_index
+int jor_rt_packet(void *p, long k, int *type, int *nsus, long *bit_index, uint8_t *bytes, int cap)
+{
+    RTChannelOracle *o = (RTChannelOracle *)p;
+    if (k < 0 || k >= (long)o->packets.size()) return -1;
+    const RTPacket &pk = o->packets[k];
+    *type = pk.type; *nsus = pk.nsus; *bit_index = pk.bit_index;
+    const int n = (int)pk.bytes.size() < cap ? (int)pk.bytes.size() : cap;
+    for (int i = 0; i < n; i++) bytes[i] = pk.bytes[i];
+    return (int)pk.bytes.size();
+}
+void jor_rt_free(void *p) { delete (RTChannelOracle *)p; }
 uint16_t jor_crc16(const uint8_t *b, int n) { return oracle_crc16(b, n); }
 }
