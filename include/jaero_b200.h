@@ -200,6 +200,26 @@ int jaero_burst_get_status_all(jaero_burst *b, jaero_burst_status *out);
 int jaero_burst_sync(jaero_burst *b);
 int64_t jaero_burst_launch_count(const jaero_burst *b);
 
+/* ---- R/T burst channel layer ----
+ * Replaces the burst branch of AeroL::Decode (JAERO/aerol.cpp:1124-1350, :1985-2031: unique-word detection with the
+ * start-of-burst timing gates, sync / time-out handling), AeroL::updateDCD (:1109-1122) and RTChannelDeleaveFECScram
+ * (JAERO/aerol.h:554-895: trial de-interleave + Decode_soft at every candidate packet length, descrambling, CRC-16
+ * decisions, byte packing). Input: the soft-bit stream a burst demodulator emits (values 0..255, -1 = start of burst).
+ * Output records are JAERO_RT_RECORD bytes: int32 type (1 = R packet, 2 = T packet), int32 number of SUs (T), int32
+ * payload length, int32 index of the packet's first bit, then the payload (R: 19 bytes; T: 6-byte header + 12 per SU). */
+#define JAERO_RT_RECORD 400
+typedef struct jaero_rt jaero_rt;
+int jaero_rt_create(double fb, int n_channels, int device_ordinal, jaero_rt **out);     /* fb 600 / 1200 (MSK) or 10500 (OQPSK) */
+void jaero_rt_destroy(jaero_rt *r);
+/* host soft bits: soft[ch * cap + i], counts[ch] values per channel (AeroL::processDemodulatedSoftBits) */
+int jaero_rt_process_softbits(jaero_rt *r, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
+/* consume (and drain) the soft bits a burst demodulator batch has produced, entirely on the device */
+int jaero_rt_process_burst(jaero_rt *r, jaero_burst *b);
+int jaero_rt_tick(jaero_rt *r);                                                          /* the 1 s updateDCD timer */
+int jaero_rt_read_packets(jaero_rt *r, uint8_t *out, int cap_packets_per_channel, int32_t *counts);
+int jaero_rt_get_stats(jaero_rt *r, int32_t *n_trial_decodes, int32_t *n_bad_packets, int32_t *dcd);   /* any may be NULL */
+int64_t jaero_rt_launch_count(const jaero_rt *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,7 +47,9 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count",
            "jaero_burst_msk_create", "jaero_burst_oqpsk_create", "jaero_burst_destroy", "jaero_burst_write", "jaero_burst_write_device",
            "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
-           "jaero_burst_launch_count"]
+           "jaero_burst_launch_count",
+           "jaero_rt_create", "jaero_rt_destroy", "jaero_rt_process_softbits", "jaero_rt_process_burst", "jaero_rt_tick",
+           "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count"]
 
 
 def lib():
@@ -100,6 +102,14 @@ def lib():
         L.jaero_burst_get_status_all.argtypes = [vp, vp]
         L.jaero_burst_sync.argtypes = [vp]
         L.jaero_burst_launch_count.argtypes = [vp]; L.jaero_burst_launch_count.restype = ctypes.c_int64
+        L.jaero_rt_create.argtypes = [ctypes.c_double, i, i, ctypes.POINTER(vp)]
+        L.jaero_rt_destroy.argtypes = [vp]; L.jaero_rt_destroy.restype = None
+        L.jaero_rt_process_softbits.argtypes = [vp, vp, sz, vp]
+        L.jaero_rt_process_burst.argtypes = [vp, vp]
+        L.jaero_rt_tick.argtypes = [vp]
+        L.jaero_rt_read_packets.argtypes = [vp, vp, i, vp]
+        L.jaero_rt_get_stats.argtypes = [vp, vp, vp, vp]
+        L.jaero_rt_launch_count.argtypes = [vp]; L.jaero_rt_launch_count.restype = ctypes.c_int64
         _lib = L
     return _lib
 
@@ -375,3 +385,62 @@ class BurstOqpskBatch(BurstMskBatch):
         self.n = n_channels
         self.soft_cap = max(4096, int(2 * fb) + 64)
         _check(lib().jaero_burst_oqpsk_create(ctypes.byref(s), n_channels, device, ctypes.byref(self.h)))
+
+
+class RTChannelBatch:
+    """R/T burst channel layer for n_channels streams: soft bits (with -1 start-of-burst markers) -> R / T packets."""
+    RECORD = 400
+
+    def __init__(self, n_channels, fb, device=0):
+        if n_channels <= 0:
+            raise JaeroError("n_channels must be positive")
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        _check(lib().jaero_rt_create(float(fb), n_channels, device, ctypes.byref(self.h)))
+
+    def process(self, soft_list):
+        """soft_list: one int16 array per channel."""
+        cap = max(1, max(len(s) for s in soft_list))
+        buf = np.zeros((self.n, cap), dtype=np.int16)
+        counts = np.zeros(self.n, dtype=np.int32)
+        for c, s in enumerate(soft_list):
+            buf[c, :len(s)] = s; counts[c] = len(s)
+        _check(lib().jaero_rt_process_softbits(self.h, _p(buf), cap, _p(counts)))
+
+    def process_burst(self, burst_batch):
+        _check(lib().jaero_rt_process_burst(self.h, burst_batch.h))
+
+    def tick(self):
+        _check(lib().jaero_rt_tick(self.h))
+
+    def read_packets(self, cap=8):
+        out = np.zeros((self.n, cap, self.RECORD), dtype=np.uint8)
+        counts = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_rt_read_packets(self.h, _p(out), cap, _p(counts)))
+        res = []
+        for c in range(self.n):
+            pk = []
+            for k in range(counts[c]):
+                hdr = out[c, k, :16].view(np.int32)
+                pk.append(dict(type=int(hdr[0]), nsus=int(hdr[1]), start_bit=int(hdr[3]), bytes=out[c, k, 16:16 + int(hdr[2])].copy()))
+            res.append(pk)
+        return res
+
+    def stats(self):
+        tr = np.zeros(self.n, dtype=np.int32); bad = np.zeros(self.n, dtype=np.int32); dcd = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_rt_get_stats(self.h, _p(tr), _p(bad), _p(dcd)))
+        return tr, bad, dcd
+
+    @property
+    def launches(self):
+        return lib().jaero_rt_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().jaero_rt_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -16,6 +16,7 @@ UNITS = [
     ("viterbi.cu", []),
     ("cfe.cu", []),
     ("pchannel.cu", []),
+    ("rtchannel.cu", []),
     ("prefilter.cu", ["-fmad=false"]),
     ("burst.cu", ["-fmad=false"]),
     ("demod_kernels.cu", ["-fmad=false"]),

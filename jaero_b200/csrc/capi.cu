@@ -1370,3 +1370,144 @@ int jaero_burst_get_status_all(jaero_burst *b, jaero_burst_status *out)
 }
 
 } // extern "C"
+
+// ====================================================================== R/T burst channel layer (§8(f)2)
+#include "rtchannel.cuh"
+
+struct jaero_rt {
+    int device; cudaStream_t stream;
+    RtParams rp;
+    std::vector<void *> allocs;
+    int16_t *d_soft_stage; int *d_count_stage; size_t stage_cap;
+    RtState *h_state; uint8_t *h_out;
+    long long launches;
+};
+
+extern "C" {
+
+int jaero_rt_create(double fb, int n_channels, int device, jaero_rt **out)
+{
+    if (!out || n_channels <= 0) { set_error("jaero_rt_create: bad argument"); return JAERO_E_ARG; }
+    const int ifb = (int)(fb >= 0.0 ? fb + 0.5 : fb - 0.5);
+    if (ifb != 600 && ifb != 1200 && ifb != 10500) { set_error("jaero_rt_create: burst R/T channels run at 600, 1200 or 10500 bps"); return JAERO_E_ARG; }
+    int ndev = 0;
+    JB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("jaero_rt_create: no such CUDA device"); return JAERO_E_CUDA; }
+    JB_CUDA(cudaSetDevice(device));
+    jaero_rt *r = new (std::nothrow) jaero_rt();
+    if (!r) { set_error("out of host memory"); return JAERO_E_ARG; }
+    r->device = device; r->d_soft_stage = 0; r->d_count_stage = 0; r->stage_cap = 0; r->h_state = 0; r->h_out = 0; r->launches = 0;
+    JB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    RtParams &rp = r->rp;
+    memset(&rp, 0, sizeof rp);
+    rp.n_channels = n_channels; rp.ifb = ifb; rp.oqpsk = (ifb == 10500);
+    rp.number_of_bits = (ifb == 10500) ? 4992 : 1152;                       // aerol.cpp:1012-1050
+    rp.total_number_of_bits = rp.oqpsk ? ifb : ifb * 3;                     // :1062-1070
+    const size_t C = n_channels;
+    int rc = 0;
+    auto alloc = [&](auto **ptr, size_t count) { int q = dev_alloc_zero(ptr, count, r->stream); if (!q) r->allocs.push_back((void *)*ptr); return q; };
+    rc |= alloc(&rp.state, C); rc |= alloc(&rp.slots, C * RT_SLOTS); rc |= alloc(&rp.blocks, C * RT_SLOTS * RT_BLOCK); rc |= alloc(&rp.out, C * RT_OUT * RT_OUT_BYTES);
+    if (rc) { jaero_rt_destroy(r); return JAERO_E_CUDA; }
+    {   // AeroLScrambler::pre_state (aerol.h:397-437)
+        std::vector<uint8_t> seq(5000);
+        int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
+        for (int a = 0; a < 5000; a++) { const int v = st[0] ^ st[14]; seq[a] = (uint8_t)v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
+        if (rt_set_scrambler(seq.data())) { jaero_rt_destroy(r); return JAERO_E_CUDA; }
+    }
+    if (rt_init(rp, r->stream)) { jaero_rt_destroy(r); return JAERO_E_CUDA; }
+    JB_CUDA(cudaStreamSynchronize(r->stream));
+    JB_CUDA(cudaMallocHost(&r->h_state, C * sizeof(RtState)));
+    JB_CUDA(cudaMallocHost(&r->h_out, C * RT_OUT * RT_OUT_BYTES));
+    *out = r;
+    return JAERO_OK;
+}
+void jaero_rt_destroy(jaero_rt *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->device);
+    cudaStreamSynchronize(r->stream);
+    for (void *q : r->allocs) cudaFree(q);
+    cudaFree(r->d_soft_stage); cudaFree(r->d_count_stage);
+    cudaFreeHost(r->h_state); cudaFreeHost(r->h_out);
+    cudaStreamDestroy(r->stream);
+    delete r;
+}
+int64_t jaero_rt_launch_count(const jaero_rt *r) { return r ? r->launches : 0; }
+
+int jaero_rt_process_softbits(jaero_rt *r, const int16_t *soft, size_t cap, const int32_t *counts)
+{
+    if (!r || !soft || !counts || cap == 0) { set_error("jaero_rt_process_softbits: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(r->device));
+    const size_t C = r->rp.n_channels;
+    if (C * cap > r->stage_cap) {
+        JB_CUDA(cudaStreamSynchronize(r->stream));
+        cudaFree(r->d_soft_stage); cudaFree(r->d_count_stage); r->d_soft_stage = 0; r->d_count_stage = 0;
+        JB_CUDA(cudaMalloc(&r->d_soft_stage, C * cap * sizeof(int16_t)));
+        JB_CUDA(cudaMalloc(&r->d_count_stage, C * sizeof(int)));
+        r->stage_cap = C * cap;
+    }
+    JB_CUDA(cudaMemcpyAsync(r->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, r->stream));
+    JB_CUDA(cudaMemcpyAsync(r->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, r->stream));
+    if (rt_process(r->rp, r->d_soft_stage, r->d_count_stage, cap, r->stream, &r->launches)) return JAERO_E_CUDA;
+    JB_CUDA(cudaStreamSynchronize(r->stream));
+    return JAERO_OK;
+}
+int jaero_rt_process_burst(jaero_rt *r, jaero_burst *b)
+{
+    if (!r || !b || r->rp.n_channels != b->p.n_channels || r->device != b->device) { set_error("jaero_rt_process_burst: demodulator mismatch"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(r->device));
+    const BurstParams &bp = b->p;
+    JB_CUDA(cudaStreamSynchronize(r->stream));
+    // on the demodulator's stream: ordered after its kernels; its soft ring is drained afterwards
+    if (rt_process(r->rp, bp.soft, bp.BI + (size_t)BI_SOFT_COUNT * bp.cpad, (size_t)bp.soft_cap, b->stream, &r->launches)) return JAERO_E_CUDA;
+    burst_soft_reset_kernel<<<(bp.n_channels + 127) / 128, 128, 0, b->stream>>>(bp);
+    JB_CUDA(cudaGetLastError());
+    r->launches++;
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    return JAERO_OK;
+}
+int jaero_rt_tick(jaero_rt *r)
+{
+    if (!r) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(r->device));
+    if (rt_tick(r->rp, r->stream)) return JAERO_E_CUDA;
+    r->launches++;
+    return JAERO_OK;
+}
+int jaero_rt_read_packets(jaero_rt *r, uint8_t *out, int cap_packets, int32_t *counts)
+{
+    if (!r || !out || !counts || cap_packets <= 0) { set_error("jaero_rt_read_packets: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(r->device));
+    const size_t C = r->rp.n_channels;
+    JB_CUDA(cudaMemcpyAsync(r->h_state, r->rp.state, C * sizeof(RtState), cudaMemcpyDeviceToHost, r->stream));
+    JB_CUDA(cudaMemcpyAsync(r->h_out, r->rp.out, C * RT_OUT * RT_OUT_BYTES, cudaMemcpyDeviceToHost, r->stream));
+    JB_CUDA(cudaStreamSynchronize(r->stream));
+    bool overflow = false;
+    for (size_t ch = 0; ch < C; ch++) {
+        const int n = r->h_state[ch].out_count;
+        overflow |= r->h_state[ch].overflow != 0 || n > cap_packets;
+        counts[ch] = n < cap_packets ? n : cap_packets;
+        for (int k = 0; k < counts[ch]; k++)
+            memcpy(out + (ch * cap_packets + k) * RT_OUT_BYTES, r->h_out + (ch * RT_OUT + k) * RT_OUT_BYTES, RT_OUT_BYTES);
+    }
+    if (rt_out_reset(r->rp, r->stream)) return JAERO_E_CUDA;
+    r->launches++;
+    if (overflow) { set_error("R/T packet queue overflow: read more often"); return JAERO_E_OVERFLOW; }
+    return JAERO_OK;
+}
+int jaero_rt_get_stats(jaero_rt *r, int32_t *n_trials, int32_t *n_bad, int32_t *dcd)
+{
+    if (!r) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(r->device));
+    const size_t C = r->rp.n_channels;
+    JB_CUDA(cudaMemcpyAsync(r->h_state, r->rp.state, C * sizeof(RtState), cudaMemcpyDeviceToHost, r->stream));
+    JB_CUDA(cudaStreamSynchronize(r->stream));
+    for (size_t ch = 0; ch < C; ch++) {
+        if (n_trials) n_trials[ch] = r->h_state[ch].n_trials;
+        if (n_bad) n_bad[ch] = r->h_state[ch].n_bad;
+        if (dcd) dcd[ch] = r->h_state[ch].datacd;
+    }
+    return JAERO_OK;
+}
+
+} // extern "C"

@@ -184,6 +184,44 @@ def check_burst(names=("burst_msk_1200_a", "burst_msk_1200_b")):
     return ok
 
 
+def check_rt():
+    """R/T burst channel layer: GPU burst demodulator -> GPU packet decoder vs the restated oracle chain."""
+    ok = True
+    for name in ("burst_msk_1200_a", "burst_msk_1200_b", "burst_oqpsk_10500"):
+        pcm = np.load(os.path.join(ROOT, "tests", "golden", name + "_excerpt.npz"))["pcm"]
+        pcm2 = np.stack([pcm, np.roll(pcm, 7001)])
+        oq = name.startswith("burst_oqpsk")
+        fb = 10500 if oq else 1200
+        kw = dict(fb=10500.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6) if oq else dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)
+        b = (jaero_b200.BurstOqpskBatch if oq else jaero_b200.BurstMskBatch)(2, **kw)
+        rt = jaero_b200.RTChannelBatch(2, fb)
+        got = [[], []]
+        for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+            b.write(pcm2[:, a:a + 4800])
+            rt.process_burst(b)
+            if k % 10 == 9:
+                rt.tick()
+            for c, pk in enumerate(rt.read_packets()):
+                got[c] += pk
+        tr, bad, dcd = rt.stats()
+        for c in range(2):
+            o = restated.OracleDemod("burst_oqpsk" if oq else "burst_msk", **kw)
+            ort = restated.OracleRTChannel(fb)
+            for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+                o.write(pcm2[c, a:a + 4800])
+                ort.process(o.take_soft())
+                if k % 10 == 9:
+                    ort.update_dcd()
+            ref = ort.packets()
+            same = len(ref) == len(got[c]) and all(r["type"] == g["type"] and r["nsus"] == g["nsus"] and np.array_equal(r["bytes"], g["bytes"]) for r, g in zip(ref, got[c]))
+            print(f"rt {name} ch{c}: packets gpu={len(got[c])} oracle={len(ref)} identical={same} trials gpu={tr[c]} oracle={ort.trials} "
+                  f"types={[g['type'] for g in got[c]]} nsus={[g['nsus'] for g in got[c]]}")
+            ok &= same and tr[c] == ort.trials and len(ref) > 0
+        b.close(); rt.close()
+    print("RT", "PASS" if ok else "FAIL")
+    return ok
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["viterbi", "oqpsk", "msk", "pchannel"]
     ok = True
@@ -191,6 +229,8 @@ if __name__ == "__main__":
         ok &= check_viterbi()
     if "oqpsk" in which:
         ok &= check_demod("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
+    if "rt" in which:
+        ok &= check_rt()
     if "burst_oqpsk" in which:
         ok &= check_burst(("burst_oqpsk_10500",))
     if "oqpsk8400" in which:
