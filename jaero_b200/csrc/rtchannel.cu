@@ -85,7 +85,7 @@ rt_frame_kernel(RtParams rp, const int16_t *__restrict__ soft, const int *__rest
                 slots[cur].fill = fill; slots[cur].closed = 1;
                 if (s.n_open < RT_SLOTS) { cur++; if (cur >= RT_SLOTS) cur = 0; s.n_open++; }
                 else s.overflow = 1;                                         // no slot left: the oldest pending packet of this call is lost (reported)
-                RtSlot ns; ns.fill = 0; ns.next_trial = 64 * 5; ns.done = 0; ns.closed = 0; ns.targetSUSize = 0; ns.targetBlocks = 0; ns.start_bit = s.bits_seen;
+                RtSlot ns; ns.fill = 0; ns.next_trial = rp.oqpsk ? 64 * 2 : 64 * 5; ns.done = 0; ns.closed = 0; ns.targetSUSize = 0; ns.targetBlocks = 0; ns.start_bit = s.bits_seen;
                 slots[cur] = ns;
                 fill = 0;
             }
@@ -247,7 +247,9 @@ __global__ void rt_init_kernel(RtParams rp)
     s.lastpacketstate = RT_NOTHING;
     s.n_open = 1;                                              // the block the RT object starts with
     rp.state[ch] = s;
-    RtSlot ns; ns.fill = 0; ns.next_trial = 64 * 5; ns.done = 0; ns.closed = 0; ns.targetSUSize = 0; ns.targetBlocks = 0; ns.start_bit = 0;
+    // update() tests ((blockptr-320)%192)==0 with C's truncating %, which also holds at blockptr = 128 (aerol.h:794): the
+    // OQPSK trial sequence is 128, 320, 512, ...; updateMSK() additionally requires blockptr/64 in {5, target, 11, 50}
+    RtSlot ns; ns.fill = 0; ns.next_trial = rp.oqpsk ? 64 * 2 : 64 * 5; ns.done = 0; ns.closed = 0; ns.targetSUSize = 0; ns.targetBlocks = 0; ns.start_bit = 0;
     rp.slots[(size_t)ch * RT_SLOTS] = ns;
 }
 __global__ void rt_out_reset_kernel(RtParams rp)

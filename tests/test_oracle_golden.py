@@ -194,3 +194,24 @@ def test_synthetic_pchannel_signal_decodes():
     assert ok.sum() >= 26 * 3
     assert all(bytes(x) in tx for x in b[ok == 1])
     assert abs(d.state()["ebno"] - 10.0) < 1.0
+
+
+@pytest.mark.parametrize("name", ["burst_msk_1200_a", "burst_msk_1200_b", "burst_oqpsk_10500"])
+def test_rt_channel_oracle_decodes_crc_valid_packets(golden, name):
+    """SURVEY 8(f)2: the restated burst branch of AeroL::Decode + RTChannelDeleaveFECScram turns the reference's soft bits
+    into T packets whose header and signal-unit CRC-16s verify (self-certifying: de-interleaver, Viterbi restatement,
+    scrambler and CRC all have to be right), identical to the committed golden, and independent of how the stream is cut."""
+    case = golden[name]
+    soft, _, _ = _run_restated(case, load_excerpt(case["excerpt"]))
+    rt = restated.OracleRTChannel(case["kw"]["fb"])
+    rt.process(soft)
+    pk = rt.packets()
+    assert len(pk) == len(case["rt_packets"]) >= 2
+    for q, g in zip(pk, case["rt_packets"]):
+        assert q["type"] == g["type"] == 2 and q["nsus"] == g["nsus"] and len(q["bytes"]) == g["n_bytes"]
+        assert hashlib.sha256(q["bytes"].tobytes()).hexdigest() == g["sha256"]
+    rt2 = restated.OracleRTChannel(case["kw"]["fb"])
+    for a in range(0, len(soft), 33):
+        rt2.process(soft[a:a + 33], vector_semantics=True)
+    pk2 = rt2.packets()
+    assert len(pk2) == len(pk) and all(np.array_equal(a["bytes"], b["bytes"]) for a, b in zip(pk, pk2))

@@ -41,7 +41,15 @@ def run_case(name, case, chunk=4800):
         p = restated.OraclePChannel(case["kw"]["fb"])
         p.process(soft)
         su, ok, fr = p.take_sus()
+    rt_packets = []
+    if case["kind"].startswith("burst"):
+        # R/T packet layer (restated AeroL burst branch; pinned by the CRC-16s it verifies) on the reference's soft bits
+        rt = restated.OracleRTChannel(case["kw"]["fb"])
+        rt.process(soft)
+        rt_packets = [dict(type=q["type"], nsus=q["nsus"], n_bytes=int(len(q["bytes"])), sha256=hashlib.sha256(q["bytes"].tobytes()).hexdigest())
+                      for q in rt.packets()]
     return {
+        "rt_packets": rt_packets,
         "kind": case["kind"], "kw": case["kw"], "excerpt": case.get("excerpt", name), "chunk": chunk,
         "dcd_schedule": sched or [],
         "n_soft": int(len(soft)), "soft_sha256": hashlib.sha256(soft.astype("<i2").tobytes()).hexdigest(),
