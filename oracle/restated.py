@@ -208,3 +208,40 @@ class OracleRTChannel:
     def close(self):
         if self.h:
             lib().jor_rt_free(self.h); self.h = None
+
+
+class OracleCChannel:
+    """Restated AeroL::DecodeC (8400 bps C-channel): soft bits -> per frame 3 sub-band signal units (+CRC) and 25 x 12 voice bytes."""
+
+    def __init__(self):
+        L = lib()
+        L.jor_cchan_new.restype = ctypes.c_void_p
+        L.jor_cchan_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.jor_cchan_update_dcd.argtypes = [ctypes.c_void_p]
+        L.jor_cchan_dcd.argtypes = [ctypes.c_void_p]
+        L.jor_cchan_frame_count.restype = ctypes.c_long; L.jor_cchan_frame_count.argtypes = [ctypes.c_void_p]
+        L.jor_cchan_take.restype = ctypes.c_long; L.jor_cchan_take.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
+        L.jor_cchan_free.argtypes = [ctypes.c_void_p]
+        self.h = L.jor_cchan_new()
+
+    def process(self, soft):
+        soft = np.ascontiguousarray(soft, dtype=np.int16)
+        lib().jor_cchan_process(self.h, _p(soft), len(soft))
+
+    def update_dcd(self):
+        lib().jor_cchan_update_dcd(self.h)
+
+    @property
+    def dcd(self):
+        return bool(lib().jor_cchan_dcd(self.h))
+
+    def take_frames(self):
+        n = lib().jor_cchan_frame_count(self.h)
+        su = np.zeros((n, 3, 12), dtype=np.uint8); ok = np.zeros((n, 3), dtype=np.int32); voice = np.zeros((n, 300), dtype=np.uint8)
+        if n:
+            lib().jor_cchan_take(self.h, _p(su), _p(ok), _p(voice), n)
+        return su, ok, voice
+
+    def close(self):
+        if self.h:
+            lib().jor_cchan_free(self.h); self.h = None

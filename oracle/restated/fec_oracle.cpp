@@ -420,3 +420,114 @@ void RTChannelOracle::updateDCD()                              // aerol.cpp:1109
     else { if (datacdcountdown < 0) datacdcountdown = 0; }
     if (datacd && !datacdcountdown) datacd = false;
 }
+
+
+// ====================================================================================== C channel (8400 bps)
+namespace {
+const uint64_t C_PRE1 = 216866263330005ULL, C_PRE2 = 3012071630031408ULL;   // aerol.cpp:953-954 (Q word, I word), 52 bits
+const uint64_t C_MASK = (1ULL << 52) - 1;
+// OQPSKPreambleDetectorAndAmbiguityCorrection::Update (aerol.cpp:848-896), tollerence 6: the second buffer is only
+// shifted when the first one does not match
+int c_uw_update(uint64_t &b1, uint64_t &b2, int val, bool &inverted)
+{
+    b1 = ((b1 << 1) | (uint64_t)val) & C_MASK;
+    int xorsum = __builtin_popcountll(b1 ^ C_PRE1);
+    if (xorsum >= 52 - 6) { inverted = true; return 1; }
+    if (xorsum <= 6) { inverted = false; return 1; }
+    b2 = ((b2 << 1) | (uint64_t)val) & C_MASK;
+    xorsum = __builtin_popcountll(b2 ^ C_PRE2);
+    if (xorsum >= 52 - 6) { inverted = true; return 1; }
+    if (xorsum <= 6) { inverted = false; return 1; }
+    return 0;
+}
+}
+
+CChannelOracle::CChannelOracle() : codec(24)
+{
+    b1_real = b2_real = b1_imag = b2_imag = 0; inv_real = inv_imag = false;
+    realimag = 0; gotsync_last = 0; cntr = 1000000000; index = 0;                  // AeroL ctor: index = 0 (aerol.cpp:957)
+    block.assign(4 * 64, 0);
+    dl2.assign(2714 - 6 + 1, 0); dl2_ptr = 0;                                       // dl2.setLength(2714-6) (aerol.cpp:1037)
+    {
+        int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
+        scr.resize(5000);
+        for (int a = 0; a < 5000; a++) { const int v = st[0] ^ st[14]; scr[a] = v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
+    }
+    datacdcountdown = 0; datacd = false; bits_seen = 0; nframes = 0;
+}
+
+void CChannelOracle::process(const short *bits, int n)
+{
+    const int NumberOfBits = 4096;
+    for (int i = 0; i < n; i++) {
+        bits_seen++;
+        int bit = (((uint8_t)bits[i]) >= 128) ? 1 : 0;
+        int soft_bit = (uint16_t)bits[i];
+        int gotsync = 0;
+        realimag++; realimag %= 2;
+        const bool search = (cntr > NumberOfBits - 112 || cntr <= 0);
+        if (realimag) {
+            if (search) { gotsync = c_uw_update(b1_real, b2_real, bit, inv_real); if (!gotsync_last) { gotsync_last = gotsync; gotsync = 0; } else gotsync_last = 0; }
+            else { gotsync = 0; gotsync_last = 0; }
+            if (inv_real) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
+        } else {
+            if (search) { gotsync = c_uw_update(b1_imag, b2_imag, bit, inv_imag); if (!gotsync_last) { gotsync_last = gotsync; gotsync = 0; } else gotsync_last = 0; }
+            else { gotsync = 0; gotsync_last = 0; }
+            if (inv_imag) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
+        }
+        if (gotsync) { cntr = -1; index = -1; deleavered.clear(); }            // :2286-2296 (scrambler.reset: position 0 per frame)
+        else {
+            if (cntr < 1000000000) cntr++;
+            if (cntr <= NumberOfBits - 1) { index++; if (index >= 0 && index < 256) block[index] = soft_bit; }
+            if (index == 255) {                                                // :2308-2319 deinterleave_ba(block, 4)
+                for (int j = 0; j < 4; j++) for (int r = 0; r < 64; r++) deleavered.push_back((uint8_t)block[((r * 27) % 64) * 4 + j]);
+                index = -1;
+            }
+            if (cntr == NumberOfBits - 1) {                                    // :2320-2498 frame complete
+                std::vector<uint8_t> dep;                                      // depunture_soft_block(..., 4, true) (:2505-2518)
+                { int ptr = 0; for (int k = 0; k + 1 < (int)deleavered.size(); k++) { ptr++; dep.push_back(deleavered[k]); if (ptr >= 3) dep.push_back(128); ptr %= 3; } }
+                std::vector<int> dec = codec.decode(dep.data(), (int)dep.size());
+                dec.resize(2714, 0);
+                for (size_t h = 0; h < dec.size(); h++) { dl2[dl2_ptr] = dec[h]; dl2_ptr++; dl2_ptr %= (int)dl2.size(); dec[h] = dl2[dl2_ptr]; }
+                for (size_t h = 0; h < dec.size(); h++) dec[h] ^= scr[h];
+                CFrame fr; memset(&fr, 0, sizeof fr); fr.bit_index = bits_seen;
+                std::vector<uint8_t> info; int charptr = 0; uint8_t ch = 0; int nsu = 0;
+                for (int y = 0; y < 24; y++) {
+                    const int offset = y * (1 + 96 + 12);
+                    for (int h = offset + 97; h < offset + 109; h++) {
+                        ch |= (uint8_t)(dec[h] * 128);
+                        charptr++; charptr %= 8;
+                        if (charptr == 0) { info.push_back(ch); ch = 0; } else ch >>= 1;
+                    }
+                    if (info.size() == 12) {
+                        const uint16_t crc_calc = oracle_crc16(info.data(), 10);
+                        const uint16_t crc_rec = (uint16_t)((info[11] << 8) | info[10]);
+                        const bool ok = crc_calc == crc_rec;
+                        if (ok) { if (datacdcountdown < 12) datacdcountdown += 2; }
+                        else { if (datacdcountdown > 0) datacdcountdown -= 5; }
+                        if (!datacd && datacdcountdown > 2) datacd = true;
+                        if (nsu < 3) { memcpy(fr.su[nsu].bytes, info.data(), 12); fr.su[nsu].crc_ok = ok ? 1 : 0; fr.su[nsu].frame = nframes; nsu++; }
+                        info.clear();
+                    }
+                }
+                int bitsin = 0, vb = 0;
+                for (int h = 1; h < 2714; h++) {                               // voice payload: 25 x 96 bits (:2457-2479)
+                    ch |= (uint8_t)(dec[h] * 128);
+                    charptr++; charptr %= 8;
+                    if (charptr == 0) { if (vb < 300) fr.voice[vb++] = ch; ch = 0; } else ch >>= 1;
+                    bitsin++;
+                    if (bitsin == 96) { bitsin = 0; h += 13; }
+                }
+                frames.push_back(fr); nframes++;
+                index = -1;
+            }
+        }
+    }
+}
+
+void CChannelOracle::updateDCD()
+{
+    if (datacdcountdown > 0) datacdcountdown -= 3;
+    else { if (datacdcountdown < 0) datacdcountdown = 0; }
+    if (datacd && !datacdcountdown) datacd = false;
+}

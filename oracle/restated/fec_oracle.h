@@ -55,6 +55,23 @@ struct PChannelOracle
 };
 uint16_t oracle_crc16(const uint8_t *bytes, int n);
 
+// ---- AeroL::DecodeC, 8400 bps C-channel (JAERO/aerol.cpp:2187-2500; dual-UW detector :848-896; PuncturedCode :2505-2518)
+struct CFrame { SignalUnit su[3]; uint8_t voice[300]; long bit_index; };
+struct CChannelOracle
+{
+    uint64_t b1_real, b2_real, b1_imag, b2_imag; bool inv_real, inv_imag;     // OQPSKPreambleDetectorAndAmbiguityCorrection x2
+    int realimag, gotsync_last; long cntr; int index;
+    std::vector<int> block; std::vector<uint8_t> deleavered;
+    ContinuousViterbiOracle codec;
+    std::vector<int> dl2; int dl2_ptr;
+    std::vector<int> scr;
+    int datacdcountdown; bool datacd;
+    std::vector<CFrame> frames; long bits_seen, nframes;
+    CChannelOracle();
+    void process(const short *soft, int n);
+    void updateDCD();
+};
+
 // ---- burst (R/T channel) branch of AeroL::Decode (JAERO/aerol.cpp:1124-1350, :1985-2031) with
 // RTChannelDeleaveFECScram (JAERO/aerol.h:554-895), minus all text output / ACARS parsing.
 struct RTPacket { int type; int nsus; long bit_index; std::vector<uint8_t> bytes; };   // type 1 = R packet (19 bytes), 2 = T packet (6+12n)

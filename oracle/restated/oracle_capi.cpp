@@ -124,6 +124,25 @@ long jor_pchan_su_take(void *p, uint8_t *bytes12, int *crc_ok, long *frame, long
     o->sus.erase(o->sus.begin(), o->sus.begin() + n); return n;
 }
 void jor_pchan_free(void *p) { delete (PChannelOracle *)p; }
+// ---- C channel (8400)
+void *jor_cchan_new() { return new CChannelOracle(); }
+void jor_cchan_process(void *p, const short *soft, int n) { ((CChannelOracle *)p)->process(soft, n); }
+void jor_cchan_update_dcd(void *p) { ((CChannelOracle *)p)->updateDCD(); }
+int jor_cchan_dcd(void *p) { return ((CChannelOracle *)p)->datacd ? 1 : 0; }
+long jor_cchan_frame_count(void *p) { return (long)((CChannelOracle *)p)->frames.size(); }
+// frames: su [n][3][12], crc_ok [n][3], voice [n][300]
+long jor_cchan_take(void *p, uint8_t *su, int *crc_ok, uint8_t *voice, long cap)
+{
+    CChannelOracle *o = (CChannelOracle *)p;
+    long n = (long)o->frames.size(); if (n > cap) n = cap;
+    for (long k = 0; k < n; k++) {
+        for (int q = 0; q < 3; q++) { for (int b = 0; b < 12; b++) su[(k * 3 + q) * 12 + b] = o->frames[k].su[q].bytes[b]; crc_ok[k * 3 + q] = o->frames[k].su[q].crc_ok; }
+        for (int b = 0; b < 300; b++) voice[k * 300 + b] = o->frames[k].voice[b];
+    }
+    o->frames.erase(o->frames.begin(), o->frames.begin() + n);
+    return n;
+}
+void jor_cchan_free(void *p) { delete (CChannelOracle *)p; }
 // ---- R/T burst channel
 void *jor_rt_new(int fb) { return new RTChannelOracle(fb); }
 void jor_rt_process(void *p, const short *soft, int n, int vector_semantics) { ((RTChannelOracle *)p)->process(soft, n, vector_semantics != 0); }
