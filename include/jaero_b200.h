@@ -220,6 +220,23 @@ int jaero_rt_read_packets(jaero_rt *r, uint8_t *out, int cap_packets_per_channel
 int jaero_rt_get_stats(jaero_rt *r, int32_t *n_trial_decodes, int32_t *n_bad_packets, int32_t *dcd);   /* any may be NULL */
 int64_t jaero_rt_launch_count(const jaero_rt *r);
 
+/* ---- C-channel (8400 bps) frame layer ----
+ * Replaces AeroL::DecodeC (JAERO/aerol.cpp:2187-2500): dual unique-word detector with I/Q ambiguity correction
+ * (:848-896), 16 x (64 x 4) de-interleave, PuncturedCode::depunture_soft_block(...,4) (:2505-2518), Decode_Continuous,
+ * delay line, scrambler, the three sub-band signal units per frame with CRC-16 + DCD countdown, the 25 x 12-byte voice
+ * payload (what Voicesignal carries to the vocoder). Output records are JAERO_C_RECORD bytes: 3 x {12 SU bytes, crc_ok,
+ * 3 pad}, 300 voice bytes, int32 frame number. */
+#define JAERO_C_RECORD 352
+typedef struct jaero_cchannel jaero_cchannel;
+int jaero_cchannel_create(int n_channels, int device_ordinal, jaero_cchannel **out);
+void jaero_cchannel_destroy(jaero_cchannel *c);
+int jaero_cchannel_process_batch(jaero_cchannel *c, jaero_batch *b);      /* consume (and drain) an 8400 bps batch's soft bits on the device; DCD fed back */
+int jaero_cchannel_process_softbits(jaero_cchannel *c, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
+int jaero_cchannel_tick(jaero_cchannel *c, jaero_batch *b);               /* the 1 s updateDCD timer; b may be NULL */
+int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames_per_channel, int32_t *counts);
+int jaero_cchannel_get_stats(jaero_cchannel *c, int32_t *dcd, int64_t *su_total, int64_t *su_ok);   /* any may be NULL */
+int64_t jaero_cchannel_launch_count(const jaero_cchannel *c);
+
 #ifdef __cplusplus
 }
 #endif

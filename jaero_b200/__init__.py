@@ -49,7 +49,9 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
            "jaero_burst_launch_count",
            "jaero_rt_create", "jaero_rt_destroy", "jaero_rt_process_softbits", "jaero_rt_process_burst", "jaero_rt_tick",
-           "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count"]
+           "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count",
+           "jaero_cchannel_create", "jaero_cchannel_destroy", "jaero_cchannel_process_batch", "jaero_cchannel_process_softbits",
+           "jaero_cchannel_tick", "jaero_cchannel_read_frames", "jaero_cchannel_get_stats", "jaero_cchannel_launch_count"]
 
 
 def lib():
@@ -110,6 +112,14 @@ def lib():
         L.jaero_rt_read_packets.argtypes = [vp, vp, i, vp]
         L.jaero_rt_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_rt_launch_count.argtypes = [vp]; L.jaero_rt_launch_count.restype = ctypes.c_int64
+        L.jaero_cchannel_create.argtypes = [i, i, ctypes.POINTER(vp)]
+        L.jaero_cchannel_destroy.argtypes = [vp]; L.jaero_cchannel_destroy.restype = None
+        L.jaero_cchannel_process_batch.argtypes = [vp, vp]
+        L.jaero_cchannel_process_softbits.argtypes = [vp, vp, sz, vp]
+        L.jaero_cchannel_tick.argtypes = [vp, vp]
+        L.jaero_cchannel_read_frames.argtypes = [vp, vp, i, vp]
+        L.jaero_cchannel_get_stats.argtypes = [vp, vp, vp, vp]
+        L.jaero_cchannel_launch_count.argtypes = [vp]; L.jaero_cchannel_launch_count.restype = ctypes.c_int64
         _lib = L
     return _lib
 
@@ -438,6 +448,63 @@ class RTChannelBatch:
     def close(self):
         if self.h:
             lib().jaero_rt_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CChannelBatch:
+    """C-channel (8400 bps) frame layer: soft bits -> per frame three sub-band signal units (+CRC) and 25 x 12 voice bytes."""
+    RECORD = 352
+
+    def __init__(self, n_channels, device=0):
+        if n_channels <= 0:
+            raise JaeroError("n_channels must be positive")
+        self.h = ctypes.c_void_p()
+        self.n = n_channels
+        _check(lib().jaero_cchannel_create(n_channels, device, ctypes.byref(self.h)))
+
+    def process(self, soft_list):
+        cap = max(1, max(len(s) for s in soft_list))
+        buf = np.zeros((self.n, cap), dtype=np.int16)
+        counts = np.zeros(self.n, dtype=np.int32)
+        for c, s in enumerate(soft_list):
+            buf[c, :len(s)] = s; counts[c] = len(s)
+        _check(lib().jaero_cchannel_process_softbits(self.h, _p(buf), cap, _p(counts)))
+
+    def process_batch(self, batch):
+        _check(lib().jaero_cchannel_process_batch(self.h, batch.h))
+
+    def tick(self, batch=None):
+        _check(lib().jaero_cchannel_tick(self.h, batch.h if batch is not None else None))
+
+    def read_frames(self, cap=8):
+        """per channel: (su[n,3,12], crc_ok[n,3], voice[n,300], frame[n])"""
+        out = np.zeros((self.n, cap, self.RECORD), dtype=np.uint8)
+        counts = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_cchannel_read_frames(self.h, _p(out), cap, _p(counts)))
+        res = []
+        for c in range(self.n):
+            r = out[c, :counts[c]]
+            su = r[:, :48].reshape(-1, 3, 16)
+            res.append((su[:, :, :12].copy(), su[:, :, 12].astype(np.int32), r[:, 48:348].copy(), r[:, 348:352].copy().view(np.int32).reshape(-1)))
+        return res
+
+    def stats(self):
+        dcd = np.zeros(self.n, dtype=np.int32); tot = np.zeros(self.n, dtype=np.int64); ok = np.zeros(self.n, dtype=np.int64)
+        _check(lib().jaero_cchannel_get_stats(self.h, _p(dcd), _p(tot), _p(ok)))
+        return dcd, tot, ok
+
+    @property
+    def launches(self):
+        return lib().jaero_cchannel_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().jaero_cchannel_destroy(self.h); self.h = None
 
     def __del__(self):
         try:

@@ -17,6 +17,7 @@ UNITS = [
     ("cfe.cu", []),
     ("pchannel.cu", []),
     ("rtchannel.cu", []),
+    ("cchannel.cu", []),
     ("prefilter.cu", ["-fmad=false"]),
     ("burst.cu", ["-fmad=false"]),
     ("demod_kernels.cu", ["-fmad=false"]),

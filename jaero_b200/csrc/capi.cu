@@ -1511,3 +1511,146 @@ int jaero_rt_get_stats(jaero_rt *r, int32_t *n_trials, int32_t *n_bad, int32_t *
 }
 
 } // extern "C"
+
+// ====================================================================== C-channel (8400 bps) frame layer (§8(f)3)
+#include "cchannel.cuh"
+
+struct jaero_cchannel {
+    int device; cudaStream_t stream, cur_stream;
+    CChanParams cp;
+    std::vector<void *> allocs;
+    uint8_t *vit_overlap; int *vit_overlap_len, *vit_renorm, *vit_valid;
+    int16_t *d_soft_stage; int *d_count_stage; size_t stage_cap;
+    CChanState *h_state; uint8_t *h_out;
+    long long launches;
+};
+
+extern "C" {
+
+int jaero_cchannel_create(int n_channels, int device, jaero_cchannel **out)
+{
+    if (!out || n_channels <= 0) { set_error("jaero_cchannel_create: bad argument"); return JAERO_E_ARG; }
+    int ndev = 0;
+    JB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("jaero_cchannel_create: no such CUDA device"); return JAERO_E_CUDA; }
+    JB_CUDA(cudaSetDevice(device));
+    jaero_cchannel *c = new (std::nothrow) jaero_cchannel();
+    if (!c) { set_error("out of host memory"); return JAERO_E_ARG; }
+    c->device = device; c->d_soft_stage = 0; c->d_count_stage = 0; c->stage_cap = 0; c->h_state = 0; c->h_out = 0; c->launches = 0;
+    JB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->cur_stream = c->stream;
+    CChanParams &cp = c->cp;
+    memset(&cp, 0, sizeof cp);
+    cp.n_channels = n_channels; cp.dl2_len = 2714 - 6 + 1;                     // dl2.setLength(2714-6) (aerol.cpp:1037)
+    const size_t C = n_channels;
+    int rc = 0;
+    auto alloc = [&](auto **ptr, size_t count) { int q = dev_alloc_zero(ptr, count, c->stream); if (!q) c->allocs.push_back((void *)*ptr); return q; };
+    rc |= alloc(&cp.state, C); rc |= alloc(&cp.coded, C * CC_QUEUE * CC_CODED_PITCH); rc |= alloc(&cp.decoded, C * CC_QUEUE * CC_DEC);
+    rc |= alloc(&cp.ready, C); rc |= alloc(&cp.dl2, C * cp.dl2_len); rc |= alloc(&cp.out, C * CC_OUT * CC_RECORD);
+    rc |= alloc(&c->vit_overlap, C * 64); rc |= alloc(&c->vit_overlap_len, C); rc |= alloc(&c->vit_renorm, C); rc |= alloc(&c->vit_valid, C);
+    if (rc) { jaero_cchannel_destroy(c); return JAERO_E_CUDA; }
+    {
+        std::vector<uint8_t> seq(5000);
+        int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
+        for (int a = 0; a < 5000; a++) { const int v = st[0] ^ st[14]; seq[a] = (uint8_t)v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
+        if (cchan_set_scrambler(seq.data())) { jaero_cchannel_destroy(c); return JAERO_E_CUDA; }
+    }
+    if (cchan_init(cp, c->stream)) { jaero_cchannel_destroy(c); return JAERO_E_CUDA; }
+    JB_CUDA(cudaStreamSynchronize(c->stream));
+    JB_CUDA(cudaMallocHost(&c->h_state, C * sizeof(CChanState)));
+    JB_CUDA(cudaMallocHost(&c->h_out, C * CC_OUT * CC_RECORD));
+    *out = c;
+    return JAERO_OK;
+}
+void jaero_cchannel_destroy(jaero_cchannel *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void *q : c->allocs) cudaFree(q);
+    cudaFree(c->d_soft_stage); cudaFree(c->d_count_stage);
+    cudaFreeHost(c->h_state); cudaFreeHost(c->h_out);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+int64_t jaero_cchannel_launch_count(const jaero_cchannel *c) { return c ? c->launches : 0; }
+
+int jaero_cchannel_process_batch(jaero_cchannel *c, jaero_batch *b)
+{
+    if (!c || !b || c->cp.n_channels != b->p.n_channels || c->device != b->device) { set_error("jaero_cchannel_process_batch: batch mismatch"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(c->device));
+    const DemodParams &dp = b->p;
+    int *dcd = dp.I + (size_t)I_DCD * dp.cpad;
+    c->cur_stream = b->stream;
+    if (cchan_process(c->cp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, (size_t)dp.soft_cap, dcd, c->vit_overlap, c->vit_overlap_len,
+                      c->vit_renorm, c->vit_valid, b->stream, &c->launches)) return JAERO_E_CUDA;
+    soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
+    JB_CUDA(cudaGetLastError());
+    c->launches++;
+    return JAERO_OK;
+}
+int jaero_cchannel_process_softbits(jaero_cchannel *c, const int16_t *soft, size_t cap, const int32_t *counts)
+{
+    if (!c || !soft || !counts || cap == 0) { set_error("jaero_cchannel_process_softbits: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(c->device));
+    const size_t C = c->cp.n_channels;
+    if (C * cap > c->stage_cap) {
+        JB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_soft_stage); cudaFree(c->d_count_stage); c->d_soft_stage = 0; c->d_count_stage = 0;
+        JB_CUDA(cudaMalloc(&c->d_soft_stage, C * cap * sizeof(int16_t)));
+        JB_CUDA(cudaMalloc(&c->d_count_stage, C * sizeof(int)));
+        c->stage_cap = C * cap;
+    }
+    JB_CUDA(cudaStreamSynchronize(c->cur_stream));
+    c->cur_stream = c->stream;
+    JB_CUDA(cudaMemcpyAsync(c->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+    JB_CUDA(cudaMemcpyAsync(c->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (cchan_process(c->cp, c->d_soft_stage, c->d_count_stage, cap, nullptr, c->vit_overlap, c->vit_overlap_len, c->vit_renorm, c->vit_valid,
+                      c->stream, &c->launches)) return JAERO_E_CUDA;
+    JB_CUDA(cudaStreamSynchronize(c->stream));
+    return JAERO_OK;
+}
+int jaero_cchannel_tick(jaero_cchannel *c, jaero_batch *b)
+{
+    if (!c || (b && b->p.n_channels != c->cp.n_channels)) { set_error("jaero_cchannel_tick: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(c->device));
+    if (cchan_tick(c->cp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : c->cur_stream)) return JAERO_E_CUDA;
+    c->launches++;
+    return JAERO_OK;
+}
+int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames, int32_t *counts)
+{
+    if (!c || !out || !counts || cap_frames <= 0) { set_error("jaero_cchannel_read_frames: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(c->device));
+    const size_t C = c->cp.n_channels;
+    JB_CUDA(cudaMemcpyAsync(c->h_state, c->cp.state, C * sizeof(CChanState), cudaMemcpyDeviceToHost, c->cur_stream));
+    JB_CUDA(cudaMemcpyAsync(c->h_out, c->cp.out, C * CC_OUT * CC_RECORD, cudaMemcpyDeviceToHost, c->cur_stream));
+    JB_CUDA(cudaStreamSynchronize(c->cur_stream));
+    bool overflow = false;
+    for (size_t ch = 0; ch < C; ch++) {
+        const int n = c->h_state[ch].out_count;
+        overflow |= c->h_state[ch].overflow != 0 || n > cap_frames;
+        counts[ch] = n < cap_frames ? n : cap_frames;
+        for (int k = 0; k < counts[ch]; k++) memcpy(out + (ch * cap_frames + k) * CC_RECORD, c->h_out + (ch * CC_OUT + k) * CC_RECORD, CC_RECORD);
+    }
+    if (cchan_out_reset(c->cp, c->cur_stream)) return JAERO_E_CUDA;
+    c->launches++;
+    if (overflow) { set_error("C-channel frame queue overflow: read more often"); return JAERO_E_OVERFLOW; }
+    return JAERO_OK;
+}
+int jaero_cchannel_get_stats(jaero_cchannel *c, int32_t *dcd, int64_t *su_total, int64_t *su_ok)
+{
+    if (!c) { set_error("null handle"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(c->device));
+    const size_t C = c->cp.n_channels;
+    JB_CUDA(cudaMemcpyAsync(c->h_state, c->cp.state, C * sizeof(CChanState), cudaMemcpyDeviceToHost, c->cur_stream));
+    JB_CUDA(cudaStreamSynchronize(c->cur_stream));
+    for (size_t ch = 0; ch < C; ch++) {
+        if (dcd) dcd[ch] = c->h_state[ch].datacd;
+        if (su_total) su_total[ch] = c->h_state[ch].su_total;
+        if (su_ok) su_ok[ch] = c->h_state[ch].su_ok;
+    }
+    return JAERO_OK;
+}
+
+} // extern "C"

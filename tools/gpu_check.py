@@ -184,6 +184,41 @@ def check_burst(names=("burst_msk_1200_a", "burst_msk_1200_b")):
     return ok
 
 
+def check_cchannel():
+    """C-channel (8400 bps): GPU demodulator -> GPU frame layer (DCD fed back on the device) vs the restated oracle chain."""
+    pcm = np.load(os.path.join(ROOT, "tests", "golden", "oqpsk_8400_excerpt.npz"))["pcm"]
+    pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 2 // 3).astype(np.int16)])
+    kw = dict(fb=8400, freq_center=8000, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)
+    b = jaero_b200.DemodBatch("oqpsk", 2, **kw)
+    cc = jaero_b200.CChannelBatch(2)
+    got = [[], []]
+    for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+        b.write(pcm2[:, a:a + 4800])
+        cc.process_batch(b)
+        if k % 10 == 9:
+            cc.tick(b)
+        for c, fr in enumerate(cc.read_frames()):
+            got[c].append(fr)
+    dcd, tot, okc = cc.stats()
+    ok = True
+    for c in range(2):
+        o = restated.OracleDemod("oqpsk", **kw); oc = restated.OracleCChannel()
+        for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+            o.write(pcm2[c, a:a + 4800])
+            oc.process(o.take_soft())
+            o.set_dcd(int(oc.dcd))
+            if k % 10 == 9:
+                oc.update_dcd(); o.set_dcd(int(oc.dcd))
+        su, cok, voice = oc.take_frames()
+        gsu = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]]); gv = np.concatenate([g[2] for g in got[c]])
+        same = gsu.shape == su.shape and np.array_equal(gsu, su) and np.array_equal(gok, cok) and np.array_equal(gv, voice)
+        print(f"cchannel ch{c}: frames gpu={len(gsu)} oracle={len(su)} SU crc_ok gpu={int(gok.sum())} oracle={int(cok.sum())} identical={same} dcd gpu={dcd[c]} oracle={int(oc.dcd)}")
+        ok &= same and len(su) > 5 and int(cok.sum()) > 10 and dcd[c] == int(oc.dcd)
+    b.close(); cc.close()
+    print("CCHANNEL", "PASS" if ok else "FAIL")
+    return ok
+
+
 def check_rt():
     """R/T burst channel layer: GPU burst demodulator -> GPU packet decoder vs the restated oracle chain."""
     ok = True
@@ -229,6 +264,8 @@ if __name__ == "__main__":
         ok &= check_viterbi()
     if "oqpsk" in which:
         ok &= check_demod("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True))
+    if "cchannel" in which:
+        ok &= check_cchannel()
     if "rt" in which:
         ok &= check_rt()
     if "burst_oqpsk" in which:
