@@ -327,6 +327,42 @@ def test_rt_channel_packets_on_reference_recordings(golden, name):
     assert [hashlib.sha256(g["bytes"].tobytes()).hexdigest() for g in got[0]] == [q["sha256"] for q in case["rt_packets"]]
 
 
+def test_c_channel_frames_on_reference_recording(golden):
+    """SURVEY 8(f)3 end to end on the GPU: 8400 bps demodulator (K6 + K1a') -> C-channel frame layer with the soft bits
+    and the DCD feedback staying on the device; signal units, CRC flags and voice bytes identical to the oracle chain."""
+    jb = _import()
+    case = golden["oqpsk_8400"]
+    pcm = load_excerpt("oqpsk_8400")
+    pcm2 = np.stack([pcm, (pcm.astype(np.int32) * 2 // 3).astype(np.int16)])
+    kw = dict(case["kw"])
+    b = jb.DemodBatch("oqpsk", 2, **kw)
+    cc = jb.CChannelBatch(2)
+    got = [[], []]
+    for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+        b.write(pcm2[:, a:a + 4800])
+        cc.process_batch(b)
+        if k % 10 == 9:
+            cc.tick(b)
+        for c, fr in enumerate(cc.read_frames()):
+            got[c].append(fr)
+    dcd, tot, okc = cc.stats()
+    b.close(); cc.close()
+    for c in range(2):
+        o = restated.OracleDemod("oqpsk", **kw); oc = restated.OracleCChannel()
+        for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+            o.write(pcm2[c, a:a + 4800])
+            oc.process(o.take_soft())
+            o.set_dcd(int(oc.dcd))
+            if k % 10 == 9:
+                oc.update_dcd(); o.set_dcd(int(oc.dcd))
+        su, cok, voice = oc.take_frames()
+        gsu = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]]); gv = np.concatenate([g[2] for g in got[c]])
+        assert gsu.shape == su.shape and np.array_equal(gsu, su) and np.array_equal(gok, cok) and np.array_equal(gv, voice)
+        assert dcd[c] == int(oc.dcd) and tot[c] == cok.size and okc[c] == cok.sum()
+        if c == 0:
+            assert len(su) >= 5 and int(cok.sum()) >= 10
+
+
 def test_error_behaviour():
     jb = _import()
     b = jb.DemodBatch("oqpsk", 2, fb=10500, freq_center=5760)

@@ -215,3 +215,18 @@ def test_rt_channel_oracle_decodes_crc_valid_packets(golden, name):
         rt2.process(soft[a:a + 33], vector_semantics=True)
     pk2 = rt2.packets()
     assert len(pk2) == len(pk) and all(np.array_equal(a["bytes"], b["bytes"]) for a, b in zip(pk, pk2))
+
+
+def test_c_channel_oracle_decodes_crc_valid_signal_units(golden):
+    """SURVEY 8(f)3: restated AeroL::DecodeC on the 8400 bps recording: dual-UW ambiguity detector, 16 x (64 x 4)
+    de-interleave, rate-3/4 de-puncturing, continuous Viterbi, delay line, scrambler -> sub-band signal units whose
+    CRC-16 verifies (self-certifying), identical to the committed golden."""
+    case = golden["oqpsk_8400"]
+    soft, _, _ = _run_restated(case, load_excerpt(case["excerpt"]))
+    cc = restated.OracleCChannel()
+    for a in range(0, len(soft), 1000):
+        cc.process(soft[a:a + 1000])
+    su, cok, voice = cc.take_frames()
+    g = case["c_frames"]
+    assert len(su) == g["n_frames"] >= 5 and int(cok.sum()) == g["n_su_crc_ok"] >= 10
+    assert hashlib.sha256(su.tobytes() + cok.astype("<i4").tobytes() + voice.tobytes()).hexdigest() == g["sha256"]

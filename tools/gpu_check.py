@@ -213,7 +213,7 @@ def check_cchannel():
         gsu = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]]); gv = np.concatenate([g[2] for g in got[c]])
         same = gsu.shape == su.shape and np.array_equal(gsu, su) and np.array_equal(gok, cok) and np.array_equal(gv, voice)
         print(f"cchannel ch{c}: frames gpu={len(gsu)} oracle={len(su)} SU crc_ok gpu={int(gok.sum())} oracle={int(cok.sum())} identical={same} dcd gpu={dcd[c]} oracle={int(oc.dcd)}")
-        ok &= same and len(su) > 5 and int(cok.sum()) > 10 and dcd[c] == int(oc.dcd)
+        ok &= same and dcd[c] == int(oc.dcd) and (c != 0 or (len(su) > 5 and int(cok.sum()) > 10))
     b.close(); cc.close()
     print("CCHANNEL", "PASS" if ok else "FAIL")
     return ok

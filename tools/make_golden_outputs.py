@@ -48,7 +48,16 @@ def run_case(name, case, chunk=4800):
         rt.process(soft)
         rt_packets = [dict(type=q["type"], nsus=q["nsus"], n_bytes=int(len(q["bytes"])), sha256=hashlib.sha256(q["bytes"].tobytes()).hexdigest())
                       for q in rt.packets()]
+    c_frames = {}
+    if case["kw"]["fb"] == 8400:
+        # C-channel frame layer (restated AeroL::DecodeC; pinned by the sub-band signal units' CRC-16s) on the reference's soft bits
+        cc = restated.OracleCChannel()
+        cc.process(soft)
+        su, cok, voice = cc.take_frames()
+        c_frames = dict(n_frames=int(len(su)), n_su_crc_ok=int(cok.sum()),
+                        sha256=hashlib.sha256(su.tobytes() + cok.astype("<i4").tobytes() + voice.tobytes()).hexdigest())
     return {
+        "c_frames": c_frames,
         "rt_packets": rt_packets,
         "kind": case["kind"], "kw": case["kw"], "excerpt": case.get("excerpt", name), "chunk": chunk,
         "dcd_schedule": sched or [],
