@@ -218,6 +218,9 @@ struct jaero_batch {
     bool profiling;
     // asynchronous coarse estimator (see jaero_batch_write_device)
     bool async_cfe; cudaStream_t cfe_stream; cudaEvent_t ev_seg_done, ev_cfe_done[2]; int cfe_count; int bb_phys;
+    // host-input pipelining (jaero_batch_write): the H2D copy is cut into column slices on a copy stream; a segment only
+    // waits for the slices it reads
+    cudaStream_t copy_stream; cudaEvent_t ev_slice[8], ev_stage_free; int n_slices, slice_len, next_slice;
     bool use_pipe;              // 10500 bps: warp-specialised segment kernel (JAERO_OQPSK_PIPE=0 selects the single-warp one, for A/B profiling)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_seg, ev_cfe;
     double prof_samples;
@@ -312,6 +315,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     b->own_stream = b->stream; b->profiling = false; b->prof_samples = 0;
     { const char *e = getenv("JAERO_OQPSK_PIPE"); b->use_pipe = !(e && e[0] == '0'); }
+    b->copy_stream = 0; b->ev_stage_free = 0; for (int k = 0; k < 8; k++) b->ev_slice[k] = 0; b->n_slices = 0; b->slice_len = 0; b->next_slice = 0;
     b->async_cfe = false; b->cfe_stream = 0; b->ev_seg_done = 0; b->ev_cfe_done[0] = b->ev_cfe_done[1] = 0; b->cfe_count = 0; b->bb_phys = 0;
     DemodParams &p = b->p;
     memset(&p, 0, sizeof p);
@@ -522,6 +526,9 @@ void jaero_batch_destroy(jaero_batch *b)
     cudaSetDevice(b->device);
     cudaStreamSynchronize(b->stream);
     if (b->cfe_stream) { cudaStreamSynchronize(b->cfe_stream); cudaStreamDestroy(b->cfe_stream); }
+    if (b->copy_stream) { cudaStreamSynchronize(b->copy_stream); cudaStreamDestroy(b->copy_stream); }
+    if (b->ev_stage_free) cudaEventDestroy(b->ev_stage_free);
+    for (int k = 0; k < 8; k++) if (b->ev_slice[k]) cudaEventDestroy(b->ev_slice[k]);
     if (b->ev_seg_done) cudaEventDestroy(b->ev_seg_done);
     for (int k = 0; k < 2; k++) if (b->ev_cfe_done[k]) cudaEventDestroy(b->ev_cfe_done[k]);
     for (void *q : b->allocs) cudaFree(q);
@@ -591,6 +598,7 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         d_pcm = b->d_stage; stride = pitch;
     }
     if (b->pre_on) {
+        while (b->next_slice < b->n_slices) { JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_slice[b->next_slice], 0)); b->next_slice++; }
         // K6 over the whole call first (oqpskdemodulator.cpp:343-381), then the per-sample loop consumes its output
         const size_t C = p.n_channels, xs = (n + 7) & ~(size_t)7;
         if (C * xs > b->x_cap) {
@@ -626,6 +634,10 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         a.sample0 = b->samples; a.i0 = i0; a.i1 = i1; a.skip_a_first = resume ? 1 : 0; a.stop_after_a = stop_after_a ? 1 : 0;
         a.apply_cfe = resume ? 1 : 0; a.bb_pos = bb0; a.coarse_counter = cc0;
         a.cfe_wait = (resume && b->async_cfe) ? b->cfe_count : 0;
+        while (b->next_slice < b->n_slices && b->next_slice * b->slice_len < i1) {   // input slices this segment reads
+            JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_slice[b->next_slice], 0));
+            b->next_slice++;
+        }
         cudaEvent_t e0 = 0, e1 = 0;
         if (b->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
         int r = (p.kind == JAERO_KIND_OQPSK) ? ((b->use_pipe && !p.xpre) ? oqpsk_pipe_launch(p, a, d_pcm, stride, b->stream)
@@ -679,6 +691,8 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
     }
     if (launch(seg_start, (int)n, false, seg_bb, seg_cc)) return JAERO_E_CUDA;
     b->samples += ((int)n - seg_start);
+    while (b->next_slice < b->n_slices) { JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_slice[b->next_slice], 0)); b->next_slice++; }
+    b->n_slices = 0; b->next_slice = 0;
     b->bb_pos = bb; b->coarse_counter = cc; b->bb_phys = bbp;
     if (cfe_in_flight) JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_cfe_done[b->cfe_count & 1], 0));   // join: a call leaves nothing in flight
     if (b->pre_on) {                                               // :608 mixer_fir_pre.SetFreq(mixer2_freq_sum/i)
@@ -702,8 +716,29 @@ int jaero_batch_write(jaero_batch *b, const int16_t *pcm, size_t n, size_t strid
         JB_CUDA(cudaMalloc(&b->d_stage, C * pitch * sizeof(int16_t)));
         b->stage_cap = C * pitch;
     }
-    JB_CUDA(cudaMemcpy2DAsync(b->d_stage, pitch * sizeof(int16_t), pcm, stride * sizeof(int16_t), n * sizeof(int16_t), C,
-                              cudaMemcpyHostToDevice, b->stream));
+    if (n < 8192) {
+        JB_CUDA(cudaMemcpy2DAsync(b->d_stage, pitch * sizeof(int16_t), pcm, stride * sizeof(int16_t), n * sizeof(int16_t), C,
+                                  cudaMemcpyHostToDevice, b->stream));
+        return jaero_batch_write_device(b, b->d_stage, n, pitch);
+    }
+    // long calls: copy in column slices on a second stream so that the transfer of later samples overlaps the
+    // demodulation of earlier ones (pinned host memory makes the copies truly asynchronous)
+    if (!b->copy_stream) {
+        JB_CUDA(cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking));
+        JB_CUDA(cudaEventCreateWithFlags(&b->ev_stage_free, cudaEventDisableTiming));
+        for (int k = 0; k < 8; k++) JB_CUDA(cudaEventCreateWithFlags(&b->ev_slice[k], cudaEventDisableTiming));
+    }
+    JB_CUDA(cudaEventRecord(b->ev_stage_free, b->stream));          // everything already queued that reads the staging buffer
+    JB_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ev_stage_free, 0));
+    b->slice_len = (int)((((n + 7) / 8) + 7) & ~(size_t)7);
+    b->n_slices = 0; b->next_slice = 0;
+    for (size_t s0 = 0; s0 < n; s0 += (size_t)b->slice_len) {
+        const size_t len = std::min((size_t)b->slice_len, n - s0);
+        JB_CUDA(cudaMemcpy2DAsync(b->d_stage + s0, pitch * sizeof(int16_t), pcm + s0, stride * sizeof(int16_t), len * sizeof(int16_t), C,
+                                  cudaMemcpyHostToDevice, b->copy_stream));
+        JB_CUDA(cudaEventRecord(b->ev_slice[b->n_slices], b->copy_stream));
+        b->n_slices++;
+    }
     return jaero_batch_write_device(b, b->d_stage, n, pitch);
 }
 
