@@ -363,6 +363,38 @@ def test_c_channel_frames_on_reference_recording(golden):
             assert len(su) >= 5 and int(cok.sum()) >= 10
 
 
+@pytest.mark.parametrize("kind,name,kw", [
+    ("oqpsk", "oqpsk_10500", dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)),
+    ("msk", "msk_600", dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True)),
+])
+def test_pipeline_kernels_with_tiny_and_odd_writes(kind, name, kw):
+    """The warp-specialised segment kernels hand samples between warps through named barriers; writes of 1, 2, 3 ... samples
+    (launches whose loop body runs 0, 1 or 2 times, estimator triggers on the first / last sample of a call) must give the
+    same stream as regular 4800-sample writes."""
+    jb = _import()
+    pcm = load_excerpt(name)[:48000 * 3]
+    pcm2 = np.stack([pcm, pcm[::-1].copy(), (pcm // 2).astype(np.int16)])
+    ref, st_ref = _run_gpu(kind, pcm2, kw, 4800)
+    b = jb.DemodBatch(kind, 3, **kw)
+    acc = [[] for _ in range(3)]
+    pattern = [1, 2, 3, 1, 5, 4093, 1, 1, 2, 4096, 7, 2047, 1, 2049, 31, 33, 4800, 64, 1]
+    a = 0; k = 0
+    while a < pcm2.shape[1]:
+        n = min(pattern[k % len(pattern)], pcm2.shape[1] - a)
+        b.write(pcm2[:, a:a + n]); a += n; k += 1
+        if k % 6 == 0:
+            for c, s_ in enumerate(b.read_softbits()):
+                acc[c].append(s_)
+    for c, s_ in enumerate(b.read_softbits()):
+        acc[c].append(s_)
+    st = b.status()
+    b.close()
+    for c in range(3):
+        assert np.array_equal(np.concatenate(acc[c]), ref[c])
+        for key in ("mixer2_freq", "mixer2_wtptr", "st_wtptr", "mse", "agc"):
+            assert st[c][key] == st_ref[c][key], key
+
+
 def test_error_behaviour():
     jb = _import()
     b = jb.DemodBatch("oqpsk", 2, fb=10500, freq_center=5760)
