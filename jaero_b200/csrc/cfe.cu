@@ -436,15 +436,22 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
             double *y = pl.y + (size_t)ch * N;
             const bool bigchange = p.I[(size_t)I_ZERO_BB * p.cpad + ch] != 0;     // y[i]=20 pending (coarsefreqestimate.cpp:87)
             const int kk = threadIdx.x & 15, k2b = threadIdx.x >> 4;
+            // y is only ever read by the fold search, for bins within [lo-epb-1, hi+epb+1] (coarsefreqestimate.cpp:112-130):
+            // bins outside that window are neither loaded, evaluated (log10) nor stored
+            const int need_lo = pl.lo - pl.expectedpeakbin - 1, need_hi = pl.hi + pl.expectedpeakbin + 1;
             double yo[8];                                                         // requested before the transform, consumed after it
 #pragma unroll
-            for (int i = 0; i < 8; i++) yo[i] = bigchange ? 20.0 : y[(16 * q + kk) + 128 * ((k2b + 16 * i + 64) & 127)];
+            for (int i = 0; i < 8; i++) {
+                const int i_sh = (16 * q + kk) + 128 * ((k2b + 16 * i + 64) & 127);
+                yo[i] = (bigchange || i_sh < need_lo || i_sh > need_hi) ? 20.0 : y[i_sh];
+            }
             cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int k2 = k2b + 16 * i;
                 const int i_sh = (16 * q + kk) + 128 * ((k2 + 64) & 127);         // fftshift (:105)
+                if (i_sh < need_lo || i_sh > need_hi) continue;
                 const double2 x = bufB[kk * CC_RS + cc_ph(k2)];
                 // 10*log10(max(|x|,1)) = 5*log10(max(|x|^2,1))
                 y[i_sh] = yo[i] * 0.9 + 0.1 * 5 * log10(fmax(x.x * x.x + x.y * x.y, 1.0));   // :108
