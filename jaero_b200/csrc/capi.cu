@@ -640,7 +640,7 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         }
         cudaEvent_t e0 = 0, e1 = 0;
         if (b->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
-        int r = (p.kind == JAERO_KIND_OQPSK) ? ((b->use_pipe && !p.xpre) ? oqpsk_pipe_launch(p, a, d_pcm, stride, b->stream)
+        int r = (p.kind == JAERO_KIND_OQPSK) ? ((b->use_pipe && !p.xpre && p.fb > 8400) ? oqpsk_pipe_launch(p, a, d_pcm, stride, b->stream)
                                                                           : oqpsk_segment_launch(p, a, d_pcm, stride, b->stream))
                                              : ((b->use_pipe && (p.agc_len % 32) == 0 && (p.ebno_len % 32) == 0) ? msk_pipe_launch(p, a, d_pcm, stride, b->stream)
                                                                                                                       : msk_segment_launch(p, a, d_pcm, stride, b->stream));

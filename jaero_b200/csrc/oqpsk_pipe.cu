@@ -12,7 +12,7 @@
 //   * the symbol-rate tail after the carrier update (bias rotate, 400-symbol delay, MSE, soft bits) feeds nothing back
 //     inside a call.
 //
-// Five warps of one CTA each own a slice of the per-sample work of the same 32 channels (lane = channel in every warp)
+// Six warps of one CTA each own a slice of the per-sample work of the same 32 channels (lane = channel in every warp)
 // and hand their results to the next warp through shared memory, ordered by named barriers (bar.arrive / bar.sync on
 // alternating ids, one producer warp + one consumer warp per barrier):
 //
@@ -20,23 +20,25 @@
 //   warp E  EbNo + AGC running sums (TMA-staged ring tiles), AGC gain, clip, timing feed-forward chain     -> sig2, st_eta, d8out
 //   warp T  input: PCM tiles (TMA), coarse-estimator ring write (mixer_center); symbol-timing PLL: arg of
 //           the timing-error phasor, st_osc nudges, strobe test                                            -> dval, (strobe, fraction)
-//   warp K  strobe interpolation, carrier error + loop filter, carrier NCO; mixes the NEXT input sample
-//           and puts it into the FIR window                                                                 -> cval, (pt_qpsk, ct_ec)
+//   warp K1 strobe interpolation, carrier error (tanh x2), loop filter                                      -> ct_ec, (pt_qpsk, ct_ec)
+//   warp K2 carrier NCO (phase / frequency update, advance, table look-up); mixes the NEXT input sample
+//           and puts it into the FIR window                                                                 -> cval
 //   warp S  marg MA(800), 400-symbol delay, bias rotate, MSE, soft bits
 //
-// The only loop that remains serial is K(n-1) -> newest FIR tap -> E(n+1) -> T(n+1) -> K(n+1): it advances two samples per
-// turn, and K(n) runs inside it. F, S and the bulk of the FIR are off that loop entirely.
+// The only loop that remains serial is K2(n-1) -> newest FIR tap -> E(n+1) -> T(n+1) -> K1(n+1) -> K2(n+1): it advances two
+// samples per turn; K1(n+1) overlaps K2(n). F, S and the bulk of the FIR are off that loop entirely. Back-pressure from S
+// (slot free) uses two mbarriers: the 16 named barriers are all taken by the seven forward signals.
 #include "demod_device.cuh"
 
 namespace jb {
 
-static const int PP_THREADS = 160;
+static const int PP_THREADS = 192;
 // shared memory map (bytes): FIR windows | ring tiles x6 | PCM tiles x2 | mbarriers | hand-off slots
-static const int PP_HF = 14;                        // doubles per lane in a hand-off slot
+static const int PP_HF = 16;                        // doubles per lane in a hand-off slot
 static const int PP_SM_HAND = 2 * PP_HF * 32 * 8;  // [2 slots][PP_HF doubles][32 lanes]
 static const int PP_SM_TOTAL = OQ_SM_TOTAL + PP_SM_HAND;
 // named barriers (0 is __syncthreads)
-enum { BAR_X = 1, BAR_YT = 3, BAR_Z = 5, BAR_W = 7, BAR_V = 9, BAR_YK = 11, BAR_U = 13 };
+enum { BAR_X = 1, BAR_YT = 3, BAR_Z = 5, BAR_W = 7, BAR_P = 9, BAR_YK = 11, BAR_U = 13 };
 
 __device__ __forceinline__ void nb_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
@@ -62,7 +64,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const int ch = ch_raw;                                    // dead lanes run on their (allocated) pad column with zero input
     const int nlive = min(OQ_THREADS, p.n_channels - (int)blockIdx.x * OQ_THREADS);
     const size_t cpad = p.cpad;
-    if (threadIdx.x == 0) { for (int k = 0; k < 4; k++) mbar_init(&bars[k], 1); }
+    if (threadIdx.x == 0) { for (int k = 0; k < 4; k++) mbar_init(&bars[k], 1); mbar_init(&bars[4], 32); mbar_init(&bars[5], 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();                                           // (0) mbarriers usable
 
@@ -72,16 +74,13 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     // hand-off slot layout: slot s, field f -> hand[(s * 12 + f) * 32 + lane]
     //   f 0,1: sig2raw (F->E)   f 2,3: sig2 (E->K)   f 4,5: st_eta, d8out (E->T)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (K->S)
-    //   f 10,11,12: strobe flag, FractionOfSampleItPassesBy, next input sample (T->K)   f 13 (slot 0): first input sample (T->K)
+    //   f 10,11,12: strobe flag, FractionOfSampleItPassesBy, next input sample (T->K1/K2)   f 13 (slot 0): first input sample (T->K2)
+    //   f 14,15: carrier-update flag, ct_ec (K1->K2)
 #define HAND(s, f) hand[((s) * PP_HF + (f)) * 32 + lane]
 
-    // ======================================================================================= warp K: carrier loop
-    if (warp == 3) {
+    // ======================================================================================= warp K2: carrier NCO + mixer
+    if (warp == 4) {
         Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
-        Biquad lf = {LD(D_LF_X1), LD(D_LF_X2), LD(D_LF_Y1), LD(D_LF_Y2)};
-        double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
-        double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
-        int yui = LI(I_YUI), sig2l_init = LI(I_SIG2L_INIT);
         // ---- FreqOffsetEstimateSlot (oqpskdemodulator.cpp:629-677), re-entrant in the reference: it runs after the ring
         // write and before the mixer of the same sample.
         if (a.apply_cfe) {
@@ -139,46 +138,18 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 __threadfence_block();
                 nb_arrive(BAR_X + 0);                          // X_0
             }
-            const double fbr = p.fb;
             for (int j = 0; j < nB; j++) {
                 const int sl = j & 1;
                 // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
                 const int m2_spec = osc_next_index(m2);
                 const double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
-                nb_sync(BAR_YK + sl);                          // sig2 of this sample (warp E)
-                double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
-                nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
-                const double strobe = HAND(sl, 10), frac = HAND(sl, 11), dnext = HAND(sl, 12);
-                if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
-                double sy_flag = 0.0, sy_x = 0.0, sy_y = 0.0, sy_ec = 0.0;
-                if (strobe != 0.0) {                                              // :488
-                    const double pt_last = frac, pt_this = 1.0 - pt_last;
-                    const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
-                    yui ^= 1;                                                     // yui++; yui%=2;
-                    if (!yui) pt_d = pt;
-                    else {
-                        const double2 pt_qpsk = make_double2(pt.x, pt_d.y);       // :503
-                        const double ct_xt = tanh(pt.y) * pt.x;
-                        const double ct_xt_d = tanh(pt_d.x) * pt_d.y;
-                        double ct_ec = ct_xt_d - ct_xt;
-                        if (ct_ec > M_PI) ct_ec = M_PI;
-                        if (ct_ec < -M_PI) ct_ec = -M_PI;
-                        if (fbr > 8400) {                                         // :518-525
-                            ct_ec = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
-                            if (ct_ec > M_PI_2) ct_ec = M_PI_2;
-                            if (ct_ec < -M_PI_2) ct_ec = -M_PI_2;
-                            osc_increase_phase_deg(m2, 1.0 * ct_ec);
-                            osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, Fs);
-                        } else {                                                  // :526-532
-                            osc_increase_phase_deg(m2, 1.0 * ct_ec);
-                            const double lfo = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
-                            osc_set_freq(m2, (0.5 * 0.01 * lfo) + m2.freq, Fs);
-                        }
-                        sy_flag = 1.0; sy_x = pt_qpsk.x; sy_y = pt_qpsk.y; sy_ec = ct_ec;
-                    }
+                nb_sync(BAR_P + sl);                           // P_j: carrier error of this sample (warp K1)
+                const double upd = HAND(sl, 14), ct_ec = HAND(sl, 15), dnext = HAND(sl, 12);
+                if (upd != 0.0) {                                                 // :518-525, fb > 8400 (the host only uses this kernel there)
+                    osc_increase_phase_deg(m2, 1.0 * ct_ec);
+                    osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, Fs);
                 }
-                sig2_last = sig2;                                                 // :596
-                osc_next_frame(m2);                                               // :600 (st_osc / st_osc_ref live in warp T, mixer_center in warp F)
+                osc_next_frame(m2);                                               // :600 (st_osc / st_osc_ref live in warp T, mixer_center in warp T)
                 {
                     const int t = osc_index(m2.ptr);
                     if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
@@ -191,24 +162,66 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     __threadfence_block();
                     nb_arrive(BAR_X + ((j + 1) & 1));          // X_{j+1}
                 }
-                // symbol hand-off to warp S (slot reuse is gated by V)
-                if (j >= 2) nb_sync(BAR_V + sl);               // V_{j-2}: S has read slot sl
+            }
+        }
+        LD(D_M2_PTR) = m2.ptr; LD(D_M2_STEP) = m2.step; LD(D_M2_FREQ) = m2.freq; LD(D_M2_LAST) = m2.last;
+    }
+    // ======================================================================================= warp K1: carrier error
+    else if (warp == 3) {
+        Biquad lf = {LD(D_LF_X1), LD(D_LF_X2), LD(D_LF_Y1), LD(D_LF_Y2)};
+        double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
+        double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
+        int yui = LI(I_YUI), sig2l_init = LI(I_SIG2L_INIT);
+        __syncthreads();                                       // (1)
+        if (nB > 0) {
+            unsigned vph = 0u;                                 // parities of the two slot-free mbarriers
+            for (int j = 0; j < nB; j++) {
+                const int sl = j & 1;
+                nb_sync(BAR_YK + sl);                          // sig2 of this sample (warp E)
+                double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
+                nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
+                const double strobe = HAND(sl, 10), frac = HAND(sl, 11);
+                if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
+                double sy_flag = 0.0, sy_x = 0.0, sy_y = 0.0, sy_ec = 0.0, k2_upd = 0.0, k2_ec = 0.0;
+                if (strobe != 0.0) {                                              // :488
+                    const double pt_last = frac, pt_this = 1.0 - pt_last;
+                    const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
+                    yui ^= 1;                                                     // yui++; yui%=2;
+                    if (!yui) pt_d = pt;
+                    else {
+                        const double2 pt_qpsk = make_double2(pt.x, pt_d.y);       // :503
+                        const double ct_xt = tanh(pt.y) * pt.x;
+                        const double ct_xt_d = tanh(pt_d.x) * pt_d.y;
+                        double ct_ec = ct_xt_d - ct_xt;
+                        if (ct_ec > M_PI) ct_ec = M_PI;
+                        if (ct_ec < -M_PI) ct_ec = -M_PI;
+                        // :518-525 (fb > 8400: the loop filter sits in front of the NCO update; the host only uses this kernel there)
+                        ct_ec = biquad_update(lf, ct_ec, p.lf_a1, p.lf_a2, p.lf_b0, p.lf_b1, p.lf_b2);
+                        if (ct_ec > M_PI_2) ct_ec = M_PI_2;
+                        if (ct_ec < -M_PI_2) ct_ec = -M_PI_2;
+                        k2_upd = 1.0; k2_ec = ct_ec;
+                        sy_flag = 1.0; sy_x = pt_qpsk.x; sy_y = pt_qpsk.y; sy_ec = ct_ec;
+                    }
+                }
+                sig2_last = sig2;                                                 // :596
+                // slot sl's K1->K2 fields were read by K2(j-2), which precedes X_{j-1} -> ... -> U_j: free
+                HAND(sl, 14) = k2_upd; HAND(sl, 15) = k2_ec;
+                __threadfence_block();
+                nb_arrive(BAR_P + sl);                         // P_j
+                // symbol hand-off to warp S; slot reuse is gated by S's arrival on the slot's mbarrier
+                if (j >= 2) { mbar_wait(&bars[4 + sl], (vph >> sl) & 1u); vph ^= (1u << sl); }
                 HAND(sl, 6) = sy_x; HAND(sl, 7) = sy_y; HAND(sl, 8) = sy_ec; HAND(sl, 9) = sy_flag;
                 __threadfence_block();
                 nb_arrive(BAR_W + sl);                         // W_j
             }
-            // drain: S still owes the V arrivals of the last two slots
-            if (nB >= 2) nb_sync(BAR_V + (nB & 1));            // V_{nB-2}
-            nb_sync(BAR_V + ((nB - 1) & 1));                   // V_{nB-1}
         }
-        LD(D_M2_PTR) = m2.ptr; LD(D_M2_STEP) = m2.step; LD(D_M2_FREQ) = m2.freq; LD(D_M2_LAST) = m2.last;
         LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
         LD(D_SIG2L_RE) = sig2_last.x; LD(D_SIG2L_IM) = sig2_last.y;
         LD(D_PTD_RE) = pt_d.x; LD(D_PTD_IM) = pt_d.y;
         LI(I_YUI) = yui; LI(I_SIG2L_INIT) = sig2l_init;
     }
     // ======================================================================================= warp S: symbol-rate tail
-    else if (warp == 4) {
+    else if (warp == 5) {
         double marg_sum = LD(D_MARG_SUM), marg_val = LD(D_MARG_VAL);
         double pm_sum = LD(D_MSE_PM_SUM), ma_sum = LD(D_MSE_MA_SUM), mse = LD(D_MSE);
         double lastmse = LD(D_LASTMSE);
@@ -228,8 +241,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             const int sl = j & 1;
             nb_sync(BAR_W + sl);                               // W_j
             const double fx = HAND(sl, 6), fy = HAND(sl, 7), fec = HAND(sl, 8), fl = HAND(sl, 9);
-            __threadfence_block();
-            nb_arrive(BAR_V + sl);                             // V_j: slot read
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[4 + sl])) : "memory");   // slot read (release)
             if (fl != 0.0) {
                 double2 pt_qpsk = make_double2(fx, fy);
                 const double ct_ec = fec;
@@ -562,7 +574,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp K
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
-    for (int k = warp; k < OQ_NT1; k += 5) {
+    for (int k = warp; k < OQ_NT1; k += 6) {
         p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
         p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
     }
