@@ -32,6 +32,23 @@ ALG_BYTES_PER_SAMPLE = 194.2          # faithful fp64 state in
 STEP_SAMPLES = 48000                  # 1 s = 2 P-channel frames per channel per step
 
 
+
+def _ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K1a launch, from the committed ncu --set full capture (None if absent)."""
+    import csv
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_oqpsk_pipe_v8_full_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, row = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            tot += float(row[i].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return tot
+    except Exception:
+        return None
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,7 +323,7 @@ def main():
     seg_s = prof["segment_ms"] * 1e-3
     achieved = (ALG_BYTES_PER_SAMPLE * prof["samples"] * C) / seg_s / 1e9 if seg_s > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "oqpsk_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": _ncu_traffic_bytes(), "traffic_source": "profiles/r01_oqpsk_pipe_v8_full_raw.csv (ncu --set full, one launch = 4096 samples x 4096 channels)",
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "alg_bytes_per_sample": ALG_BYTES_PER_SAMPLE,
                 "avg_launch_ms": prof["segment_ms"] / max(1, prof["segment_launches"]), "launches": prof["segment_launches"],
