@@ -184,123 +184,188 @@ hilbert_block_kernel(HilbertStream h, int first_block)
 }
 
 // ------------------------------------------------------------------------------------------------ front end
-__global__ void __launch_bounds__(64)
+// Everything in front of the trident test is feed-forward (AGC -> alignment delays -> burst-timing statistic -> peak
+// detector), but every stage is a running sum or a delay line over a long ring in HBM: ten "value written len samples ago"
+// reads per sample. All ring positions advance in lock-step, so the reads of the NEXT block of 8 samples are issued with
+// cp.async (global -> shared, 8 / 16 bytes per thread, a warp's 32 channels are one contiguous row segment) while the
+// current block is computed from shared memory; the per-sample loop itself never waits on HBM. Writes go straight to the rings.
+static const int BF_T = 64, BF_B = 8;            // threads per CTA, samples per staged block
+static const int BF_N2 = 4, BF_N1 = 7;           // staged double2 / double fields per sample
+static const int BF_SMEM = 2 * BF_B * (BF_N2 * 16 + BF_N1 * 8) * BF_T;
+
+__device__ __forceinline__ void cp_async8(void *dst, const void *src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory"); }
+
+__global__ void __launch_bounds__(BF_T)
 burst_front_kernel(BurstParams p, long long sample0, int n)
 {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= p.n_channels) return;
+    extern __shared__ __align__(16) unsigned char bf_smem[];
+    double2 *st2 = reinterpret_cast<double2 *>(bf_smem);                                  // [2][B][N2][T]
+    double *st1 = reinterpret_cast<double *>(bf_smem + 2 * BF_B * BF_N2 * 16 * BF_T);     // [2][B][N1][T]
+    const int tid = threadIdx.x;
+    const int ch_raw = blockIdx.x * blockDim.x + tid;
+    const bool live = ch_raw < p.n_channels;
+    const int ch = live ? ch_raw : p.n_channels - 1;         // dead threads shadow the last channel (loads only; they store nothing)
     const size_t cp = p.cpad;
     double agc_sum = BD(BD_AGC_SUM), agc_val = BD(BD_AGC_VAL);
     double2 btma_sum = make_double2(BD(BD_BTMA_SUM_RE), BD(BD_BTMA_SUM_IM));
     double mav1_sum = BD(BD_MAV1_SUM), pd_lastdy = BD(BD_PD_LASTDY), pd_maxval = BD(BD_PD_MAXVAL);
     int pd_cntdown = BI(BI_PD_CNTDOWN), pd_maxposcnt = BI(BI_PD_MAXPOSCNT);
     int tri_ptr = BI(BI_TRI_PTR), tri_slot = BI(BI_TRI_SLOT), nev = 0;
-    // lock-step ring positions
+    const int pd1_sz = 2 * p.pd_len + 1, pd2_sz = p.pd_len + 1, pd3_sz = 2 * p.pd_len + 1;
+    // lock-step ring positions of the sample being computed
     int agc_pos = (int)(sample0 % p.agc_len), d1_pos = (int)(sample0 % p.d1_len), d2_pos = (int)(sample0 % p.d2_len);
     int btd1_pos = (int)(sample0 % p.btd1_len), btma_pos = (int)(sample0 % p.btma_len), mav1_pos = (int)(sample0 % p.mav1_len);
     int btdiff_pos = (int)(sample0 % p.btdiff_len);
-    int pd1_pos = (int)(sample0 % (2 * p.pd_len + 1)), pd2_pos = (int)(sample0 % (p.pd_len + 1)), pd3_pos = (int)(sample0 % (2 * p.pd_len + 1));
-    const int pd1_sz = 2 * p.pd_len + 1, pd2_sz = p.pd_len + 1, pd3_sz = 2 * p.pd_len + 1;
+    int pd1_pos = (int)(sample0 % pd1_sz), pd2_pos = (int)(sample0 % pd2_sz), pd3_pos = (int)(sample0 % pd3_sz);
     const double2 *an = p.analytic + (size_t)ch * p.astride;
     double *vtd = p.vtd + (size_t)ch * p.astride;
     double *tri = p.tri + (size_t)ch * BURST_MAXEV * p.tri_sz;
-    for (int i = 0; i < n; i++) {
-        double2 cval = an[i];
-        {   // agc->Update(std::abs(cval)); cval*=agc->AGCVal  (:412-413)
-            const double ab = hypot(cval.x, cval.y);
-            const size_t e = (size_t)agc_pos * cp + ch;
-            agc_sum = agc_sum - p.agc_ring[e]; agc_sum = agc_sum + fabs(ab); p.agc_ring[e] = fabs(ab);
-            agc_pos++; if (agc_pos >= p.agc_len) agc_pos = 0;
-            agc_val = 1.414213562 / fmax(agc_sum / ((double)p.agc_len), 0.000001);
-            agc_val = fmax(agc_val, 0.000001);
-            cval = make_double2(cval.x * agc_val, cval.y * agc_val);
-        }
-        double2 cval_d;                                                   // d1.update_dont_touch(cval) (:416)
-        { p.d1_ring[(size_t)d1_pos * cp + ch] = cval; d1_pos++; if (d1_pos >= p.d1_len) d1_pos = 0; cval_d = p.d1_ring[(size_t)d1_pos * cp + ch]; }
-        {                                                                 // d2.update_dont_touch(real(cval_d)) (:419)
-            p.d2_ring[(size_t)d2_pos * cp + ch] = cval_d.x; d2_pos++; if (d2_pos >= p.d2_len) d2_pos = 0;
-            vtd[i] = p.d2_ring[(size_t)d2_pos * cp + ch];
-        }
-        // burst timing statistic (:422-427)
-        double2 dly;                                                      // bt_d1.update(cval): Delay<cpx>(SPS)
-        {
-            p.btd1_ring[(size_t)btd1_pos * cp + ch] = cval;
-            int io = btd1_pos - (p.btd1_len - 1); if (io < 0) io += p.btd1_len;
-            int in_ = io + 1; if (in_ >= p.btd1_len) in_ = 0;
-            const double2 older = p.btd1_ring[(size_t)io * cp + ch], newer = p.btd1_ring[(size_t)in_ * cp + ch];
-            const double w = p.btd1_wv[btd1_pos];
-            dly = make_double2(w * newer.x + (1.0 - w) * older.x, w * newer.y + (1.0 - w) * older.y);
-            btd1_pos++; if (btd1_pos >= p.btd1_len) btd1_pos = 0;
-        }
-        const double2 prod = b_mul(cval, make_double2(dly.x, -dly.y));     // cval*std::conj(...)
-        double2 mav;                                                       // bt_ma1.UpdateSigned (TMovingAverage<cpx>)
-        {
-            const size_t e = (size_t)btma_pos * cp + ch;
-            const double2 old = p.btma_ring[e];
-            btma_sum = make_double2(btma_sum.x - old.x, btma_sum.y - old.y);
-            btma_sum = make_double2(btma_sum.x + prod.x, btma_sum.y + prod.y);
-            p.btma_ring[e] = prod;
-            btma_pos++; if (btma_pos >= p.btma_len) btma_pos = 0;
-            mav = make_double2(btma_sum.x / ((double)p.btma_len), btma_sum.y / ((double)p.btma_len));
-        }
-        double fastarm = hypot(mav.x, mav.y);
-        {   // mav1->UpdateSigned
-            const size_t e = (size_t)mav1_pos * cp + ch;
-            mav1_sum = mav1_sum - p.mav1_ring[e]; mav1_sum = mav1_sum + (fastarm); p.mav1_ring[e] = (fastarm);
-            mav1_pos++; if (mav1_pos >= p.mav1_len) mav1_pos = 0;
-            fastarm = mav1_sum / ((double)p.mav1_len);
-        }
-        {   // fastarm-=bt_ma_diff.update(fastarm): Delay<double>(126*SPS)
-            p.btdiff_ring[(size_t)btdiff_pos * cp + ch] = fastarm;
-            int io = btdiff_pos - (p.btdiff_len - 1); if (io < 0) io += p.btdiff_len;
-            int in_ = io + 1; if (in_ >= p.btdiff_len) in_ = 0;
-            const double older = p.btdiff_ring[(size_t)io * cp + ch], newer = p.btdiff_ring[(size_t)in_ * cp + ch];
-            const double w = p.btdiff_wv[btdiff_pos];
-            fastarm -= (w * newer + (1.0 - w) * older);
-            btdiff_pos++; if (btdiff_pos >= p.btdiff_len) btdiff_pos = 0;
-        }
-        if (fastarm < 0) fastarm = 0;
-        double bt_sig = fastarm * fastarm;
-        if (bt_sig > 500) bt_sig = 500;
-        // PeakDetector::update (DSP.h:526-562)
-        bool peak = false;
-        {
-            double val = bt_sig;
-            p.pd3_ring[(size_t)pd3_pos * cp + ch] = val; pd3_pos++; if (pd3_pos >= pd3_sz) pd3_pos = 0;      // d3.update_dont_touch
-            p.pd1_ring[(size_t)pd1_pos * cp + ch] = val; pd1_pos++; if (pd1_pos >= pd1_sz) pd1_pos = 0;      // d1.update_dont_touch
-            const double dy = val - p.pd1_ring[(size_t)pd1_pos * cp + ch];
-            p.pd2_ring[(size_t)pd2_pos * cp + ch] = val; pd2_pos++; if (pd2_pos >= pd2_sz) pd2_pos = 0;      // d2.update(val)
-            val = p.pd2_ring[(size_t)pd2_pos * cp + ch];
-            if ((!pd_cntdown) && (val > p.pd_threshold) && ((pd_lastdy >= 0 && dy < 0))) {
-                pd_cntdown = 2 * p.pd_len;
-                // d3.findmaxpos: scan the ring from its current position, first maximum wins (DSP.h:467-481)
-                int mp = 0, q = pd3_pos;
-                double mv = p.pd3_ring[(size_t)q * cp + ch];
-                for (int k = 0; k < pd3_sz; k++) {
-                    const double x = p.pd3_ring[(size_t)q * cp + ch];
-                    if (x > mv) { mv = x; mp = k; }
-                    q++; if (q >= pd3_sz) q = 0;
-                }
-                pd_maxval = mv; pd_maxposcnt = mp;
+    const double r_agc = 1.0 / ((double)p.agc_len), r_btma = 1.0 / ((double)p.btma_len), r_mav1 = 1.0 / ((double)p.mav1_len);
+    auto wrap = [](int v, int len) { while (v >= len) v -= len; return v; };
+    // a ring shorter than the staging distance (bt_d1 of the burst OQPSK mode: 11 slots) is read at the point of use instead
+    const bool btd1_direct = p.btd1_len < 2 * BF_B + 3;
+    // stage the ring reads of the next `cnt` samples into buffer b (the staging stream keeps its own ring positions)
+    int f_agc = agc_pos, f_d1 = d1_pos, f_d2 = d2_pos, f_btd1 = btd1_pos, f_btma = btma_pos, f_mav1 = mav1_pos, f_btdiff = btdiff_pos;
+    int f_pd1 = pd1_pos, f_pd2 = pd2_pos;
+    auto stage = [&](int b, int cnt) {
+        for (int k = 0; k < cnt; k++) {
+            double2 *d2p = st2 + ((size_t)(b * BF_B + k) * BF_N2) * BF_T + tid;
+            double *d1p = st1 + ((size_t)(b * BF_B + k) * BF_N1) * BF_T + tid;
+            cp_async16(d2p + 0 * BF_T, p.d1_ring + (size_t)wrap(f_d1 + 1, p.d1_len) * cp + ch);
+            if (!btd1_direct) {
+                cp_async16(d2p + 1 * BF_T, p.btd1_ring + (size_t)wrap(f_btd1 + 1, p.btd1_len) * cp + ch);
+                cp_async16(d2p + 2 * BF_T, p.btd1_ring + (size_t)wrap(f_btd1 + 2, p.btd1_len) * cp + ch);
             }
-            if (pd_cntdown > 0) pd_cntdown--;
-            pd_lastdy = dy;
-            if (!pd_maxposcnt) { pd_maxposcnt--; peak = true; }
-            else if (pd_maxposcnt > 0) pd_maxposcnt--;
+            cp_async16(d2p + 3 * BF_T, p.btma_ring + (size_t)f_btma * cp + ch);
+            cp_async8(d1p + 0 * BF_T, p.agc_ring + (size_t)f_agc * cp + ch);
+            cp_async8(d1p + 1 * BF_T, p.d2_ring + (size_t)wrap(f_d2 + 1, p.d2_len) * cp + ch);
+            cp_async8(d1p + 2 * BF_T, p.mav1_ring + (size_t)f_mav1 * cp + ch);
+            cp_async8(d1p + 3 * BF_T, p.btdiff_ring + (size_t)wrap(f_btdiff + 1, p.btdiff_len) * cp + ch);
+            cp_async8(d1p + 4 * BF_T, p.btdiff_ring + (size_t)wrap(f_btdiff + 2, p.btdiff_len) * cp + ch);
+            cp_async8(d1p + 5 * BF_T, p.pd1_ring + (size_t)wrap(f_pd1 + 1, pd1_sz) * cp + ch);
+            cp_async8(d1p + 6 * BF_T, p.pd2_ring + (size_t)wrap(f_pd2 + 1, pd2_sz) * cp + ch);
+            f_agc = wrap(f_agc + 1, p.agc_len); f_d1 = wrap(f_d1 + 1, p.d1_len); f_d2 = wrap(f_d2 + 1, p.d2_len);
+            f_btd1 = wrap(f_btd1 + 1, p.btd1_len); f_btma = wrap(f_btma + 1, p.btma_len); f_mav1 = wrap(f_mav1 + 1, p.mav1_len);
+            f_btdiff = wrap(f_btdiff + 1, p.btdiff_len); f_pd1 = wrap(f_pd1 + 1, pd1_sz); f_pd2 = wrap(f_pd2 + 1, pd2_sz);
         }
-        if (peak) tri_ptr = 0;                                            // :430-435
-        if (tri_ptr < p.tri_sz) {                                         // :437-442
-            tri[(size_t)tri_slot * p.tri_sz + tri_ptr] = cval_d.x;
-            tri_ptr++;
-        } else if (tri_ptr == p.tri_sz) {                                 // fill complete -> event; the FFTs run after this kernel
-            tri_ptr++;
-            if (nev < BURST_MAXEV) {
-                p.ev_sample[(size_t)ch * BURST_MAXEV + nev] = i | (tri_slot << 24);
-                nev++;
-                tri_slot++; if (tri_slot >= BURST_MAXEV) tri_slot = 0;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, min(BF_B, n));
+    for (int blk = 0, i0 = 0; i0 < n; blk++, i0 += BF_B) {
+        const int b = blk & 1, cnt = min(BF_B, n - i0);
+        if (i0 + BF_B < n) { stage(b ^ 1, min(BF_B, n - i0 - BF_B)); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int k = 0; k < cnt; k++) {
+            const int i = i0 + k;
+            const double2 *s2 = st2 + ((size_t)(b * BF_B + k) * BF_N2) * BF_T + tid;
+            const double *s1 = st1 + ((size_t)(b * BF_B + k) * BF_N1) * BF_T + tid;
+            double2 cval = an[i];
+            {   // agc->Update(std::abs(cval)); cval*=agc->AGCVal  (:412-413)
+                const double ab = hypot(cval.x, cval.y);
+                agc_sum = agc_sum - s1[0 * BF_T]; agc_sum = agc_sum + fabs(ab);
+                if (live) p.agc_ring[(size_t)agc_pos * cp + ch] = fabs(ab);
+                agc_pos++; if (agc_pos >= p.agc_len) agc_pos = 0;
+                agc_val = 1.414213562 / fmax(div_exact(agc_sum, (double)p.agc_len, r_agc), 0.000001);
+                agc_val = fmax(agc_val, 0.000001);
+                cval = make_double2(cval.x * agc_val, cval.y * agc_val);
+            }
+            // d1.update_dont_touch(cval) (:416): the slot read is the one after the slot written
+            if (live) p.d1_ring[(size_t)d1_pos * cp + ch] = cval;
+            d1_pos++; if (d1_pos >= p.d1_len) d1_pos = 0;
+            const double2 cval_d = s2[0 * BF_T];
+            {                                                                 // d2.update_dont_touch(real(cval_d)) (:419)
+                if (live) p.d2_ring[(size_t)d2_pos * cp + ch] = cval_d.x;
+                d2_pos++; if (d2_pos >= p.d2_len) d2_pos = 0;
+                if (live) vtd[i] = s1[1 * BF_T];
+            }
+            // burst timing statistic (:422-427)
+            double2 dly;                                                      // bt_d1.update(cval): Delay<cpx>(SPS)
+            {
+                if (live) p.btd1_ring[(size_t)btd1_pos * cp + ch] = cval;
+                double2 older, newer;
+                if (btd1_direct) {
+                    __syncwarp();                                                 // (dead threads never store; live ones read their own column)
+                    older = p.btd1_ring[(size_t)wrap(btd1_pos + 1, p.btd1_len) * cp + ch];
+                    newer = p.btd1_ring[(size_t)wrap(btd1_pos + 2, p.btd1_len) * cp + ch];
+                } else { older = s2[1 * BF_T]; newer = s2[2 * BF_T]; }
+                const double w = p.btd1_wv[btd1_pos];
+                dly = make_double2(w * newer.x + (1.0 - w) * older.x, w * newer.y + (1.0 - w) * older.y);
+                btd1_pos++; if (btd1_pos >= p.btd1_len) btd1_pos = 0;
+            }
+            const double2 prod = b_mul(cval, make_double2(dly.x, -dly.y));     // cval*std::conj(...)
+            double2 mav;                                                       // bt_ma1.UpdateSigned (TMovingAverage<cpx>)
+            {
+                const double2 old = s2[3 * BF_T];
+                btma_sum = make_double2(btma_sum.x - old.x, btma_sum.y - old.y);
+                btma_sum = make_double2(btma_sum.x + prod.x, btma_sum.y + prod.y);
+                if (live) p.btma_ring[(size_t)btma_pos * cp + ch] = prod;
+                btma_pos++; if (btma_pos >= p.btma_len) btma_pos = 0;
+                mav = make_double2(div_exact(btma_sum.x, (double)p.btma_len, r_btma), div_exact(btma_sum.y, (double)p.btma_len, r_btma));
+            }
+            double fastarm = hypot(mav.x, mav.y);
+            {   // mav1->UpdateSigned
+                mav1_sum = mav1_sum - s1[2 * BF_T]; mav1_sum = mav1_sum + (fastarm);
+                if (live) p.mav1_ring[(size_t)mav1_pos * cp + ch] = (fastarm);
+                mav1_pos++; if (mav1_pos >= p.mav1_len) mav1_pos = 0;
+                fastarm = div_exact(mav1_sum, (double)p.mav1_len, r_mav1);
+            }
+            {   // fastarm-=bt_ma_diff.update(fastarm): Delay<double>(126*SPS)
+                if (live) p.btdiff_ring[(size_t)btdiff_pos * cp + ch] = fastarm;
+                const double older = s1[3 * BF_T], newer = s1[4 * BF_T];
+                const double w = p.btdiff_wv[btdiff_pos];
+                fastarm -= (w * newer + (1.0 - w) * older);
+                btdiff_pos++; if (btdiff_pos >= p.btdiff_len) btdiff_pos = 0;
+            }
+            if (fastarm < 0) fastarm = 0;
+            double bt_sig = fastarm * fastarm;
+            if (bt_sig > 500) bt_sig = 500;
+            // PeakDetector::update (DSP.h:526-562)
+            bool peak = false;
+            {
+                double val = bt_sig;
+                if (live) p.pd3_ring[(size_t)pd3_pos * cp + ch] = val;        // d3.update_dont_touch
+                pd3_pos++; if (pd3_pos >= pd3_sz) pd3_pos = 0;
+                if (live) p.pd1_ring[(size_t)pd1_pos * cp + ch] = val;        // d1.update_dont_touch
+                pd1_pos++; if (pd1_pos >= pd1_sz) pd1_pos = 0;
+                const double dy = val - s1[5 * BF_T];
+                if (live) p.pd2_ring[(size_t)pd2_pos * cp + ch] = val;        // d2.update(val)
+                pd2_pos++; if (pd2_pos >= pd2_sz) pd2_pos = 0;
+                val = s1[6 * BF_T];
+                if ((!pd_cntdown) && (val > p.pd_threshold) && ((pd_lastdy >= 0 && dy < 0))) {
+                    pd_cntdown = 2 * p.pd_len;
+                    // d3.findmaxpos: scan the ring from its current position, first maximum wins (DSP.h:467-481)
+                    int mp = 0, q = pd3_pos;
+                    double mv = p.pd3_ring[(size_t)q * cp + ch];
+                    for (int kk = 0; kk < pd3_sz; kk++) {
+                        const double x = p.pd3_ring[(size_t)q * cp + ch];
+                        if (x > mv) { mv = x; mp = kk; }
+                        q++; if (q >= pd3_sz) q = 0;
+                    }
+                    pd_maxval = mv; pd_maxposcnt = mp;
+                }
+                if (pd_cntdown > 0) pd_cntdown--;
+                pd_lastdy = dy;
+                if (!pd_maxposcnt) { pd_maxposcnt--; peak = true; }
+                else if (pd_maxposcnt > 0) pd_maxposcnt--;
+            }
+            if (peak) tri_ptr = 0;                                            // :430-435
+            if (tri_ptr < p.tri_sz) {                                         // :437-442
+                if (live) tri[(size_t)tri_slot * p.tri_sz + tri_ptr] = cval_d.x;
+                tri_ptr++;
+            } else if (tri_ptr == p.tri_sz) {                                 // fill complete -> event; the FFTs run after this kernel
+                tri_ptr++;
+                if (nev < BURST_MAXEV) {
+                    if (live) p.ev_sample[(size_t)ch * BURST_MAXEV + nev] = i | (tri_slot << 24);
+                    nev++;
+                    tri_slot++; if (tri_slot >= BURST_MAXEV) tri_slot = 0;
+                }
             }
         }
     }
+    if (!live) return;
     BD(BD_AGC_SUM) = agc_sum; BD(BD_AGC_VAL) = agc_val; BD(BD_BTMA_SUM_RE) = btma_sum.x; BD(BD_BTMA_SUM_IM) = btma_sum.y;
     BD(BD_MAV1_SUM) = mav1_sum; BD(BD_PD_LASTDY) = pd_lastdy; BD(BD_PD_MAXVAL) = pd_maxval;
     BI(BI_PD_CNTDOWN) = pd_cntdown; BI(BI_PD_MAXPOSCNT) = pd_maxposcnt; BI(BI_TRI_PTR) = tri_ptr; BI(BI_TRI_SLOT) = tri_slot; BI(BI_NEV) = nev;
@@ -886,7 +951,8 @@ int hilbert_block_launch(const HilbertStream &h, int n_channels, int first_block
 }
 int burst_front_launch(const BurstParams &p, long long sample0, int n, cudaStream_t s)
 {
-    burst_front_kernel<<<(p.n_channels + 63) / 64, 64, 0, s>>>(p, sample0, n);
+    JB_CUDA(cudaFuncSetAttribute(burst_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BF_SMEM));
+    burst_front_kernel<<<(p.n_channels + BF_T - 1) / BF_T, BF_T, BF_SMEM, s>>>(p, sample0, n);
     JB_CUDA(cudaGetLastError());
     return 0;
 }
