@@ -100,8 +100,10 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
             const unsigned short t = s.frameinfo; s.frameinfo = s.lastframeinfo; s.lastframeinfo = t;
         }
         if (s.cntr >= 16) {                                                  // :1540-1552
-            int idx = (s.cntr - pp.bits_in_header) % block_len;
+            int idx = s.cntr - pp.bits_in_header;                            // (cntr-BitsInHeader)%block_len, negative -> 0, without a division
             if (idx < 0) idx = 0;
+            if (idx >= 8 * block_len) idx %= block_len;                      // only while cntr sits at its 1e9 idle value
+            while (idx >= block_len) idx -= block_len;
             const int q = s.blocks_ready < PCHAN_QUEUE ? s.blocks_ready : PCHAN_QUEUE - 1;
             pp.blocks[((size_t)ch * PCHAN_QUEUE + q) * block_len + idx] = (uint8_t)soft_bit;
             if (idx == block_len - 1) {
@@ -157,13 +159,25 @@ pchan_su_kernel(PChanParams pp, int *__restrict__ demod_dcd)
         const PChanBlockMeta m = pp.meta[(size_t)ch * PCHAN_QUEUE + q];
         const uint8_t *dec = pp.decoded + ((size_t)ch * PCHAN_QUEUE + q) * half;
         int charptr = 0; unsigned ch8 = 0; int outb = m.info_off;
-        for (int h = 0; h < m.n_valid; h++) {
-            int b = dec[h];
-            dl2[s.dl2_ptr] = (uint8_t)b; s.dl2_ptr++; if (s.dl2_ptr >= pp.dl2_len) s.dl2_ptr = 0; b = dl2[s.dl2_ptr];   // aerol.h:465-473
-            b ^= c_scr[m.scr_pos + h];                                       // aerol.h:421-429
-            ch8 |= (unsigned)b * 128u;                                       // aerol.cpp:1568-1580
-            charptr++; charptr %= 8;
-            if (charptr == 0) { if (outb < pp.info_cap) info[outb] = (uint8_t)ch8; outb++; ch8 = 0; } else ch8 >>= 1;
+        // DelayLine::update (aerol.h:465-473) writes slot ptr and returns slot ptr+1, a value stored dl2_len-1 steps earlier:
+        // groups of 16 steps read their 16 outputs and 16 inputs first (independent loads), then write
+        for (int h0 = 0; h0 < m.n_valid; h0 += 16) {
+            const int cnt = min(16, m.n_valid - h0);
+            uint8_t oldv[16], newv[16];
+            {
+                int rp = s.dl2_ptr + 1; if (rp >= pp.dl2_len) rp = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) if (k < cnt) { oldv[k] = dl2[rp]; newv[k] = dec[h0 + k]; rp++; if (rp >= pp.dl2_len) rp = 0; }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) if (k < cnt) {
+                dl2[s.dl2_ptr] = newv[k]; s.dl2_ptr++; if (s.dl2_ptr >= pp.dl2_len) s.dl2_ptr = 0;
+                int b = oldv[k];
+                b ^= c_scr[m.scr_pos + h0 + k];                              // aerol.h:421-429
+                ch8 |= (unsigned)b * 128u;                                   // aerol.cpp:1568-1580
+                charptr++; charptr %= 8;
+                if (charptr == 0) { if (outb < pp.info_cap) info[outb] = (uint8_t)ch8; outb++; ch8 = 0; } else ch8 >>= 1;
+            }
         }
         if (m.frame_done) {                                                  // :1582-1610
             const int nsu = outb / 12;
