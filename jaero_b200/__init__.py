@@ -304,6 +304,16 @@ class PChannelBatch:
                         r[:, 14].astype(np.int32) | (r[:, 15].astype(np.int32) << 8)))
         return res
 
+    def read_sus_raw(self, out=None, counts=None):
+        """The C-ABI call without per-channel Python objects: (records[n_channels, su_cap, 16] uint8, counts[n_channels]);
+        record = 12 SU bytes, crc_ok, index in frame, frame number (lo, hi)."""
+        if out is None:
+            out = np.empty((self.n, self.su_cap, 16), dtype=np.uint8)
+        if counts is None:
+            counts = np.zeros(self.n, dtype=np.int32)
+        _check(lib().jaero_pchannel_read_sus(self.h, _p(out), self.su_cap, _p(counts)))
+        return out, counts
+
     def discard_sus(self):
         _check(lib().jaero_pchannel_discard_sus(self.h))
 
