@@ -237,6 +237,19 @@ int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames_p
 int jaero_cchannel_get_stats(jaero_cchannel *c, int32_t *dcd, int64_t *su_total, int64_t *su_ok);   /* any may be NULL */
 int64_t jaero_cchannel_launch_count(const jaero_cchannel *c);
 
+/* ---- ingest router (host side) ----
+ * The reference's many-channel feed is one ZMQ PUB topic per channel, each message three frames
+ * [topic][uint32 sample rate][int16 PCM] (JAERO/zmq_audioreceiver.cpp:37-87; the subscription is the first 5 bytes of the
+ * topic, :46) delivered to dataReceived(audio, sampleRate). The router takes the frames as the transport delivers them (no
+ * libzmq dependency), files the PCM under the matching channel and feeds whole batches to jaero_batch_write. */
+typedef struct jaero_ingest jaero_ingest;
+int jaero_ingest_create(int n_channels, const char *const *topics, uint32_t sample_rate, size_t capacity_samples, jaero_ingest **out);
+void jaero_ingest_destroy(jaero_ingest *g);
+/* returns the channel index (>= 0) or a negative error */
+int jaero_ingest_message(jaero_ingest *g, const void *topic, size_t topic_len, const void *rate, size_t rate_len, const void *pcm, size_t pcm_bytes);
+size_t jaero_ingest_available(const jaero_ingest *g);                  /* samples every channel has */
+int jaero_ingest_flush(jaero_ingest *g, jaero_batch *b, size_t n_samples);
+
 #ifdef __cplusplus
 }
 #endif

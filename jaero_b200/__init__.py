@@ -51,7 +51,8 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_rt_create", "jaero_rt_destroy", "jaero_rt_process_softbits", "jaero_rt_process_burst", "jaero_rt_tick",
            "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count",
            "jaero_cchannel_create", "jaero_cchannel_destroy", "jaero_cchannel_process_batch", "jaero_cchannel_process_softbits",
-           "jaero_cchannel_tick", "jaero_cchannel_read_frames", "jaero_cchannel_get_stats", "jaero_cchannel_launch_count"]
+           "jaero_cchannel_tick", "jaero_cchannel_read_frames", "jaero_cchannel_get_stats", "jaero_cchannel_launch_count",
+           "jaero_ingest_create", "jaero_ingest_destroy", "jaero_ingest_message", "jaero_ingest_available", "jaero_ingest_flush"]
 
 
 def lib():
@@ -120,6 +121,11 @@ def lib():
         L.jaero_cchannel_read_frames.argtypes = [vp, vp, i, vp]
         L.jaero_cchannel_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_cchannel_launch_count.argtypes = [vp]; L.jaero_cchannel_launch_count.restype = ctypes.c_int64
+        L.jaero_ingest_create.argtypes = [i, ctypes.POINTER(ctypes.c_char_p), ctypes.c_uint32, sz, ctypes.POINTER(vp)]
+        L.jaero_ingest_destroy.argtypes = [vp]; L.jaero_ingest_destroy.restype = None
+        L.jaero_ingest_message.argtypes = [vp, ctypes.c_char_p, sz, ctypes.c_char_p, sz, vp, sz]
+        L.jaero_ingest_available.argtypes = [vp]; L.jaero_ingest_available.restype = sz
+        L.jaero_ingest_flush.argtypes = [vp, vp, sz]
         _lib = L
     return _lib
 
@@ -515,6 +521,45 @@ class CChannelBatch:
     def close(self):
         if self.h:
             lib().jaero_cchannel_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class IngestRouter:
+    """ZMQ-style [topic][uint32 rate][int16 PCM] messages -> per-channel staging -> DemodBatch.write (host side, no libzmq)."""
+
+    def __init__(self, topics, sample_rate=48000, capacity_samples=192000):
+        self.n = len(topics)
+        arr = (ctypes.c_char_p * self.n)(*[t.encode() if isinstance(t, str) else t for t in topics])
+        self.h = ctypes.c_void_p()
+        _check(lib().jaero_ingest_create(self.n, arr, int(sample_rate), int(capacity_samples), ctypes.byref(self.h)))
+
+    def message(self, topic, rate_frame, pcm_frame):
+        """three frames of one multipart message (bytes); returns the channel index"""
+        topic = topic.encode() if isinstance(topic, str) else bytes(topic)
+        pcm_frame = bytes(pcm_frame)
+        buf = ctypes.create_string_buffer(pcm_frame, len(pcm_frame))
+        rc = lib().jaero_ingest_message(self.h, topic, len(topic), bytes(rate_frame), len(rate_frame), ctypes.cast(buf, ctypes.c_void_p), len(pcm_frame))
+        if rc < 0:
+            raise JaeroError(lib().jaero_last_error().decode())
+        return rc
+
+    @property
+    def available(self):
+        return int(lib().jaero_ingest_available(self.h))
+
+    def flush(self, batch, n=None):
+        n = self.available if n is None else n
+        _check(lib().jaero_ingest_flush(self.h, batch.h, n))
+        return n
+
+    def close(self):
+        if self.h:
+            lib().jaero_ingest_destroy(self.h); self.h = None
 
     def __del__(self):
         try:

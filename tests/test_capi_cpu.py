@@ -1,3 +1,4 @@
+import numpy as np
 """CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
 include/jaero_b200.h declares; without a GPU the product fails loudly instead of falling back."""
 import ctypes
@@ -53,3 +54,25 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r'#include\s*[<"][^>"]*oracle', txt), f
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "libjaero_oracle" not in txt and "libjaero_ref" not in txt, f
+
+
+def test_ingest_router_files_messages_by_topic_prefix():
+    """SURVEY 8(f)4 (host side): [topic][uint32 rate][int16 PCM] messages (zmq_audioreceiver.cpp:37-87) are filed under the
+    channel whose 5-byte subscription prefix matches; a foreign rate or topic is rejected; no GPU involved."""
+    import struct
+    import jaero_b200
+    r = jaero_b200.IngestRouter(["VFO01-long-name", "VFO02", "abc"], sample_rate=48000, capacity_samples=1000)
+    rate = struct.pack("<I", 48000)
+    pcm = np.arange(300, dtype=np.int16).tobytes()
+    assert r.message(b"VFO02", rate, pcm) == 1
+    assert r.message(b"VFO01 whatever follows", rate, pcm[:200]) == 0          # prefix of 5 bytes, as ZMQ_SUBSCRIBE with length 5
+    assert r.available == 0                                                    # channel 2 has nothing yet
+    assert r.message(b"abc", rate, pcm[:101]) == 2                             # odd byte count: 50 samples
+    assert r.available == 50
+    with pytest.raises(jaero_b200.JaeroError, match="no channel"):
+        r.message(b"other", rate, pcm)
+    with pytest.raises(jaero_b200.JaeroError, match="sample rate"):
+        r.message(b"abc", struct.pack("<I", 44100), pcm)
+    with pytest.raises(jaero_b200.JaeroError, match="4 bytes"):
+        r.message(b"abc", b"\x00\x00", pcm)
+    r.close()

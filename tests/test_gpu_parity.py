@@ -395,6 +395,36 @@ def test_pipeline_kernels_with_tiny_and_odd_writes(kind, name, kw):
             assert st[c][key] == st_ref[c][key], key
 
 
+def test_ingest_router_feeds_a_batch_like_direct_writes():
+    """Messages of uneven sizes per channel, flushed whenever every channel has data, give the same soft bits as write()."""
+    import struct
+    jb = _import()
+    pcm = load_excerpt("oqpsk_10500")[:48000 * 3]
+    pcm2 = np.stack([pcm, pcm[::-1].copy()])
+    kw = dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)
+    ref, _ = _run_gpu("oqpsk", pcm2, kw, 4800)
+    b = jb.DemodBatch("oqpsk", 2, **kw)
+    r = jb.IngestRouter(["CHAN0", "CHAN1"], 48000, capacity_samples=60000)
+    rate = struct.pack("<I", 48000)
+    pos = [0, 0]; sizes = [[4800, 1234, 9000], [7000, 4800, 333]]
+    acc = [[], []]; k = 0
+    while min(pos) < pcm2.shape[1]:
+        for c in range(2):
+            n = min(sizes[c][k % 3], pcm2.shape[1] - pos[c])
+            if n:
+                assert r.message(b"CHAN%d" % c, rate, pcm2[c, pos[c]:pos[c] + n].tobytes()) == c
+                pos[c] += n
+        k += 1
+        if r.available:
+            r.flush(b)
+            for c, s_ in enumerate(b.read_softbits()):
+                acc[c].append(s_)
+    assert r.available == 0
+    b.close(); r.close()
+    for c in range(2):
+        assert np.array_equal(np.concatenate(acc[c]), ref[c])
+
+
 def test_error_behaviour():
     jb = _import()
     b = jb.DemodBatch("oqpsk", 2, fb=10500, freq_center=5760)
