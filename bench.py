@@ -106,15 +106,22 @@ def make_pcm_gpu(envs_t, ch0, n_ch, ebn0_db, device):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """nvidia-smi polled every 100 ms from BEFORE the warm-up (its start-up takes longer than a short timed region);
+    only the rows received between mark_begin() and stop() - i.e. during the timed region - are reported."""
+
     def __init__(self, gpu_index):
         self.rows = []
         self.proc = None
         self.gpu = gpu_index
+        self.t_begin = None
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -122,14 +129,18 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        for t, r in self.rows:
+            if t < t0 or t > t_end + 0.05:
+                continue
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -262,19 +273,20 @@ def main():
         pch.tick(batch)
         pch.discard_sus()          # results stay on the device for the HBM-resident measurement
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()             # nvidia-smi needs longer to start than a short timed region lasts: start it before the warm-up
     for _ in range(max(3, a.warmup)):
         step_device()
     torch.cuda.synchronize()
     shard.barrier()
 
     # ---- timed region (device, CUDA events on the launching stream)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     l0 = batch.launches + pch.launches
     batch.set_profiling(True); batch.get_profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); shard.barrier()
+    clocks.mark_begin()
     e0.record(stream)
     for _ in range(a.steps):
         step_device()
