@@ -425,6 +425,23 @@ def test_ingest_router_feeds_a_batch_like_direct_writes():
         assert np.array_equal(np.concatenate(acc[c]), ref[c])
 
 
+@pytest.mark.parametrize("fb", [1200, 10500])
+def test_rt_channel_known_answer_r_packets(fb):
+    """Known-answer R packets (both polarities, different payloads per channel) through the GPU R/T layer."""
+    from conftest import synthetic_r_packet_stream
+    jb = _import()
+    payloads = [((np.arange(17) * (7 + 2 * c) + c) % 256).astype(np.uint8) for c in range(5)]
+    streams = [synthetic_r_packet_stream(fb, payloads[c], invert=bool(c & 1)) for c in range(5)]
+    rt = jb.RTChannelBatch(5, fb)
+    for a in range(0, max(len(s_) for s_ in streams), 97):           # odd chunking: packets straddle calls
+        rt.process([s_[a:a + 97] for s_ in streams])
+    got = rt.read_packets()
+    rt.close()
+    for c in range(5):
+        assert len(got[c]) == 1 and got[c][0]["type"] == 1
+        assert np.array_equal(got[c][0]["bytes"][:17], payloads[c]) and len(got[c][0]["bytes"]) == 19
+
+
 def test_error_behaviour():
     jb = _import()
     b = jb.DemodBatch("oqpsk", 2, fb=10500, freq_center=5760)

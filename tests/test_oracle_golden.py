@@ -230,3 +230,18 @@ def test_c_channel_oracle_decodes_crc_valid_signal_units(golden):
     g = case["c_frames"]
     assert len(su) == g["n_frames"] >= 5 and int(cok.sum()) == g["n_su_crc_ok"] >= 10
     assert hashlib.sha256(su.tobytes() + cok.astype("<i4").tobytes() + voice.tobytes()).hexdigest() == g["sha256"]
+
+
+@pytest.mark.parametrize("fb", [1200, 10500])
+@pytest.mark.parametrize("invert", [False, True])
+def test_rt_channel_oracle_known_answer_r_packet(fb, invert):
+    """A synthetic R-channel packet (encoder written from the specification side: CRC-16, scrambler, K=7 109/79 code, 64 x 5
+    interleaver, unique word) is decoded back to its 19 bytes by the restated receive chain, in either signal polarity."""
+    from conftest import synthetic_r_packet_stream
+    payload = (np.arange(17) * 37 + 11).astype(np.uint8)
+    soft = synthetic_r_packet_stream(fb, payload, invert=invert)
+    rt = restated.OracleRTChannel(fb)
+    rt.process(soft)
+    pk = rt.packets()
+    assert len(pk) == 1 and pk[0]["type"] == 1 and len(pk[0]["bytes"]) == 19
+    assert np.array_equal(pk[0]["bytes"][:17], payload)
