@@ -18,9 +18,9 @@
 //
 //   warp F  55-tap FIR of the mixed samples                                                                -> sig2raw
 //   warp E  EbNo + AGC running sums (TMA-staged ring tiles), AGC gain, clip, timing feed-forward chain     -> sig2, st_eta, d8out
-//   warp T  input: PCM tiles (TMA), coarse-estimator ring write (mixer_center); symbol-timing PLL: arg of
-//           the timing-error phasor, st_osc nudges, strobe test                                            -> dval, (strobe, fraction)
-//   warp K1 strobe interpolation, carrier error (tanh x2), loop filter                                      -> ct_ec, (pt_qpsk, ct_ec)
+//   warp T  symbol-timing PLL: arg of the timing-error phasor, st_osc nudges, strobe test                  -> (strobe, fraction)
+//   warp K1 input: PCM tiles (TMA), coarse-estimator ring write (mixer_center) - done while it waits -;
+//           strobe interpolation, carrier error (tanh x2), loop filter                                      -> dval, ct_ec, (pt_qpsk, ct_ec)
 //   warp K2 carrier NCO (phase / frequency update, advance, table look-up); mixes the NEXT input sample
 //           and puts it into the FIR window                                                                 -> cval
 //   warp S  marg MA(800), 400-symbol delay, bias rotate, MSE, soft bits
@@ -74,7 +74,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     // hand-off slot layout: slot s, field f -> hand[(s * 12 + f) * 32 + lane]
     //   f 0,1: sig2raw (F->E)   f 2,3: sig2 (E->K)   f 4,5: st_eta, d8out (E->T)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (K->S)
-    //   f 10,11,12: strobe flag, FractionOfSampleItPassesBy, next input sample (T->K1/K2)   f 13 (slot 0): first input sample (T->K2)
+    //   f 10,11: strobe flag, FractionOfSampleItPassesBy (T->K1)   f 12: next input sample (K1->K2)   f 13 (slot 0): first input sample (K1->K2)
     //   f 14,15: carrier-update flag, ct_ec (K1->K2)
 #define HAND(s, f) hand[((s) * PP_HF + (f)) * 32 + lane]
 
@@ -118,7 +118,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
                     double2 *rowz = p.bb + (size_t)ch * p.bb_len;             // :667 bbcycbuff[j]=0
                     if (live) for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);
-                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp T reloads mixer_center after the barrier
+                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp K1 reloads mixer_center after the barrier
                 }
             } else countdown = 4;
             if (mse > p.signalthreshold) LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;   // :674-675
@@ -130,7 +130,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
             int fir_pos = (int)(S0 % OQ_NT1);                  // slot of the sample being mixed
             {   // cval of the first sample (:453)
-                const double dval = HAND(0, 13);               // first input sample, decoded by warp T before barrier (1)
+                const double dval = HAND(0, 13);               // first input sample, decoded by warp K1 before barrier (1)
                 const double cre = c2_re * dval, cim = c2_im * dval;
                 s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
                 s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
@@ -172,11 +172,75 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
         double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
         int yui = LI(I_YUI), sig2l_init = LI(I_SIG2L_INIT);
-        __syncthreads();                                       // (1)
-        if (nB > 0) {
+        // ---- input stage (this warp waits most of the time: it also decodes the PCM, fills the estimator ring and hands the
+        // next input sample to warp K2)
+        const int16_t *row = pcm + (size_t)ch * stride;
+        // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
+        auto pcm_bytes = [&](int tile) -> unsigned {
+            long long left = (long long)stride - (long long)tile * OQ_T;
+            if (left > OQ_T) left = OQ_T;
+            return left > 0 ? (unsigned)(left * 2) : 0u;
+        };
+        auto pcm_load = [&](int tile) {
+            const int b = tile & 1;
+            const unsigned nb = pcm_bytes(tile);
+            fence_proxy_async();
+            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
+            __syncwarp();
+            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
+        };
+        unsigned phases = 0u;
+#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
+        int pt = a.i0 / OQ_T;                                     // current PCM tile
+        bool pcm_next_issued = false;
+        pcm_load(pt);
+        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+        PP_WAIT(2 + (pt & 1));
+        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
+        int pk_blk = -1;
+        auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:390); ii advances by one per call
+            if ((ii >> 5) != pt) {                                // entered the next PCM tile (warp-uniform)
+                pt = ii >> 5;
+                PP_WAIT(2 + (pt & 1));
+                pcm_next_issued = false;
+                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+            }
+            if ((ii >> 3) != pk_blk) {
+                pk_blk = ii >> 3;
+                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
+            }
+            const int k = ii & 7;
+            const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
+            int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+            if (!live) v = 0;
+            return ((double)v) / 32768.0;
+        };
+        double dcur = dval_at(a.i0);
+        HAND(0, 13) = dcur;
+        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
+        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
+        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
+        const int bbn = p.bb_len;
+        const bool cpu_reduce = p.cpu_reduce != 0;
+        double cc_re, cc_im;
+        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+        {
             unsigned vph = 0u;                                 // parities of the two slot-free mbarriers
-            for (int j = 0; j < nB; j++) {
-                const int sl = j & 1;
+            for (int i = a.i0; i < a.i1; i++) {
+                const int j = i - a.i0, sl = j & 1;
+                // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
+                if (!(i == a.i0 && a.skip_a_first)) {
+                    if (coarse_counter >= Fs || !cpu_reduce) {
+                        if (live) bb_row[bb_pos] = make_double2(cc_re * dcur, cc_im * dcur);
+                        bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
+                    }
+                }
+                if (i == a.i1 - 1 && a.stop_after_a) break;
+                coarse_counter++;                                                 // :431
+                osc_next_frame(mc);                                               // :601
+                { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+                const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
                 nb_sync(BAR_YK + sl);                          // sig2 of this sample (warp E)
                 double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
                 nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
@@ -205,9 +269,10 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 }
                 sig2_last = sig2;                                                 // :596
                 // slot sl's K1->K2 fields were read by K2(j-2), which precedes X_{j-1} -> ... -> U_j: free
-                HAND(sl, 14) = k2_upd; HAND(sl, 15) = k2_ec;
+                HAND(sl, 14) = k2_upd; HAND(sl, 15) = k2_ec; HAND(sl, 12) = dnxt;
                 __threadfence_block();
                 nb_arrive(BAR_P + sl);                         // P_j
+                dcur = dnxt;
                 // symbol hand-off to warp S; slot reuse is gated by S's arrival on the slot's mbarrier
                 if (j >= 2) { mbar_wait(&bars[4 + sl], (vph >> sl) & 1u); vph ^= (1u << sl); }
                 HAND(sl, 6) = sy_x; HAND(sl, 7) = sy_y; HAND(sl, 8) = sy_ec; HAND(sl, 9) = sy_flag;
@@ -215,6 +280,8 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 nb_arrive(BAR_W + sl);                         // W_j
             }
         }
+        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
+        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
         LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
         LD(D_SIG2L_RE) = sig2_last.x; LD(D_SIG2L_IM) = sig2_last.y;
         LD(D_PTD_RE) = pt_d.x; LD(D_PTD_IM) = pt_d.y;
@@ -293,77 +360,16 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
         LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;
     }
-    // ======================================================================================= warp T: input + symbol-timing PLL
+    // ======================================================================================= warp T: symbol-timing PLL
     else if (warp == 2) {
         Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
         Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
-        const int16_t *row = pcm + (size_t)ch * stride;
-        // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
-        auto pcm_bytes = [&](int tile) -> unsigned {
-            long long left = (long long)stride - (long long)tile * OQ_T;
-            if (left > OQ_T) left = OQ_T;
-            return left > 0 ? (unsigned)(left * 2) : 0u;
-        };
-        auto pcm_load = [&](int tile) {
-            const int b = tile & 1;
-            const unsigned nb = pcm_bytes(tile);
-            fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
-            __syncwarp();
-            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
-        };
-        unsigned phases = 0u;
-#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
-        int pt = a.i0 / OQ_T;                                     // current PCM tile
-        bool pcm_next_issued = false;
-        pcm_load(pt);
-        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-        PP_WAIT(2 + (pt & 1));
-        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
-        int pk_blk = -1;
-        auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:390); ii advances by one per call
-            if ((ii >> 5) != pt) {                                // entered the next PCM tile (warp-uniform)
-                pt = ii >> 5;
-                PP_WAIT(2 + (pt & 1));
-                pcm_next_issued = false;
-                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-            }
-            if ((ii >> 3) != pk_blk) {
-                pk_blk = ii >> 3;
-                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
-            }
-            const int k = ii & 7;
-            const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
-            int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
-            if (!live) v = 0;
-            return ((double)v) / 32768.0;
-        };
-        double dcur = dval_at(a.i0);
-        HAND(0, 13) = dcur;
-        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
-        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
-        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
-        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
-        const int bbn = p.bb_len;
-        const bool cpu_reduce = p.cpu_reduce != 0;
+        __syncthreads();                                       // (1)
         const double ee = p.ee;
-        double cs_re, cs_im, cc_re, cc_im;
+        double cs_re, cs_im;
         { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
-        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-        for (int i = a.i0; i < a.i1; i++) {
-            const int j = i - a.i0, sl = j & 1;
-            // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
-            if (!(i == a.i0 && a.skip_a_first)) {
-                if (coarse_counter >= Fs || !cpu_reduce) {
-                    if (live) bb_row[bb_pos] = make_double2(cc_re * dcur, cc_im * dcur);
-                    bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
-                }
-            }
-            if (i == a.i1 - 1 && a.stop_after_a) break;
-            coarse_counter++;                                                 // :431
-            osc_next_frame(mc);                                               // :601
-            { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-            const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
+        for (int j = 0; j < nB; j++) {
+            const int sl = j & 1;
             nb_sync(BAR_YT + sl);                              // st_eta, d8out of this sample (warp E)
             const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
             const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
@@ -374,18 +380,15 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), Fs);
             double frac = 0.0;
             const bool strobe = osc_have_passed_point(st, ee, frac);          // :488
-            // slot sl's T->K fields were read by K(j-2), which precedes X_{j-1} -> Z_j -> (E) -> this point: free
-            HAND(sl, 10) = strobe ? 1.0 : 0.0; HAND(sl, 11) = frac; HAND(sl, 12) = dnxt;
+            // slot sl's T->K1 fields were read by K1(j-2), which precedes X_{j-1} -> Z_j -> (E) -> this point: free
+            HAND(sl, 10) = strobe ? 1.0 : 0.0; HAND(sl, 11) = frac;
             __threadfence_block();
             nb_arrive(BAR_U + sl);
             osc_next_frame(st); osc_next_frame(sr);                           // :602-603
             { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
-            dcur = dnxt;
         }
-        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
         LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
         LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
-        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
     // ======================================================================================= warp E: envelope chain
     else if (warp == 1) {
