@@ -16,11 +16,10 @@
 // and hand their results to the next warp through shared memory, ordered by named barriers (bar.arrive / bar.sync on
 // alternating ids, one producer warp + one consumer warp per barrier):
 //
-//   warp F  55-tap FIR of the mixed samples                                                                -> sig2raw
+//   warp F  input: PCM tiles (TMA), coarse-estimator ring write (mixer_center); 55-tap FIR of the mixed samples -> dval, sig2raw
 //   warp E  EbNo + AGC running sums (TMA-staged ring tiles), AGC gain, clip, timing feed-forward chain     -> sig2, st_eta, d8out
 //   warp T  symbol-timing PLL: arg of the timing-error phasor, st_osc nudges, strobe test                  -> (strobe, fraction)
-//   warp K1 input: PCM tiles (TMA), coarse-estimator ring write (mixer_center) - done while it waits -;
-//           strobe interpolation, carrier error (tanh x2), loop filter                                      -> dval, ct_ec, (pt_qpsk, ct_ec)
+//   warp K1 strobe interpolation, carrier error (tanh x2), loop filter                                      -> ct_ec, (pt_qpsk, ct_ec)
 //   warp K2 carrier NCO (phase / frequency update, advance, table look-up); mixes the NEXT input sample
 //           and puts it into the FIR window                                                                 -> cval
 //   warp S  marg MA(800), 400-symbol delay, bias rotate, MSE, soft bits
@@ -46,6 +45,7 @@ __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;
 #define LD(idx) p.D[(size_t)(idx) * cpad + ch]
 #define LI(idx) p.I[(size_t)(idx) * cpad + ch]
 
+#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
 __global__ void __launch_bounds__(PP_THREADS)
 oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
 {
@@ -74,7 +74,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
     const double *__restrict__ cos_t = p.cos_t, *__restrict__ sin_t = p.sin_t;
     // hand-off slot layout: slot s, field f -> hand[(s * 12 + f) * 32 + lane]
     //   f 0,1: sig2raw (F->E)   f 2,3: sig2 (E->K)   f 4,5: st_eta, d8out (E->T)   f 6..9: pt_qpsk.x, pt_qpsk.y, ct_ec, flag (K->S)
-    //   f 10,11: strobe flag, FractionOfSampleItPassesBy (T->K1)   f 12: next input sample (K1->K2)   f 13 (slot 0): first input sample (K1->K2)
+    //   f 10,11: strobe flag, FractionOfSampleItPassesBy (T->K1)   f 12: next input sample (F->K2)   f 13 (slot 0): first input sample (F->K2)
     //   f 14,15: carrier-update flag, ct_ec (K1->K2)
 #define HAND(s, f) hand[((s) * PP_HF + (f)) * 32 + lane]
 
@@ -118,7 +118,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                     LI(I_ZERO_BB) = 1;                                        // y[]=20 is applied by the estimator kernel on its next run
                     double2 *rowz = p.bb + (size_t)ch * p.bb_len;             // :667 bbcycbuff[j]=0
                     if (live) for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);
-                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp K1 reloads mixer_center after the barrier
+                    LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp F reloads mixer_center after the barrier
                 }
             } else countdown = 4;
             if (mse > p.signalthreshold) LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;   // :674-675
@@ -130,7 +130,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
             int fir_pos = (int)(S0 % OQ_NT1);                  // slot of the sample being mixed
             {   // cval of the first sample (:453)
-                const double dval = HAND(0, 13);               // first input sample, decoded by warp K1 before barrier (1)
+                const double dval = HAND(0, 13);               // first input sample, decoded by warp F before barrier (1)
                 const double cre = c2_re * dval, cim = c2_im * dval;
                 s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
                 s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
@@ -172,75 +172,11 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
         double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
         int yui = LI(I_YUI), sig2l_init = LI(I_SIG2L_INIT);
-        // ---- input stage (this warp waits most of the time: it also decodes the PCM, fills the estimator ring and hands the
-        // next input sample to warp K2)
-        const int16_t *row = pcm + (size_t)ch * stride;
-        // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
-        auto pcm_bytes = [&](int tile) -> unsigned {
-            long long left = (long long)stride - (long long)tile * OQ_T;
-            if (left > OQ_T) left = OQ_T;
-            return left > 0 ? (unsigned)(left * 2) : 0u;
-        };
-        auto pcm_load = [&](int tile) {
-            const int b = tile & 1;
-            const unsigned nb = pcm_bytes(tile);
-            fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
-            __syncwarp();
-            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
-        };
-        unsigned phases = 0u;
-#define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
-        int pt = a.i0 / OQ_T;                                     // current PCM tile
-        bool pcm_next_issued = false;
-        pcm_load(pt);
-        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-        PP_WAIT(2 + (pt & 1));
-        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
-        int pk_blk = -1;
-        auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:390); ii advances by one per call
-            if ((ii >> 5) != pt) {                                // entered the next PCM tile (warp-uniform)
-                pt = ii >> 5;
-                PP_WAIT(2 + (pt & 1));
-                pcm_next_issued = false;
-                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-            }
-            if ((ii >> 3) != pk_blk) {
-                pk_blk = ii >> 3;
-                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
-            }
-            const int k = ii & 7;
-            const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
-            int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
-            if (!live) v = 0;
-            return ((double)v) / 32768.0;
-        };
-        double dcur = dval_at(a.i0);
-        HAND(0, 13) = dcur;
-        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
-        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
-        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
-        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
-        const int bbn = p.bb_len;
-        const bool cpu_reduce = p.cpu_reduce != 0;
-        double cc_re, cc_im;
-        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+        __syncthreads();                                       // (1)
         {
             unsigned vph = 0u;                                 // parities of the two slot-free mbarriers
-            for (int i = a.i0; i < a.i1; i++) {
-                const int j = i - a.i0, sl = j & 1;
-                // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
-                if (!(i == a.i0 && a.skip_a_first)) {
-                    if (coarse_counter >= Fs || !cpu_reduce) {
-                        if (live) bb_row[bb_pos] = make_double2(cc_re * dcur, cc_im * dcur);
-                        bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
-                    }
-                }
-                if (i == a.i1 - 1 && a.stop_after_a) break;
-                coarse_counter++;                                                 // :431
-                osc_next_frame(mc);                                               // :601
-                { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-                const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
+            for (int j = 0; j < nB; j++) {
+                const int sl = j & 1;
                 nb_sync(BAR_YK + sl);                          // sig2 of this sample (warp E)
                 double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
                 nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
@@ -269,10 +205,9 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 }
                 sig2_last = sig2;                                                 // :596
                 // slot sl's K1->K2 fields were read by K2(j-2), which precedes X_{j-1} -> ... -> U_j: free
-                HAND(sl, 14) = k2_upd; HAND(sl, 15) = k2_ec; HAND(sl, 12) = dnxt;
+                HAND(sl, 14) = k2_upd; HAND(sl, 15) = k2_ec;
                 __threadfence_block();
                 nb_arrive(BAR_P + sl);                         // P_j
-                dcur = dnxt;
                 // symbol hand-off to warp S; slot reuse is gated by S's arrival on the slot's mbarrier
                 if (j >= 2) { mbar_wait(&bars[4 + sl], (vph >> sl) & 1u); vph ^= (1u << sl); }
                 HAND(sl, 6) = sy_x; HAND(sl, 7) = sy_y; HAND(sl, 8) = sy_ec; HAND(sl, 9) = sy_flag;
@@ -280,8 +215,6 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
                 nb_arrive(BAR_W + sl);                         // W_j
             }
         }
-        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
-        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
         LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
         LD(D_SIG2L_RE) = sig2_last.x; LD(D_SIG2L_IM) = sig2_last.y;
         LD(D_PTD_RE) = pt_d.x; LD(D_PTD_IM) = pt_d.y;
@@ -550,38 +483,101 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         LD(D_DLY8_0) = d8_0; LD(D_DLY8_1) = d8_1; LD(D_DLY8_2) = d8_2;
         LD(D_RES_X1) = res.x1; LD(D_RES_X2) = res.x2; LD(D_RES_Y1) = res.y1; LD(D_RES_Y2) = res.y2;
     }
-    // ======================================================================================= warp F: matched filter
+    // ======================================================================================= warp F: input + matched filter
     else {
         for (int k = 0; k < OQ_NT1; k++) {
             const double vr = p.fir_re[(size_t)k * cpad + ch], vi = p.fir_im[(size_t)k * cpad + ch];
             s_re[k * OQ_THREADS + lane] = vr; s_re[(k + OQ_NT1) * OQ_THREADS + lane] = vr;
             s_im[k * OQ_THREADS + lane] = vi; s_im[(k + OQ_NT1) * OQ_THREADS + lane] = vi;
         }
-        __syncthreads();                                       // (1)
+        const int16_t *row = pcm + (size_t)ch * stride;
+        // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
+        auto pcm_bytes = [&](int tile) -> unsigned {
+            long long left = (long long)stride - (long long)tile * OQ_T;
+            if (left > OQ_T) left = OQ_T;
+            return left > 0 ? (unsigned)(left * 2) : 0u;
+        };
+        auto pcm_load = [&](int tile) {
+            const int b = tile & 1;
+            const unsigned nb = pcm_bytes(tile);
+            fence_proxy_async();
+            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
+            __syncwarp();
+            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
+        };
+        unsigned phases = 0u;
+        int pt = a.i0 / OQ_T;                                     // current PCM tile
+        bool pcm_next_issued = false;
+        pcm_load(pt);
+        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+        PP_WAIT(2 + (pt & 1));
+        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
+        int pk_blk = -1;
+        auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:390); ii advances by one per call
+            if ((ii >> 5) != pt) {                                // entered the next PCM tile (warp-uniform)
+                pt = ii >> 5;
+                PP_WAIT(2 + (pt & 1));
+                pcm_next_issued = false;
+                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
+            }
+            if ((ii >> 3) != pk_blk) {
+                pk_blk = ii >> 3;
+                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
+            }
+            const int k = ii & 7;
+            const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
+            int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
+            if (!live) v = 0;
+            return ((double)v) / 32768.0;
+        };
+        double dcur = dval_at(a.i0);
+        HAND(0, 13) = dcur;
+        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
+        Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+        int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
+        double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
+        const int bbn = p.bb_len;
+        const bool cpu_reduce = p.cpu_reduce != 0;
+        double cc_re, cc_im;
+        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
         // output j (:456) = sum over the 55 mixed samples older than sample i0+j; the newest of them (slot `tail`) is produced
-        // by warp K one sample earlier, the 54 older terms are summed ahead of that
+        // by warp K2 one sample earlier, the 54 older terms are summed ahead of that
         int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);
         double nfre = 0, nfim = 0;
         if (nB > 0) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
-        for (int j = 0; j < nB; j++) {
+        for (int i = a.i0; i < a.i1; i++) {
+            const int j = i - a.i0, sl = j & 1;
+            // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
+            if (!(i == a.i0 && a.skip_a_first)) {
+                if (coarse_counter >= Fs || !cpu_reduce) {
+                    if (live) bb_row[bb_pos] = make_double2(cc_re * dcur, cc_im * dcur);
+                    bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
+                }
+            }
+            if (i == a.i1 - 1 && a.stop_after_a) break;
+            coarse_counter++;                                                 // :431
+            osc_next_frame(mc);                                               // :601
+            { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+            const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
             if (j > 0) nb_sync(BAR_X + ((j - 1) & 1));        // X_{j-1}
             nfre += c_taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += c_taps[54] * s_im[tail * OQ_THREADS + lane];
-            const int sl = j & 1;
-            // slot sl's F->E fields were read by E(j-2) before its Y arrivals -> K(j-2) -> X_{j-1}: free
-            HAND(sl, 0) = nfre; HAND(sl, 1) = nfim;
+            // slot sl's F->E / F->K2 fields were read by E(j-2) / K2(j-2), both before X_{j-1}: free
+            HAND(sl, 0) = nfre; HAND(sl, 1) = nfim; HAND(sl, 12) = dnxt;
             __threadfence_block();
             nb_arrive(BAR_Z + sl);                             // Z_j
             tail++; if (tail >= OQ_NT1) tail = 0;
             if (j + 1 < nB) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+            dcur = dnxt;
         }
-        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp K
+        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
+        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp K2
+        LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
     for (int k = warp; k < OQ_NT1; k += 6) {
         p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
         p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
     }
-#undef PP_WAIT
 #undef HAND
 }
 
@@ -598,3 +594,5 @@ int oqpsk_pipe_launch(const DemodParams &p, const SegmentArgs &a, const int16_t 
 #undef LD
 #undef LI
 } // namespace jb
+
+#undef PP_WAIT
