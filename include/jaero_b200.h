@@ -250,6 +250,49 @@ int jaero_ingest_message(jaero_ingest *g, const void *topic, size_t topic_len, c
 size_t jaero_ingest_available(const jaero_ingest *g);                  /* samples every channel has */
 int jaero_ingest_flush(jaero_ingest *g, jaero_batch *b, size_t n_samples);
 
+/* ---- ISU / SSU reassembly and ACARS block parsing (host side) ----
+ * One handle per channel. Replaces RISUData::update (JAERO/aerol.cpp:27-112), ISUData::update (:151-214),
+ * ParserISU::parse (:340-487) and ACARSDefragmenter (:221-329), fed the way AeroL::Decode feeds them (:1357-1399 R
+ * packets, :1497-1513 T packets, :1900-1925 P-channel signal units). Pure host code, no device. The aircraft-database
+ * look-up of ParserISU::acarslookupresult (:493-520) is not part of this library; only its removal of the leading dots of
+ * the registration is applied. Input signal units must be CRC-valid (the device layers report crc_ok per unit). */
+#define JAERO_REASM_ACARS 0      /* record kinds */
+#define JAERO_REASM_ERROR 1      /* text = the reference's Errorsignal string */
+#define JAERO_REASM_COMPLETE 1   /* push return bits: an ISU completed */
+#define JAERO_REASM_MISSING 2    /* a subsequent signal unit had no open sequence */
+#define JAERO_REASM_PARSED 4     /* the completed ISU was accepted by the parser */
+#define JAERO_ACARS_NONACARS 1   /* flags: user data is not an ACARS block, text = its bytes in hex */
+#define JAERO_ACARS_DOWNLINK 2
+#define JAERO_ACARS_VALID 4
+#define JAERO_ACARS_HASTEXT 8
+#define JAERO_ACARS_MORE 16
+typedef struct jaero_acars_record {
+    int32_t kind;
+    uint32_t aes_id;                 /* ISUItem: AESID, GESID, QNO, REFNO, SEQNO, NOOCTLESTINLASTSSU */
+    uint8_t ges_id, qno, refno, seqno, last_octets;
+    uint8_t mode, tak, block_id;     /* ACARSItem: MODE, TAK, BI */
+    uint8_t label[2], label_len;     /* LABEL */
+    uint8_t reg[7], reg_len;         /* PLANEREG */
+    uint8_t flags;                   /* JAERO_ACARS_* */
+    uint32_t userdata_len;           /* bytes of ISU user data the record was parsed from */
+    uint32_t text_len;               /* bytes of message text (or error text) */
+} jaero_acars_record;
+typedef struct jaero_reasm jaero_reasm;
+int jaero_reasm_create(jaero_reasm **out);
+void jaero_reasm_destroy(jaero_reasm *h);
+int jaero_reasm_reset(jaero_reasm *h);                                      /* AeroL::setSettings (:992-993) */
+int jaero_reasm_short_frame(jaero_reasm *h);                                /* the short-frame reset (:1997) */
+/* one P- or T-channel signal unit (first 10 of its 12 bytes are used); returns JAERO_REASM_* bits or a negative error */
+int jaero_reasm_push_su(jaero_reasm *h, const uint8_t *su, int downlink);
+/* one R-channel packet (first 17 of its 19 bytes are used) */
+int jaero_reasm_push_r(jaero_reasm *h, const uint8_t *info, int downlink);
+/* one T-channel packet as jaero_rt_read_packets returns it: 6-byte header + n_sus x 12 bytes */
+int jaero_reasm_push_t_packet(jaero_reasm *h, const uint8_t *info, int n_sus);
+int jaero_reasm_pending(const jaero_reasm *h);
+/* pops the oldest record; returns the text length, -1 when there is none, -2 when cap < rec->text_len (nothing popped) */
+long jaero_reasm_pop(jaero_reasm *h, jaero_acars_record *rec, char *text, size_t cap);
+int jaero_reasm_get_stats(const jaero_reasm *h, uint64_t *isus, uint64_t *messages, uint64_t *errors, uint64_t *missing);   /* any may be NULL */
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,15 @@ class Status(ctypes.Structure):
                [("samples", ctypes.c_int64), ("softbits", ctypes.c_int64), ("dcd", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+class AcarsRecord(ctypes.Structure):
+    """jaero_acars_record (include/jaero_b200.h)."""
+    _fields_ = [("kind", ctypes.c_int32), ("aes_id", ctypes.c_uint32),
+                ("ges_id", ctypes.c_uint8), ("qno", ctypes.c_uint8), ("refno", ctypes.c_uint8), ("seqno", ctypes.c_uint8),
+                ("last_octets", ctypes.c_uint8), ("mode", ctypes.c_uint8), ("tak", ctypes.c_uint8), ("block_id", ctypes.c_uint8),
+                ("label", ctypes.c_uint8 * 2), ("label_len", ctypes.c_uint8), ("reg", ctypes.c_uint8 * 7), ("reg_len", ctypes.c_uint8),
+                ("flags", ctypes.c_uint8), ("userdata_len", ctypes.c_uint32), ("text_len", ctypes.c_uint32)]
+
+
 EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaero_batch_destroy", "jaero_batch_channels",
            "jaero_batch_write", "jaero_batch_write_device", "jaero_batch_sync", "jaero_batch_read_softbits",
            "jaero_batch_softbits_device", "jaero_batch_reset_softbits", "jaero_batch_set_dcd",
@@ -52,7 +61,9 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count",
            "jaero_cchannel_create", "jaero_cchannel_destroy", "jaero_cchannel_process_batch", "jaero_cchannel_process_softbits",
            "jaero_cchannel_tick", "jaero_cchannel_read_frames", "jaero_cchannel_get_stats", "jaero_cchannel_launch_count",
-           "jaero_ingest_create", "jaero_ingest_destroy", "jaero_ingest_message", "jaero_ingest_available", "jaero_ingest_flush"]
+           "jaero_ingest_create", "jaero_ingest_destroy", "jaero_ingest_message", "jaero_ingest_available", "jaero_ingest_flush",
+           "jaero_reasm_create", "jaero_reasm_destroy", "jaero_reasm_reset", "jaero_reasm_short_frame", "jaero_reasm_push_su",
+           "jaero_reasm_push_r", "jaero_reasm_push_t_packet", "jaero_reasm_pending", "jaero_reasm_pop", "jaero_reasm_get_stats"]
 
 
 def lib():
@@ -126,6 +137,15 @@ def lib():
         L.jaero_ingest_message.argtypes = [vp, ctypes.c_char_p, sz, ctypes.c_char_p, sz, vp, sz]
         L.jaero_ingest_available.argtypes = [vp]; L.jaero_ingest_available.restype = sz
         L.jaero_ingest_flush.argtypes = [vp, vp, sz]
+        L.jaero_reasm_create.argtypes = [ctypes.POINTER(vp)]
+        L.jaero_reasm_destroy.argtypes = [vp]; L.jaero_reasm_destroy.restype = None
+        L.jaero_reasm_reset.argtypes = [vp]; L.jaero_reasm_short_frame.argtypes = [vp]
+        L.jaero_reasm_push_su.argtypes = [vp, ctypes.c_char_p, i]
+        L.jaero_reasm_push_r.argtypes = [vp, ctypes.c_char_p, i]
+        L.jaero_reasm_push_t_packet.argtypes = [vp, ctypes.c_char_p, i]
+        L.jaero_reasm_pending.argtypes = [vp]
+        L.jaero_reasm_pop.argtypes = [vp, ctypes.POINTER(AcarsRecord), vp, sz]; L.jaero_reasm_pop.restype = ctypes.c_long
+        L.jaero_reasm_get_stats.argtypes = [vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -560,6 +580,78 @@ class IngestRouter:
     def close(self):
         if self.h:
             lib().jaero_ingest_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Reassembler:
+    """Per-channel ISU/SSU reassembly + ACARS parsing + defragmentation (host side; mirrors the reference's ISUData,
+    RISUData, ParserISU and ACARSDefragmenter, JAERO/aerol.cpp:4-487). Feed CRC-valid signal units only."""
+
+    COMPLETE, MISSING, PARSED = 1, 2, 4
+
+    def __init__(self):
+        self.h = ctypes.c_void_p()
+        _check(lib().jaero_reasm_create(ctypes.byref(self.h)))
+
+    def reset(self):
+        _check(lib().jaero_reasm_reset(self.h))
+
+    def short_frame(self):
+        _check(lib().jaero_reasm_short_frame(self.h))
+
+    def push_su(self, su, downlink=False):
+        su = bytes(bytearray(su))
+        if len(su) < 10:
+            raise ValueError("a signal unit has at least 10 bytes")
+        return lib().jaero_reasm_push_su(self.h, su, int(downlink))
+
+    def push_r(self, info, downlink=True):
+        info = bytes(bytearray(info))
+        if len(info) < 17:
+            raise ValueError("an R-channel packet has at least 17 bytes")
+        return lib().jaero_reasm_push_r(self.h, info, int(downlink))
+
+    def push_t_packet(self, info, n_sus):
+        info = bytes(bytearray(info))
+        if len(info) < 6 + 12 * n_sus:
+            raise ValueError("T packet shorter than its SU count")
+        return lib().jaero_reasm_push_t_packet(self.h, info, int(n_sus))
+
+    def pop_all(self):
+        """list of dicts; text is bytes (message text, hex dump for non-ACARS user data, or the error string)"""
+        out = []
+        rec = AcarsRecord(); cap = 4096; buf = ctypes.create_string_buffer(cap)
+        while True:
+            n = lib().jaero_reasm_pop(self.h, ctypes.byref(rec), buf, cap)
+            if n == -1:
+                break
+            if n == -2:
+                cap = int(rec.text_len) + 1; buf = ctypes.create_string_buffer(cap)
+                continue
+            if n < 0:
+                raise JaeroError("jaero_reasm_pop failed")
+            f = rec.flags
+            out.append(dict(kind=rec.kind, aesid=rec.aes_id, gesid=rec.ges_id, qno=rec.qno, refno=rec.refno, seqno=rec.seqno,
+                            nooct=rec.last_octets, mode=rec.mode, tak=rec.tak, bi=rec.block_id,
+                            nonacars=bool(f & 1), downlink=bool(f & 2), valid=bool(f & 4), hastext=bool(f & 8), moretocome=bool(f & 16),
+                            label=bytes(rec.label[:rec.label_len]), reg=bytes(rec.reg[:rec.reg_len]), text=buf.raw[:n],
+                            userdata_len=rec.userdata_len))
+        return out
+
+    def stats(self):
+        v = (ctypes.c_uint64 * 4)()
+        a = ctypes.addressof(v)
+        _check(lib().jaero_reasm_get_stats(self.h, a, a + 8, a + 16, a + 24))
+        return dict(isus=v[0], messages=v[1], errors=v[2], missing=v[3])
+
+    def close(self):
+        if self.h:
+            lib().jaero_reasm_destroy(self.h); self.h = None
 
     def __del__(self):
         try:

@@ -18,6 +18,7 @@ UNITS = [
     ("pchannel.cu", []),
     ("rtchannel.cu", []),
     ("cchannel.cu", []),
+    ("reassembly.cu", []),
     ("prefilter.cu", ["-fmad=false"]),
     ("burst.cu", ["-fmad=false"]),
     ("demod_kernels.cu", ["-fmad=false"]),

@@ -152,3 +152,69 @@ def run_demod_job(args):
     out = (d.take_soft(), d.state(), d.take_cfe_log())
     d.close()
     return out
+
+
+class RefReasm:
+    """The reference's own RISUData / ISUData / ParserISU / ACARSDefragmenter (JAERO/aerol.cpp:4-487), compiled
+    verbatim into oracle/_ref/libjaero_ref_reasm.so by oracle/Makefile (ref_reasm_driver.cpp)."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libjaero_ref_reasm.so"))
+            L.jref_reasm_new.restype = ctypes.c_void_p
+            for f in ("jref_reasm_free", "jref_reasm_reset", "jref_reasm_short_frame"):
+                getattr(L, f).argtypes = [ctypes.c_void_p]
+            L.jref_reasm_su.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+            L.jref_reasm_r.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+            L.jref_reasm_pending.argtypes = [ctypes.c_void_p]
+            L.jref_reasm_pop.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            cls._lib = L
+        return cls._lib
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libjaero_ref_reasm.so"))
+
+    def __init__(self):
+        self.h = self.lib().jref_reasm_new()
+
+    def reset(self):
+        self.lib().jref_reasm_reset(self.h)
+
+    def short_frame(self):
+        self.lib().jref_reasm_short_frame(self.h)
+
+    def push_su(self, su, burstmode=False):
+        return self.lib().jref_reasm_su(self.h, bytes(bytearray(su[:10])), int(burstmode))
+
+    def push_r(self, info, burstmode=True):
+        return self.lib().jref_reasm_r(self.h, bytes(bytearray(info[:17])), int(burstmode))
+
+    def pop_all(self):
+        out = []
+        meta = (ctypes.c_uint * 16)(); cap = 1 << 16; text = (ctypes.c_ubyte * cap)()
+        while True:
+            n = self.lib().jref_reasm_pop(self.h, meta, text, cap)
+            if n < 0:
+                break
+            out.append(reasm_record(list(meta), bytes(text[:n])))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib().jref_reasm_free(self.h); self.h = None
+
+
+def reasm_record(m, t):
+    """meta/text layout shared by the reference driver and the oracle: see ref_reasm_driver.cpp jref_reasm_pop."""
+    o = 0
+    label = t[o:o + m[11]]; o += m[11]
+    reg = t[o:o + m[12]]; o += m[12]
+    msg = t[o:o + m[13]]; o += m[13]
+    ud = t[o:o + m[14]]
+    return dict(kind=m[0], aesid=m[1], gesid=m[2], qno=m[3], refno=m[4], seqno=m[5], nooct=m[6], mode=m[7], tak=m[8], bi=m[9],
+                nonacars=bool(m[10] & 1), downlink=bool(m[10] & 2), valid=bool(m[10] & 4), hastext=bool(m[10] & 8),
+                moretocome=bool(m[10] & 16), label=label.hex(), reg=reg.hex(), message=msg.hex(), userdata=ud.hex())

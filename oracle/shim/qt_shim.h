@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
+#include <cstdarg>
+#include <cctype>
 #include <cassert>
 #include <algorithm>
 #include <initializer_list>
@@ -78,6 +80,7 @@ public:
     void removeFirst() { v.erase(v.begin()); }
     void removeLast() { v.pop_back(); }
     void remove(int i, int n = 1) { v.erase(v.begin() + i, v.begin() + i + n); }
+    void removeAt(int i) { v.erase(v.begin() + i); }
     void insert(int i, const T &t) { v.insert(v.begin() + i, t); }
     QVector<T> mid(int pos, int len = -1) const
     {
@@ -119,7 +122,8 @@ public:
     const char *constData() const { return v.data(); }
     operator const char *() const { return v.data(); }
     char at(int i) const { return v[i]; }
-    char &operator[](int i) { return v[i]; }
+    // Qt5: assigning through the non-const operator[] past the end grows the array (QByteRef); new bytes are zero here
+    char &operator[](int i) { if (i >= (int)v.size()) v.resize(i + 1); return v[i]; }
     char operator[](int i) const { return v[i]; }
     void push_back(char c) { v.push_back(c); }
     QByteArray &append(char c) { v.push_back(c); return *this; }
@@ -140,6 +144,13 @@ public:
     std::vector<char> v;
 };
 
+class QChar
+{
+public:
+    QChar(char ch = 0) : c(ch) {}
+    char c;
+};
+
 class QString
 {
 public:
@@ -152,11 +163,33 @@ public:
     static QString number(double d) { return QString(std::to_string(d)); }
     static QString number(int d) { return QString(std::to_string(d)); }
     template <class A> QString arg(const A &) const { return *this; }
+    // arg(value, fieldWidth, base, fillChar): replaces the %1 marker (the only one in the sources compiled here)
+    QString arg(long long v, int width, int base, QChar fill) const
+    {
+        char digits[72]; int n = 0;
+        unsigned long long u = (unsigned long long)(v < 0 ? -v : v);
+        do { int d = (int)(u % (unsigned)base); digits[n++] = (char)(d < 10 ? '0' + d : 'a' + d - 10); u /= (unsigned)base; } while (u);
+        std::string t; if (v < 0) t += '-';
+        while (n) t += digits[--n];
+        while ((int)t.size() < width) t.insert(t.begin(), fill.c);
+        std::string r = s; size_t k = r.find("%1");
+        if (k != std::string::npos) r.replace(k, 2, t);
+        return QString(r);
+    }
+    QString &sprintf(const char *fmt, ...)
+    {
+        char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        s = buf; return *this;
+    }
+    QString toUpper() const { std::string r = s; for (char &c : r) c = (char)toupper((unsigned char)c); return QString(r); }
+    int size() const { return (int)s.size(); }
     bool isEmpty() const { return s.empty(); }
     void clear() { s.clear(); }
+    bool operator==(const QString &o) const { return s == o.s; }
     QByteArray toLatin1() const { return QByteArray(s.c_str()); }
     std::string s;
 };
+typedef QList<QString> QStringList;
 
 struct QDebugSink
 {

@@ -2,6 +2,7 @@
 oracle on the same inputs. Integer/byte outputs (soft bits after hard decision, Viterbi bits, SU bytes, CRC
 flags) must be bit-exact; floating-point loop state within 1e-6 relative (north_star allows 1e-4)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -440,6 +441,50 @@ def test_rt_channel_known_answer_r_packets(fb):
     for c in range(5):
         assert len(got[c]) == 1 and got[c][0]["type"] == 1
         assert np.array_equal(got[c][0]["bytes"][:17], payloads[c]) and len(got[c][0]["bytes"]) == 19
+
+
+def test_recording_to_acars_end_to_end():
+    """240 s 10.5k recording -> device demodulator -> device P-channel frame layer -> host reassembly == the ACARS records the
+    reference's own demodulator + reassembly code produce (tests/golden/reasm_golden.json, tools/make_reasm_golden.py)."""
+    import json
+    import reasm_synth
+    jb = _import()
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pcm_full", "oqpsk_10500.npy")
+    if not os.path.exists(path):
+        pytest.skip("full-length recording fixture not present (git-ignored; made by tools/make_fixtures.py)")
+    pcm = np.load(path)
+    with open(os.path.join(os.path.dirname(path), "..", "reasm_golden.json")) as fh:
+        want = json.load(fh)["p_recording_10500"]["records"]
+    want_sus = reasm_synth.unpack_stream(np.load(os.path.join(os.path.dirname(path), "..", "reasm_su_streams.npz"))["p_recording_10500"])
+    kw = dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)
+    b = jb.DemodBatch("oqpsk", 2, **kw)
+    pc = jb.PChannelBatch(2, 10500)
+    rs = [jb.Reassembler(), jb.Reassembler()]
+    sus = [[], []]
+    chunk = 4800
+
+    def drain():
+        for c, (su, ok, _, _) in enumerate(pc.read_sus()):
+            for k in range(len(ok)):
+                if ok[k]:
+                    sus[c].append(bytes(su[k, :10])); rs[c].push_su(su[k])
+
+    for k, a in enumerate(range(0, len(pcm), chunk)):
+        x = pcm[a:a + chunk]
+        b.write(np.stack([x, x]))
+        pc.process_softbits(b.read_softbits())
+        if k % 5 == 4:
+            drain()
+    drain()
+    for c in range(2):
+        assert sus[c] == [e[1] for e in want_sus]                        # the CRC-valid signal units, byte for byte
+        got = rs[c].pop_all()
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g["kind"] == w["kind"] and g["aesid"] == w["aesid"] and g["text"] == bytes.fromhex(w["message"])
+            assert g["reg"] == bytes.fromhex(w["reg"]) and g["label"] == bytes.fromhex(w["label"]) and g["bi"] == w["bi"]
+        rs[c].close()
+    b.close(); pc.close()
 
 
 def test_error_behaviour():

@@ -1,0 +1,71 @@
+"""Generate tests/golden/reasm_golden.json: the reference's own ISU/SSU reassembly + ACARS parse (oracle/_ref/
+libjaero_ref_reasm.so = JAERO/aerol.cpp:4-487 compiled verbatim) run over
+  (1) the CRC-valid P-channel signal units of the full 10.5k recording (tests/golden/pcm_full/oqpsk_10500.npy,
+      demodulated by the verbatim reference demodulator, framed by the restated AeroL P-channel decoder);
+  (2) the CRC-valid T/R packets of the burst recordings;
+  (3) seeded synthetic SU streams that exercise multi-block ACARS, interleaved sequences, lost SSUs, parity errors,
+      R-channel 1/2/3-SU sequences and the garbage cases.
+The SU byte streams themselves are committed (tests/golden/reasm_su_streams.npz) so the tests need neither the
+recordings nor /root/reference. Build container only."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import ref, restated  # noqa: E402
+import reasm_synth  # noqa: E402  (tests/reasm_synth.py)
+
+
+def recording_sus():
+    import multiprocessing as mp
+    pcm = np.load(os.path.join(ROOT, "tests", "golden", "pcm_full", "oqpsk_10500.npy"))
+    kw = dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as pool:
+        soft, state, cfe = pool.apply(ref.run_demod_job, (("oqpsk", kw, pcm, 4800, None),))
+    p = restated.OraclePChannel(10500)
+    p.process(soft)
+    su, ok, fr = p.take_sus()
+    print("recording: %d SUs, %d CRC ok" % (len(ok), int(ok.sum())))
+    return su[ok != 0][:, :10].copy()
+
+
+def run_stream(stream):
+    r = ref.RefReasm()
+    rcs = []
+    for e in stream:
+        kind = e[0]
+        if kind == "su":
+            rcs.append(r.push_su(e[1], e[2]))
+        elif kind == "r":
+            rcs.append(r.push_r(e[1], e[2]))
+        elif kind == "reset":
+            r.reset(); rcs.append(0)
+        elif kind == "short":
+            r.short_frame(); rcs.append(0)
+    out = r.pop_all()
+    r.close()
+    return rcs, out
+
+
+if __name__ == "__main__":
+    streams = {}
+    rec = recording_sus()
+    streams["p_recording_10500"] = [("su", bytes(x), False) for x in rec]
+    for name, s in reasm_synth.synthetic_streams().items():
+        streams[name] = s
+    gold = {}
+    arrays = {}
+    for name, s in streams.items():
+        rcs, out = run_stream(s)
+        gold[name] = dict(return_codes=rcs, records=out)
+        arrays[name] = reasm_synth.pack_stream(s)
+        n_acars = sum(1 for o in out if o["kind"] == 0 and not o["nonacars"])
+        print(name, "events", len(s), "records", len(out), "acars", n_acars, "errors", sum(1 for o in out if o["kind"] == 1))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reasm_su_streams.npz"), **arrays)
+    with open(os.path.join(ROOT, "tests", "golden", "reasm_golden.json"), "w") as fh:
+        json.dump(gold, fh, indent=0, sort_keys=True)
