@@ -54,7 +54,8 @@ def _same(got, want):
         assert got["userdata_len"] == len(want["userdata"]) // 2
 
 
-@pytest.mark.parametrize("name", ["p_recording_10500", "p_synthetic", "t_synthetic", "r_synthetic", "garbage"])
+@pytest.mark.parametrize("name", ["p_recording_10500", "rt_recording_burst_oqpsk_10500", "rt_recording_burst_msk_1200_a", "rt_recording_burst_msk_1200_b",
+                                  "p_synthetic", "t_synthetic", "r_synthetic", "garbage"])
 def test_reassembly_matches_reference_golden(name):
     gold, streams = _gold()
     rcs, out, st = _run_product(streams[name])

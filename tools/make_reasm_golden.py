@@ -34,6 +34,28 @@ def recording_sus():
     return su[ok != 0][:, :10].copy()
 
 
+def burst_recording_events(name, kind, kw):
+    """R/T packets of a full-length burst recording (verbatim reference demodulator, restated R/T packet layer whose packets
+    are CRC-16 verified) as reassembly events, in AeroL::Decode's order (JAERO/aerol.cpp:1357-1399, 1480-1516)."""
+    import multiprocessing as mp
+    pcm = np.load(os.path.join(ROOT, "tests", "golden", "pcm_full", name + ".npy"))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as pool:
+        soft, state, cfe = pool.apply(ref.run_demod_job, ((kind, kw, pcm, 4800, None),))
+    rt = restated.OracleRTChannel(kw["fb"])
+    rt.process(soft)
+    ev = []
+    for q in rt.packets():
+        b = bytes(q["bytes"])
+        if q["type"] == 1:
+            ev.append(("r", b[:17], True))
+        else:
+            for k in range(q["nsus"]):
+                ev.append(("su", b[6 + 12 * k:6 + 12 * k + 10], True))
+    print(name, "packets", len(rt.packets()), "events", len(ev))
+    return ev
+
+
 def run_stream(stream):
     r = ref.RefReasm()
     rcs = []
@@ -56,6 +78,10 @@ if __name__ == "__main__":
     streams = {}
     rec = recording_sus()
     streams["p_recording_10500"] = [("su", bytes(x), False) for x in rec]
+    streams["rt_recording_burst_oqpsk_10500"] = burst_recording_events(
+        "burst_oqpsk_10500", "burst_oqpsk", dict(fb=10500.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6))
+    for nm in ("burst_msk_1200_a", "burst_msk_1200_b"):
+        streams["rt_recording_" + nm] = burst_recording_events(nm, "burst_msk", dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6))
     for name, s in reasm_synth.synthetic_streams().items():
         streams[name] = s
     gold = {}
