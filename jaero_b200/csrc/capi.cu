@@ -26,6 +26,16 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 } // namespace jb
 using namespace jb;
 
+// A create call that fails half-way (any JB_CUDA early return) hands the partly built object to its destroy function.
+template <class T> struct CreateGuard {
+    T *obj; void (*destroy)(T *);
+    CreateGuard(T *o, void (*d)(T *)) : obj(o), destroy(d) {}
+    ~CreateGuard() { if (obj) destroy(obj); }
+    void release() { obj = 0; }
+    CreateGuard(const CreateGuard &) = delete;
+    CreateGuard &operator=(const CreateGuard &) = delete;
+};
+
 struct jaero_viterbi {
     int n_channels, pad, device;
     cudaStream_t stream;
@@ -55,6 +65,7 @@ int jaero_viterbi_create(int n_channels, int paddinglength, int device, jaero_vi
     JB_CUDA(cudaSetDevice(device));
     jaero_viterbi *v = new (std::nothrow) jaero_viterbi();
     if (!v) { set_error("out of host memory"); return JAERO_E_ARG; }
+    CreateGuard<jaero_viterbi> guard(v, jaero_viterbi_destroy);
     memset(v, 0, sizeof *v);
     v->n_channels = n_channels; v->pad = paddinglength; v->device = device;
     JB_CUDA(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
@@ -65,6 +76,7 @@ int jaero_viterbi_create(int n_channels, int paddinglength, int device, jaero_vi
     JB_CUDA(cudaMemsetAsync(v->d_overlap, 0, (size_t)n_channels * 64, v->stream));
     JB_CUDA(cudaMemsetAsync(v->d_overlap_len, 0, (size_t)n_channels * sizeof(int), v->stream));
     JB_CUDA(cudaMemsetAsync(v->d_renorm, 0, (size_t)n_channels * sizeof(int), v->stream));
+    guard.release();
     *out = v;
     return JAERO_OK;
 }
@@ -309,6 +321,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     JB_CUDA(cudaSetDevice(device));
     jaero_batch *b = new (std::nothrow) jaero_batch();
     if (!b) { set_error("out of host memory"); return JAERO_E_ARG; }
+    CreateGuard<jaero_batch> guard(b, jaero_batch_destroy);
     b->set = *s; b->device = device; b->samples = 0; b->bb_pos = 0; b->coarse_counter = 0;
     b->d_stage = 0; b->stage_cap = 0; b->launches = 0;
     b->pre_on = false; b->fir_fill = 0; b->fir_blocks = 0; b->d_x = 0; b->x_cap = 0;
@@ -412,7 +425,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     }
     rc |= batch_alloc(b, &p.soft, (size_t)n_channels * p.soft_cap);
     rc |= batch_alloc(b, &p.cfe_est_out, (size_t)cp);
-    if (rc) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+    if (rc) return JAERO_E_CUDA;
 
     // trig tables exactly as TrigLookUp builds them (DSP.cpp:19-20), computed with the host libm
     {
@@ -420,7 +433,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         for (int i = 0; i < jb::WTSIZE; i++) sn[i] = (sin(2 * M_PI * ((double)i) / jb::WTSIZE));
         for (int i = 0; i < jb::WTSIZE; i++) cs[i] = (sin(M_PI_2 + 2 * M_PI * ((double)i) / jb::WTSIZE));
         double *ds, *dc;
-        if (batch_alloc(b, &ds, (size_t)jb::WTSIZE) || batch_alloc(b, &dc, (size_t)jb::WTSIZE)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+        if (batch_alloc(b, &ds, (size_t)jb::WTSIZE) || batch_alloc(b, &dc, (size_t)jb::WTSIZE)) return JAERO_E_CUDA;
         JB_CUDA(cudaMemcpyAsync(ds, sn.data(), sn.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         JB_CUDA(cudaMemcpyAsync(dc, cs.data(), cs.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         JB_CUDA(cudaStreamSynchronize(b->stream));
@@ -452,7 +465,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
             if (!(e && e[0] == '0')) c.clusters = cfe_cluster_capacity();
         }
         if (batch_alloc(b, &c.tw, (size_t)c.nfft) || batch_alloc(b, &c.work_a, (size_t)c.group * c.nfft) ||
-            batch_alloc(b, &c.work_b, (size_t)c.group * c.nfft) || batch_alloc(b, &c.y, (size_t)n_channels * c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+            batch_alloc(b, &c.work_b, (size_t)c.group * c.nfft) || batch_alloc(b, &c.y, (size_t)n_channels * c.nfft)) return JAERO_E_CUDA;
         JB_CUDA(cudaMemcpyAsync(c.tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
         if (c.is8400) {                                                       // raised-cosine window (coarsefreqestimate.cpp:62-74)
             std::vector<double> win(c.nfft, 0.0);
@@ -463,7 +476,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
                 if (i >= c.nfft) break;
                 win[c.nfft - i] = val; win[i] = val;
             }
-            if (batch_alloc(b, &c.window, (size_t)c.nfft)) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+            if (batch_alloc(b, &c.window, (size_t)c.nfft)) return JAERO_E_CUDA;
             JB_CUDA(cudaMemcpyAsync(c.window, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         }
         JB_CUDA(cudaStreamSynchronize(b->stream));
@@ -491,7 +504,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         rc2 |= batch_alloc(b, &f.outblk, (size_t)n_channels * FIR_L);
         rc2 |= batch_alloc(b, &q.osc, (size_t)4 * cp);
         rc2 |= batch_alloc(b, &p.m2_freq_sum, (size_t)cp);
-        if (rc2) { jaero_batch_destroy(b); return JAERO_E_CUDA; }
+        if (rc2) return JAERO_E_CUDA;
         JB_CUDA(cudaMemcpyAsync(f.H, H.data(), NF * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
         JB_CUDA(cudaMemcpyAsync(f.tw, tw.data(), NF * sizeof(double2), cudaMemcpyHostToDevice, b->stream));
         // mixer_fir_pre.SetFreq(freq_center,Fs) is only done in the ctor, with the ctor's 8000 Hz (oqpskdemodulator.cpp:21,115)
@@ -516,6 +529,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)I_COUNT * cp * sizeof(int)));
     JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)D_COUNT * cp * sizeof(double)));
     JB_CUDA(cudaMallocHost(&b->h_soft_stage, (size_t)n_channels * p.soft_cap * sizeof(int16_t)));
+    guard.release();
     *out = b;
     return JAERO_OK;
 }
@@ -877,6 +891,7 @@ int jaero_pchannel_create(int n_channels, double fb, int device, jaero_pchannel 
     JB_CUDA(cudaSetDevice(device));
     jaero_pchannel *p = new (std::nothrow) jaero_pchannel();
     if (!p) { set_error("out of host memory"); return JAERO_E_ARG; }
+    CreateGuard<jaero_pchannel> guard(p, jaero_pchannel_destroy);
     p->device = device; p->launches = 0; p->d_soft_stage = 0; p->d_count_stage = 0; p->stage_cap = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     p->cur_stream = p->stream;
@@ -905,17 +920,18 @@ int jaero_pchannel_create(int n_channels, double fb, int device, jaero_pchannel 
     rc |= pc_alloc(p, &p->vit_overlap_len, C);
     rc |= pc_alloc(p, &p->vit_renorm, C);
     rc |= pc_alloc(p, &p->vit_valid, C);
-    if (rc) { jaero_pchannel_destroy(p); return JAERO_E_CUDA; }
+    if (rc) return JAERO_E_CUDA;
     {   // AeroLScrambler::pre_state (aerol.h:397-419)
         int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
         std::vector<uint8_t> seq(5000);
         for (int a = 0; a < 5000; a++) { int v = st[0] ^ st[14]; seq[a] = (uint8_t)v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
-        if (pchan_set_scrambler(seq.data())) { jaero_pchannel_destroy(p); return JAERO_E_CUDA; }
+        if (pchan_set_scrambler(seq.data())) return JAERO_E_CUDA;
     }
-    if (pchan_init(pp, p->stream)) { jaero_pchannel_destroy(p); return JAERO_E_CUDA; }
+    if (pchan_init(pp, p->stream)) return JAERO_E_CUDA;
     JB_CUDA(cudaStreamSynchronize(p->stream));
     JB_CUDA(cudaMallocHost(&p->h_state, C * sizeof(PChanState)));
     JB_CUDA(cudaMallocHost(&p->h_su, C * pp.su_cap * 16));
+    guard.release();
     *out = p;
     return JAERO_OK;
 }
@@ -1131,6 +1147,7 @@ static int burst_create(const jaero_settings *s, int n_channels, int device, int
     JB_CUDA(cudaSetDevice(device));
     jaero_burst *b = new (std::nothrow) jaero_burst();
     if (!b) { set_error("out of host memory"); return JAERO_E_ARG; }
+    CreateGuard<jaero_burst> guard(b, jaero_burst_destroy);
     b->device = device; b->samples = 0; b->hil_fill = 0; b->hil_blocks = 0; b->d_stage = 0; b->stage_cap = 0; b->launches = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     BurstParams &p = b->p;
@@ -1233,13 +1250,13 @@ static int burst_create(const jaero_settings *s, int n_channels, int device, int
     b->ev_round = 128;
     rc |= bu_alloc(b, &b->tw32k, (size_t)TRI_N); rc |= bu_alloc(b, &b->wa, (size_t)2 * b->ev_round * TRI_N); rc |= bu_alloc(b, &b->wb, (size_t)2 * b->ev_round * TRI_N);
     rc |= bu_alloc(b, &b->d_ev_list, (size_t)2 * C * BURST_MAXEV);
-    if (rc) { jaero_burst_destroy(b); return JAERO_E_CUDA; }
+    if (rc) return JAERO_E_CUDA;
     {
         std::vector<double> sn(jb::WTSIZE), cs(jb::WTSIZE);
         for (int i = 0; i < jb::WTSIZE; i++) sn[i] = (sin(2 * M_PI * ((double)i) / jb::WTSIZE));
         for (int i = 0; i < jb::WTSIZE; i++) cs[i] = (sin(M_PI_2 + 2 * M_PI * ((double)i) / jb::WTSIZE));
         double *ds, *dc;
-        if (bu_alloc(b, &ds, (size_t)jb::WTSIZE) || bu_alloc(b, &dc, (size_t)jb::WTSIZE)) { jaero_burst_destroy(b); return JAERO_E_CUDA; }
+        if (bu_alloc(b, &ds, (size_t)jb::WTSIZE) || bu_alloc(b, &dc, (size_t)jb::WTSIZE)) return JAERO_E_CUDA;
         JB_CUDA(cudaMemcpyAsync(ds, sn.data(), sn.size() * 8, cudaMemcpyHostToDevice, b->stream));
         JB_CUDA(cudaMemcpyAsync(dc, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice, b->stream));
         p.sin_t = ds; p.cos_t = dc;
@@ -1272,6 +1289,7 @@ static int burst_create(const jaero_settings *s, int n_channels, int device, int
     JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)BI_COUNT * cp * sizeof(int)));
     JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)BD_COUNT * cp * sizeof(double)));
     JB_CUDA(cudaMallocHost(&b->h_soft, C * p.soft_cap * sizeof(int16_t)));
+    guard.release();
     *out = b;
     return JAERO_OK;
 }
@@ -1431,6 +1449,7 @@ int jaero_rt_create(double fb, int n_channels, int device, jaero_rt **out)
     JB_CUDA(cudaSetDevice(device));
     jaero_rt *r = new (std::nothrow) jaero_rt();
     if (!r) { set_error("out of host memory"); return JAERO_E_ARG; }
+    CreateGuard<jaero_rt> guard(r, jaero_rt_destroy);
     r->device = device; r->d_soft_stage = 0; r->d_count_stage = 0; r->stage_cap = 0; r->h_state = 0; r->h_out = 0; r->launches = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     RtParams &rp = r->rp;
@@ -1442,17 +1461,18 @@ int jaero_rt_create(double fb, int n_channels, int device, jaero_rt **out)
     int rc = 0;
     auto alloc = [&](auto **ptr, size_t count) { int q = dev_alloc_zero(ptr, count, r->stream); if (!q) r->allocs.push_back((void *)*ptr); return q; };
     rc |= alloc(&rp.state, C); rc |= alloc(&rp.slots, C * RT_SLOTS); rc |= alloc(&rp.blocks, C * RT_SLOTS * RT_BLOCK); rc |= alloc(&rp.out, C * RT_OUT * RT_OUT_BYTES);
-    if (rc) { jaero_rt_destroy(r); return JAERO_E_CUDA; }
+    if (rc) return JAERO_E_CUDA;
     {   // AeroLScrambler::pre_state (aerol.h:397-437)
         std::vector<uint8_t> seq(5000);
         int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
         for (int a = 0; a < 5000; a++) { const int v = st[0] ^ st[14]; seq[a] = (uint8_t)v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
-        if (rt_set_scrambler(seq.data())) { jaero_rt_destroy(r); return JAERO_E_CUDA; }
+        if (rt_set_scrambler(seq.data())) return JAERO_E_CUDA;
     }
-    if (rt_init(rp, r->stream)) { jaero_rt_destroy(r); return JAERO_E_CUDA; }
+    if (rt_init(rp, r->stream)) return JAERO_E_CUDA;
     JB_CUDA(cudaStreamSynchronize(r->stream));
     JB_CUDA(cudaMallocHost(&r->h_state, C * sizeof(RtState)));
     JB_CUDA(cudaMallocHost(&r->h_out, C * RT_OUT * RT_OUT_BYTES));
+    guard.release();
     *out = r;
     return JAERO_OK;
 }
@@ -1571,6 +1591,7 @@ int jaero_cchannel_create(int n_channels, int device, jaero_cchannel **out)
     JB_CUDA(cudaSetDevice(device));
     jaero_cchannel *c = new (std::nothrow) jaero_cchannel();
     if (!c) { set_error("out of host memory"); return JAERO_E_ARG; }
+    CreateGuard<jaero_cchannel> guard(c, jaero_cchannel_destroy);
     c->device = device; c->d_soft_stage = 0; c->d_count_stage = 0; c->stage_cap = 0; c->h_state = 0; c->h_out = 0; c->launches = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->cur_stream = c->stream;
@@ -1583,17 +1604,18 @@ int jaero_cchannel_create(int n_channels, int device, jaero_cchannel **out)
     rc |= alloc(&cp.state, C); rc |= alloc(&cp.coded, C * CC_QUEUE * CC_CODED_PITCH); rc |= alloc(&cp.decoded, C * CC_QUEUE * CC_DEC);
     rc |= alloc(&cp.ready, C); rc |= alloc(&cp.dl2, C * cp.dl2_len); rc |= alloc(&cp.out, C * CC_OUT * CC_RECORD);
     rc |= alloc(&c->vit_overlap, C * 64); rc |= alloc(&c->vit_overlap_len, C); rc |= alloc(&c->vit_renorm, C); rc |= alloc(&c->vit_valid, C);
-    if (rc) { jaero_cchannel_destroy(c); return JAERO_E_CUDA; }
+    if (rc) return JAERO_E_CUDA;
     {
         std::vector<uint8_t> seq(5000);
         int st[15] = {1, 1, 0, 1, 0, 0, 1, 0, 1, 0, 1, 1, 0, 0, 1};
         for (int a = 0; a < 5000; a++) { const int v = st[0] ^ st[14]; seq[a] = (uint8_t)v; for (int i = 14; i > 0; i--) st[i] = st[i - 1]; st[0] = v; }
-        if (cchan_set_scrambler(seq.data())) { jaero_cchannel_destroy(c); return JAERO_E_CUDA; }
+        if (cchan_set_scrambler(seq.data())) return JAERO_E_CUDA;
     }
-    if (cchan_init(cp, c->stream)) { jaero_cchannel_destroy(c); return JAERO_E_CUDA; }
+    if (cchan_init(cp, c->stream)) return JAERO_E_CUDA;
     JB_CUDA(cudaStreamSynchronize(c->stream));
     JB_CUDA(cudaMallocHost(&c->h_state, C * sizeof(CChanState)));
     JB_CUDA(cudaMallocHost(&c->h_out, C * CC_OUT * CC_RECORD));
+    guard.release();
     *out = c;
     return JAERO_OK;
 }
