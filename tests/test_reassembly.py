@@ -134,3 +134,30 @@ def test_reassembly_matches_reference_live(seed):
     assert len(out) == len(want)
     for g, w in zip(out, want):
         _same(g, w)
+
+
+@pytest.mark.parametrize("name", ["p_recording_10500", "rt_recording_burst_oqpsk_10500", "p_synthetic", "t_synthetic", "r_synthetic", "garbage"])
+def test_restated_oracle_matches_reference_golden(name):
+    """oracle/reasm_restated.py (the plain-Python restatement) is pinned by the verbatim reference build's golden records"""
+    from oracle import reasm_restated
+    gold, streams = _gold()
+    o = reasm_restated.Reassembly()
+    rcs = []
+    for e in streams[name]:
+        if e[0] == "su":
+            rcs.append(o.push_su(e[1], e[2]))
+        elif e[0] == "r":
+            rcs.append(o.push_r(e[1], e[2]))
+        elif e[0] == "reset":
+            o.reset(); rcs.append(0)
+        else:
+            o.short_frame(); rcs.append(0)
+    got = o.pop_all()
+    want = gold[name]
+    assert rcs == want["return_codes"]
+    assert len(got) == len(want["records"])
+    for g, w in zip(got, want["records"]):
+        if w["kind"] == 1:
+            assert g["kind"] == 1 and g["message"] == w["message"]
+        else:
+            assert g == {k: w[k] for k in g}, (g, w)
