@@ -116,6 +116,10 @@ int jaero_batch_reset_softbits(jaero_batch *b);
 
 int jaero_batch_set_dcd(jaero_batch *b, int channel, int dcd);            /* channel<0: all */
 int jaero_batch_set_center_freq(jaero_batch *b, int channel, double hz);  /* CenterFreqChangedSlot */
+/* setAFC / setSQL / setCPUReduce of the reference classes: every channel of the batch, effective from the next write */
+int jaero_batch_set_afc(jaero_batch *b, int state);
+int jaero_batch_set_sql(jaero_batch *b, int state);
+int jaero_batch_set_cpu_reduce(jaero_batch *b, int state);
 int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out);
 int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out /* [n_channels] */);
 /* kernel launches issued by this batch so far (for bench.py's gpu_launches) */
@@ -196,6 +200,8 @@ int jaero_burst_write(jaero_burst *b, const int16_t *pcm, size_t n_samples, size
 int jaero_burst_write_device(jaero_burst *b, const int16_t *d_pcm, size_t n_samples, size_t channel_stride);
 int jaero_burst_read_softbits(jaero_burst *b, int16_t *out, size_t cap_per_channel, int32_t *counts);
 int jaero_burst_set_dcd(jaero_burst *b, int channel, int dcd);
+int jaero_burst_set_afc(jaero_burst *b, int state);                       /* setAFC (the constructors start with AFC on) */
+int jaero_burst_set_sql(jaero_burst *b, int state);
 int jaero_burst_get_status_all(jaero_burst *b, jaero_burst_status *out);
 int jaero_burst_sync(jaero_burst *b);
 int64_t jaero_burst_launch_count(const jaero_burst *b);

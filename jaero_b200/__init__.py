@@ -46,7 +46,8 @@ class AcarsRecord(ctypes.Structure):
 EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaero_batch_destroy", "jaero_batch_channels",
            "jaero_batch_write", "jaero_batch_write_device", "jaero_batch_sync", "jaero_batch_read_softbits",
            "jaero_batch_softbits_device", "jaero_batch_reset_softbits", "jaero_batch_set_dcd",
-           "jaero_batch_set_center_freq", "jaero_batch_get_status", "jaero_batch_get_status_all",
+           "jaero_batch_set_center_freq", "jaero_batch_set_afc", "jaero_batch_set_sql", "jaero_batch_set_cpu_reduce",
+           "jaero_burst_set_afc", "jaero_burst_set_sql", "jaero_batch_get_status", "jaero_batch_get_status_all",
            "jaero_batch_launch_count", "jaero_batch_set_stream", "jaero_batch_set_profiling",
            "jaero_batch_get_profile", "jaero_viterbi_create", "jaero_viterbi_destroy",
            "jaero_viterbi_decode_continuous", "jaero_viterbi_decode_continuous_device", "jaero_viterbi_decode_block",
@@ -85,6 +86,8 @@ def lib():
         L.jaero_batch_reset_softbits.argtypes = [vp]
         L.jaero_batch_set_dcd.argtypes = [vp, i, i]
         L.jaero_batch_set_center_freq.argtypes = [vp, i, d]
+        L.jaero_batch_set_afc.argtypes = [vp, i]; L.jaero_batch_set_sql.argtypes = [vp, i]; L.jaero_batch_set_cpu_reduce.argtypes = [vp, i]
+        L.jaero_burst_set_afc.argtypes = [vp, i]; L.jaero_burst_set_sql.argtypes = [vp, i]
         L.jaero_batch_get_status.argtypes = [vp, i, ctypes.POINTER(Status)]
         L.jaero_batch_get_status_all.argtypes = [vp, vp]
         L.jaero_batch_launch_count.argtypes = [vp]; L.jaero_batch_launch_count.restype = ctypes.c_int64

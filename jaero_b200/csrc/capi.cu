@@ -818,6 +818,27 @@ int jaero_batch_set_center_freq(jaero_batch *b, int channel, double hz)
     JB_CUDA(cudaGetLastError());
     return JAERO_OK;
 }
+// setAFC / setSQL / setCPUReduce (oqpskdemodulator.cpp:149-167, mskdemodulator.cpp:113-131): plain flags the sample loop reads;
+// the kernels take them by value at every launch, so a change applies from the next write on
+int jaero_batch_set_afc(jaero_batch *b, int state)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    b->p.afc = state ? 1 : 0;
+    return JAERO_OK;
+}
+int jaero_batch_set_sql(jaero_batch *b, int state)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    b->p.sql = state ? 1 : 0;
+    return JAERO_OK;
+}
+int jaero_batch_set_cpu_reduce(jaero_batch *b, int state)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    if (b->async_cfe) { set_error("jaero_batch_set_cpu_reduce: not available with JAERO_ASYNC_CFE=1"); return JAERO_E_STATE; }
+    b->p.cpu_reduce = state ? 1 : 0;
+    return JAERO_OK;
+}
 int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out)
 {
     if (!b || !out) { set_error("null argument"); return JAERO_E_ARG; }
@@ -1400,6 +1421,18 @@ int jaero_burst_set_dcd(jaero_burst *b, int channel, int dcd)
     JB_CUDA(cudaSetDevice(b->device));
     burst_set_int_kernel<<<(b->p.n_channels + 127) / 128, 128, 0, b->stream>>>(b->p, BI_DCD, channel, dcd ? 1 : 0);
     JB_CUDA(cudaGetLastError());
+    return JAERO_OK;
+}
+int jaero_burst_set_afc(jaero_burst *b, int state)                  // burstmskdemodulator.cpp / burstoqpskdemodulator.cpp setAFC
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    b->p.afc = state ? 1 : 0;
+    return JAERO_OK;
+}
+int jaero_burst_set_sql(jaero_burst *b, int state)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    b->p.sql = state ? 1 : 0;
     return JAERO_OK;
 }
 int jaero_burst_get_status_all(jaero_burst *b, jaero_burst_status *out)
