@@ -54,7 +54,7 @@ def _same(got, want):
         assert got["userdata_len"] == len(want["userdata"]) // 2
 
 
-@pytest.mark.parametrize("name", ["p_recording_10500", "rt_recording_burst_oqpsk_10500", "rt_recording_burst_msk_1200_a", "rt_recording_burst_msk_1200_b",
+@pytest.mark.parametrize("name", ["p_recording_10500", "p_recording_600", "rt_recording_burst_oqpsk_10500", "rt_recording_burst_msk_1200_a", "rt_recording_burst_msk_1200_b",
                                   "p_synthetic", "t_synthetic", "r_synthetic", "garbage"])
 def test_reassembly_matches_reference_golden(name):
     gold, streams = _gold()
@@ -136,7 +136,7 @@ def test_reassembly_matches_reference_live(seed):
         _same(g, w)
 
 
-@pytest.mark.parametrize("name", ["p_recording_10500", "rt_recording_burst_oqpsk_10500", "p_synthetic", "t_synthetic", "r_synthetic", "garbage"])
+@pytest.mark.parametrize("name", ["p_recording_10500", "p_recording_600", "rt_recording_burst_oqpsk_10500", "p_synthetic", "t_synthetic", "r_synthetic", "garbage"])
 def test_restated_oracle_matches_reference_golden(name):
     """oracle/reasm_restated.py (the plain-Python restatement) is pinned by the verbatim reference build's golden records"""
     from oracle import reasm_restated

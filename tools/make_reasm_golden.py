@@ -20,14 +20,14 @@ from oracle import ref, restated  # noqa: E402
 import reasm_synth  # noqa: E402  (tests/reasm_synth.py)
 
 
-def recording_sus():
+def recording_sus(name="oqpsk_10500", kind="oqpsk", kw=None):
     import multiprocessing as mp
-    pcm = np.load(os.path.join(ROOT, "tests", "golden", "pcm_full", "oqpsk_10500.npy"))
-    kw = dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)
+    pcm = np.load(os.path.join(ROOT, "tests", "golden", "pcm_full", name + ".npy"))
+    kw = kw or dict(fb=10500, freq_center=5760, lockingbw=10500, fft_power=14, signalthreshold=0.65, afc=True)
     ctx = mp.get_context("spawn")
     with ctx.Pool(1) as pool:
-        soft, state, cfe = pool.apply(ref.run_demod_job, (("oqpsk", kw, pcm, 4800, None),))
-    p = restated.OraclePChannel(10500)
+        soft, state, cfe = pool.apply(ref.run_demod_job, ((kind, kw, pcm, 4800, None),))
+    p = restated.OraclePChannel(kw["fb"])
     p.process(soft)
     su, ok, fr = p.take_sus()
     print("recording: %d SUs, %d CRC ok" % (len(ok), int(ok.sum())))
@@ -78,6 +78,8 @@ if __name__ == "__main__":
     streams = {}
     rec = recording_sus()
     streams["p_recording_10500"] = [("su", bytes(x), False) for x in rec]
+    rec600 = recording_sus("msk_600", "msk", dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True))
+    streams["p_recording_600"] = [("su", bytes(x), False) for x in rec600]      # BASELINE configs[0]: decoded ISUs of the 600 bps recording
     streams["rt_recording_burst_oqpsk_10500"] = burst_recording_events(
         "burst_oqpsk_10500", "burst_oqpsk", dict(fb=10500.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6))
     for nm in ("burst_msk_1200_a", "burst_msk_1200_b"):
