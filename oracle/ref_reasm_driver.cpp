@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE ONLY. Driver around the reference's OWN ISU/SSU reassembly code: RISUData, ISUData,
 // ACARSDefragmenter (JAERO/aerol.cpp:4-329) and ParserISU::parse (JAERO/aerol.cpp:340-487), compiled VERBATIM.
 // aerol.cpp / aerol.h as a whole need Qt GUI/SQL/network and cannot be built here, so the Makefile slices the
-// two line ranges out of the files where they lie under /root/reference into oracle/_ref/gen/ (git-ignored, never
-// committed) and this file includes them. Hand-written here: the ParserISU constructor, the two signal bodies, a
+// two line ranges out of the files where they lie under /root/reference into a scratch directory (oracle/_ref/gen/,
+// removed again after the compile; nothing of it is ever committed) and this file includes them. Hand-written here: the ParserISU constructor, the two signal bodies, a
 // stand-in for the aircraft-database look-up (no database: the look-up result is empty, JAERO/aerol.cpp:493-520)
 // and the three-line SU dispatch of AeroL::Decode (JAERO/aerol.cpp:1357-1399, 1497-1513, 1900-1925).
 #include "qt_shim.h"
