@@ -199,6 +199,16 @@ class DemodBatch:
     def sync(self):
         _check(lib().jaero_batch_sync(self.h))
 
+    def set_afc(self, state):
+        """setAFC / setSQL / setCPUReduce of the reference classes, every channel, from the next write on"""
+        _check(lib().jaero_batch_set_afc(self.h, int(bool(state))))
+
+    def set_sql(self, state):
+        _check(lib().jaero_batch_set_sql(self.h, int(bool(state))))
+
+    def set_cpu_reduce(self, state):
+        _check(lib().jaero_batch_set_cpu_reduce(self.h, int(bool(state))))
+
     def read_softbits(self):
         out = np.zeros((self.n, self.soft_cap), dtype=np.int16)
         counts = np.zeros(self.n, dtype=np.int32)
