@@ -79,7 +79,7 @@ typedef struct jaero_status {
     double center_wtptr;
     double st_ref_wtptr;
     int64_t samples;      /* samples consumed so far */
-    int64_t softbits;     /* soft bits emitted so far */
+    int64_t softbits;     /* soft values emitted so far (drained + still in the ring; burst markers included) */
     int32_t dcd;
     int32_t reserved;
 } jaero_status;
@@ -168,6 +168,10 @@ int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b);
 int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
 /* AeroL::updateDCD: call once per second of signal (the reference's 1 s QTimer). b may be NULL. */
 int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b);
+/* Limits of one process call: a channel may hand over up to one full soft-bit ring (max(4096, 2*fb+64) values, i.e. 2 s of
+ * signal at 10500 bps, 3.4 / 6.8 s at 1200 / 600 bps); more than that, or more signal units than jaero_pchannel_su_capacity()
+ * left unread, raises the overflow flag: the next read_sus returns JAERO_E_OVERFLOW and the affected frames are incomplete. */
+int jaero_pchannel_su_capacity(const jaero_pchannel *p);   /* SUs a channel can hold between two reads */
 /* Drain decoded signal units: out[(ch*cap + k)*16 + 0..11] = SU bytes, [12] = CRC ok, [13] = index in frame,
  * [14..15] = frame number (LE). counts[ch] = SUs written. HOST pointers. */
 int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap_per_channel, int32_t *counts);
@@ -251,7 +255,8 @@ int64_t jaero_cchannel_launch_count(const jaero_cchannel *c);
 typedef struct jaero_ingest jaero_ingest;
 int jaero_ingest_create(int n_channels, const char *const *topics, uint32_t sample_rate, size_t capacity_samples, jaero_ingest **out);
 void jaero_ingest_destroy(jaero_ingest *g);
-/* returns the channel index (>= 0) or a negative error */
+/* returns the channel index (>= 0) or a negative error. JAERO_E_OVERFLOW: the channel's buffer cannot take the whole message;
+ * NOTHING of it was filed - flush the batch (jaero_ingest_flush) and hand the same message over again. */
 int jaero_ingest_message(jaero_ingest *g, const void *topic, size_t topic_len, const void *rate, size_t rate_len, const void *pcm, size_t pcm_bytes);
 size_t jaero_ingest_available(const jaero_ingest *g);                  /* samples every channel has */
 int jaero_ingest_flush(jaero_ingest *g, jaero_batch *b, size_t n_samples);

@@ -54,7 +54,7 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_viterbi_reset", "jaero_viterbi_sync", "jaero_viterbi_launch_count",
            "jaero_pchannel_create", "jaero_pchannel_destroy", "jaero_pchannel_process_batch",
            "jaero_pchannel_process_softbits", "jaero_pchannel_tick", "jaero_pchannel_read_sus",
-           "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count",
+           "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count", "jaero_pchannel_su_capacity",
            "jaero_burst_msk_create", "jaero_burst_oqpsk_create", "jaero_burst_destroy", "jaero_burst_write", "jaero_burst_write_device",
            "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
            "jaero_burst_launch_count",
@@ -110,6 +110,7 @@ def lib():
         L.jaero_pchannel_discard_sus.argtypes = [vp]
         L.jaero_pchannel_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_pchannel_launch_count.argtypes = [vp]; L.jaero_pchannel_launch_count.restype = ctypes.c_int64
+        L.jaero_pchannel_su_capacity.argtypes = [vp]
         L.jaero_burst_msk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_oqpsk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_destroy.argtypes = [vp]; L.jaero_burst_destroy.restype = None
@@ -314,8 +315,8 @@ class PChannelBatch:
     def __init__(self, n_channels, fb, device=0):
         self.h = ctypes.c_void_p()
         self.n = n_channels
-        self.su_cap = 4 * (int({600: 1152, 1200: 1152, 10500: 4992}[int(fb)]) // 2 // 96) + 8
         _check(lib().jaero_pchannel_create(n_channels, float(fb), device, ctypes.byref(self.h)))
+        self.su_cap = int(lib().jaero_pchannel_su_capacity(self.h))
 
     def process_batch(self, batch):
         _check(lib().jaero_pchannel_process_batch(self.h, batch.h))

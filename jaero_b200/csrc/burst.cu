@@ -19,13 +19,6 @@
 
 namespace jb {
 
-__constant__ double c_btaps[MAX_TAPS];
-int burst_set_taps(const double *taps, int n)
-{
-    if (n > MAX_TAPS) { set_error("too many FIR taps"); return -1; }
-    JB_CUDA(cudaMemcpyToSymbol(c_btaps, taps, n * sizeof(double)));
-    return 0;
-}
 
 #define BD(idx) p.BD[(size_t)(idx) * p.cpad + ch]
 #define BI(idx) p.BI[(size_t)(idx) * p.cpad + ch]
@@ -499,7 +492,7 @@ trident_peaks_oqpsk_kernel(BurstParams p, const int *__restrict__ ev_list, int n
 
 // ------------------------------------------------------------------------------------------------ demodulator tail
 __global__ void __launch_bounds__(32)
-burst_back_kernel(BurstParams p, int n)
+burst_back_kernel(const __grid_constant__ BurstParams p, int n)
 {
     extern __shared__ double bsm[];
     const int lane = threadIdx.x;
@@ -582,7 +575,7 @@ burst_back_kernel(BurstParams p, int n)
             s_re[fir_pos * 32 + lane] = cre; s_im[fir_pos * 32 + lane] = cim;
             fir_pos++; if (fir_pos >= nt1) fir_pos = 0;
             double sre = 0, sim = 0;
-            { int tp = fir_pos; for (int k = 0; k < p.ntaps; k++) { sre += c_btaps[k] * s_re[tp * 32 + lane]; sim += c_btaps[k] * s_im[tp * 32 + lane]; tp++; if (tp >= nt1) tp = 0; } }
+            { int tp = fir_pos; for (int k = 0; k < p.ntaps; k++) { sre += p.taps[k] * s_re[tp * 32 + lane]; sim += p.taps[k] * s_im[tp * 32 + lane]; tp++; if (tp >= nt1) tp = 0; } }
             double2 sig2 = make_double2(sre, sim);
             if (cntr > (p.start_processing * sps) && cntr < p.end_rotation) {       // :606-626 preamble symbol tone
                 double2 spt = cmul(cmul(sig2, strot), make_double2(0.0, 1.0));
@@ -709,7 +702,7 @@ burst_back_kernel(BurstParams p, int n)
 // BurstOqpskDemodulator::writeDataSlot after the trident check (burstoqpskdemodulator.cpp:508-733). Unlike the MSK burst
 // tail this one runs on every sample, so all its sample-rate rings advance in lock-step.
 __global__ void __launch_bounds__(32)
-burst_oqpsk_back_kernel(BurstParams p, long long sample0, int n, int new_write)
+burst_oqpsk_back_kernel(const __grid_constant__ BurstParams p, long long sample0, int n, int new_write)
 {
     extern __shared__ double bsm[];
     const int lane = threadIdx.x;
@@ -778,7 +771,7 @@ burst_oqpsk_back_kernel(BurstParams p, long long sample0, int n, int new_write)
         s_re[fir_pos * 32 + lane] = cre; s_im[fir_pos * 32 + lane] = cim;
         fir_pos++; if (fir_pos >= nt1) fir_pos = 0;
         double sre = 0, sim = 0;
-        { int tp = fir_pos; for (int k = 0; k < p.ntaps; k++) { sre += c_btaps[k] * s_re[tp * 32 + lane]; sim += c_btaps[k] * s_im[tp * 32 + lane]; tp++; if (tp >= nt1) tp = 0; } }
+        { int tp = fir_pos; for (int k = 0; k < p.ntaps; k++) { sre += p.taps[k] * s_re[tp * 32 + lane]; sim += p.taps[k] * s_im[tp * 32 + lane]; tp++; if (tp >= nt1) tp = 0; } }
         double2 sig2 = make_double2(sre, sim);
         if (startstop > 0) { startstop--; if (cntr < 1000000) cntr++; if (mse < 0.75) startstop = p.startstopstart; }   // :515-524
         if (startstop == 0) { startstop--; sig_false++; }                 // :525-529

@@ -67,9 +67,9 @@ struct BurstParams {
     size_t astride;
     int16_t *soft;                         // [ch][soft_cap]
     const double *sin_t, *cos_t;
+    double taps[160];                      // matched-filter taps of THIS demodulator (kernel parameter block; MAX_TAPS of demod.cuh)
 };
 
-int burst_set_taps(const double *taps, int n);
 int hilbert_exchange_launch(const HilbertStream &h, const BurstParams &p, const int16_t *pcm, size_t stride, int pcm0, int i0, int i1, int fill0, cudaStream_t s);
 int hilbert_block_launch(const HilbertStream &h, int n_channels, int first_block, cudaStream_t s);
 int burst_front_launch(const BurstParams &p, long long sample0, int n, cudaStream_t s);

@@ -224,7 +224,7 @@ struct jaero_batch {
     // 8400 bps pre-filter (K6)
     bool pre_on; PreParams pre; FirStream fir; int fir_fill; long long fir_blocks; double2 *d_x; size_t x_cap;
     int16_t *h_soft_stage;      // pinned
-    int *h_ints; double *h_dbls;   // pinned mirrors of I / D
+    int *h_ints; double *h_dbls; long long *h_soft_total;   // pinned mirrors of I / D / soft_total
     long long launches;
     cudaStream_t own_stream;
     bool profiling;
@@ -277,6 +277,7 @@ __global__ void soft_reset_kernel(DemodParams p)
     const int pending = p.I[(size_t)I_SOFT_PENDING * p.cpad + ch];
     int16_t *ring = p.soft + (size_t)ch * p.soft_cap;
     for (int k = 0; k < pending; k++) ring[k] = ring[count + k];
+    p.soft_total[ch] += count;
     count = 0;
 }
 __global__ void set_int_kernel(DemodParams p, int idx, int channel, int value)
@@ -345,7 +346,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         p.marg_len = 800; p.dt_len = 401; p.mse_len = 400;                    // :44-45,53
         const double T = s->Fs / (s->fb / 2);                                 // :221
         if (!delay_weights(T / 4.0, &p.k41, p.w41v) || !delay_weights(T / 8.0, &p.k8, p.w8v) || p.k41 > 3 || p.k8 > 3) {
-            set_error("unsupported fractional delay for this Fs/fb"); delete b; return JAERO_E_ARG; }
+            set_error("unsupported fractional delay for this Fs/fb"); return JAERO_E_ARG; }
         if (s->fb == 8400) {                                                  // :243-250 (the 10 Hz set, assigned last, wins)
             p.res_b0 = 0.0012845857864470789; p.res_b1 = 0; p.res_b2 = -0.0012845857864470789;
             p.res_a1 = -0.90681461999279889; p.res_a2 = 0.99743082842710584;
@@ -360,7 +361,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         st_freq = s->fb;                                                      // :270
     } else {
         p.sps = (int)(s->Fs / s->fb);                                         // mskdemodulator.cpp:149
-        if (2 * p.sps > MAX_TAPS) { set_error("MSK: 2*SamplesPerSymbol exceeds the supported FIR length"); delete b; return JAERO_E_ARG; }
+        if (2 * p.sps > MAX_TAPS) { set_error("MSK: 2*SamplesPerSymbol exceeds the supported FIR length"); return JAERO_E_ARG; }
         taps.resize(2 * p.sps);
         for (int i = 0; i < 2 * p.sps; i++) taps[i] = sin(M_PI * i / (2.0 * p.sps)) / (2.0 * p.sps);   // :164-170
         p.agc_len = (int)round(1 * s->Fs);                                    // :173
@@ -379,10 +380,11 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         st_freq = s->fb / 2;                                                  // :159
     }
     if ((p.agc_len % 32) || (p.ebno_len % 32) || p.agc_len < 96 || p.ebno_len < 96) {
-        set_error("unsupported sample rate: the AGC / EbNo window lengths must be multiples of 32 samples"); delete b; return JAERO_E_ARG; }
+        set_error("unsupported sample rate: the AGC / EbNo window lengths must be multiples of 32 samples"); return JAERO_E_ARG; }
     p.ntaps = (int)taps.size();
     p.soft_cap = std::max(4096, (int)(2 * s->fb) + 64);
-    if (demod_set_taps(taps.data(), p.ntaps)) { delete b; return JAERO_E_CUDA; }
+    if (p.ntaps > MAX_TAPS) { set_error("too many FIR taps"); return JAERO_E_ARG; }
+    for (int k = 0; k < p.ntaps; k++) p.taps[k] = taps[k];   // per-batch: the taps ride in the kernel parameter block
 
     const size_t cp = p.cpad;
     int rc = 0;
@@ -424,6 +426,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         rc |= batch_alloc(b, &p.dly8_ring, (size_t)(p.sps / 2 + 1) * cp);
     }
     rc |= batch_alloc(b, &p.soft, (size_t)n_channels * p.soft_cap);
+    rc |= batch_alloc(b, &p.soft_total, (size_t)cp);
     rc |= batch_alloc(b, &p.cfe_est_out, (size_t)cp);
     if (rc) return JAERO_E_CUDA;
 
@@ -528,6 +531,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     }
     JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)I_COUNT * cp * sizeof(int)));
     JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)D_COUNT * cp * sizeof(double)));
+    JB_CUDA(cudaMallocHost(&b->h_soft_total, cp * sizeof(long long)));
     JB_CUDA(cudaMallocHost(&b->h_soft_stage, (size_t)n_channels * p.soft_cap * sizeof(int16_t)));
     guard.release();
     *out = b;
@@ -547,10 +551,10 @@ void jaero_batch_destroy(jaero_batch *b)
     for (int k = 0; k < 2; k++) if (b->ev_cfe_done[k]) cudaEventDestroy(b->ev_cfe_done[k]);
     for (void *q : b->allocs) cudaFree(q);
     cudaFree(b->d_stage); cudaFree(b->d_x);
-    cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage);
+    cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage); cudaFreeHost(b->h_soft_total);
     for (auto &e : b->ev_seg) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : b->ev_cfe) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    cudaStreamDestroy(b->own_stream);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
 }
 int jaero_batch_channels(const jaero_batch *b) { return b ? b->p.n_channels : 0; }
@@ -845,6 +849,7 @@ int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out)
     JB_CUDA(cudaSetDevice(b->device));
     const size_t cp = b->p.cpad;
     JB_CUDA(cudaMemcpyAsync(b->h_dbls, b->p.D, (size_t)D_COUNT * cp * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    JB_CUDA(cudaMemcpyAsync(b->h_soft_total, b->p.soft_total, cp * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
     if (pull_ints(b)) return JAERO_E_CUDA;
     for (int ch = 0; ch < b->p.n_channels; ch++) {
         auto D = [&](int i) { return b->h_dbls[(size_t)i * cp + ch]; };
@@ -855,7 +860,7 @@ int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out)
         s.ebno = D(D_EB_EBNO); s.marg = D(D_MARG_VAL); s.cfe_est = D(D_CFE_EST);
         s.n_sig_true = I(I_SIG_TRUE); s.n_sig_false = I(I_SIG_FALSE);
         s.center_wtptr = D(D_MC_PTR); s.st_ref_wtptr = D(D_SR_PTR);
-        s.samples = b->samples; s.softbits = 0; s.dcd = I(I_DCD); s.reserved = 0;
+        s.samples = b->samples; s.softbits = b->h_soft_total[ch] + I(I_SOFT_COUNT); s.dcd = I(I_DCD); s.reserved = 0;
     }
     return JAERO_OK;
 }
@@ -926,13 +931,15 @@ int jaero_pchannel_create(int n_channels, double fb, int device, jaero_pchannel 
     }
     pp.block_len = pp.cols * 64;
     pp.info_cap = pp.number_of_bits / 16 + 16;
-    pp.su_cap = 4 * (pp.number_of_bits / 2 / 96) + 8;
+    // queue depth: a demodulator soft ring holds max(4096, 2*fb+64) values (jaero_batch_create); a call may hand all of them over
+    pp.queue = std::max(PCHAN_QUEUE_MIN, std::max(4096, 2 * ifb + 64) / pp.block_len + 2);
+    pp.su_cap = pp.queue * (pp.number_of_bits / 2 / 96) + 8;
     const size_t C = n_channels;
     int rc = 0;
     rc |= pc_alloc(p, &pp.state, C);
-    rc |= pc_alloc(p, &pp.blocks, C * PCHAN_QUEUE * pp.block_len);
-    rc |= pc_alloc(p, &pp.decoded, C * PCHAN_QUEUE * (pp.block_len / 2));
-    rc |= pc_alloc(p, &pp.meta, C * PCHAN_QUEUE);
+    rc |= pc_alloc(p, &pp.blocks, C * pp.queue * pp.block_len);
+    rc |= pc_alloc(p, &pp.decoded, C * pp.queue * (pp.block_len / 2));
+    rc |= pc_alloc(p, &pp.meta, C * pp.queue);
     rc |= pc_alloc(p, &pp.ready, C);
     rc |= pc_alloc(p, &pp.dl2, C * pp.dl2_len);
     rc |= pc_alloc(p, &pp.infofield, C * pp.info_cap);
@@ -968,6 +975,7 @@ void jaero_pchannel_destroy(jaero_pchannel *p)
     delete p;
 }
 int64_t jaero_pchannel_launch_count(const jaero_pchannel *p) { return p ? p->launches : 0; }
+int jaero_pchannel_su_capacity(const jaero_pchannel *p) { return p ? p->pp.su_cap : 0; }
 
 int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b)
 {
@@ -978,7 +986,7 @@ int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b)
     // everything runs on the batch's stream so it is ordered after the demodulator segments
     p->cur_stream = b->stream;
     if (pchan_process(p->pp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, dp.soft_cap, dcd, p->vit_overlap, p->vit_overlap_len,
-                      p->vit_renorm, p->vit_valid, PCHAN_QUEUE, b->stream, &p->launches)) return JAERO_E_CUDA;
+                      p->vit_renorm, p->vit_valid, p->pp.queue, b->stream, &p->launches)) return JAERO_E_CUDA;
     soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
     JB_CUDA(cudaGetLastError());
     p->launches++;
@@ -1001,7 +1009,7 @@ int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size
     JB_CUDA(cudaMemcpyAsync(p->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
     JB_CUDA(cudaMemcpyAsync(p->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     if (pchan_process(p->pp, p->d_soft_stage, p->d_count_stage, (int)cap, nullptr, p->vit_overlap, p->vit_overlap_len,
-                      p->vit_renorm, p->vit_valid, PCHAN_QUEUE, p->stream, &p->launches)) return JAERO_E_CUDA;
+                      p->vit_renorm, p->vit_valid, p->pp.queue, p->stream, &p->launches)) return JAERO_E_CUDA;
     JB_CUDA(cudaStreamSynchronize(p->stream));
     return JAERO_OK;
 }
@@ -1009,7 +1017,7 @@ int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b)
 {
     if (!p || (b && b->p.n_channels != p->pp.n_channels)) { set_error("jaero_pchannel_tick: bad argument"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(p->device));
-    if (pchan_tick(p->pp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->stream)) return JAERO_E_CUDA;
+    if (pchan_tick(p->pp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->cur_stream)) return JAERO_E_CUDA;
     p->launches++;
     return JAERO_OK;
 }
@@ -1185,11 +1193,11 @@ static int burst_create(const jaero_settings *s, int n_channels, int device, int
     if (kind == 1) { p.sps = (int)SPS; p.ntaps = 55; taps = rrc_taps(1.0, 55, 48000, 10500 / 2.0); }    // ctor :38-46
     else {
         p.ntaps = 2 * p.sps;
-        if (p.ntaps > MAX_TAPS) { set_error("burst MSK: matched filter too long"); delete b; return JAERO_E_ARG; }
+        if (p.ntaps > MAX_TAPS) { set_error("burst MSK: matched filter too long"); return JAERO_E_ARG; }
         taps.resize(p.ntaps);
         for (int i = 0; i < p.ntaps; i++) taps[i] = sin(M_PI * i / (2.0 * SPS)) / (2.0 * SPS);      // :173-177
     }
-    if (burst_set_taps(taps.data(), p.ntaps)) { delete b; return JAERO_E_CUDA; }
+    for (int k = 0; k < p.ntaps; k++) p.taps[k] = taps[k];
     p.agc_len = (int)round(1 * p.Fs);
     auto qround = [](double d) { return d >= 0.0 ? int(d + 0.5) : int(d - double(int(d - 1)) + 0.5) + int(d - 1); };
     double btdiff_fd = 0;
@@ -1222,13 +1230,13 @@ static int burst_create(const jaero_settings *s, int n_channels, int device, int
     int kk;
     std::vector<double> w_btd1, w_btdiff, w_a1, w_tmp;
     if (!delay_table(1.0 * SPS, w_btd1, &kk) || !delay_table(btdiff_fd, w_btdiff, &kk) || !delay_table(SPS / 2.0, w_a1, &p.a1_k)) {
-        set_error("burst: unsupported delay"); delete b; return JAERO_E_ARG; }
+        set_error("burst: unsupported delay"); return JAERO_E_ARG; }
     if (kind == 0) {
-        if (!delay_w1(SPS / 2.0, &p.d8_k, &p.d8_w)) { set_error("burst MSK: unsupported delay"); delete b; return JAERO_E_ARG; }
+        if (!delay_w1(SPS / 2.0, &p.d8_k, &p.d8_w)) { set_error("burst MSK: unsupported delay"); return JAERO_E_ARG; }
         p.eb_len = (int)(0.15 * p.Fs); p.agc2_len = (int)round((SPS * 128.0 / p.Fs) * p.Fs); p.ds_len = p.sps + 1; p.msema_len = 75;
     } else {
         const double sps0 = 2.0 * 48000 / 10500;                  // ctor :48-52
-        if (!delay_weights(sps0 / 4.0, &p.k41, p.w41v) || !delay_weights(sps0 / 8.0, &p.k8, p.w8v)) { set_error("burst OQPSK: unsupported delay"); delete b; return JAERO_E_ARG; }
+        if (!delay_weights(sps0 / 4.0, &p.k41, p.w41v) || !delay_weights(sps0 / 8.0, &p.k8, p.w8v)) { set_error("burst OQPSK: unsupported delay"); return JAERO_E_ARG; }
         p.d8_k = 1; p.ds_len = 1;
         p.eb_len = (int)(SPS * (256.0)); p.agc2_len = (int)round((SPS * 64.0 / p.Fs) * p.Fs); p.msema_len = 128;
     }
@@ -1324,7 +1332,7 @@ void jaero_burst_destroy(jaero_burst *b)
     for (void *q : b->allocs) cudaFree(q);
     cudaFree(b->d_stage);
     cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft);
-    cudaStreamDestroy(b->stream);
+    if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
 int64_t jaero_burst_launch_count(const jaero_burst *b) { return b ? b->launches : 0; }
@@ -1793,7 +1801,9 @@ int jaero_ingest_message(jaero_ingest *g, const void *topic, size_t topic_len, c
     g->messages++;
     size_t n = pcm_bytes / 2;                                                   // writeData: len/2 int16 samples
     const size_t room = g->cap - g->fill[ch];
-    if (n > room) { g->dropped_bytes += (long long)(n - room) * 2; n = room; set_error("jaero_ingest_message: channel buffer full, samples dropped"); }
+    // a full channel buffer refuses the whole message (nothing is filed, so the caller can flush and re-send): dropping
+    // the tail silently would desynchronise this channel against the lock-step batch
+    if (n > room) { g->dropped_bytes += (long long)n * 2; set_error("jaero_ingest_message: channel buffer full (flush the batch, then re-send this message)"); return JAERO_E_OVERFLOW; }
     memcpy(g->pcm.data() + (size_t)ch * g->cap + g->fill[ch], pcm, n * 2);
     g->fill[ch] += n;
     return ch;

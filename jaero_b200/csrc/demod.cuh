@@ -76,11 +76,15 @@ struct DemodParams {
     double2 *dsmpl_ring;              // MSK delayedsmpl [(sps+1)][cpad]
     double *dly8_ring;                // MSK delayt8 (integer delay SPS/2) [(sps/2+1)][cpad]
     int16_t *soft;                    // [ch][soft_cap]
+    long long *soft_total;            // [cpad] soft values drained from the ring so far (jaero_status.softbits)
     const double *sin_t, *cos_t;      // the reference's 19999-entry tables (DSP.cpp:19-20), built on the host
     double *cfe_est_out;              // [ch] value CoarseFreqEstimate would emit this epoch
     const double2 *xpre;              // 8400 bps: K6 output of the current call [ch][xstride] (null otherwise)
     size_t xstride;
     double *m2_freq_sum;              // 8400 bps: running mixer2_freq_sum of the current call [cpad]
+    // matched-filter taps of THIS batch (FIR::FIRSetPoint, DSP.cpp:283-286). They travel in the kernel parameter block
+    // (constant bank, uniform loads), so batches of different modes can be alive on one GPU at the same time.
+    double taps[MAX_TAPS];
 };
 
 // Uniform (lock-step) positions the host tracks and passes per launch.
@@ -96,7 +100,6 @@ struct SegmentArgs {
                                       // it waits until *cfe_flag >= cfe_wait
 };
 
-int demod_set_taps(const double *taps, int n);
 int oqpsk_segment_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s);
 int oqpsk_pipe_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s);
 int msk_pipe_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s);

@@ -29,7 +29,7 @@ __device__ __forceinline__ double diff_update_soft(double &last, double soft)
 }
 
 __global__ void __launch_bounds__(MSK_THREADS)
-msk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride,
+msk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride,
                    int d8_k, double d8_w)
 {
     extern __shared__ double smem_d[];
@@ -107,8 +107,8 @@ msk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__re
             int tp = fir_pos;
 #pragma unroll 8
             for (int k = 0; k < ntaps; k++) {
-                sre += c_taps[k] * s_re[tp * MSK_THREADS + lane];
-                sim += c_taps[k] * s_im[tp * MSK_THREADS + lane];
+                sre += p.taps[k] * s_re[tp * MSK_THREADS + lane];
+                sim += p.taps[k] * s_im[tp * MSK_THREADS + lane];
                 tp++; if (tp >= nt1) tp = 0;
             }
         }

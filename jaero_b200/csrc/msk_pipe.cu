@@ -37,20 +37,20 @@ __device__ __forceinline__ double mp_diff_update_soft(double &last, double soft)
 
 // sum_{k<cnt} taps[k0+k] * ring[(start+k) % nt1] for both components, in tap order (DSP.cpp:296-303), as two
 // contiguous runs of the ring
-__device__ __forceinline__ void mp_fir_run(const double *__restrict__ s_re, const double *__restrict__ s_im, int lane, int nt1, int start, int cnt,
+__device__ __forceinline__ void mp_fir_run(const DemodParams &p, const double *__restrict__ s_re, const double *__restrict__ s_im, int lane, int nt1, int start, int cnt,
                                            double &sre, double &sim)
 {
     int k = 0, tp = start;
     const int first = min(cnt, nt1 - start);
 #pragma unroll 8
-    for (; k < first; k++, tp++) { sre += c_taps[k] * s_re[tp * 32 + lane]; sim += c_taps[k] * s_im[tp * 32 + lane]; }
+    for (; k < first; k++, tp++) { sre += p.taps[k] * s_re[tp * 32 + lane]; sim += p.taps[k] * s_im[tp * 32 + lane]; }
     tp = 0;
 #pragma unroll 8
-    for (; k < cnt; k++, tp++) { sre += c_taps[k] * s_re[tp * 32 + lane]; sim += c_taps[k] * s_im[tp * 32 + lane]; }
+    for (; k < cnt; k++, tp++) { sre += p.taps[k] * s_re[tp * 32 + lane]; sim += p.taps[k] * s_im[tp * 32 + lane]; }
 }
 
 __global__ void __launch_bounds__(MP_THREADS)
-msk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride, int d8_k, double d8_w)
+msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride, int d8_k, double d8_w)
 {
     extern __shared__ __align__(128) unsigned char mp_smem_raw[];
     const int ntaps = p.ntaps, nt1 = ntaps + 1;
@@ -456,11 +456,11 @@ msk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restr
         // by warp K one sample earlier, the ntaps-1 older terms are summed ahead of that (same order as DSP.cpp:296-303)
         int tail = (int)((S0 + nt1 - 1) % nt1);
         double nfre = 0, nfim = 0;
-        auto older = [&]() { nfre = 0; nfim = 0; int st0 = tail + 2; if (st0 >= nt1) st0 -= nt1; mp_fir_run(s_re, s_im, lane, nt1, st0, ntaps - 1, nfre, nfim); };
+        auto older = [&]() { nfre = 0; nfim = 0; int st0 = tail + 2; if (st0 >= nt1) st0 -= nt1; mp_fir_run(p, s_re, s_im, lane, nt1, st0, ntaps - 1, nfre, nfim); };
         if (nB > 0) older();
         for (int j = 0; j < nB; j++) {
             if (j > 0) nb_sync(MB_X + ((j - 1) & 1));         // X_{j-1}
-            nfre += c_taps[ntaps - 1] * s_re[tail * 32 + lane]; nfim += c_taps[ntaps - 1] * s_im[tail * 32 + lane];
+            nfre += p.taps[ntaps - 1] * s_re[tail * 32 + lane]; nfim += p.taps[ntaps - 1] * s_im[tail * 32 + lane];
             const int sl = j & 1;
             HAND(sl, 0) = nfre; HAND(sl, 1) = nfim;
             __threadfence_block();

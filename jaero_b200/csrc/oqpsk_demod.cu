@@ -17,15 +17,6 @@
 
 namespace jb {
 
-__constant__ double c_taps[MAX_TAPS];
-
-int demod_set_taps(const double *taps, int n)
-{
-    if (n > MAX_TAPS) { set_error("too many FIR taps"); return -1; }
-    JB_CUDA(cudaMemcpyToSymbol(c_taps, taps, n * sizeof(double)));
-    return 0;
-}
-
 static const int OQ_THREADS = 32;
 static const int OQ_NT1 = 56;             // 55 taps + 1 (FIR ring, DSP.cpp:277)
 static const int OQ_FIRROWS = 2 * OQ_NT1; // every entry is stored twice so any 55-entry window is contiguous
@@ -46,24 +37,24 @@ static const int OQ_SM_TOTAL_PRE = OQ_SM_TOTAL + 2 * OQ_SM_X;
 
 // 55-tap FIR over a contiguous window (oldest first), exactly the accumulation order of
 // FIR::FIRUpdateAndProcess (DSP.cpp:296-303): outsum += points[i]*buff[tptr], i = 0..54.
-__device__ __forceinline__ void fir55(const double *__restrict__ wre, const double *__restrict__ wim, double &ore, double &oim)
+__device__ __forceinline__ void fir55(const DemodParams &p, const double *__restrict__ wre, const double *__restrict__ wim, double &ore, double &oim)
 {
     double sre = 0, sim = 0;
 #pragma unroll
     for (int k = 0; k < 55; k++) {
-        sre += c_taps[k] * wre[k * OQ_THREADS];
-        sim += c_taps[k] * wim[k * OQ_THREADS];
+        sre += p.taps[k] * wre[k * OQ_THREADS];
+        sim += p.taps[k] * wim[k * OQ_THREADS];
     }
     ore = sre; oim = sim;
 }
 // the first 54 terms of the same sum (everything except the newest sample, which is still being mixed)
-__device__ __forceinline__ void fir54(const double *__restrict__ wre, const double *__restrict__ wim, double &ore, double &oim)
+__device__ __forceinline__ void fir54(const DemodParams &p, const double *__restrict__ wre, const double *__restrict__ wim, double &ore, double &oim)
 {
     double sre = 0, sim = 0;
 #pragma unroll
     for (int k = 0; k < 54; k++) {
-        sre += c_taps[k] * wre[k * OQ_THREADS];
-        sim += c_taps[k] * wim[k * OQ_THREADS];
+        sre += p.taps[k] * wre[k * OQ_THREADS];
+        sim += p.taps[k] * wim[k * OQ_THREADS];
     }
     ore = sre; oim = sim;
 }
@@ -72,7 +63,7 @@ __device__ __forceinline__ void fir54(const double *__restrict__ wre, const doub
 // mixer2.CIS * cval_prefiltered[i] (K6 output, staged like the PCM rows), and mixer2's frequency is summed per sample.
 template <bool PRE>
 __global__ void __launch_bounds__(OQ_THREADS)
-oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride,
+oqpsk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride,
                      const double2 *__restrict__ xpre, size_t xstride, double *__restrict__ m2_freq_sum)
 {
     extern __shared__ __align__(128) unsigned char oq_smem_raw[];
@@ -266,7 +257,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
     double fre = 0, fim = 0;
     if (!PRE) {
         int newest = fir_pos - 1; if (newest < 0) newest += OQ_NT1;
-        fir55(s_re + (newest + 2) * OQ_THREADS + lane, s_im + (newest + 2) * OQ_THREADS + lane, fre, fim);
+        fir55(p, s_re + (newest + 2) * OQ_THREADS + lane, s_im + (newest + 2) * OQ_THREADS + lane, fre, fim);
     }
     double m2sum = PRE ? (a.new_write ? 0.0 : m2_freq_sum[ch]) : 0.0;     // mixer2_freq_sum (:385,447)
 
@@ -317,7 +308,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
         // The 54 older terms are summed first (same order as DSP.cpp:296-303), the newest term is appended once the mixed
         // sample is available.
         double nfre = 0, nfim = 0;
-        if (!PRE) fir54(s_re + (fir_pos + 2) * OQ_THREADS + lane, s_im + (fir_pos + 2) * OQ_THREADS + lane, nfre, nfim);
+        if (!PRE) fir54(p, s_re + (fir_pos + 2) * OQ_THREADS + lane, s_im + (fir_pos + 2) * OQ_THREADS + lane, nfre, nfim);
         if (PRE) {
             // sig2 = mixer2.WTCISValue()*cval_prefiltered[i] (:440); mixer2_freq_sum+=mixer2.GetFreqHz() (:447)
             double2 xv = *reinterpret_cast<const double2 *>(t_x + (pt & 1) * OQ_SM_X + lane * OQ_XROW + po * 16);
@@ -475,7 +466,7 @@ oqpsk_segment_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__
             const double cre = c2_re * dval, cim = c2_im * dval;
             s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
             s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
-            nfre += c_taps[54] * cre; nfim += c_taps[54] * cim;
+            nfre += p.taps[54] * cre; nfim += p.taps[54] * cim;
             fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
         }
         osc_next_frame(m2); osc_next_frame(st); osc_next_frame(sr);       // :600-603 (mixer_center advanced above)

@@ -47,7 +47,7 @@ __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;
 
 #define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
 __global__ void __launch_bounds__(PP_THREADS)
-oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
+oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
 {
     extern __shared__ __align__(128) unsigned char pp_smem_raw[];
     double *s_re = reinterpret_cast<double *>(pp_smem_raw);   // [OQ_FIRROWS][32]
@@ -544,7 +544,7 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
         // by warp K2 one sample earlier, the 54 older terms are summed ahead of that
         int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);
         double nfre = 0, nfim = 0;
-        if (nB > 0) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+        if (nB > 0) fir54(p, s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
         for (int i = a.i0; i < a.i1; i++) {
             const int j = i - a.i0, sl = j & 1;
             // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
@@ -560,13 +560,13 @@ oqpsk_pipe_kernel(const DemodParams p, const SegmentArgs a, const int16_t *__res
             { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
             const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
             if (j > 0) nb_sync(BAR_X + ((j - 1) & 1));        // X_{j-1}
-            nfre += c_taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += c_taps[54] * s_im[tail * OQ_THREADS + lane];
+            nfre += p.taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += p.taps[54] * s_im[tail * OQ_THREADS + lane];
             // slot sl's F->E / F->K2 fields were read by E(j-2) / K2(j-2), both before X_{j-1}: free
             HAND(sl, 0) = nfre; HAND(sl, 1) = nfim; HAND(sl, 12) = dnxt;
             __threadfence_block();
             nb_arrive(BAR_Z + sl);                             // Z_j
             tail++; if (tail >= OQ_NT1) tail = 0;
-            if (j + 1 < nB) fir54(s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+            if (j + 1 < nB) fir54(p, s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
             dcur = dnxt;
         }
         if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));

@@ -56,7 +56,7 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     PChanState s = pp.state[ch];
     const int n = soft_count[ch];
     const int16_t *bits = soft + (size_t)ch * soft_cap;
-    const int block_len = pp.block_len;
+    const int block_len = pp.block_len, QD = pp.queue;
     s.blocks_ready = 0;
     // the soft-bit row is read 8 values (16 B) at a time, the next group requested while the current one is consumed
     // (soft and soft_cap*2 are 16-byte multiples: cudaMalloc base, capacity rounded by the caller)
@@ -104,17 +104,19 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
             if (idx < 0) idx = 0;
             if (idx >= 8 * block_len) idx %= block_len;                      // only while cntr sits at its 1e9 idle value
             while (idx >= block_len) idx -= block_len;
-            const int q = s.blocks_ready < PCHAN_QUEUE ? s.blocks_ready : PCHAN_QUEUE - 1;
-            pp.blocks[((size_t)ch * PCHAN_QUEUE + q) * block_len + idx] = (uint8_t)soft_bit;
+            // every slot holds a completed block the Viterbi stage has not decoded yet: this bit has nowhere to go. Flag it
+            // (read_sus / get_stats report JAERO_E_OVERFLOW) instead of overwriting a queued block.
+            if (s.blocks_ready >= QD) s.queue_overflow = 1;
+            else pp.blocks[((size_t)ch * QD + s.blocks_ready) * block_len + idx] = (uint8_t)soft_bit;
             if (idx == block_len - 1) {
                 // block complete: queue it for the Viterbi stage with what the SU stage needs to know
-                if (s.blocks_ready < PCHAN_QUEUE) {
+                if (s.blocks_ready < QD) {
                     PChanBlockMeta m;
                     const int nbits = s.first_decode_done ? block_len / 2 : block_len / 2 - (pp.paddinglength / 2 + 1);
                     m.scr_pos = s.scr_pos; m.info_off = s.info_len; m.n_valid = nbits;
                     m.frame_done = ((s.cntr - pp.bits_in_header) == (pp.number_of_bits - 1)) ? 1 : 0;   // :1582
                     m.frame_index = s.nframes;
-                    pp.meta[(size_t)ch * PCHAN_QUEUE + s.blocks_ready] = m;
+                    pp.meta[(size_t)ch * QD + s.blocks_ready] = m;
                     s.scr_pos += nbits;                                      // scrambler.update advances by deconvol.size()
                     s.info_len += nbits / 8;                                 // whole bytes appended (:1568-1580)
                     s.first_decode_done = 1;
@@ -123,9 +125,9 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
                 } else s.queue_overflow = 1;
                 // the partially filled next block starts from the same buffer contents in the reference (it reuses
                 // `block`); copy forward so stale positions match if a frame is cut short
-                if (s.blocks_ready < PCHAN_QUEUE) {
-                    const uint8_t *srcb = pp.blocks + ((size_t)ch * PCHAN_QUEUE + (s.blocks_ready - 1)) * block_len;
-                    uint8_t *dstb = pp.blocks + ((size_t)ch * PCHAN_QUEUE + s.blocks_ready) * block_len;
+                if (s.blocks_ready < QD) {
+                    const uint8_t *srcb = pp.blocks + ((size_t)ch * QD + (s.blocks_ready - 1)) * block_len;
+                    uint8_t *dstb = pp.blocks + ((size_t)ch * QD + s.blocks_ready) * block_len;
                     if ((block_len & 15) == 0) {
                         const int4 *s4 = reinterpret_cast<const int4 *>(srcb); int4 *d4 = reinterpret_cast<int4 *>(dstb);
                         for (int k = 0; k < block_len / 16; k++) d4[k] = s4[k];
@@ -140,7 +142,7 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     }
     s.bits_seen += n;
     // carry the partially filled block of slot `blocks_ready` back to slot 0 for the next call
-    if (s.blocks_ready > 0 && s.blocks_ready < PCHAN_QUEUE) s.carry_slot = s.blocks_ready; else s.carry_slot = 0;
+    if (s.blocks_ready > 0 && s.blocks_ready < QD) s.carry_slot = s.blocks_ready; else s.carry_slot = 0;
     pp.state[ch] = s;
     pp.ready[ch] = s.blocks_ready;
     if (demod_dcd) demod_dcd[ch] = s.datacd;
@@ -152,12 +154,12 @@ pchan_su_kernel(PChanParams pp, int *__restrict__ demod_dcd)
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= pp.n_channels) return;
     PChanState s = pp.state[ch];
-    const int block_len = pp.block_len, half = block_len / 2;
+    const int block_len = pp.block_len, half = block_len / 2, QD = pp.queue;
     uint8_t *dl2 = pp.dl2 + (size_t)ch * pp.dl2_len;
     uint8_t *info = pp.infofield + (size_t)ch * pp.info_cap;
     for (int q = 0; q < s.blocks_ready; q++) {
-        const PChanBlockMeta m = pp.meta[(size_t)ch * PCHAN_QUEUE + q];
-        const uint8_t *dec = pp.decoded + ((size_t)ch * PCHAN_QUEUE + q) * half;
+        const PChanBlockMeta m = pp.meta[(size_t)ch * QD + q];
+        const uint8_t *dec = pp.decoded + ((size_t)ch * QD + q) * half;
         int charptr = 0; unsigned ch8 = 0; int outb = m.info_off;
         // DelayLine::update (aerol.h:465-473) writes slot ptr and returns slot ptr+1, a value stored dl2_len-1 steps earlier:
         // groups of 16 steps read their 16 outputs and 16 inputs first (independent loads), then write
@@ -214,8 +216,8 @@ pchan_su_kernel(PChanParams pp, int *__restrict__ demod_dcd)
     }
     // move the partially filled block to slot 0
     if (s.carry_slot > 0) {
-        const uint8_t *srcb = pp.blocks + ((size_t)ch * PCHAN_QUEUE + s.carry_slot) * block_len;
-        uint8_t *dstb = pp.blocks + ((size_t)ch * PCHAN_QUEUE) * block_len;
+        const uint8_t *srcb = pp.blocks + ((size_t)ch * QD + s.carry_slot) * block_len;
+        uint8_t *dstb = pp.blocks + ((size_t)ch * QD) * block_len;
         for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
         s.carry_slot = 0;
     }
@@ -271,7 +273,7 @@ int pchan_process(const PChanParams &pp, const int16_t *d_soft, const int *d_sof
     for (int q = 0; q < max_queue; q++) {
         if (viterbi_launch(pp.blocks + (size_t)q * pp.block_len, pp.block_len, pp.cols, 0, pp.paddinglength, vit_overlap, vit_overlap_len,
                            vit_renorm, pp.decoded + (size_t)q * (pp.block_len / 2), vit_valid, pp.n_channels, st,
-                           (size_t)PCHAN_QUEUE * pp.block_len, (size_t)PCHAN_QUEUE * (pp.block_len / 2), pp.ready, q)) return -1;
+                           (size_t)pp.queue * pp.block_len, (size_t)pp.queue * (pp.block_len / 2), pp.ready, q)) return -1;
         (*launches)++;
     }
     pchan_su_kernel<<<grid, 64, 0, st>>>(pp, demod_dcd);

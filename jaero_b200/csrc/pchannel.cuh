@@ -3,7 +3,9 @@
 #include <cstdint>
 namespace jb {
 
-static const int PCHAN_QUEUE = 4;            // completed blocks a channel may queue within one process() call
+static const int PCHAN_QUEUE_MIN = 4;        // completed blocks a channel may queue within one process() call: at least this many;
+                                             // PChanParams::queue is sized at create time from the demodulator's soft-bit ring
+                                             // (2 s of soft bits) so that a full ring never overflows it
 
 struct PChanState {                          // members of AeroL used by Decode (JAERO/aerol.h:937-1016)
     unsigned sr_plain, sr_imag, sr_real;     // preamble detector buffers as 32-bit shift registers
@@ -22,10 +24,11 @@ struct PChanBlockMeta { int scr_pos, info_off, n_valid, frame_done, frame_index;
 struct PChanParams {
     int n_channels, oqpsk, cols, block_len, number_of_bits, bits_in_header, total_number_of_bits, paddinglength;
     int dl2_len, info_cap, su_cap;
+    int queue;              // block slots per channel (>= PCHAN_QUEUE_MIN)
     PChanState *state;
-    uint8_t *blocks;        // [ch][PCHAN_QUEUE][block_len] interleaved soft values
-    uint8_t *decoded;       // [ch][PCHAN_QUEUE][block_len/2]
-    PChanBlockMeta *meta;   // [ch][PCHAN_QUEUE]
+    uint8_t *blocks;        // [ch][queue][block_len] interleaved soft values
+    uint8_t *decoded;       // [ch][queue][block_len/2]
+    PChanBlockMeta *meta;   // [ch][queue]
     int *ready;             // [ch] blocks queued by the frame stage
     uint8_t *dl2;           // [ch][dl2_len]
     uint8_t *infofield;     // [ch][info_cap]

@@ -68,7 +68,7 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, size_t in_stride, size_t 
         // Decode_Continuous: mid(paddinglength+1, n/2); positions never written by the decoder read as 0
         const int pos = pad + 1;
         for (int k = lane; k < nbits; k += 32) out[k] = (pos + k < sets) ? obits[pos + k] : (uint8_t)0;
-        if (lane == 0 && n_valid) n_valid[ch] = (sets - pos < nbits) ? (sets - pos) : nbits;   // QVector::mid truncation
+        if (lane == 0 && n_valid) { int nv = (sets - pos < nbits) ? (sets - pos) : nbits; n_valid[ch] = nv < 0 ? 0 : nv; }   // QVector::mid truncation (empty, never negative)
         // keep right(62) of the new (code-order) block, zero-extended to 62
         const int kk = n_soft < 62 ? n_soft : 62;
         for (int k = lane; k < 62; k += 32) overlap[ch * 64 + k] = (k < kk) ? sbuf[ov + n_soft - kk + k] : (uint8_t)0;

@@ -1,0 +1,187 @@
+"""GPU tests of the C-ABI boundary itself (pytest -m gpu): error returns of every create path, several demodulator
+modes alive on one GPU at once (the reference keeps all four demodulators alive, JAERO/mainwindow.cpp:198-237),
+queue limits of the frame layer, the ingest router's back-pressure."""
+import ctypes
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import has_cuda, load_excerpt
+from oracle import restated
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not has_cuda(), reason="needs a CUDA device")]
+
+
+def _import():
+    import jaero_b200
+    return jaero_b200
+
+
+def _raw_create(jb, kind, n_channels, fb, Fs, fft_power=14, lockingbw=10500.0):
+    s = jb.Settings(kind, fft_power, 8000.0, lockingbw, float(fb), float(Fs), 0.65, 0, 0, 0, 1)
+    h = ctypes.c_void_p()
+    rc = jb.lib().jaero_batch_create(ctypes.byref(s), n_channels, None, 0, ctypes.byref(h))
+    if rc == 0:
+        jb.lib().jaero_batch_destroy(h)
+    return rc, jb.lib().jaero_last_error().decode()
+
+
+def test_every_create_error_branch_returns_an_error():
+    """Each early exit of jaero_batch_create / jaero_burst_*_create must come back as a negative code with a message and
+    leave the process alive (round 1 aborted here: the create guard freed the object a second time)."""
+    jb = _import()
+    OQ, MSK = jb.KIND_OQPSK, jb.KIND_MSK
+    cases = [
+        (OQ, 2, 10500, 44100, 14),      # AGC window (4*Fs) fine, fractional delays of T/4, T/8 not representable -> "unsupported"
+        (OQ, 2, 10500, 48001, 14),      # AGC / EbNo windows not a multiple of 32 samples
+        (OQ, 2, 10500, 192000, 14),     # T/4 = 9.14 samples: delay line longer than the kernels keep
+        (MSK, 2, 100, 48000, 13),       # 2*SPS = 960 taps > MAX_TAPS
+        (MSK, 2, 600, 48010, 13),       # AGC window not a multiple of 32
+        (OQ, 0, 10500, 48000, 14),      # n_channels = 0
+        (OQ, 2, 10500, 48000, 9),       # coarsefreqest_fft_power out of range
+        (OQ, 2, -1, 48000, 14),         # fb <= 0
+        (7, 2, 10500, 48000, 14),       # unknown kind
+    ]
+    for kind, n, fb, Fs, power in cases:
+        rc, msg = _raw_create(jb, kind, n, fb, Fs, power)
+        assert rc < 0 and msg, (kind, n, fb, Fs, power, rc, msg)
+    for _ in range(3):                   # repeated failures do not corrupt the allocator
+        rc, _m = _raw_create(jb, OQ, 2, 10500, 44100)
+        assert rc < 0
+    with pytest.raises(jb.JaeroError):
+        jb.BurstMskBatch(2, fb=1200, Fs=44100)
+    with pytest.raises(jb.JaeroError):
+        jb.BurstMskBatch(2, fb=300)
+    with pytest.raises(jb.JaeroError):
+        jb.BurstOqpskBatch(2, fb=8400)
+    with pytest.raises(jb.JaeroError):
+        jb.PChannelBatch(2, 8400)
+    with pytest.raises(jb.JaeroError):
+        jb.RTChannelBatch(2, 8400)
+    with pytest.raises(jb.JaeroError):
+        jb.ViterbiBatch(2, 23)
+    # and a good create still works afterwards
+    rc, msg = _raw_create(jb, OQ, 2, 10500, 48000)
+    assert rc == 0, msg
+
+
+def test_four_demodulator_modes_alive_at_once(golden):
+    """MSK-600, OQPSK-10.5k, burst MSK and burst OQPSK batches created up front and written in an interleaved order: each
+    must give exactly the stream it gives alone (= the oracle's). The matched-filter taps are per batch (kernel parameter
+    block); a process-global tap table would hand the last-created mode's taps to all of them."""
+    jb = _import()
+    names = ["msk_600", "oqpsk_10500", "burst_msk_1200_a", "burst_oqpsk_10500"]
+    secs = {"msk_600": 8, "oqpsk_10500": 4, "burst_msk_1200_a": 10, "burst_oqpsk_10500": 6}
+    objs, pcms, accs, oracles = {}, {}, {}, {}
+    for nm in names:                                            # create ALL first
+        case = golden[nm]
+        pcm = load_excerpt(case.get("excerpt", nm))[:48000 * secs[nm]]
+        pcms[nm] = np.stack([pcm, (pcm.astype(np.int32) * 2 // 3).astype(np.int16)])
+        kw = dict(case["kw"])
+        if case["kind"] == "burst_msk":
+            objs[nm] = jb.BurstMskBatch(2, **kw)
+        elif case["kind"] == "burst_oqpsk":
+            objs[nm] = jb.BurstOqpskBatch(2, **kw)
+        else:
+            objs[nm] = jb.DemodBatch(case["kind"], 2, **kw)
+        accs[nm] = [[], []]
+        oracles[nm] = [restated.OracleDemod(case["kind"], **kw) for _ in range(2)]
+    chunk = 4800
+    nmax = max(p.shape[1] for p in pcms.values())
+    for k, a in enumerate(range(0, nmax, chunk)):
+        order = names if k % 2 == 0 else names[::-1]           # interleaved, alternating order
+        for nm in order:
+            x = pcms[nm][:, a:a + chunk]
+            if x.shape[1] == 0:
+                continue
+            objs[nm].write(x)
+            for c, s in enumerate(objs[nm].read_softbits()):
+                accs[nm][c].append(s)
+    for nm in names:
+        objs[nm].close()
+        for c in range(2):
+            o = oracles[nm][c]
+            for a in range(0, pcms[nm].shape[1], chunk):
+                o.write(pcms[nm][c, a:a + chunk])
+            so = o.take_soft(); sg = np.concatenate(accs[nm][c])
+            assert len(so) == len(sg) and len(so) > 100, nm
+            assert np.array_equal(so < 0, sg < 0) and np.array_equal(so >= 128, sg >= 128), nm
+            assert np.abs(so.astype(int) - sg.astype(int)).max(initial=0) <= 1, nm
+
+
+def test_two_msk_rates_alive_at_once(golden):
+    """MSK 600 (160 taps) and MSK 1200 (80 taps) share every kernel and differ only in parameters."""
+    jb = _import()
+    pcm = load_excerpt("msk_600")[:48000 * 6]
+    kw6 = dict(golden["msk_600"]["kw"])
+    kw12 = dict(kw6, fb=1200, lockingbw=1800)
+    b6 = jb.DemodBatch("msk", 1, **kw6)
+    b12 = jb.DemodBatch("msk", 1, **kw12)
+    o6 = restated.OracleDemod("msk", **kw6); o12 = restated.OracleDemod("msk", **kw12)
+    g6, g12 = [], []
+    for a in range(0, len(pcm), 6000):
+        x = pcm[None, a:a + 6000]
+        b12.write(x); b6.write(x)
+        g6.append(b6.read_softbits()[0]); g12.append(b12.read_softbits()[0])
+        o6.write(pcm[a:a + 6000]); o12.write(pcm[a:a + 6000])
+    st6, st12 = b6.status()[0], b12.status()[0]
+    b6.close(); b12.close()
+    for g, o, st in ((g6, o6, st6), (g12, o12, st12)):
+        so = o.take_soft(); sg = np.concatenate(g)
+        assert len(so) == len(sg) and np.array_equal(so >= 128, sg >= 128)
+        os_ = o.state()
+        for key in ("mixer2_freq", "mse", "agc", "st_wtptr"):
+            assert abs(st[key] - os_[key]) <= 1e-6 * max(abs(os_[key]), 1e-9), key
+        assert st["softbits"] == len(so)                        # jaero_status.softbits counts what was emitted
+
+
+def test_pchannel_takes_a_full_soft_ring_and_flags_anything_beyond():
+    """One process call may hand over a whole demodulator ring (2 s at 10.5k = 4.2 blocks + the carried partial block):
+    same SUs as feeding the oracle; a host call that delivers more than the queue holds raises JAERO_E_OVERFLOW on the
+    next read instead of returning corrupted signal units."""
+    jb = _import()
+    from jaero_b200 import synth
+    C = 2
+    pcm = np.stack([synth.oqpsk_pchannel_pcm(14, fc=8000.0, seed=5 + c, ebn0_db=12.0) for c in range(C)])
+    kw = dict(fb=10500, freq_center=8000.0, lockingbw=10500, fft_power=14, signalthreshold=0.65)
+    b = jb.DemodBatch("oqpsk", C, **kw)
+    pc = jb.PChannelBatch(C, 10500)
+    od = [restated.OracleDemod("oqpsk", **kw) for _ in range(C)]
+    op = [restated.OraclePChannel(10500) for _ in range(C)]
+    got = [[], []]
+    step = 47000                                                 # just under one second per write ...
+    for k, a in enumerate(range(0, pcm.shape[1], step)):
+        b.write(pcm[:, a:a + step])
+        for c in range(C):
+            od[c].write(pcm[c, a:a + step])
+        if k % 2 == 1:                                           # ... frame layer only every second write: ~20.5k soft bits per call
+            pc.process_batch(b)
+            for c in range(C):
+                op[c].process(od[c].take_soft()); od[c].set_dcd(op[c].dcd)
+            for c, r in enumerate(pc.read_sus()):
+                got[c].append(r)
+    for c in range(C):
+        gb = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]])
+        rb, rok, _ = op[c].take_sus()
+        assert np.array_equal(gb, rb) and np.array_equal(gok, rok) and rok.sum() > 50
+    b.close()
+    # beyond the queue: 40 000 soft values in one host call (the queue holds floor(21064/4992)+2 = 6 blocks)
+    soft = [np.full(40000, 200, dtype=np.int16) for _ in range(C)]
+    pc.process_softbits(soft)
+    with pytest.raises(jb.JaeroError, match="overflow"):
+        pc.read_sus()
+    pc.close()
+
+
+def test_ingest_router_refuses_a_message_that_does_not_fit():
+    jb = _import()
+    r = jb.IngestRouter(["CHAN0", "CHAN1"], 48000, capacity_samples=1000)
+    rate = struct.pack("<I", 48000)
+    x = np.arange(600, dtype=np.int16).tobytes()
+    assert r.message(b"CHAN0", rate, x) == 0
+    with pytest.raises(jb.JaeroError, match="full"):
+        r.message(b"CHAN0", rate, x)                             # 1200 > 1000: refused as a whole, nothing filed
+    assert r.message(b"CHAN1", rate, x) == 1
+    assert r.available == 600                                    # channel 0 still holds exactly the first message
+    r.close()
