@@ -192,7 +192,7 @@ class DemodBatch:
         assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n
         if not pcm.flags.c_contiguous:
             pcm = np.ascontiguousarray(pcm)
-        _check(lib().jaero_batch_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2))
+        _check(lib().jaero_batch_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2 if pcm.shape[0] > 1 else pcm.shape[1]))
 
     def write_device(self, dev_ptr, n_samples, stride):
         _check(lib().jaero_batch_write_device(self.h, ctypes.c_void_p(dev_ptr), n_samples, stride))
@@ -400,7 +400,7 @@ class BurstMskBatch:
         assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n
         if not pcm.flags.c_contiguous:
             pcm = np.ascontiguousarray(pcm)
-        _check(lib().jaero_burst_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2))
+        _check(lib().jaero_burst_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2 if pcm.shape[0] > 1 else pcm.shape[1]))
 
     def read_softbits(self):
         out = np.zeros((self.n, self.soft_cap), dtype=np.int16)

@@ -85,22 +85,41 @@ def frame_params(fb):
     raise ValueError("unsupported P-channel rate")
 
 
-def pchannel_bits(fb, n_frames, seed=0, return_sus=False):
-    """Serial channel bits for n_frames P-channel frames (and the signal units they carry)."""
+def pchannel_bits(fb, n_frames, seed=0, return_sus=False, loop=False, even_parity=False):
+    """Serial channel bits for n_frames P-channel frames (and the signal units they carry).
+    loop=True: the convolutional encoder starts in the state it ends in (tail-biting), so the frame sequence can be
+    repeated for ever without a decoding glitch at the seam. even_parity=True: the SUs are re-drawn until the whole bit
+    sequence has even parity (needed to close a differentially pre-coded MSK waveform on itself)."""
     fp = frame_params(fb)
     rng = np.random.default_rng(seed)
     uw_bits = np.array([(UW >> (31 - i)) & 1 for i in range(32)], dtype=np.uint8)
     info_bits_per_frame = fp["blocks"] * 64 * fp["cols"] // 2
     n_sus = info_bits_per_frame // 96
     scr = scrambler_sequence(info_bits_per_frame)
-    enc_state = 0
-    frames, all_sus = [], []
+    for _attempt in range(64):
+        out = _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop)
+        if not even_parity or (int(out[0].sum()) & 1) == 0:
+            break
+    else:
+        raise RuntimeError("no even-parity frame sequence found")
+    return out if return_sus else out[0]
+
+
+def _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop):
+    payloads, all_sus, dummies = [], [], []
     for f in range(n_frames):
         sus = [make_su(rng, 0x01 if (k % 3) else None) for k in range(n_sus)]
         all_sus.append(np.stack(sus))
-        payload = np.concatenate(sus)
-        bits = np.unpackbits(payload, bitorder="little")          # LSB-first (aerol.cpp:1568-1580)
-        bits = bits ^ scr                                         # scrambler restarts every frame (:2010,2015)
+        payloads.append(np.unpackbits(np.concatenate(sus), bitorder="little") ^ scr)   # LSB-first (aerol.cpp:1568-1580); the
+        #                                                           scrambler restarts every frame (:2010,2015)
+        dummies.append(rng.integers(0, 2, size=fp["header_extra"], dtype=np.uint8))
+    enc_state = 0
+    if loop:                                                      # encoder state after the last frame = its last 7 input bits
+        for b in payloads[-1][-7:]:
+            enc_state = ((enc_state << 1) | int(b)) & 127
+    frames = []
+    for f in range(n_frames):
+        bits = payloads[f]
         coded, enc_state = conv_encode_stream(bits, enc_state)
         blocks = [interleave(coded[b * 64 * fp["cols"]:(b + 1) * 64 * fp["cols"]], fp["cols"]) for b in range(fp["blocks"])]
         header = np.array([(0x1000 | ((f & 15) << 4) | (f & 15)) >> (15 - i) & 1 for i in range(16)], dtype=np.uint8)
@@ -108,14 +127,10 @@ def pchannel_bits(fb, n_frames, seed=0, return_sus=False):
             uw = np.repeat(uw_bits, 2)                            # same word on both arms (aerol.cpp:959-960)
         else:
             uw = uw_bits
-        dummy = rng.integers(0, 2, size=fp["header_extra"], dtype=np.uint8)
-        frame = np.concatenate([uw, header, dummy] + blocks)
+        frame = np.concatenate([uw, header, dummies[f]] + blocks)
         assert len(frame) == fp["frame_bits"], (len(frame), fp["frame_bits"])
         frames.append(frame)
-    bits = np.concatenate(frames)
-    if return_sus:
-        return bits, np.stack(all_sus)
-    return bits
+    return np.concatenate(frames), np.stack(all_sus)
 
 
 def rrc_pulse(alpha, span_symbols, sps):
@@ -183,5 +198,42 @@ def to_passband_int16(env, fc, Fs=48000.0, ebn0_db=None, fb=10500.0, rms=0.2, ph
 def oqpsk_pchannel_pcm(n_frames, fc=8000.0, seed=0, ebn0_db=None, fb=10500.0, Fs=48000.0, phase=0.0, delay=0, return_sus=False):
     bits, sus = pchannel_bits(fb, n_frames, seed, return_sus=True)
     env = oqpsk_envelope(bits, fb, Fs)
+    pcm = to_passband_int16(env, fc, Fs, ebn0_db, fb, phase=phase, rng=np.random.default_rng(seed + 12345), delay=delay)
+    return (pcm, sus) if return_sus else pcm
+
+
+def msk_envelope(bits, fb, Fs=48000.0):
+    """Complex envelope of the (circular) MSK signal the continuous MSK demodulator decodes to `bits`.
+    The demodulator treats MSK as offset QPSK with half-sine pulses (matched filter sin(pi i / (2 SPS)), i < 2 SPS,
+    mskdemodulator.cpp:164-170): serial slot n (SPS = Fs/fb samples) carries arm symbol a_n, even slots on the quadrature arm,
+    odd slots on the in-phase arm, each pulse two slots long. It emits DiffDecode(imag), then -DiffDecode(real)
+    (mskdemodulator.cpp:451-469, DSP.cpp:531-563), i.e. bit_n = NOT([sign a_n != sign a_(n-1)] XOR (n odd)). The pre-coder below
+    inverts that; it closes on itself when the number of bits is even and their parity is even."""
+    n_bits = len(bits)
+    sps = int(round(Fs / fb))
+    assert abs(sps - Fs / fb) < 1e-9 and n_bits % 2 == 0
+    # sign changes between consecutive arm symbols. The polarity (the final ^ 1) was fixed empirically against the reference
+    # demodulator, as SURVEY.md App. D prescribes: the continuous-mode unique-word detector is not polarity invariant
+    # (PreambleDetector, aerol.cpp:744-750), so only this variant reaches CRC-valid signal units.
+    x = bits.astype(np.int64) ^ (np.arange(n_bits) & 1) ^ 1
+    assert (int(x.sum()) & 1) == 0, "bit sequence must have even parity to loop"
+    sgn = np.cumsum(x) & 1                                       # sgn_n = sgn_(n-1) ^ x_n with sgn_(-1) = 0
+    a = 1.0 - 2.0 * sgn                                          # 0 -> +1
+    pulse = np.sin(np.pi * np.arange(2 * sps) / (2.0 * sps))
+    L = n_bits * sps
+    q = np.zeros(L); i = np.zeros(L)
+    for n in range(n_bits):
+        idx = (n * sps + np.arange(2 * sps)) % L
+        if n & 1:
+            i[idx] += a[n] * pulse
+        else:
+            q[idx] += a[n] * pulse
+    return i + 1j * q
+
+
+def msk_pchannel_pcm(n_frames, fc=2000.0, seed=0, ebn0_db=None, fb=1200.0, Fs=48000.0, phase=0.0, delay=0, return_sus=False):
+    """BASELINE cfg 2 signal: differentially pre-coded 600 / 1200 bps MSK P-channel frames, real passband int16."""
+    bits, sus = pchannel_bits(fb, n_frames, seed, return_sus=True, loop=True, even_parity=True)
+    env = msk_envelope(bits, fb, Fs)
     pcm = to_passband_int16(env, fc, Fs, ebn0_db, fb, phase=phase, rng=np.random.default_rng(seed + 12345), delay=delay)
     return (pcm, sus) if return_sus else pcm

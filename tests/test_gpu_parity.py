@@ -131,7 +131,7 @@ def _assert_parity(soft_g, st_g, soft_o, st_o):
     assert st_g["n_sig_true"] == st_o["n_sig_true"] and st_g["n_sig_false"] == st_o["n_sig_false"]
 
 
-@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600"])
+@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600", "msk_1200", "msk_1200_noafc_dcd"])
 def test_demod_parity_on_reference_recordings(golden, name):
     case = golden[name]
     pcm = load_excerpt(case["excerpt"])
@@ -145,8 +145,15 @@ def test_demod_parity_on_reference_recordings(golden, name):
     # channel 0 is the committed golden produced by the verbatim reference build
     assert len(soft_g[0]) == case["n_soft"]
     if hashlib.sha256(soft_g[0].astype("<i2").tobytes()).hexdigest() != case["soft_sha256"]:
-        # allowed: isolated +-1 LSB soft differences; hard decisions were already checked identical above
-        pass
+        # The only admissible difference from the verbatim reference's stream: isolated soft values one LSB off (a libm call
+        # rounding the other way just at a quantiser step; never across 127/128, that was asserted above). The restated oracle
+        # IS sha-identical to the golden (tests/test_oracle_golden.py), so the indices can be listed against it.
+        soft_o, _ = _run_oracle(case["kind"], pcm2[0], kw, case["chunk"], sched)
+        assert hashlib.sha256(soft_o.astype("<i2").tobytes()).hexdigest() == case["soft_sha256"]
+        diff = np.nonzero(soft_g[0] != soft_o)[0]
+        assert len(diff) <= max(2, len(soft_o) // 5000), "too many soft values differ from the reference: %s" % diff[:20]
+        assert np.abs(soft_g[0][diff].astype(int) - soft_o[diff].astype(int)).max() == 1
+        print("golden %s: %d of %d soft values one LSB off the verbatim reference at indices %s" % (name, len(diff), len(soft_o), diff.tolist()))
 
 
 @pytest.mark.parametrize("ebn0", [6.0, 8.0, 10.0, None])
@@ -163,6 +170,68 @@ def test_oqpsk_parity_synthetic_ebn0_sweep(ebn0):
         soft_o, st_o = _run_oracle("oqpsk", pcm2[c], kw, 6000)
         _assert_parity(soft_g[c], st_g[c], soft_o, st_o)
     assert sum(len(s) for s in soft_g) > 10000
+
+
+def test_msk1200_parity_synthetic_cfg2():
+    """BASELINE cfg 2 signal model (continuous 1200 bps MSK P-channel, Eb/N0 = 8 dB, carriers 2000 +- 200 Hz, random phase and
+    timing): soft bits / loop state against the oracle, then the device P-channel layer against the oracle's, DCD fed back on
+    both sides at the same boundaries (DCD switches the MSK timing-loop gain, mskdemodulator.cpp:387-405)."""
+    jb = _import()
+    from jaero_b200 import synth
+    C = 5
+    fcs = [2000.0, 1831.0, 2177.0, 2064.5, 1950.25]
+    pcm2 = np.stack([np.tile(synth.msk_pchannel_pcm(4, fc=fcs[c], seed=500 + c, ebn0_db=8.0, fb=1200.0, phase=1.3 * c, delay=7 * c), 3) for c in range(C)])
+    kw = dict(fb=1200, freq_center=2000.0, lockingbw=1800, fft_power=13, signalthreshold=0.5, afc=False)
+    soft_g, st_g = _run_gpu("msk", pcm2, kw, 6000)
+    for c in range(C):
+        soft_o, st_o = _run_oracle("msk", pcm2[c], kw, 6000)
+        _assert_parity(soft_g[c], st_g[c], soft_o, st_o)
+    assert all(len(s) == len(soft_g[0]) for s in soft_g) and len(soft_g[0]) > 12000
+    # demodulator + frame layer with the DCD loop closed
+    b = jb.DemodBatch("msk", C, **kw)
+    pc = jb.PChannelBatch(C, 1200)
+    od = [restated.OracleDemod("msk", **kw) for _ in range(C)]
+    op = [restated.OraclePChannel(1200) for _ in range(C)]
+    got = [[] for _ in range(C)]
+    for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+        b.write(pcm2[:, a:a + 4800]); pc.process_batch(b)
+        for c in range(C):
+            od[c].set_dcd(op[c].dcd); od[c].write(pcm2[c, a:a + 4800]); op[c].process(od[c].take_soft())
+        if k % 10 == 9:
+            pc.tick(b)
+            for c in range(C):
+                op[c].update_dcd()
+            for c, r in enumerate(pc.read_sus()):
+                got[c].append(r)
+    for c, r in enumerate(pc.read_sus()):
+        got[c].append(r)
+    st = b.status()
+    for c in range(C):
+        gb = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]])
+        rb, rok, _ = op[c].take_sus()
+        assert np.array_equal(gb, rb) and np.array_equal(gok, rok)
+        o = od[c].state()
+        for key in ("mixer2_freq", "st_wtptr", "mse", "agc"):
+            assert abs(st[c][key] - o[key]) <= STATE_TOL * max(abs(o[key]), 1e-9), key
+    assert sum(int(np.concatenate([g[1] for g in got[c]]).sum()) for c in range(C)) >= 40 * C // 2
+    b.close(); pc.close()
+
+
+def test_msk1200_full_size_batch_consistency():
+    """BASELINE cfg 2 size (1024 channels): channels fed the same stream agree whatever warp / CTA they sit in, and match the oracle."""
+    from jaero_b200 import synth
+    C = 1024
+    variants = np.stack([synth.msk_pchannel_pcm(3, fc=1900.0 + 70 * v, seed=900 + v, ebn0_db=8.0, fb=1200.0, phase=0.9 * v, delay=11 * v) for v in range(4)])
+    idx = (np.arange(C) * 7 + np.arange(C) // 32) % 4
+    pcm2 = np.ascontiguousarray(variants[idx])
+    kw = dict(fb=1200, freq_center=2000.0, lockingbw=1800, fft_power=13, signalthreshold=0.5, afc=True)
+    soft, st = _run_gpu("msk", pcm2, kw, 9999, read_every=2)
+    for v in range(4):
+        members = np.nonzero(idx == v)[0]
+        assert all(np.array_equal(soft[members[0]], soft[m]) for m in members[1:])
+        assert len({st[m]["mixer2_wtptr"] for m in members}) == 1 and len({st[m]["mse"] for m in members}) == 1
+        so, sto = _run_oracle("msk", variants[v], kw, 9999)
+        _assert_parity(soft[members[0]], st[members[0]], so, sto)
 
 
 def test_chunking_and_settings_variants():

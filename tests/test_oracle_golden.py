@@ -109,8 +109,8 @@ def _run_restated(case, pcm):
     return d.take_soft(), d.state(), d.take_cfe_log()
 
 
-@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600", "burst_msk_1200_a", "burst_msk_1200_b",
-                                  "burst_oqpsk_10500"])
+@pytest.mark.parametrize("name", ["oqpsk_10500", "oqpsk_10500_noafc_dcd", "oqpsk_8400", "msk_600", "msk_1200", "msk_1200_noafc_dcd",
+                                  "burst_msk_1200_a", "burst_msk_1200_b", "burst_oqpsk_10500"])
 def test_restated_oracle_matches_reference_golden(golden, name):
     """The restatement reproduces the verbatim reference bit for bit on the recordings (soft bits, coarse
     estimates, loop state) — golden values were produced by oracle/_ref (tools/make_golden_outputs.py)."""
@@ -127,7 +127,7 @@ def test_restated_oracle_matches_reference_golden(golden, name):
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["oqpsk_10500", "msk_600"])
+@pytest.mark.parametrize("name", ["oqpsk_10500", "msk_600", "msk_1200"])
 def test_restated_oracle_matches_reference_live(golden, name):
     """Same comparison against the live oracle/_ref library (fresh process: the reference has function statics)."""
     import multiprocessing as mp
@@ -245,3 +245,26 @@ def test_rt_channel_oracle_known_answer_r_packet(fb, invert):
     pk = rt.packets()
     assert len(pk) == 1 and pk[0]["type"] == 1 and len(pk[0]["bytes"]) == 19
     assert np.array_equal(pk[0]["bytes"][:17], payload)
+
+
+@pytest.mark.parametrize("fb", [1200, 600])
+def test_msk_generator_known_answer_through_the_oracle(fb):
+    """BASELINE cfg 2 signal model: the differentially pre-coded MSK P-channel generator (jaero_b200.synth) and the oracle's
+    continuous MSK demodulator + P-channel layer are inverse to each other: every CRC-valid signal unit that comes out is one
+    that went in, in order, and after lock all of them come out (Eb/N0 = 12 dB)."""
+    from jaero_b200 import synth
+    n_frames = 8
+    pcm, sus = synth.msk_pchannel_pcm(n_frames, fc=2011.0, seed=77 + fb, ebn0_db=12.0, fb=float(fb), phase=2.2, delay=5, return_sus=True)
+    pcm = np.tile(pcm, 2)                                        # the frame sequence loops seamlessly (tail-biting code, even parity)
+    d = restated.OracleDemod("msk", fb=fb, freq_center=2000.0, lockingbw=1800 if fb == 1200 else 900, fft_power=13, signalthreshold=0.5)
+    p = restated.OraclePChannel(fb)
+    for a in range(0, len(pcm), 4800):
+        d.write(pcm[a:a + 4800]); p.process(d.take_soft()); d.set_dcd(p.dcd)
+    su, ok, fr = p.take_sus()
+    sent = [bytes(x) for x in sus.reshape(-1, 12)] * 2
+    got = [bytes(x) for x in su[ok.astype(bool)]]
+    assert len(got) >= len(sent) - 4 * sus.shape[1]              # at most the first frames (lock + decoder latency) are missing
+    # in order: got is a contiguous run of `sent` (which repeats with the loop)
+    k0 = sent.index(got[0])
+    assert got == sent[k0:k0 + len(got)]
+    assert int(ok.sum()) == len(ok) - int((~ok.astype(bool))[:2 * sus.shape[1]].sum())   # no CRC failure after the first two frames

@@ -25,6 +25,10 @@ CASES = {
     "burst_msk_1200_b": dict(kind="burst_msk", nosu=True, kw=dict(fb=1200.0, freq_center=1000.0, lockingbw=1800.0, signalthreshold=0.6)),
     "burst_oqpsk_10500": dict(kind="burst_oqpsk", nosu=True, kw=dict(fb=10500.0, freq_center=8000.0, lockingbw=10500.0, signalthreshold=0.6)),
     "msk_600": dict(kind="msk", kw=dict(fb=600, freq_center=1000, lockingbw=900, fft_power=13, signalthreshold=0.5, afc=True)),
+    # BASELINE cfg 2 (continuous 1200 bps MSK, mskdemodulator.cpp:189-250 branch): synthetic fixture (tools/make_synth_fixtures.py)
+    "msk_1200": dict(kind="msk", kw=dict(fb=1200, freq_center=2000, lockingbw=1800, fft_power=13, signalthreshold=0.5, afc=True)),
+    "msk_1200_noafc_dcd": dict(kind="msk", excerpt="msk_1200", dcd_at=144000,
+                               kw=dict(fb=1200, freq_center=2030, lockingbw=1800, fft_power=13, signalthreshold=0.5, afc=False)),
 }
 
 
