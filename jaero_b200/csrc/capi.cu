@@ -236,6 +236,7 @@ struct jaero_batch {
     bool use_pipe;              // 10500 bps: warp-specialised segment kernel (JAERO_OQPSK_PIPE=0 selects the single-warp one, for A/B profiling)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_seg, ev_cfe;
     double prof_samples;
+    int trace_state;            // JAERO_PIPE_TRACE: 0 = armed, 1 = done
 };
 
 namespace {
@@ -656,6 +657,13 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
             JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_slice[b->next_slice], 0));
             b->next_slice++;
         }
+        long long *d_trace = 0;
+        if (const char *tf = getenv("JAERO_PIPE_TRACE")) {   // development aid: stage time stamps of one K1a launch
+            if (!b->trace_state && b->launches > 40 && (i1 - i0) > 4000 && p.kind == JAERO_KIND_OQPSK && b->use_pipe && !p.xpre && p.fb > 8400) {
+                (void)tf; cudaMalloc(&d_trace, 64 * 16 * sizeof(long long)); cudaMemset(d_trace, 0, 64 * 16 * sizeof(long long));
+                a.trace = d_trace; a.trace_j0 = 2000;
+            }
+        }
         cudaEvent_t e0 = 0, e1 = 0;
         if (b->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, b->stream); }
         int r = (p.kind == JAERO_KIND_OQPSK) ? ((b->use_pipe && !p.xpre && p.fb > 8400) ? oqpsk_pipe_launch(p, a, d_pcm, stride, b->stream)
@@ -663,6 +671,16 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
                                              : ((b->use_pipe && (p.agc_len % 32) == 0 && (p.ebno_len % 32) == 0) ? msk_pipe_launch(p, a, d_pcm, stride, b->stream)
                                                                                                                       : msk_segment_launch(p, a, d_pcm, stride, b->stream));
         if (b->profiling) { cudaEventRecord(e1, b->stream); b->ev_seg.push_back({e0, e1}); b->prof_samples += (i1 - i0 - (stop_after_a ? 1 : 0)); }
+        if (d_trace) {
+            std::vector<long long> h(64 * 16);
+            cudaStreamSynchronize(b->stream);
+            cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(getenv("JAERO_PIPE_TRACE"), "w")) {
+                for (int jj = 0; jj < 64; jj++) { for (int k = 0; k < 16; k++) fprintf(f, "%lld ", h[jj * 16 + k]); fprintf(f, "\n"); }
+                fclose(f);
+            }
+            cudaFree(d_trace); a.trace = 0; b->trace_state = 1;
+        }
         b->launches++;
         a.new_write = 0;
         return r;
@@ -887,7 +905,10 @@ struct jaero_pchannel {
     int16_t *d_soft_stage; int *d_count_stage; size_t stage_cap;
     PChanState *h_state; uint8_t *h_su;
     long long launches;
-    cudaStream_t cur_stream;     // stream of the most recent process call (the batch's stream for process_batch)
+    // Stream ordering between this layer's own stream and a demodulator batch's stream (which the layer never keeps: the
+    // batch may be destroyed first). Work launched on a batch's stream is followed by ev_batch, which `stream` waits for;
+    // work on `stream` sets own_dirty, and the next call that uses a batch's stream orders that stream behind ev_own.
+    cudaEvent_t ev_batch, ev_own; bool own_dirty;
 };
 
 namespace {
@@ -901,6 +922,18 @@ __global__ void pchan_su_reset_kernel(PChanParams pp)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch < pp.n_channels) { pp.state[ch].su_count = 0; pp.state[ch].queue_overflow = 0; }
+}
+// a call is about to launch on a batch's stream `bs`: order it behind whatever this layer queued on its own stream
+template <class L> int pc_enter(L *p, cudaStream_t bs)
+{
+    if (p->own_dirty) { JB_CUDA(cudaEventRecord(p->ev_own, p->stream)); JB_CUDA(cudaStreamWaitEvent(bs, p->ev_own, 0)); p->own_dirty = false; }
+    return 0;
+}
+// ... and the layer's own stream behind what was just launched on `bs` (the batch's stream handle is not kept)
+template <class L> int pc_leave(L *p, cudaStream_t bs)
+{
+    JB_CUDA(cudaEventRecord(p->ev_batch, bs)); JB_CUDA(cudaStreamWaitEvent(p->stream, p->ev_batch, 0));
+    return 0;
 }
 } // namespace
 
@@ -920,7 +953,9 @@ int jaero_pchannel_create(int n_channels, double fb, int device, jaero_pchannel 
     CreateGuard<jaero_pchannel> guard(p, jaero_pchannel_destroy);
     p->device = device; p->launches = 0; p->d_soft_stage = 0; p->d_count_stage = 0; p->stage_cap = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    p->cur_stream = p->stream;
+    JB_CUDA(cudaEventCreateWithFlags(&p->ev_batch, cudaEventDisableTiming));
+    JB_CUDA(cudaEventCreateWithFlags(&p->ev_own, cudaEventDisableTiming));
+    p->own_dirty = false;
     PChanParams &pp = p->pp;
     memset(&pp, 0, sizeof pp);
     pp.n_channels = n_channels; pp.paddinglength = 24;                          // aerol.cpp:940
@@ -971,7 +1006,9 @@ void jaero_pchannel_destroy(jaero_pchannel *p)
     for (void *q : p->allocs) cudaFree(q);
     cudaFree(p->d_soft_stage); cudaFree(p->d_count_stage);
     cudaFreeHost(p->h_state); cudaFreeHost(p->h_su);
-    cudaStreamDestroy(p->stream);
+    if (p->ev_batch) cudaEventDestroy(p->ev_batch);
+    if (p->ev_own) cudaEventDestroy(p->ev_own);
+    if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
 int64_t jaero_pchannel_launch_count(const jaero_pchannel *p) { return p ? p->launches : 0; }
@@ -984,13 +1021,13 @@ int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b)
     const DemodParams &dp = b->p;
     int *dcd = dp.I + (size_t)I_DCD * dp.cpad;
     // everything runs on the batch's stream so it is ordered after the demodulator segments
-    p->cur_stream = b->stream;
+    if (pc_enter(p, b->stream)) return JAERO_E_CUDA;
     if (pchan_process(p->pp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, dp.soft_cap, dcd, p->vit_overlap, p->vit_overlap_len,
                       p->vit_renorm, p->vit_valid, p->pp.queue, b->stream, &p->launches)) return JAERO_E_CUDA;
     soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
     JB_CUDA(cudaGetLastError());
     p->launches++;
-    return JAERO_OK;
+    return pc_leave(p, b->stream) ? JAERO_E_CUDA : JAERO_OK;
 }
 int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size_t cap, const int32_t *counts)
 {
@@ -1004,8 +1041,7 @@ int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size
         JB_CUDA(cudaMalloc(&p->d_count_stage, C * sizeof(int)));
         p->stage_cap = C * cap;
     }
-    JB_CUDA(cudaStreamSynchronize(p->cur_stream));
-    p->cur_stream = p->stream;
+    p->own_dirty = true;
     JB_CUDA(cudaMemcpyAsync(p->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, p->stream));
     JB_CUDA(cudaMemcpyAsync(p->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     if (pchan_process(p->pp, p->d_soft_stage, p->d_count_stage, (int)cap, nullptr, p->vit_overlap, p->vit_overlap_len,
@@ -1017,14 +1053,15 @@ int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b)
 {
     if (!p || (b && b->p.n_channels != p->pp.n_channels)) { set_error("jaero_pchannel_tick: bad argument"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(p->device));
-    if (pchan_tick(p->pp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->cur_stream)) return JAERO_E_CUDA;
+    if (b) { if (pc_enter(p, b->stream)) return JAERO_E_CUDA; } else p->own_dirty = true;
+    if (pchan_tick(p->pp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->stream)) return JAERO_E_CUDA;
     p->launches++;
-    return JAERO_OK;
+    return (b && pc_leave(p, b->stream)) ? JAERO_E_CUDA : JAERO_OK;
 }
 static int pc_pull_state(jaero_pchannel *p)
 {
-    JB_CUDA(cudaDeviceSynchronize());
-    JB_CUDA(cudaMemcpy(p->h_state, p->pp.state, (size_t)p->pp.n_channels * sizeof(PChanState), cudaMemcpyDeviceToHost));
+    JB_CUDA(cudaMemcpyAsync(p->h_state, p->pp.state, (size_t)p->pp.n_channels * sizeof(PChanState), cudaMemcpyDeviceToHost, p->stream));
+    JB_CUDA(cudaStreamSynchronize(p->stream));          // p->stream is ordered behind every batch-stream call (pc_leave)
     return 0;
 }
 int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap, int32_t *counts)
@@ -1036,22 +1073,23 @@ int jaero_pchannel_read_sus(jaero_pchannel *p, uint8_t *out, size_t cap, int32_t
     bool overflow = false; int maxc = 0;
     for (int ch = 0; ch < pp.n_channels; ch++) { maxc = std::max(maxc, p->h_state[ch].su_count); overflow |= p->h_state[ch].queue_overflow != 0 || (size_t)p->h_state[ch].su_count > cap; }
     if (overflow) { set_error("P-channel queue overflow: call process/read more often"); return JAERO_E_OVERFLOW; }
-    if (maxc) JB_CUDA(cudaMemcpy(p->h_su, pp.su_out, (size_t)pp.n_channels * pp.su_cap * 16, cudaMemcpyDeviceToHost));
+    if (maxc) { JB_CUDA(cudaMemcpyAsync(p->h_su, pp.su_out, (size_t)pp.n_channels * pp.su_cap * 16, cudaMemcpyDeviceToHost, p->stream)); JB_CUDA(cudaStreamSynchronize(p->stream)); }
     for (int ch = 0; ch < pp.n_channels; ch++) {
         counts[ch] = p->h_state[ch].su_count;
         if (counts[ch]) memcpy(out + (size_t)ch * cap * 16, p->h_su + (size_t)ch * pp.su_cap * 16, (size_t)counts[ch] * 16);
     }
-    pchan_su_reset_kernel<<<(pp.n_channels + 127) / 128, 128, 0, p->cur_stream>>>(pp);
+    pchan_su_reset_kernel<<<(pp.n_channels + 127) / 128, 128, 0, p->stream>>>(pp);
     JB_CUDA(cudaGetLastError());
-    JB_CUDA(cudaStreamSynchronize(p->cur_stream));
+    p->own_dirty = true;
     return JAERO_OK;
 }
 int jaero_pchannel_discard_sus(jaero_pchannel *p)
 {
     if (!p) { set_error("null handle"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(p->device));
-    pchan_su_reset_kernel<<<(p->pp.n_channels + 127) / 128, 128, 0, p->cur_stream>>>(p->pp);
+    pchan_su_reset_kernel<<<(p->pp.n_channels + 127) / 128, 128, 0, p->stream>>>(p->pp);
     JB_CUDA(cudaGetLastError());
+    p->own_dirty = true;
     p->launches++;
     return JAERO_OK;
 }
@@ -1612,7 +1650,7 @@ int jaero_rt_get_stats(jaero_rt *r, int32_t *n_trials, int32_t *n_bad, int32_t *
 #include "cchannel.cuh"
 
 struct jaero_cchannel {
-    int device; cudaStream_t stream, cur_stream;
+    int device; cudaStream_t stream; cudaEvent_t ev_batch, ev_own; bool own_dirty;   // stream ordering as in jaero_pchannel
     CChanParams cp;
     std::vector<void *> allocs;
     uint8_t *vit_overlap; int *vit_overlap_len, *vit_renorm, *vit_valid;
@@ -1635,7 +1673,9 @@ int jaero_cchannel_create(int n_channels, int device, jaero_cchannel **out)
     CreateGuard<jaero_cchannel> guard(c, jaero_cchannel_destroy);
     c->device = device; c->d_soft_stage = 0; c->d_count_stage = 0; c->stage_cap = 0; c->h_state = 0; c->h_out = 0; c->launches = 0;
     JB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->cur_stream = c->stream;
+    JB_CUDA(cudaEventCreateWithFlags(&c->ev_batch, cudaEventDisableTiming));
+    JB_CUDA(cudaEventCreateWithFlags(&c->ev_own, cudaEventDisableTiming));
+    c->own_dirty = false;
     CChanParams &cp = c->cp;
     memset(&cp, 0, sizeof cp);
     cp.n_channels = n_channels; cp.dl2_len = 2714 - 6 + 1;                     // dl2.setLength(2714-6) (aerol.cpp:1037)
@@ -1668,7 +1708,9 @@ void jaero_cchannel_destroy(jaero_cchannel *c)
     for (void *q : c->allocs) cudaFree(q);
     cudaFree(c->d_soft_stage); cudaFree(c->d_count_stage);
     cudaFreeHost(c->h_state); cudaFreeHost(c->h_out);
-    cudaStreamDestroy(c->stream);
+    if (c->ev_batch) cudaEventDestroy(c->ev_batch);
+    if (c->ev_own) cudaEventDestroy(c->ev_own);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 int64_t jaero_cchannel_launch_count(const jaero_cchannel *c) { return c ? c->launches : 0; }
@@ -1679,13 +1721,13 @@ int jaero_cchannel_process_batch(jaero_cchannel *c, jaero_batch *b)
     JB_CUDA(cudaSetDevice(c->device));
     const DemodParams &dp = b->p;
     int *dcd = dp.I + (size_t)I_DCD * dp.cpad;
-    c->cur_stream = b->stream;
+    if (pc_enter(c, b->stream)) return JAERO_E_CUDA;
     if (cchan_process(c->cp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, (size_t)dp.soft_cap, dcd, c->vit_overlap, c->vit_overlap_len,
                       c->vit_renorm, c->vit_valid, b->stream, &c->launches)) return JAERO_E_CUDA;
     soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
     JB_CUDA(cudaGetLastError());
     c->launches++;
-    return JAERO_OK;
+    return pc_leave(c, b->stream) ? JAERO_E_CUDA : JAERO_OK;
 }
 int jaero_cchannel_process_softbits(jaero_cchannel *c, const int16_t *soft, size_t cap, const int32_t *counts)
 {
@@ -1699,8 +1741,7 @@ int jaero_cchannel_process_softbits(jaero_cchannel *c, const int16_t *soft, size
         JB_CUDA(cudaMalloc(&c->d_count_stage, C * sizeof(int)));
         c->stage_cap = C * cap;
     }
-    JB_CUDA(cudaStreamSynchronize(c->cur_stream));
-    c->cur_stream = c->stream;
+    c->own_dirty = true;
     JB_CUDA(cudaMemcpyAsync(c->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
     JB_CUDA(cudaMemcpyAsync(c->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (cchan_process(c->cp, c->d_soft_stage, c->d_count_stage, cap, nullptr, c->vit_overlap, c->vit_overlap_len, c->vit_renorm, c->vit_valid,
@@ -1712,18 +1753,19 @@ int jaero_cchannel_tick(jaero_cchannel *c, jaero_batch *b)
 {
     if (!c || (b && b->p.n_channels != c->cp.n_channels)) { set_error("jaero_cchannel_tick: bad argument"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(c->device));
-    if (cchan_tick(c->cp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : c->cur_stream)) return JAERO_E_CUDA;
+    if (b) { if (pc_enter(c, b->stream)) return JAERO_E_CUDA; } else c->own_dirty = true;
+    if (cchan_tick(c->cp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : c->stream)) return JAERO_E_CUDA;
     c->launches++;
-    return JAERO_OK;
+    return (b && pc_leave(c, b->stream)) ? JAERO_E_CUDA : JAERO_OK;
 }
 int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames, int32_t *counts)
 {
     if (!c || !out || !counts || cap_frames <= 0) { set_error("jaero_cchannel_read_frames: bad argument"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(c->device));
     const size_t C = c->cp.n_channels;
-    JB_CUDA(cudaMemcpyAsync(c->h_state, c->cp.state, C * sizeof(CChanState), cudaMemcpyDeviceToHost, c->cur_stream));
-    JB_CUDA(cudaMemcpyAsync(c->h_out, c->cp.out, C * CC_OUT * CC_RECORD, cudaMemcpyDeviceToHost, c->cur_stream));
-    JB_CUDA(cudaStreamSynchronize(c->cur_stream));
+    JB_CUDA(cudaMemcpyAsync(c->h_state, c->cp.state, C * sizeof(CChanState), cudaMemcpyDeviceToHost, c->stream));
+    JB_CUDA(cudaMemcpyAsync(c->h_out, c->cp.out, C * CC_OUT * CC_RECORD, cudaMemcpyDeviceToHost, c->stream));
+    JB_CUDA(cudaStreamSynchronize(c->stream));
     bool overflow = false;
     for (size_t ch = 0; ch < C; ch++) {
         const int n = c->h_state[ch].out_count;
@@ -1731,7 +1773,8 @@ int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames, 
         counts[ch] = n < cap_frames ? n : cap_frames;
         for (int k = 0; k < counts[ch]; k++) memcpy(out + (ch * cap_frames + k) * CC_RECORD, c->h_out + (ch * CC_OUT + k) * CC_RECORD, CC_RECORD);
     }
-    if (cchan_out_reset(c->cp, c->cur_stream)) return JAERO_E_CUDA;
+    if (cchan_out_reset(c->cp, c->stream)) return JAERO_E_CUDA;
+    c->own_dirty = true;
     c->launches++;
     if (overflow) { set_error("C-channel frame queue overflow: read more often"); return JAERO_E_OVERFLOW; }
     return JAERO_OK;
@@ -1741,8 +1784,8 @@ int jaero_cchannel_get_stats(jaero_cchannel *c, int32_t *dcd, int64_t *su_total,
     if (!c) { set_error("null handle"); return JAERO_E_ARG; }
     JB_CUDA(cudaSetDevice(c->device));
     const size_t C = c->cp.n_channels;
-    JB_CUDA(cudaMemcpyAsync(c->h_state, c->cp.state, C * sizeof(CChanState), cudaMemcpyDeviceToHost, c->cur_stream));
-    JB_CUDA(cudaStreamSynchronize(c->cur_stream));
+    JB_CUDA(cudaMemcpyAsync(c->h_state, c->cp.state, C * sizeof(CChanState), cudaMemcpyDeviceToHost, c->stream));
+    JB_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t ch = 0; ch < C; ch++) {
         if (dcd) dcd[ch] = c->h_state[ch].datacd;
         if (su_total) su_total[ch] = c->h_state[ch].su_total;

@@ -98,6 +98,8 @@ struct SegmentArgs {
     int new_write;                    // first launch of a writeData call: latch lastmse
     int cfe_wait;                     // >0: the estimate consumed by apply_cfe is produced concurrently; a channel that needs
                                       // it waits until *cfe_flag >= cfe_wait
+    long long *trace;                 // development aid (JAERO_PIPE_TRACE): clock64 stamps of the pipeline stages of CTA 0, lane 0,
+    int trace_j0;                     // for 64 samples from loop index trace_j0 on: trace[(j-j0)*16 + stamp]; null otherwise
 };
 
 int oqpsk_segment_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d_pcm, size_t stride, cudaStream_t s);

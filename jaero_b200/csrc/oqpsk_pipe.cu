@@ -31,11 +31,18 @@
 
 namespace jb {
 
-static const int PP_THREADS = 192;
+static const int PP_THREADS = 224;                  // seven role warps
 // shared memory map (bytes): FIR windows | ring tiles x6 | PCM tiles x2 | mbarriers | hand-off slots
 static const int PP_HF = 16;                        // doubles per lane in a hand-off slot
 static const int PP_SM_HAND = 2 * PP_HF * 32 * 8;  // [2 slots][PP_HF doubles][32 lanes]
-static const int PP_SM_TOTAL = OQ_SM_TOTAL + PP_SM_HAND;
+static const int PP_NBUF = 3;                       // ring-tile buffers: a tile is reloaded into the buffer stored a whole tile earlier,
+                                                    // so the writer never waits for a bulk store to drain (with 2 buffers it stalled
+                                                    // ~12 000 cycles at every 32-sample tile boundary: 19 % of the launch)
+static const int PP_SM_BASE = OQ_SM_FIR + 3 * PP_NBUF * OQ_SM_RING + 128;           // FIR windows | ring tiles | 16 mbarriers
+static const int PP_DV = 64;                        // input-sample ring (doubles per lane): two tiles of 32, warp A -> warp K2
+static const int PP_SM_DV = PP_DV * 32 * 8;
+static const int PP_SM_BBST = 8 * 32 * 16;          // one 128-byte estimator-ring line per lane, staged before it is written
+static const int PP_SM_TOTAL = PP_SM_BASE + PP_SM_HAND + PP_SM_DV + PP_SM_BBST;
 // named barriers (0 is __syncthreads)
 enum { BAR_X = 1, BAR_YT = 3, BAR_Z = 5, BAR_W = 7, BAR_P = 9, BAR_YK = 11, BAR_U = 13 };
 
@@ -45,6 +52,7 @@ __device__ __forceinline__ void nb_sync(int id) { asm volatile("bar.sync %0, 64;
 #define LD(idx) p.D[(size_t)(idx) * cpad + ch]
 #define LI(idx) p.I[(size_t)(idx) * cpad + ch]
 
+#define TR(k) do { if (a.trace && blockIdx.x == 0 && lane == 0 && j >= a.trace_j0 && j < a.trace_j0 + 64) a.trace[(j - a.trace_j0) * 16 + (k)] = clock64(); } while (0)
 #define PP_WAIT(idx) do { mbar_wait(&bars[(idx)], (phases >> (idx)) & 1u); phases ^= (1u << (idx)); } while (0)
 __global__ void __launch_bounds__(PP_THREADS)
 oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, const int16_t *__restrict__ pcm, size_t stride)
@@ -52,19 +60,24 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
     extern __shared__ __align__(128) unsigned char pp_smem_raw[];
     double *s_re = reinterpret_cast<double *>(pp_smem_raw);   // [OQ_FIRROWS][32]
     double *s_im = s_re + OQ_FIRROWS * OQ_THREADS;
-    double *t_agc = reinterpret_cast<double *>(pp_smem_raw + OQ_SM_FIR);          // [2][T][32]
-    double *t_e1 = t_agc + 2 * OQ_T * OQ_THREADS;
-    double *t_e2 = t_e1 + 2 * OQ_T * OQ_THREADS;
-    unsigned char *t_pcm = pp_smem_raw + OQ_SM_FIR + 6 * OQ_SM_RING;              // [2][32][OQ_PROW]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(t_pcm + 2 * OQ_SM_PCM);   // ring[2], pcm[2]
-    double *hand = reinterpret_cast<double *>(pp_smem_raw + OQ_SM_TOTAL);          // [2][12][32]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *t_agc = reinterpret_cast<double *>(pp_smem_raw + OQ_SM_FIR);          // [PP_NBUF][T][32]
+    double *t_e1 = t_agc + PP_NBUF * OQ_T * OQ_THREADS;
+    double *t_e2 = t_e1 + PP_NBUF * OQ_T * OQ_THREADS;
+    // mbarriers: 0-2 ring tiles, 3-4 input tile full (A -> K2), 5-6 symbol slot free (S -> K1), 7-8 input tile empty (K2 -> A)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(pp_smem_raw + OQ_SM_FIR + 3 * PP_NBUF * OQ_SM_RING);
+    double *hand = reinterpret_cast<double *>(pp_smem_raw + PP_SM_BASE);           // [2][PP_HF][32]
+    double *dv = reinterpret_cast<double *>(pp_smem_raw + PP_SM_BASE + PP_SM_HAND);               // [PP_DV][32]
+    double2 *bbst = reinterpret_cast<double2 *>(pp_smem_raw + PP_SM_BASE + PP_SM_HAND + PP_SM_DV); // [8][32]
+    // Role ids: F 0, E 1, T 2, K1 3, K2 4, S 5, A 6 = physical warp. (Warps w and w+4 share an SM sub-partition and its FP64
+    // pipe. Other placements were measured on B200 - E next to K2, or E / T alone with F, A, S packed together using two
+    // placeholder warps - and were 0-5 % slower than this one: the stages are bound by their own dependent-issue chains.)
+    const int lane = threadIdx.x & 31;
+    const int warp = (int)(threadIdx.x >> 5);
     const int ch_raw = blockIdx.x * OQ_THREADS + lane;
     const bool live = ch_raw < p.n_channels;
     const int ch = ch_raw;                                    // dead lanes run on their (allocated) pad column with zero input
-    const int nlive = min(OQ_THREADS, p.n_channels - (int)blockIdx.x * OQ_THREADS);
     const size_t cpad = p.cpad;
-    if (threadIdx.x == 0) { for (int k = 0; k < 4; k++) mbar_init(&bars[k], 1); mbar_init(&bars[4], 32); mbar_init(&bars[5], 32); }
+    if (threadIdx.x == 0) { for (int k = 0; k < 3; k++) mbar_init(&bars[k], 1); for (int k = 3; k < 9; k++) mbar_init(&bars[k], 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();                                           // (0) mbarriers usable
 
@@ -129,8 +142,10 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             double c2_re, c2_im;
             { const int t = osc_index(m2.ptr); c2_re = cos_t[t]; c2_im = sin_t[t]; }
             int fir_pos = (int)(S0 % OQ_NT1);                  // slot of the sample being mixed
+            unsigned kph = 0u;                                 // parities of the two input-tile-full mbarriers
+            mbar_wait(&bars[3], 0u); kph ^= 1u;                // input tile 0 (warp A)
             {   // cval of the first sample (:453)
-                const double dval = HAND(0, 13);               // first input sample, decoded by warp F before barrier (1)
+                const double dval = dv[lane];
                 const double cre = c2_re * dval, cim = c2_im * dval;
                 s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
                 s_im[fir_pos * OQ_THREADS + lane] = cim; s_im[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cim;
@@ -143,8 +158,20 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
                 const int m2_spec = osc_next_index(m2);
                 const double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
+                double dnext = 0.0;                            // input sample j+1, decoded by warp A a tile or two ahead
+                if (j + 1 < nB) {
+                    const int e = j + 1, tb = (e >> 5) & 1;
+                    if ((e & 31) == 0) { mbar_wait(&bars[3 + tb], (kph >> tb) & 1u); kph ^= (1u << tb); }
+                    dnext = dv[(e & (PP_DV - 1)) * 32 + lane];
+                    if ((e & 31) == 31) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[7 + tb])) : "memory");   // tile read
+                }
+                // a carrier update moves the pointer by ct_ec degrees = 55.6 * ct_ec entries: a few entries in lock, so the
+                // entry needed after an update sits in the speculated 128-byte line or one of its neighbours
+                l1_prefetch(cos_t + max(m2_spec - 16, 0)); l1_prefetch(cos_t + min(m2_spec + 16, WTSIZE - 1));
+                l1_prefetch(sin_t + max(m2_spec - 16, 0)); l1_prefetch(sin_t + min(m2_spec + 16, WTSIZE - 1));
                 nb_sync(BAR_P + sl);                           // P_j: carrier error of this sample (warp K1)
-                const double upd = HAND(sl, 14), ct_ec = HAND(sl, 15), dnext = HAND(sl, 12);
+                TR(8);
+                const double upd = HAND(sl, 14), ct_ec = HAND(sl, 15);
                 if (upd != 0.0) {                                                 // :518-525, fb > 8400 (the host only uses this kernel there)
                     osc_increase_phase_deg(m2, 1.0 * ct_ec);
                     osc_set_freq(m2, (0.01 * ct_ec) + m2.freq, Fs);
@@ -154,6 +181,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                     const int t = osc_index(m2.ptr);
                     if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
                 }
+                TR(13);
                 if (j + 1 < nB) {   // the next sample's mixed value enters the FIR ring (:453-456)
                     const double cre = c2_re * dnext, cim = c2_im * dnext;
                     s_re[fir_pos * OQ_THREADS + lane] = cre; s_re[(fir_pos + OQ_NT1) * OQ_THREADS + lane] = cre;
@@ -161,6 +189,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                     fir_pos++; if (fir_pos >= OQ_NT1) fir_pos = 0;
                     __threadfence_block();
                     nb_arrive(BAR_X + ((j + 1) & 1));          // X_{j+1}
+                    TR(9);
                 }
             }
         }
@@ -172,6 +201,10 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         double2 sig2_last = make_double2(LD(D_SIG2L_RE), LD(D_SIG2L_IM));
         double2 pt_d = make_double2(LD(D_PTD_RE), LD(D_PTD_IM));
         int yui = LI(I_YUI), sig2l_init = LI(I_SIG2L_INIT);
+        // tanh(pt_d.x) only changes when pt_d does (on the strobes of the other arm): it is evaluated right after that strobe's
+        // hand-off instead of on the carrier-update sample, where it sat on the feedback loop
+        double th_ptd = tanh(pt_d.x);
+        bool th_stale = false;
         __syncthreads();                                       // (1)
         {
             unsigned vph = 0u;                                 // parities of the two slot-free mbarriers
@@ -181,17 +214,18 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 double2 sig2 = make_double2(HAND(sl, 2), HAND(sl, 3));
                 nb_sync(BAR_U + sl);                           // strobe decision of this sample (warp T)
                 const double strobe = HAND(sl, 10), frac = HAND(sl, 11);
+                TR(6);
                 if (!sig2l_init) { sig2_last = sig2; sig2l_init = 1; }            // :487 static initialiser
                 double sy_flag = 0.0, sy_x = 0.0, sy_y = 0.0, sy_ec = 0.0, k2_upd = 0.0, k2_ec = 0.0;
                 if (strobe != 0.0) {                                              // :488
                     const double pt_last = frac, pt_this = 1.0 - pt_last;
                     const double2 pt = make_double2(pt_this * sig2.x + pt_last * sig2_last.x, pt_this * sig2.y + pt_last * sig2_last.y);
                     yui ^= 1;                                                     // yui++; yui%=2;
-                    if (!yui) pt_d = pt;
+                    if (!yui) { pt_d = pt; th_stale = true; }
                     else {
                         const double2 pt_qpsk = make_double2(pt.x, pt_d.y);       // :503
                         const double ct_xt = tanh(pt.y) * pt.x;
-                        const double ct_xt_d = tanh(pt_d.x) * pt_d.y;
+                        const double ct_xt_d = th_ptd * pt_d.y;
                         double ct_ec = ct_xt_d - ct_xt;
                         if (ct_ec > M_PI) ct_ec = M_PI;
                         if (ct_ec < -M_PI) ct_ec = -M_PI;
@@ -208,11 +242,13 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 HAND(sl, 14) = k2_upd; HAND(sl, 15) = k2_ec;
                 __threadfence_block();
                 nb_arrive(BAR_P + sl);                         // P_j
+                TR(7);
                 // symbol hand-off to warp S; slot reuse is gated by S's arrival on the slot's mbarrier
-                if (j >= 2) { mbar_wait(&bars[4 + sl], (vph >> sl) & 1u); vph ^= (1u << sl); }
+                if (j >= 2) { mbar_wait(&bars[5 + sl], (vph >> sl) & 1u); vph ^= (1u << sl); }
                 HAND(sl, 6) = sy_x; HAND(sl, 7) = sy_y; HAND(sl, 8) = sy_ec; HAND(sl, 9) = sy_flag;
                 __threadfence_block();
                 nb_arrive(BAR_W + sl);                         // W_j
+                if (th_stale) { th_ptd = tanh(pt_d.x); th_stale = false; }
             }
         }
         LD(D_LF_X1) = lf.x1; LD(D_LF_X2) = lf.x2; LD(D_LF_Y1) = lf.y1; LD(D_LF_Y2) = lf.y2;
@@ -241,7 +277,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             const int sl = j & 1;
             nb_sync(BAR_W + sl);                               // W_j
             const double fx = HAND(sl, 6), fy = HAND(sl, 7), fec = HAND(sl, 8), fl = HAND(sl, 9);
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[4 + sl])) : "memory");   // slot read (release)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[5 + sl])) : "memory");   // slot read (release)
             if (fl != 0.0) {
                 double2 pt_qpsk = make_double2(fx, fy);
                 const double ct_ec = fec;
@@ -303,10 +339,17 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
         for (int j = 0; j < nB; j++) {
             const int sl = j & 1;
+            // speculative request for st_osc's next table entry, issued before this sample's timing nudges are known (they move
+            // the pointer by a fraction of an entry): the L2 round trip of the look-up was the longest item of this warp's
+            // serial chain (atan2 -> nudges -> advance -> index -> load -> next sample's phasor)
+            const int st_spec = osc_next_index(st);
+            const double ns_re = cos_t[st_spec], ns_im = sin_t[st_spec];
             nb_sync(BAR_YT + sl);                              // st_eta, d8out of this sample (warp E)
             const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
+            TR(4);
             const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
             const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
+            TR(11);
             osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
             osc_advance_fraction_of_wave(st, div_exact(-st_angle_error * 0.01, 360.0, 1.0 / 360.0)); // :482
             if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);
@@ -317,8 +360,9 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             HAND(sl, 10) = strobe ? 1.0 : 0.0; HAND(sl, 11) = frac;
             __threadfence_block();
             nb_arrive(BAR_U + sl);
+            TR(5);
             osc_next_frame(st); osc_next_frame(sr);                           // :602-603
-            { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
+            { const int t = osc_index(st.ptr); if (t == st_spec) { cs_re = ns_re; cs_im = ns_im; } else { cs_re = cos_t[t]; cs_im = sin_t[t]; } }
         }
         LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
         LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
@@ -343,56 +387,56 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         const int eb_from_j = (a.i1 - a.i0) - OQ_EBNO_TAIL;       // same read-out window as oqpsk_segment_kernel
         __syncthreads();                                       // (1)
         if (nB > 0) {
-            auto ring_rows = [&](long long tile, double *&g_agc, double *&g_e1, double *&g_e2) {
-                const long long s0 = tile * OQ_T;
-                g_agc = p.agc_ring + ((size_t)(s0 % agc_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
-                if (ebno_on) {
-                    g_e1 = p.ebno_e1 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
-                    g_e2 = p.ebno_e2 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * OQ_THREADS;
-                }
+            // Ring layout of THIS kernel (the 10500 bps pipeline owns its batch's rings): [cta][slot][32 lanes], so the 32 slots x 32
+            // channels of a tile are one contiguous 8 KB block and move with ONE bulk copy per ring, issued by lane 0. (With the
+            // [slot][cpad] layout every lane issued its own 256-byte row copy; UBLKCP is a warp-uniform instruction, so those 96
+            // stores + 96 loads per tile boundary were issued one after the other: a 12 000-cycle stall every 32 samples.)
+            auto ring_tile = [&](double *ring, int len, long long tile) -> double * {
+                return ring + ((size_t)blockIdx.x * len + (size_t)((tile * OQ_T) % len)) * OQ_THREADS;
             };
             const unsigned ring_tx = (ebno_on ? 3u : 1u) * OQ_SM_RING;
-            auto ring_load = [&](long long tile) {                    // all lanes call; lane r moves row r of the tile
-                const int b = (int)(tile & 1);
-                fence_proxy_async();
-                if (lane == 0) mbar_expect_tx(&bars[b], ring_tx);
+            auto ring_load = [&](long long tile) {
+                const int b = (int)(tile % PP_NBUF);
+                fence_proxy_async();                                  // every lane: its generic accesses to the buffer precede the copy
                 __syncwarp();
-                double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
-                ring_rows(tile, g_agc, g_e1, g_e2);
-                bulk_g2s(t_agc + (b * OQ_T + lane) * OQ_THREADS, g_agc, OQ_THREADS * 8, &bars[b]);
-                if (ebno_on) {
-                    bulk_g2s(t_e1 + (b * OQ_T + lane) * OQ_THREADS, g_e1, OQ_THREADS * 8, &bars[b]);
-                    bulk_g2s(t_e2 + (b * OQ_T + lane) * OQ_THREADS, g_e2, OQ_THREADS * 8, &bars[b]);
+                if (lane == 0) {
+                    mbar_expect_tx(&bars[b], ring_tx);
+                    bulk_g2s(t_agc + b * OQ_T * OQ_THREADS, ring_tile(p.agc_ring, agc_len, tile), OQ_SM_RING, &bars[b]);
+                    if (ebno_on) {
+                        bulk_g2s(t_e1 + b * OQ_T * OQ_THREADS, ring_tile(p.ebno_e1, eb_len, tile), OQ_SM_RING, &bars[b]);
+                        bulk_g2s(t_e2 + b * OQ_T * OQ_THREADS, ring_tile(p.ebno_e2, eb_len, tile), OQ_SM_RING, &bars[b]);
+                    }
                 }
             };
             auto ring_store = [&](long long tile) {                   // write the (in-place updated) tile back to HBM
-                const int b = (int)(tile & 1);
+                const int b = (int)(tile % PP_NBUF);
                 fence_proxy_async();
                 __syncwarp();
-                double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
-                ring_rows(tile, g_agc, g_e1, g_e2);
-                bulk_s2g(g_agc, t_agc + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
-                if (ebno_on) {
-                    bulk_s2g(g_e1, t_e1 + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
-                    bulk_s2g(g_e2, t_e2 + (b * OQ_T + lane) * OQ_THREADS, OQ_THREADS * 8);
+                if (lane == 0) {
+                    bulk_s2g(ring_tile(p.agc_ring, agc_len, tile), t_agc + b * OQ_T * OQ_THREADS, OQ_SM_RING);
+                    if (ebno_on) {
+                        bulk_s2g(ring_tile(p.ebno_e1, eb_len, tile), t_e1 + b * OQ_T * OQ_THREADS, OQ_SM_RING);
+                        bulk_s2g(ring_tile(p.ebno_e2, eb_len, tile), t_e2 + b * OQ_T * OQ_THREADS, OQ_SM_RING);
+                    }
+                    bulk_commit();
                 }
-                bulk_commit();
             };
             unsigned phases = 0u;
             long long rt = S / OQ_T;                                  // current ring tile
             bool ring_next_issued = false, ring_dirty = false;
             ring_load(rt);
             if ((rt + 1) * OQ_T < S_end) { ring_load(rt + 1); ring_next_issued = true; }
-            PP_WAIT((int)(rt & 1));
+            PP_WAIT((int)(rt % PP_NBUF));
             for (int j = 0; j < nB; j++) {
                 const int sl = j & 1;
                 const int ro = (int)(S & (OQ_T - 1));
-                const int rslot = (((int)(rt & 1)) * OQ_T + ro) * OQ_THREADS + lane;   // this sample's slot in the staged ring tiles
+                const int rslot = (((int)(rt % PP_NBUF)) * OQ_T + ro) * OQ_THREADS + lane;   // this sample's slot in the staged ring tiles
                 const double w41 = p.w41v[p41], w8 = p.w8v[p8];
                 p41++; if (p41 > k41) p41 = 0;
                 p8++; if (p8 > k8) p8 = 0;
                 nb_sync(BAR_Z + sl);                           // Z_j: FIR output of this sample
                 const double sre = HAND(sl, 0), sim = HAND(sl, 1);
+                TR(2);
                 const double dabval = sqrt(sre * sre + sim * sim);                // :461
                 if (ebno_on) {                                                    // OQPSKEbNoMeasure::Update (DSP.cpp:729-744)
                     const double sq = dabval * dabval;
@@ -423,6 +467,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 }
                 double2 sig2 = make_double2(sre * agc_val, sim * agc_val);        // :466
                 const double abval = hypot(sig2.x, sig2.y);                       // :469 std::abs
+                TR(10);
                 if (abval > 2.84) { const double g = (2.84 / abval); sig2 = make_double2(g * sig2.x, g * sig2.y); }   // :470
                 // ---- symbol timing, feed-forward part (:473-477)
                 const double ab2 = abval * abval;
@@ -455,6 +500,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 __threadfence_block();
                 nb_arrive(BAR_YT + sl);                        // timing inputs -> warp T
                 nb_arrive(BAR_YK + sl);                        // sig2 -> warp K
+                TR(3);
                 // ---- ring tile bookkeeping (warp-uniform)
                 S++;
                 if ((S & (OQ_T - 1)) == 0) {
@@ -462,17 +508,19 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                     ring_dirty = false;
                     rt++;
                     if (S < S_end) {
-                        PP_WAIT((int)(rt & 1));                       // next tile (requested a tile ago)
+                        PP_WAIT((int)(rt % PP_NBUF));                 // next tile (requested a tile ago)
                         ring_next_issued = false;
                         if ((rt + 1) * OQ_T < S_end) {
-                            bulk_wait_read_all();                     // the buffer being refilled must have been read out by its store
+                            // the buffer being refilled was stored a whole tile ago: only the store committed just now may still
+                            // be reading shared memory
+                            bulk_wait_read_1();
                             ring_load(rt + 1); ring_next_issued = true;
                         }
                     }
                 }
             }
             if (ring_dirty) ring_store(rt);
-            if (ring_next_issued) PP_WAIT((int)((rt + 1) & 1));
+            if (ring_next_issued) PP_WAIT((int)((rt + 1) % PP_NBUF));
             bulk_wait_all();
         }
         LD(D_AGC_SUM) = agc_sum; LD(D_AGC_VAL) = agc_val;
@@ -483,98 +531,97 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         LD(D_DLY8_0) = d8_0; LD(D_DLY8_1) = d8_1; LD(D_DLY8_2) = d8_2;
         LD(D_RES_X1) = res.x1; LD(D_RES_X2) = res.x2; LD(D_RES_Y1) = res.y1; LD(D_RES_Y2) = res.y2;
     }
-    // ======================================================================================= warp F: input + matched filter
-    else {
+    // ======================================================================================= warp F: matched filter
+    else if (warp == 0) {
         for (int k = 0; k < OQ_NT1; k++) {
             const double vr = p.fir_re[(size_t)k * cpad + ch], vi = p.fir_im[(size_t)k * cpad + ch];
             s_re[k * OQ_THREADS + lane] = vr; s_re[(k + OQ_NT1) * OQ_THREADS + lane] = vr;
             s_im[k * OQ_THREADS + lane] = vi; s_im[(k + OQ_NT1) * OQ_THREADS + lane] = vi;
         }
+        __syncthreads();                                       // (1)
+        // output j (:456) = sum over the 55 mixed samples older than sample i0+j; the newest of them (slot `tail`) is produced
+        // by warp K2 one sample earlier, the 54 older terms are summed ahead of that
+        int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);
+        double nfre = 0, nfim = 0;
+        if (nB > 0) fir54(p, s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+        for (int j = 0; j < nB; j++) {
+            const int sl = j & 1;
+            if (j > 0) nb_sync(BAR_X + ((j - 1) & 1));        // X_{j-1}
+            TR(0);
+            nfre += p.taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += p.taps[54] * s_im[tail * OQ_THREADS + lane];
+            // slot sl's F->E fields were read by E(j-2), before X_{j-1}: free
+            HAND(sl, 0) = nfre; HAND(sl, 1) = nfim;
+            __threadfence_block();
+            nb_arrive(BAR_Z + sl);                             // Z_j
+            TR(1);
+            tail++; if (tail >= OQ_NT1) tail = 0;
+            if (j + 1 < nB) fir54(p, s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
+        }
+        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp K2
+    }
+    // ======================================================================================= warp A: input + coarse-estimator ring
+    else {
         const int16_t *row = pcm + (size_t)ch * stride;
-        // PCM: tile t covers buffer samples [32t, 32t+32) of every channel row (16 B aligned: stride % 8 == 0, host-checked)
-        auto pcm_bytes = [&](int tile) -> unsigned {
-            long long left = (long long)stride - (long long)tile * OQ_T;
-            if (left > OQ_T) left = OQ_T;
-            return left > 0 ? (unsigned)(left * 2) : 0u;
+        // PCM: each lane reads its own channel row 8 samples (16 bytes) at a time with plain vector loads, one block ahead of use
+        // (rows are 16-byte aligned and a multiple of 8 samples long: host-checked). The bulk-copy tiles used before cost 32
+        // serialised copy instructions per 32 samples (one per lane) for 64 bytes each.
+        const int4 *row4 = reinterpret_cast<const int4 *>(row);
+        auto ld_blk = [&](int blk) -> int4 {
+            return (live && (long long)blk * 8 < (long long)stride) ? __ldg(row4 + blk) : make_int4(0, 0, 0, 0);
         };
-        auto pcm_load = [&](int tile) {
-            const int b = tile & 1;
-            const unsigned nb = pcm_bytes(tile);
-            fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
-            __syncwarp();
-            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
-        };
-        unsigned phases = 0u;
-        int pt = a.i0 / OQ_T;                                     // current PCM tile
-        bool pcm_next_issued = false;
-        pcm_load(pt);
-        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-        PP_WAIT(2 + (pt & 1));
-        int4 pk = make_int4(0, 0, 0, 0);                          // 8 consecutive PCM samples of this lane's channel
-        int pk_blk = -1;
+        int pk_blk = a.i0 >> 3;
+        int4 pk = ld_blk(pk_blk), pk_next = ld_blk(pk_blk + 1);   // 8 consecutive PCM samples of this lane's channel, and the next 8
         auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:390); ii advances by one per call
-            if ((ii >> 5) != pt) {                                // entered the next PCM tile (warp-uniform)
-                pt = ii >> 5;
-                PP_WAIT(2 + (pt & 1));
-                pcm_next_issued = false;
-                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-            }
-            if ((ii >> 3) != pk_blk) {
-                pk_blk = ii >> 3;
-                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
-            }
+            if ((ii >> 3) != pk_blk) { pk_blk = ii >> 3; pk = pk_next; pk_next = ld_blk(pk_blk + 1); }
             const int k = ii & 7;
             const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
             int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
             if (!live) v = 0;
             return ((double)v) / 32768.0;
         };
-        double dcur = dval_at(a.i0);
-        HAND(0, 13) = dcur;
         __syncthreads();                                       // (1) the slot may have re-centred mixer_center
         Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
         int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
         double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
-        const int bbn = p.bb_len;
+        const int bbn = p.bb_len;                               // a multiple of 8
         const bool cpu_reduce = p.cpu_reduce != 0;
         double cc_re, cc_im;
         { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-        // output j (:456) = sum over the 55 mixed samples older than sample i0+j; the newest of them (slot `tail`) is produced
-        // by warp K2 one sample earlier, the 54 older terms are summed ahead of that
-        int tail = (int)((S0 + OQ_NT1 - 1) % OQ_NT1);
-        double nfre = 0, nfim = 0;
-        if (nB > 0) fir54(p, s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
-        for (int i = a.i0; i < a.i1; i++) {
-            const int j = i - a.i0, sl = j & 1;
+        // This warp runs ahead of the demodulator loop: nothing it computes depends on the loop (PCM, mixer_center, the estimator
+        // ring). It decodes the input into a two-tile ring for warp K2 and writes the estimator ring one full 128-byte line (8
+        // samples) per lane at a time, so that every 32-byte sector reaches HBM whole.
+        const int n = a.i1 - a.i0;
+        unsigned aph = 0u;                                      // parities of the two input-tile-empty mbarriers
+        int line_first = bb_pos & 7;                            // entries of the open line below this index were written by an earlier launch
+        for (int e = 0; e < n; e++) {
+            const int tb = (e >> 5) & 1;
+            if ((e & 31) == 0 && e >= PP_DV) { mbar_wait(&bars[7 + tb], (aph >> tb) & 1u); aph ^= (1u << tb); }
+            const double dcur = dval_at(a.i0 + e);
+            dv[(e & (PP_DV - 1)) * 32 + lane] = dcur;
             // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
-            if (!(i == a.i0 && a.skip_a_first)) {
+            if (!(e == 0 && a.skip_a_first)) {
                 if (coarse_counter >= Fs || !cpu_reduce) {
-                    if (live) bb_row[bb_pos] = make_double2(cc_re * dcur, cc_im * dcur);
+                    bbst[(bb_pos & 7) * 32 + lane] = make_double2(cc_re * dcur, cc_im * dcur);
+                    if ((bb_pos & 7) == 7) {
+                        if (live) for (int k = line_first; k < 8; k++) bb_row[(bb_pos & ~7) + k] = bbst[k * 32 + lane];
+                        line_first = 0;
+                    }
                     bb_pos++; if (bb_pos >= bbn) bb_pos = 0;
                 }
             }
-            if (i == a.i1 - 1 && a.stop_after_a) break;
-            coarse_counter++;                                                 // :431
-            osc_next_frame(mc);                                               // :601
-            { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
-            const double dnxt = (i + 1 < a.i1) ? dval_at(i + 1) : 0.0;
-            if (j > 0) nb_sync(BAR_X + ((j - 1) & 1));        // X_{j-1}
-            nfre += p.taps[54] * s_re[tail * OQ_THREADS + lane]; nfim += p.taps[54] * s_im[tail * OQ_THREADS + lane];
-            // slot sl's F->E / F->K2 fields were read by E(j-2) / K2(j-2), both before X_{j-1}: free
-            HAND(sl, 0) = nfre; HAND(sl, 1) = nfim; HAND(sl, 12) = dnxt;
-            __threadfence_block();
-            nb_arrive(BAR_Z + sl);                             // Z_j
-            tail++; if (tail >= OQ_NT1) tail = 0;
-            if (j + 1 < nB) fir54(p, s_re + (tail + 2) * OQ_THREADS + lane, s_im + (tail + 2) * OQ_THREADS + lane, nfre, nfim);
-            dcur = dnxt;
+            if (!(e == n - 1 && a.stop_after_a)) {
+                coarse_counter++;                                                 // :431
+                osc_next_frame(mc);                                               // :601
+                { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+            }
+            if ((e & 31) == 31 || e == n - 1)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[3 + tb])) : "memory");   // tile (or the rest) complete
         }
-        if (pcm_next_issued) PP_WAIT(2 + ((pt + 1) & 1));
-        if (nB > 0) nb_sync(BAR_X + ((nB - 1) & 1));          // X_{nB-1}: pair the last arrival of warp K2
+        if (live) for (int k = line_first; k < (bb_pos & 7); k++) bb_row[(bb_pos & ~7) + k] = bbst[k * 32 + lane];   // the open line
         LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
-    for (int k = warp; k < OQ_NT1; k += 6) {
+    for (int k = (int)(threadIdx.x >> 5); k < OQ_NT1; k += PP_THREADS / 32) {
         p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
         p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
     }
@@ -596,3 +643,4 @@ int oqpsk_pipe_launch(const DemodParams &p, const SegmentArgs &a, const int16_t 
 } // namespace jb
 
 #undef PP_WAIT
+#undef TR

@@ -88,24 +88,21 @@ def frame_params(fb):
 def pchannel_bits(fb, n_frames, seed=0, return_sus=False, loop=False, even_parity=False):
     """Serial channel bits for n_frames P-channel frames (and the signal units they carry).
     loop=True: the convolutional encoder starts in the state it ends in (tail-biting), so the frame sequence can be
-    repeated for ever without a decoding glitch at the seam. even_parity=True: the SUs are re-drawn until the whole bit
-    sequence has even parity (needed to close a differentially pre-coded MSK waveform on itself)."""
+    repeated for ever without a decoding glitch at the seam. even_parity=True: the whole bit sequence is given even parity
+    (needed to close a differentially pre-coded MSK waveform on itself) by setting the super-frame marker of the last frame's
+    header when necessary - with a tail-biting rate-1/2 code of two odd-weight polynomials the coded bits always have even
+    parity, so only the 16 header bits decide."""
     fp = frame_params(fb)
     rng = np.random.default_rng(seed)
     uw_bits = np.array([(UW >> (31 - i)) & 1 for i in range(32)], dtype=np.uint8)
     info_bits_per_frame = fp["blocks"] * 64 * fp["cols"] // 2
     n_sus = info_bits_per_frame // 96
     scr = scrambler_sequence(info_bits_per_frame)
-    for _attempt in range(64):
-        out = _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop)
-        if not even_parity or (int(out[0].sum()) & 1) == 0:
-            break
-    else:
-        raise RuntimeError("no even-parity frame sequence found")
+    out = _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop, even_parity)
     return out if return_sus else out[0]
 
 
-def _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop):
+def _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop, even_parity=False):
     payloads, all_sus, dummies = [], [], []
     for f in range(n_frames):
         sus = [make_su(rng, 0x01 if (k % 3) else None) for k in range(n_sus)]
@@ -117,12 +114,14 @@ def _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop):
     if loop:                                                      # encoder state after the last frame = its last 7 input bits
         for b in payloads[-1][-7:]:
             enc_state = ((enc_state << 1) | int(b)) & 127
-    frames = []
+    frames, headers_at = [], []
     for f in range(n_frames):
         bits = payloads[f]
         coded, enc_state = conv_encode_stream(bits, enc_state)
         blocks = [interleave(coded[b * 64 * fp["cols"]:(b + 1) * 64 * fp["cols"]], fp["cols"]) for b in range(fp["blocks"])]
+        # formatid(4) = 1 | supfrmaker(4) | framecounter1(4) | framecounter2(4)  (aerol.cpp:1275-1319)
         header = np.array([(0x1000 | ((f & 15) << 4) | (f & 15)) >> (15 - i) & 1 for i in range(16)], dtype=np.uint8)
+        headers_at.append(sum(len(x) for x in frames) + len(uw_bits) * (2 if fp["uw_interleaved"] else 1))
         if fp["uw_interleaved"]:
             uw = np.repeat(uw_bits, 2)                            # same word on both arms (aerol.cpp:959-960)
         else:
@@ -130,7 +129,10 @@ def _pchannel_bits_once(fp, rng, n_frames, uw_bits, n_sus, scr, loop):
         frame = np.concatenate([uw, header, dummies[f]] + blocks)
         assert len(frame) == fp["frame_bits"], (len(frame), fp["frame_bits"])
         frames.append(frame)
-    return np.concatenate(frames), np.stack(all_sus)
+    allbits = np.concatenate(frames)
+    if even_parity and (int(allbits.sum()) & 1):
+        allbits[headers_at[-1] + 7] ^= 1                          # last frame: supfrmaker 0 -> 1
+    return allbits, np.stack(all_sus)
 
 
 def rrc_pulse(alpha, span_symbols, sps):

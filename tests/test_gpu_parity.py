@@ -212,7 +212,8 @@ def test_msk1200_parity_synthetic_cfg2():
         assert np.array_equal(gb, rb) and np.array_equal(gok, rok)
         o = od[c].state()
         for key in ("mixer2_freq", "st_wtptr", "mse", "agc"):
-            assert abs(st[c][key] - o[key]) <= STATE_TOL * max(abs(o[key]), 1e-9), key
+            scale = 19999.0 if key.endswith("wtptr") else max(abs(o[key]), 1e-9)   # a table pointer is a phase: error relative to one cycle
+            assert abs(st[c][key] - o[key]) <= STATE_TOL * scale, key
     assert sum(int(np.concatenate([g[1] for g in got[c]]).sum()) for c in range(C)) >= 40 * C // 2
     b.close(); pc.close()
 
