@@ -402,6 +402,10 @@ class BurstMskBatch:
             pcm = np.ascontiguousarray(pcm)
         _check(lib().jaero_burst_write(self.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2 if pcm.shape[0] > 1 else pcm.shape[1]))
 
+    def write_device(self, dev_ptr, n_samples, stride):
+        """writeData from a DEVICE buffer [n_channels][stride] int16"""
+        _check(lib().jaero_burst_write_device(self.h, ctypes.c_void_p(dev_ptr), n_samples, stride))
+
     def read_softbits(self):
         out = np.zeros((self.n, self.soft_cap), dtype=np.int16)
         counts = np.zeros(self.n, dtype=np.int32)

@@ -16,6 +16,7 @@
 namespace jb {
 
 static const int MP_THREADS = 160;
+static const int MP_NBUF = 3;                       // ring-tile buffers (see oqpsk_pipe.cu: a tile is reloaded into the buffer stored a tile earlier)
 static const int MP_HF = 16;                        // doubles per lane in a hand-off slot
 // named barriers (0 is __syncthreads)
 enum { MB_X = 1, MB_YT = 3, MB_Z = 5, MB_W = 7, MB_V = 9, MB_YK = 11, MB_U = 13 };
@@ -58,20 +59,18 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
     // shared memory map
     double *s_re = reinterpret_cast<double *>(mp_smem_raw);                        // [nt1][32]
     double *s_im = s_re + (size_t)nt1 * 32;
-    double *t_agc = s_im + (size_t)nt1 * 32;                                       // [2][T][32]
-    double *t_e1 = t_agc + 2 * OQ_T * 32;
-    double *t_e2 = t_e1 + 2 * OQ_T * 32;
-    double2 *s_ds = reinterpret_cast<double2 *>(t_e2 + 2 * OQ_T * 32);             // delayedsmpl [ds_len][32]
+    double *t_agc = s_im + (size_t)nt1 * 32;                                       // [MP_NBUF][T][32]
+    double *t_e1 = t_agc + MP_NBUF * OQ_T * 32;
+    double *t_e2 = t_e1 + MP_NBUF * OQ_T * 32;
+    double2 *s_ds = reinterpret_cast<double2 *>(t_e2 + MP_NBUF * OQ_T * 32);       // delayedsmpl [ds_len][32]
     double *s_d8 = reinterpret_cast<double *>(s_ds + (size_t)ds_len * 32);         // delayt8 [d8_len][32]
     double *hand = s_d8 + (size_t)d8_len * 32;                                     // [2][MP_HF][32]
-    unsigned char *t_pcm = reinterpret_cast<unsigned char *>(hand + 2 * MP_HF * 32);   // [2][32][OQ_PROW]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(t_pcm + 2 * OQ_SM_PCM);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(hand + 2 * MP_HF * 32);   // ring tiles [MP_NBUF]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ch = blockIdx.x * 32 + lane;
     const bool live = ch < p.n_channels;
-    const int nlive = min(32, p.n_channels - (int)blockIdx.x * 32);
     const size_t cpad = p.cpad;
-    if (threadIdx.x == 0) { for (int k = 0; k < 4; k++) mbar_init(&bars[k], 1); }
+    if (threadIdx.x == 0) { for (int k = 0; k < MP_NBUF; k++) mbar_init(&bars[k], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();                                           // (0) mbarriers usable
 
@@ -225,38 +224,15 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
         Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
         const int dcd = LI(I_DCD);
         const int16_t *row = pcm + (size_t)ch * stride;
-        auto pcm_bytes = [&](int tile) -> unsigned {
-            long long left = (long long)stride - (long long)tile * OQ_T;
-            if (left > OQ_T) left = OQ_T;
-            return left > 0 ? (unsigned)(left * 2) : 0u;
+        // PCM: vector loads of the lane's own channel row, 8 samples at a time, one block ahead of use (see oqpsk_pipe.cu)
+        const int4 *row4 = reinterpret_cast<const int4 *>(row);
+        auto ld_blk = [&](int blk) -> int4 {
+            return (live && (long long)blk * 8 < (long long)stride) ? __ldg(row4 + blk) : make_int4(0, 0, 0, 0);
         };
-        auto pcm_load = [&](int tile) {
-            const int b = tile & 1;
-            const unsigned nb = pcm_bytes(tile);
-            fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&bars[2 + b], nb * (unsigned)nlive);
-            __syncwarp();
-            if (live && nb) bulk_g2s(t_pcm + b * OQ_SM_PCM + lane * OQ_PROW, row + (size_t)tile * OQ_T, nb, &bars[2 + b]);
-        };
-        unsigned phases = 0u;
-        int pt = a.i0 / OQ_T;                                     // current PCM tile
-        bool pcm_next_issued = false;
-        pcm_load(pt);
-        if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-        MP_WAIT(2 + (pt & 1));
-        int4 pk = make_int4(0, 0, 0, 0);
-        int pk_blk = -1;
+        int pk_blk = a.i0 >> 3;
+        int4 pk = ld_blk(pk_blk), pk_next = ld_blk(pk_blk + 1);
         auto dval_at = [&](int ii) -> double {                    // ((double)*ptr)/32768.0 (:322); ii advances by one per call
-            if ((ii >> 5) != pt) {
-                pt = ii >> 5;
-                MP_WAIT(2 + (pt & 1));
-                pcm_next_issued = false;
-                if ((pt + 1) * OQ_T < a.i1) { pcm_load(pt + 1); pcm_next_issued = true; }
-            }
-            if ((ii >> 3) != pk_blk) {
-                pk_blk = ii >> 3;
-                pk = *reinterpret_cast<const int4 *>(t_pcm + (pt & 1) * OQ_SM_PCM + lane * OQ_PROW + ((ii & (OQ_T - 1)) >> 3) * 16);
-            }
+            if ((ii >> 3) != pk_blk) { pk_blk = ii >> 3; pk = pk_next; pk_next = ld_blk(pk_blk + 1); }
             const int k = ii & 7;
             const int w = (k < 2) ? pk.x : (k < 4) ? pk.y : (k < 6) ? pk.z : pk.w;
             int v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
@@ -304,7 +280,6 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
             { const int t = osc_index(st.ptr); cs_re = cos_t[t]; cs_im = sin_t[t]; }
             dcur = dnxt;
         }
-        if (pcm_next_issued) MP_WAIT(2 + ((pt + 1) & 1));
         LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
         LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
@@ -325,40 +300,36 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
         for (int k = 0; k < d8_len; k++) s_d8[k * 32 + lane] = p.dly8_ring[(size_t)k * cpad + ch];
         __syncthreads();                                       // (1)
         if (nB > 0) {
-            auto ring_rows = [&](long long tile, double *&g_agc, double *&g_e1, double *&g_e2) {
-                const long long s0 = tile * OQ_T;
-                g_agc = p.agc_ring + ((size_t)(s0 % agc_len) + lane) * cpad + (size_t)blockIdx.x * 32;
-                if (ebno_on) {
-                    g_e1 = p.ebno_e1 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * 32;
-                    g_e2 = p.ebno_e2 + ((size_t)(s0 % eb_len) + lane) * cpad + (size_t)blockIdx.x * 32;
-                }
+            // ring layout of this kernel: [cta][slot][32 lanes]; a tile (32 slots) is one contiguous 8 KB block moved by one bulk copy
+            auto ring_tile = [&](double *ring, int len, long long tile) -> double * {
+                return ring + ((size_t)blockIdx.x * len + (size_t)((tile * OQ_T) % len)) * 32;
             };
             const unsigned ring_tx = (ebno_on ? 3u : 1u) * OQ_SM_RING;
             auto ring_load = [&](long long tile) {
-                const int b = (int)(tile & 1);
+                const int b = (int)(tile % MP_NBUF);
                 fence_proxy_async();
-                if (lane == 0) mbar_expect_tx(&bars[b], ring_tx);
                 __syncwarp();
-                double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
-                ring_rows(tile, g_agc, g_e1, g_e2);
-                bulk_g2s(t_agc + (b * OQ_T + lane) * 32, g_agc, 32 * 8, &bars[b]);
-                if (ebno_on) {
-                    bulk_g2s(t_e1 + (b * OQ_T + lane) * 32, g_e1, 32 * 8, &bars[b]);
-                    bulk_g2s(t_e2 + (b * OQ_T + lane) * 32, g_e2, 32 * 8, &bars[b]);
+                if (lane == 0) {
+                    mbar_expect_tx(&bars[b], ring_tx);
+                    bulk_g2s(t_agc + b * OQ_T * 32, ring_tile(p.agc_ring, agc_len, tile), OQ_SM_RING, &bars[b]);
+                    if (ebno_on) {
+                        bulk_g2s(t_e1 + b * OQ_T * 32, ring_tile(p.ebno_e1, eb_len, tile), OQ_SM_RING, &bars[b]);
+                        bulk_g2s(t_e2 + b * OQ_T * 32, ring_tile(p.ebno_e2, eb_len, tile), OQ_SM_RING, &bars[b]);
+                    }
                 }
             };
             auto ring_store = [&](long long tile) {
-                const int b = (int)(tile & 1);
+                const int b = (int)(tile % MP_NBUF);
                 fence_proxy_async();
                 __syncwarp();
-                double *g_agc = nullptr, *g_e1 = nullptr, *g_e2 = nullptr;
-                ring_rows(tile, g_agc, g_e1, g_e2);
-                bulk_s2g(g_agc, t_agc + (b * OQ_T + lane) * 32, 32 * 8);
-                if (ebno_on) {
-                    bulk_s2g(g_e1, t_e1 + (b * OQ_T + lane) * 32, 32 * 8);
-                    bulk_s2g(g_e2, t_e2 + (b * OQ_T + lane) * 32, 32 * 8);
+                if (lane == 0) {
+                    bulk_s2g(ring_tile(p.agc_ring, agc_len, tile), t_agc + b * OQ_T * 32, OQ_SM_RING);
+                    if (ebno_on) {
+                        bulk_s2g(ring_tile(p.ebno_e1, eb_len, tile), t_e1 + b * OQ_T * 32, OQ_SM_RING);
+                        bulk_s2g(ring_tile(p.ebno_e2, eb_len, tile), t_e2 + b * OQ_T * 32, OQ_SM_RING);
+                    }
+                    bulk_commit();
                 }
-                bulk_commit();
             };
             unsigned phases = 0u;
             long long rt = S / OQ_T;                                  // current ring tile
@@ -367,11 +338,11 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
             // all multiples of 32 for the sample rates the reference uses; checked on the host)
             ring_load(rt);
             if ((rt + 1) * OQ_T < S_end) { ring_load(rt + 1); ring_next_issued = true; }
-            MP_WAIT((int)(rt & 1));
+            MP_WAIT((int)(rt % MP_NBUF));
             for (int j = 0; j < nB; j++) {
                 const int sl = j & 1;
                 const int ro = (int)(S & (OQ_T - 1));
-                const int rslot = (((int)(rt & 1)) * OQ_T + ro) * 32 + lane;
+                const int rslot = (((int)(rt % MP_NBUF)) * OQ_T + ro) * 32 + lane;
                 nb_sync(MB_Z + sl);                            // Z_j: matched filter output of this sample
                 const double sre = HAND(sl, 0), sim = HAND(sl, 1);
                 const double dabval = sqrt(sre * sre + sim * sim);                                // :372
@@ -426,17 +397,17 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
                     ring_dirty = false;
                     rt++;
                     if (S < S_end) {
-                        MP_WAIT((int)(rt & 1));
+                        MP_WAIT((int)(rt % MP_NBUF));
                         ring_next_issued = false;
                         if ((rt + 1) * OQ_T < S_end) {
-                            bulk_wait_read_all();
+                            bulk_wait_read_1();
                             ring_load(rt + 1); ring_next_issued = true;
                         }
                     }
                 }
             }
             if (ring_dirty) ring_store(rt);
-            if (ring_next_issued) MP_WAIT((int)((rt + 1) & 1));
+            if (ring_next_issued) MP_WAIT((int)((rt + 1) % MP_NBUF));
             bulk_wait_all();
         }
         for (int k = 0; k < ds_len; k++) p.dsmpl_ring[(size_t)k * cpad + ch] = s_ds[k * 32 + lane];
@@ -489,8 +460,8 @@ int msk_pipe_launch(const DemodParams &p, const SegmentArgs &a, const int16_t *d
     while (floor(dptr) < 0) dptr += (double)size;
     const double w = dptr - floor(dptr);
     const int d8_k = (int)ceil(fd);
-    const size_t smem = (size_t)2 * (p.ntaps + 1) * 32 * 8 + 6 * OQ_SM_RING + (size_t)(p.sps + 1) * 32 * 16 + (size_t)(d8_k + 1) * 32 * 8 +
-                        (size_t)2 * MP_HF * 32 * 8 + 2 * OQ_SM_PCM + 64;
+    const size_t smem = (size_t)2 * (p.ntaps + 1) * 32 * 8 + 3 * MP_NBUF * OQ_SM_RING + (size_t)(p.sps + 1) * 32 * 16 + (size_t)(d8_k + 1) * 32 * 8 +
+                        (size_t)2 * MP_HF * 32 * 8 + 64;
     JB_CUDA(cudaFuncSetAttribute(msk_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     msk_pipe_kernel<<<grid, MP_THREADS, smem, s>>>(p, a, d_pcm, stride, d8_k, w);
     JB_CUDA(cudaGetLastError());

@@ -239,3 +239,30 @@ def msk_pchannel_pcm(n_frames, fc=2000.0, seed=0, ebn0_db=None, fb=1200.0, Fs=48
     env = msk_envelope(bits, fb, Fs)
     pcm = to_passband_int16(env, fc, Fs, ebn0_db, fb, phase=phase, rng=np.random.default_rng(seed + 12345), delay=delay)
     return (pcm, sus) if return_sus else pcm
+
+
+def offset_replicas(pcm, offsets_hz, Fs=48000.0):
+    """BASELINE cfg 4 / cfg 5 replicas of a real recording: replica r = Re{ hilbert(x) e^(j 2 pi df_r n / Fs) }, re-quantised to
+    int16: a frequency offset applied to the REAL signal. numpy version (tests feed the same arrays to
+    the GPU path and to the oracle); bench.py builds the same thing with torch on the device."""
+    x = np.asarray(pcm, dtype=np.float64)
+    n = len(x)
+    X = np.fft.fft(x)
+    h = np.zeros(n)
+    h[0] = 1.0
+    if n % 2 == 0:
+        h[n // 2] = 1.0; h[1:n // 2] = 2.0
+    else:
+        h[1:(n + 1) // 2] = 2.0
+    an = np.fft.ifft(X * h)
+    t = np.arange(n) / Fs
+    out = np.empty((len(offsets_hz), n), dtype=np.int16)
+    for r, df in enumerate(offsets_hz):
+        y = np.real(an * np.exp(2j * np.pi * float(df) * t))
+        out[r] = np.clip(np.round(y), -32768, 32767).astype(np.int16)
+    return out
+
+
+def replica_offsets(r0, r1, span_hz=300.0, seed0=0xB0057):
+    """df_r = U(-span, span) from seed seed0 + r (cfg 4: span 300 Hz)."""
+    return np.array([np.random.default_rng(seed0 + r).uniform(-span_hz, span_hz) for r in range(r0, r1)])

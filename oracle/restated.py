@@ -245,3 +245,16 @@ class OracleCChannel:
     def close(self):
         if self.h:
             lib().jor_cchan_free(self.h); self.h = None
+
+
+def run_demod_job(args):
+    """(kind, kw, pcm, chunk) -> (soft, state, aux0): one restated demodulator over one stream. Module-level so that tests can
+    farm channels out to a multiprocessing pool."""
+    kind, kw, pcm, chunk = args
+    d = OracleDemod(kind, **kw)
+    for a in range(0, len(pcm), chunk):
+        d.write(pcm[a:a + chunk])
+    soft, st = d.take_soft(), d.state()
+    aux = d.take_aux(0) if kind.startswith("burst") else np.zeros(0)
+    d.close()
+    return soft, st, aux

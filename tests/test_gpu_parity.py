@@ -361,6 +361,96 @@ def test_burst_parity_on_reference_recordings(golden, name):
     assert int((np.concatenate(acc[0]) < 0).sum()) >= 2
 
 
+def test_burst_replicas_with_frequency_offsets_cfg4(golden):
+    """BASELINE cfg 4 as specified: 32 replicas of samples/1200bps_burst_sample1.wav, replica r = Re{hilbert(x) e^(j 2 pi df_r n/Fs)},
+    df_r = U(-300, 300) Hz from seed 0xB0057 + r. Every replica's acquisition lands on a different bin of the two 32768-point
+    trident FFTs (burstmskdemodulator.cpp:443-568): start-of-burst markers, estimated carrier, gain and the hard-decided soft
+    bits must equal the oracle's for each of them."""
+    import multiprocessing as mp
+    from jaero_b200 import synth
+    jb = _import()
+    case = golden["burst_msk_1200_a"]
+    base = load_excerpt("burst_msk_1200_a")
+    R = 32
+    offs = synth.replica_offsets(0, R)
+    assert len(set(np.round(offs).astype(int))) == R and np.abs(offs).max() <= 300
+    reps = synth.offset_replicas(base, offs)
+    b = jb.BurstMskBatch(R, **case["kw"])
+    acc = [[] for _ in range(R)]
+    for a in range(0, reps.shape[1], 48000):
+        b.write(reps[:, a:a + 48000])
+        for c, s in enumerate(b.read_softbits()):
+            acc[c].append(s)
+    st = b.status()
+    b.close()
+    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:
+        ref = pool.map(restated.run_demod_job, [("burst_msk", case["kw"], reps[r], 48000) for r in range(R)])
+    carriers = set()
+    for r in range(R):
+        so, os_, eb = ref[r]
+        sg = np.concatenate(acc[r])
+        assert len(so) == len(sg), r
+        assert np.array_equal(np.nonzero(so < 0)[0], np.nonzero(sg < 0)[0]), r          # -1 marker positions
+        assert np.array_equal(so >= 128, sg >= 128), r
+        assert np.abs(so.astype(int) - sg.astype(int)).max(initial=0) <= 1
+        for k in ("mixer2_freq", "vol_gain", "rotator_freq", "mse"):
+            assert abs(st[r][k] - os_[k]) <= STATE_TOL * max(abs(os_[k]), 1e-9), (r, k)
+        for k in ("n_sig_true", "n_sig_false", "cntr", "startstop"):
+            assert st[r][k] == os_[k], (r, k)
+        assert st[r]["n_ebno_emits"] == len(eb)
+        carriers.add(round(st[r]["mixer2_freq"], 1))
+    assert len(carriers) >= R - 2                                  # the offsets really spread the acquisitions over the spectrum
+    assert sum(int((np.concatenate(acc[r]) < 0).sum()) for r in range(R)) >= 2 * R
+
+
+def test_c_channel_replicas_and_two_modes_on_two_streams_cfg5(golden):
+    """BASELINE cfg 5 building blocks: (i) 8400 bps C-channel replicas with frequency offsets (the reference's recording,
+    Hilbert-rotated) through K6 + K1a' + the C-channel layer == the oracle chain; (ii) a 10.5k batch and an 8400 batch of the
+    same process written alternately (as bench.py --workload mix16384 does per rank) give what each gives alone."""
+    from jaero_b200 import synth
+    jb = _import()
+    base = load_excerpt("oqpsk_8400")
+    offs = synth.replica_offsets(0, 3, span_hz=200.0, seed0=0xC8400)
+    reps = synth.offset_replicas(base, offs)
+    kw8 = dict(golden["oqpsk_8400"]["kw"])
+    kwp = dict(golden["oqpsk_10500"]["kw"])
+    pcm_p = load_excerpt("oqpsk_10500")[:reps.shape[1]]
+    pcm_p2 = np.stack([pcm_p, pcm_p[::-1].copy()])
+    ref_p, _ = _run_gpu("oqpsk", pcm_p2, kwp, 4800)
+    b8 = jb.DemodBatch("oqpsk", 3, **kw8); cc = jb.CChannelBatch(3)
+    bp = jb.DemodBatch("oqpsk", 2, **kwp)
+    got8 = [[] for _ in range(3)]; gotp = [[], []]
+    for k, a in enumerate(range(0, reps.shape[1], 4800)):
+        b8.write(reps[:, a:a + 4800]); bp.write(pcm_p2[:, a:a + 4800])
+        cc.process_batch(b8)
+        if k % 10 == 9:
+            cc.tick(b8)
+        for c, fr in enumerate(cc.read_frames()):
+            got8[c].append(fr)
+        if k % 8 == 7:
+            for c, s_ in enumerate(bp.read_softbits()):
+                gotp[c].append(s_)
+    for c, s_ in enumerate(bp.read_softbits()):
+        gotp[c].append(s_)
+    b8.close(); cc.close(); bp.close()
+    for c in range(2):
+        assert np.array_equal(np.concatenate(gotp[c]), ref_p[c])
+    total_ok = 0
+    for c in range(3):
+        o = restated.OracleDemod("oqpsk", **kw8); oc = restated.OracleCChannel()
+        for k, a in enumerate(range(0, reps.shape[1], 4800)):
+            o.write(reps[c, a:a + 4800])
+            oc.process(o.take_soft())
+            o.set_dcd(int(oc.dcd))
+            if k % 10 == 9:
+                oc.update_dcd(); o.set_dcd(int(oc.dcd))
+        su, cok, voice = oc.take_frames()
+        gsu = np.concatenate([g[0] for g in got8[c]]); gok = np.concatenate([g[1] for g in got8[c]]); gv = np.concatenate([g[2] for g in got8[c]])
+        assert gsu.shape == su.shape and np.array_equal(gsu, su) and np.array_equal(gok, cok) and np.array_equal(gv, voice)
+        total_ok += int(cok.sum())
+    assert total_ok >= 20
+
+
 @pytest.mark.parametrize("name", ["burst_msk_1200_a", "burst_msk_1200_b", "burst_oqpsk_10500"])
 def test_rt_channel_packets_on_reference_recordings(golden, name):
     """SURVEY 8(f)2 end to end on the GPU: burst demodulator -> R/T packet layer (unique word, trial de-interleave + Viterbi
