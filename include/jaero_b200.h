@@ -120,6 +120,10 @@ int jaero_batch_set_center_freq(jaero_batch *b, int channel, double hz);  /* Cen
 int jaero_batch_set_afc(jaero_batch *b, int state);
 int jaero_batch_set_sql(jaero_batch *b, int state);
 int jaero_batch_set_cpu_reduce(jaero_batch *b, int state);
+/* connect(demodulator, SIGNAL(SignalStatus(bool)), aerol, SLOT(SignalStatusSlot(bool))) (JAERO/mainwindow.cpp:432,508): with it, a
+ * SignalStatus(false) clears the channel's DCD in the kernel and is handed to the device frame layer (jaero_pchannel_process_batch /
+ * jaero_cchannel_process_batch) as a LostSignal at its soft-bit position. Off by default (host-driven DCD via jaero_batch_set_dcd). */
+int jaero_batch_wire_signal_status(jaero_batch *b, int enabled);
 int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out);
 int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out /* [n_channels] */);
 /* kernel launches issued by this batch so far (for bench.py's gpu_launches) */
@@ -168,6 +172,16 @@ int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b);
 int jaero_pchannel_process_softbits(jaero_pchannel *p, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
 /* AeroL::updateDCD: call once per second of signal (the reference's 1 s QTimer). b may be NULL. */
 int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b);
+/* AeroL::SignalStatusSlot(false) -> AeroL::LostSignal() (JAERO/aerol.h:917-931): cntr = 1e9, DCD countdown = 0, DCD = false and
+ * DataCarrierDetect(false) to the demodulator (b may be NULL: frame layer only). channel -1 = every channel. */
+int jaero_pchannel_lost_signal(jaero_pchannel *p, jaero_batch *b, int channel);
+/* writeData with the AeroL attached the way JAERO/mainwindow.cpp:198-237,432,508 wires the objects (HOST pcm): the stream is cut
+ * in front of every coarse-estimator trigger sample and the frame layer runs at each cut, so FreqOffsetEstimateSlot reads the DCD
+ * that results from exactly the soft bits emitted before that sample, and a SignalStatus(false) reaches LostSignal before any
+ * later soft bit. Exact for OQPSK (DCD is only read in that slot); for MSK the timing-loop gain (mskdemodulator.cpp:387-405)
+ * switches at the next cut, at most one estimator epoch (bbnfft/4 samples) after the reference's emit-granular switch.
+ * Turns jaero_batch_wire_signal_status on for the batch. */
+int jaero_pchannel_write_batch(jaero_pchannel *p, jaero_batch *b, const int16_t *pcm, size_t n_samples, size_t channel_stride);
 /* Limits of one process call: a channel may hand over up to one full soft-bit ring (max(4096, 2*fb+64) values, i.e. 2 s of
  * signal at 10500 bps, 3.4 / 6.8 s at 1200 / 600 bps); more than that, or more signal units than jaero_pchannel_su_capacity()
  * left unread, raises the overflow flag: the next read_sus returns JAERO_E_OVERFLOW and the affected frames are incomplete. */
@@ -243,6 +257,8 @@ void jaero_cchannel_destroy(jaero_cchannel *c);
 int jaero_cchannel_process_batch(jaero_cchannel *c, jaero_batch *b);      /* consume (and drain) an 8400 bps batch's soft bits on the device; DCD fed back */
 int jaero_cchannel_process_softbits(jaero_cchannel *c, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
 int jaero_cchannel_tick(jaero_cchannel *c, jaero_batch *b);               /* the 1 s updateDCD timer; b may be NULL */
+int jaero_cchannel_lost_signal(jaero_cchannel *c, jaero_batch *b, int channel);   /* AeroL::LostSignal, as jaero_pchannel_lost_signal */
+int jaero_cchannel_write_batch(jaero_cchannel *c, jaero_batch *b, const int16_t *pcm, size_t n_samples, size_t channel_stride);   /* as jaero_pchannel_write_batch */
 int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames_per_channel, int32_t *counts);
 int jaero_cchannel_get_stats(jaero_cchannel *c, int32_t *dcd, int64_t *su_total, int64_t *su_ok);   /* any may be NULL */
 int64_t jaero_cchannel_launch_count(const jaero_cchannel *c);

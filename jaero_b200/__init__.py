@@ -55,6 +55,7 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_pchannel_create", "jaero_pchannel_destroy", "jaero_pchannel_process_batch",
            "jaero_pchannel_process_softbits", "jaero_pchannel_tick", "jaero_pchannel_read_sus",
            "jaero_pchannel_discard_sus", "jaero_pchannel_get_stats", "jaero_pchannel_launch_count", "jaero_pchannel_su_capacity",
+           "jaero_pchannel_lost_signal", "jaero_pchannel_write_batch", "jaero_cchannel_lost_signal", "jaero_cchannel_write_batch", "jaero_batch_wire_signal_status",
            "jaero_burst_msk_create", "jaero_burst_oqpsk_create", "jaero_burst_destroy", "jaero_burst_write", "jaero_burst_write_device",
            "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
            "jaero_burst_launch_count",
@@ -111,6 +112,9 @@ def lib():
         L.jaero_pchannel_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_pchannel_launch_count.argtypes = [vp]; L.jaero_pchannel_launch_count.restype = ctypes.c_int64
         L.jaero_pchannel_su_capacity.argtypes = [vp]
+        L.jaero_pchannel_lost_signal.argtypes = [vp, vp, i]; L.jaero_cchannel_lost_signal.argtypes = [vp, vp, i]
+        L.jaero_pchannel_write_batch.argtypes = [vp, vp, vp, sz, sz]; L.jaero_cchannel_write_batch.argtypes = [vp, vp, vp, sz, sz]
+        L.jaero_batch_wire_signal_status.argtypes = [vp, i]
         L.jaero_burst_msk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_oqpsk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_destroy.argtypes = [vp]; L.jaero_burst_destroy.restype = None
@@ -209,6 +213,10 @@ class DemodBatch:
 
     def set_cpu_reduce(self, state):
         _check(lib().jaero_batch_set_cpu_reduce(self.h, int(bool(state))))
+
+    def wire_signal_status(self, on=True):
+        """connect(demodulator, SignalStatus, aerol, SignalStatusSlot) (mainwindow.cpp:432,508)"""
+        _check(lib().jaero_batch_wire_signal_status(self.h, int(bool(on))))
 
     def read_softbits(self):
         out = np.zeros((self.n, self.soft_cap), dtype=np.int16)
@@ -331,6 +339,16 @@ class PChannelBatch:
 
     def tick(self, batch=None):
         _check(lib().jaero_pchannel_tick(self.h, batch.h if batch is not None else None))
+
+    def lost_signal(self, batch=None, channel=-1):
+        """AeroL::SignalStatusSlot(false) -> LostSignal()"""
+        _check(lib().jaero_pchannel_lost_signal(self.h, batch.h if batch is not None else None, channel))
+
+    def write_batch(self, batch, pcm):
+        """writeData with this AeroL attached as the reference wires them (cut at every estimator trigger)"""
+        pcm = np.ascontiguousarray(pcm)
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n
+        _check(lib().jaero_pchannel_write_batch(self.h, batch.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2 if pcm.shape[0] > 1 else pcm.shape[1]))
 
     def read_sus(self):
         """-> per channel: (bytes[n,12], crc_ok[n], index_in_frame[n], frame[n])"""
@@ -534,6 +552,14 @@ class CChannelBatch:
 
     def tick(self, batch=None):
         _check(lib().jaero_cchannel_tick(self.h, batch.h if batch is not None else None))
+
+    def lost_signal(self, batch=None, channel=-1):
+        _check(lib().jaero_cchannel_lost_signal(self.h, batch.h if batch is not None else None, channel))
+
+    def write_batch(self, batch, pcm):
+        pcm = np.ascontiguousarray(pcm)
+        assert pcm.dtype == np.int16 and pcm.ndim == 2 and pcm.shape[0] == self.n
+        _check(lib().jaero_cchannel_write_batch(self.h, batch.h, _p(pcm), pcm.shape[1], pcm.strides[0] // 2 if pcm.shape[0] > 1 else pcm.shape[1]))
 
     def read_frames(self, cap=8):
         """per channel: (su[n,3,12], crc_ok[n,3], voice[n,300], frame[n])"""

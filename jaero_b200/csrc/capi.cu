@@ -280,6 +280,7 @@ __global__ void soft_reset_kernel(DemodParams p)
     for (int k = 0; k < pending; k++) ring[k] = ring[count + k];
     p.soft_total[ch] += count;
     count = 0;
+    p.I[(size_t)I_LOST_N * p.cpad + ch] = 0;             // the frame layer consumed the events before the ring is reset
 }
 __global__ void set_int_kernel(DemodParams p, int idx, int channel, int value)
 {
@@ -428,6 +429,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     }
     rc |= batch_alloc(b, &p.soft, (size_t)n_channels * p.soft_cap);
     rc |= batch_alloc(b, &p.soft_total, (size_t)cp);
+    rc |= batch_alloc(b, &p.lost_pos, (size_t)LOST_CAP * cp);
     rc |= batch_alloc(b, &p.cfe_est_out, (size_t)cp);
     if (rc) return JAERO_E_CUDA;
 
@@ -854,6 +856,13 @@ int jaero_batch_set_sql(jaero_batch *b, int state)
     b->p.sql = state ? 1 : 0;
     return JAERO_OK;
 }
+// connect(demodulator, SignalStatus(bool), aerol, SignalStatusSlot(bool)) (JAERO/mainwindow.cpp:432,508)
+int jaero_batch_wire_signal_status(jaero_batch *b, int enabled)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    b->p.wire_sigstat = enabled ? 1 : 0;
+    return JAERO_OK;
+}
 int jaero_batch_set_cpu_reduce(jaero_batch *b, int state)
 {
     if (!b) { set_error("null handle"); return JAERO_E_ARG; }
@@ -1023,7 +1032,8 @@ int jaero_pchannel_process_batch(jaero_pchannel *p, jaero_batch *b)
     // everything runs on the batch's stream so it is ordered after the demodulator segments
     if (pc_enter(p, b->stream)) return JAERO_E_CUDA;
     if (pchan_process(p->pp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, dp.soft_cap, dcd, p->vit_overlap, p->vit_overlap_len,
-                      p->vit_renorm, p->vit_valid, p->pp.queue, b->stream, &p->launches)) return JAERO_E_CUDA;
+                      p->vit_renorm, p->vit_valid, p->pp.queue, b->stream, &p->launches,
+                      dp.I + (size_t)I_LOST_N * dp.cpad, dp.lost_pos, dp.cpad)) return JAERO_E_CUDA;
     soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
     JB_CUDA(cudaGetLastError());
     p->launches++;
@@ -1057,6 +1067,55 @@ int jaero_pchannel_tick(jaero_pchannel *p, jaero_batch *b)
     if (pchan_tick(p->pp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->stream)) return JAERO_E_CUDA;
     p->launches++;
     return (b && pc_leave(p, b->stream)) ? JAERO_E_CUDA : JAERO_OK;
+}
+// AeroL::SignalStatusSlot(false) -> LostSignal() (aerol.h:920-931): cntr = 1e9, DCD countdown and DCD cleared at once, and
+// DataCarrierDetect(false) reaches the demodulator (b may be NULL: frame layer only). channel -1 = every channel.
+int jaero_pchannel_lost_signal(jaero_pchannel *p, jaero_batch *b, int channel)
+{
+    if (!p || channel >= p->pp.n_channels || (b && b->p.n_channels != p->pp.n_channels)) { set_error("jaero_pchannel_lost_signal: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(p->device));
+    if (b) { if (pc_enter(p, b->stream)) return JAERO_E_CUDA; } else p->own_dirty = true;
+    if (pchan_lost(p->pp, channel, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : p->stream)) return JAERO_E_CUDA;
+    p->launches++;
+    return (b && pc_leave(p, b->stream)) ? JAERO_E_CUDA : JAERO_OK;
+}
+
+// Length of the piece of a write that ends in front of the next coarse-estimator trigger sample (the only points where the OQPSK
+// demodulator reads DCD and where SignalStatus is emitted): the lock-step counters of jaero_batch_write_device, read-only.
+static size_t piece_before_next_trigger(const jaero_batch *b, size_t n)
+{
+    const DemodParams &p = b->p;
+    const int N = p.bbnfft, trig_every = p.cpu_reduce ? N : N / 4;
+    int bb = b->bb_pos, cc = b->coarse_counter;
+    for (size_t i = 0; i < n; i++) {
+        if (cc >= p.Fs || !p.cpu_reduce) {
+            bb++; if (bb >= N) bb = 0;
+            if (bb % trig_every == 0) { if (i > 0) return i; cc = 0; }   // a trigger on the first sample opens this piece
+        }
+        cc++;
+    }
+    return n;
+}
+// writeData with the AeroL attached the way JAERO/mainwindow.cpp:198-237,432,508 wires them: the stream is cut in front of
+// every estimator trigger sample and the frame layer runs at each cut, so that the DCD the demodulator reads in
+// FreqOffsetEstimateSlot, and the LostSignal that follows a SignalStatus(false), see exactly the soft bits emitted before
+// that sample (exact for OQPSK, whose only reads of DCD are in that slot; for MSK the timing-loop gain switches at the next
+// cut, at most one estimator epoch after the reference's emit-granular switch). HOST pcm.
+int jaero_pchannel_write_batch(jaero_pchannel *p, jaero_batch *b, const int16_t *pcm, size_t n, size_t stride)
+{
+    if (!p || !b || !pcm || p->pp.n_channels != b->p.n_channels || p->device != b->device) { set_error("jaero_pchannel_write_batch: bad argument"); return JAERO_E_ARG; }
+    if (stride < n) { set_error("jaero_pchannel_write_batch: channel_stride < n_samples"); return JAERO_E_ARG; }
+    b->p.wire_sigstat = 1;
+    size_t done = 0;
+    while (done < n) {
+        const size_t k = piece_before_next_trigger(b, n - done);   // >= 1: up to, not including, the next trigger sample
+        int rc = jaero_batch_write(b, pcm + done, k, stride);
+        if (rc) return rc;
+        rc = jaero_pchannel_process_batch(p, b);
+        if (rc) return rc;
+        done += k;
+    }
+    return JAERO_OK;
 }
 static int pc_pull_state(jaero_pchannel *p)
 {
@@ -1723,7 +1782,7 @@ int jaero_cchannel_process_batch(jaero_cchannel *c, jaero_batch *b)
     int *dcd = dp.I + (size_t)I_DCD * dp.cpad;
     if (pc_enter(c, b->stream)) return JAERO_E_CUDA;
     if (cchan_process(c->cp, dp.soft, dp.I + (size_t)I_SOFT_COUNT * dp.cpad, (size_t)dp.soft_cap, dcd, c->vit_overlap, c->vit_overlap_len,
-                      c->vit_renorm, c->vit_valid, b->stream, &c->launches)) return JAERO_E_CUDA;
+                      c->vit_renorm, c->vit_valid, b->stream, &c->launches, dp.I + (size_t)I_LOST_N * dp.cpad, dp.lost_pos, dp.cpad)) return JAERO_E_CUDA;
     soft_reset_kernel<<<(dp.n_channels + 127) / 128, 128, 0, b->stream>>>(dp);
     JB_CUDA(cudaGetLastError());
     c->launches++;
@@ -1757,6 +1816,31 @@ int jaero_cchannel_tick(jaero_cchannel *c, jaero_batch *b)
     if (cchan_tick(c->cp, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : c->stream)) return JAERO_E_CUDA;
     c->launches++;
     return (b && pc_leave(c, b->stream)) ? JAERO_E_CUDA : JAERO_OK;
+}
+int jaero_cchannel_lost_signal(jaero_cchannel *c, jaero_batch *b, int channel)     // AeroL::LostSignal, see jaero_pchannel_lost_signal
+{
+    if (!c || channel >= c->cp.n_channels || (b && b->p.n_channels != c->cp.n_channels)) { set_error("jaero_cchannel_lost_signal: bad argument"); return JAERO_E_ARG; }
+    JB_CUDA(cudaSetDevice(c->device));
+    if (b) { if (pc_enter(c, b->stream)) return JAERO_E_CUDA; } else c->own_dirty = true;
+    if (cchan_lost(c->cp, channel, b ? b->p.I + (size_t)I_DCD * b->p.cpad : nullptr, b ? b->stream : c->stream)) return JAERO_E_CUDA;
+    c->launches++;
+    return (b && pc_leave(c, b->stream)) ? JAERO_E_CUDA : JAERO_OK;
+}
+int jaero_cchannel_write_batch(jaero_cchannel *c, jaero_batch *b, const int16_t *pcm, size_t n, size_t stride)   // see jaero_pchannel_write_batch
+{
+    if (!c || !b || !pcm || c->cp.n_channels != b->p.n_channels || c->device != b->device) { set_error("jaero_cchannel_write_batch: bad argument"); return JAERO_E_ARG; }
+    if (stride < n) { set_error("jaero_cchannel_write_batch: channel_stride < n_samples"); return JAERO_E_ARG; }
+    b->p.wire_sigstat = 1;
+    size_t done = 0;
+    while (done < n) {
+        const size_t k = piece_before_next_trigger(b, n - done);
+        int rc = jaero_batch_write(b, pcm + done, k, stride);
+        if (rc) return rc;
+        rc = jaero_cchannel_process_batch(c, b);
+        if (rc) return rc;
+        done += k;
+    }
+    return JAERO_OK;
 }
 int jaero_cchannel_read_frames(jaero_cchannel *c, uint8_t *out, int cap_frames, int32_t *counts)
 {

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include "common.cuh"
 #include "viterbi.cuh"
+#include "demod.cuh"
 #include "cchannel.cuh"
 
 namespace jb {
@@ -43,7 +44,8 @@ __device__ __forceinline__ int cc_uw(unsigned long long &b1, unsigned long long 
 }
 
 __global__ void __launch_bounds__(64)
-cchan_frame_kernel(CChanParams cp, const int16_t *__restrict__ soft, const int *__restrict__ soft_count, size_t soft_stride)
+cchan_frame_kernel(CChanParams cp, const int16_t *__restrict__ soft, const int *__restrict__ soft_count, size_t soft_stride,
+                   const int *__restrict__ lost_n /* may be null */, const int *__restrict__ lost_pos, size_t lost_pitch)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= cp.n_channels) return;
@@ -59,7 +61,12 @@ cchan_frame_kernel(CChanParams cp, const int16_t *__restrict__ soft, const int *
         s.carry_slot = 0;
     }
     s.frames_ready = 0;
+    // AeroL::LostSignal (aerol.h:925-931) at the recorded SignalStatus(false) positions
+    int nev = lost_n ? min(lost_n[ch], LOST_CAP) : 0, ev = 0;
+    if (lost_n && lost_n[ch] > LOST_CAP) s.overflow = 1;
+    int next_ev = nev ? lost_pos[ch] : 0x7fffffff;
     for (int i = 0; i < n; i++) {
+        while (i >= next_ev) { s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0; ev++; next_ev = ev < nev ? lost_pos[(size_t)ev * lost_pitch + ch] : 0x7fffffff; }
         const int v = bits[i];
         s.bits_seen++;
         int bit = (((unsigned char)v) >= 128) ? 1 : 0;
@@ -88,6 +95,7 @@ cchan_frame_kernel(CChanParams cp, const int16_t *__restrict__ soft, const int *
             }
         }
     }
+    if (ev < nev) { s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0; }
     s.carry_slot = (s.frames_ready > 0 && s.frames_ready < CC_QUEUE) ? s.frames_ready : 0;
     cp.state[ch] = s;
     cp.ready[ch] = s.frames_ready;
@@ -206,11 +214,26 @@ int cchan_out_reset(const CChanParams &cp, cudaStream_t st)
     JB_CUDA(cudaGetLastError());
     return 0;
 }
+__global__ void cchan_lost_kernel(CChanParams cp, int channel, int *__restrict__ demod_dcd)     // AeroL::LostSignal
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= cp.n_channels || (channel >= 0 && channel != ch)) return;
+    CChanState &s = cp.state[ch];
+    s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0;
+    if (demod_dcd) demod_dcd[ch] = 0;
+}
+int cchan_lost(const CChanParams &cp, int channel, int *demod_dcd, cudaStream_t st)
+{
+    cchan_lost_kernel<<<(cp.n_channels + 127) / 128, 128, 0, st>>>(cp, channel, demod_dcd);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
 int cchan_process(const CChanParams &cp, const int16_t *d_soft, const int *d_soft_count, size_t soft_stride, int *demod_dcd,
-                  uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, cudaStream_t st, long long *launches)
+                  uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, cudaStream_t st, long long *launches,
+                  const int *lost_n, const int *lost_pos, size_t lost_pitch)
 {
     const int grid = (cp.n_channels + 63) / 64;
-    cchan_frame_kernel<<<grid, 64, 0, st>>>(cp, d_soft, d_soft_count, soft_stride);
+    cchan_frame_kernel<<<grid, 64, 0, st>>>(cp, d_soft, d_soft_count, soft_stride, lost_n, lost_pos, lost_pitch);
     JB_CUDA(cudaGetLastError());
     (*launches)++;
     for (int q = 0; q < CC_QUEUE; q++) {

@@ -36,6 +36,8 @@ int cchan_init(const CChanParams &cp, cudaStream_t st);
 int cchan_tick(const CChanParams &cp, int *demod_dcd, cudaStream_t st);
 int cchan_out_reset(const CChanParams &cp, cudaStream_t st);
 int cchan_process(const CChanParams &cp, const int16_t *d_soft, const int *d_soft_count, size_t soft_stride, int *demod_dcd,
-                  uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, cudaStream_t st, long long *launches);
+                  uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, cudaStream_t st, long long *launches,
+                  const int *lost_n = nullptr, const int *lost_pos = nullptr, size_t lost_pitch = 0);
+int cchan_lost(const CChanParams &cp, int channel, int *demod_dcd, cudaStream_t st);
 
 } // namespace jb

@@ -13,6 +13,7 @@
 
 namespace jb {
 
+static const int LOST_CAP = 64;           // SignalStatus(false) events a channel can record between two drains of its soft ring
 static const int MAX_TAPS = 160;          // MSK 600 bps @48 kHz: 2*SPS = 160 (mskdemodulator.cpp:164)
 
 // ---- per-channel scalar state, doubles: D[idx][channel]
@@ -46,6 +47,7 @@ enum IIdx {
     I_SOFT_COUNT, I_SOFT_PENDING, I_SOFT_OVERFLOW,
     I_SIG_TRUE, I_SIG_FALSE, I_EMPTYING,                // SignalStatus counters, CoarseFreqEstimate::emptyingcountdown
     I_ZERO_BB,                                          // request: clear the baseband ring (oqpskdemodulator.cpp:667)
+    I_LOST_N,                                           // SignalStatus(false) events recorded since the soft ring was last drained
     I_COUNT
 };
 
@@ -77,6 +79,11 @@ struct DemodParams {
     double *dly8_ring;                // MSK delayt8 (integer delay SPS/2) [(sps/2+1)][cpad]
     int16_t *soft;                    // [ch][soft_cap]
     long long *soft_total;            // [cpad] soft values drained from the ring so far (jaero_status.softbits)
+    // connect(demodulator, SignalStatus(bool), aerol, SignalStatusSlot(bool)) (JAERO/mainwindow.cpp:432,508): when wired, a
+    // SignalStatus(false) at the end of FreqOffsetEstimateSlot is AeroL::LostSignal (aerol.h:921-931), which answers with
+    // DataCarrierDetect(false) at once: the kernel clears the channel's DCD and records the soft-bit position of the event for
+    // the device frame layer (lost_pos[k][ch] = soft values emitted before event k).
+    int wire_sigstat; int *lost_pos;  // [LOST_CAP][cpad]
     const double *sin_t, *cos_t;      // the reference's 19999-entry tables (DSP.cpp:19-20), built on the host
     double *cfe_est_out;              // [ch] value CoarseFreqEstimate would emit this epoch
     const double2 *xpre;              // 8400 bps: K6 output of the current call [ch][xstride] (null otherwise)

@@ -74,7 +74,7 @@ msk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, c
                 for (int j = 0; j < p.bb_len; j++) rowz[j] = make_double2(0.0, 0.0);    // :507
             }
         } else countdown = 4;
-        if (mse > p.signalthreshold) sig_false++; else sig_true++;                       // :516-517
+        if (mse > p.signalthreshold) { sig_false++; if (p.wire_sigstat) { { const int ln_ = LI(I_LOST_N); if (ln_ < LOST_CAP) p.lost_pos[(size_t)ln_ * p.cpad + ch] = LI(I_SOFT_COUNT); LI(I_LOST_N) = ln_ + 1; LI(I_DCD) = 0; } dcd = 0; } } else sig_true++;                       // :516-517
     }
 
     const int agc_len = p.agc_len, eb_len = p.ebno_len;

@@ -86,7 +86,7 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
     // ======================================================================================= warp K: carrier loop
     if (warp == 3) {
         Osc m2 = {LD(D_M2_PTR), LD(D_M2_STEP), LD(D_M2_FREQ), LD(D_M2_LAST)};
-        const int dcd = LI(I_DCD);
+        int dcd = LI(I_DCD);
         // ---- FreqOffsetEstimateSlot (mskdemodulator.cpp:490-519)
         if (a.apply_cfe) {
             Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
@@ -107,7 +107,8 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
                     LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;                        // warp T reloads mixer_center after the barrier
                 }
             } else countdown = 4;
-            if (mse > p.signalthreshold) LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;   // :516-517
+            if (mse > p.signalthreshold) { LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; if (p.wire_sigstat) { { const int ln_ = LI(I_LOST_N); if (ln_ < LOST_CAP) p.lost_pos[(size_t)ln_ * cpad + ch] = LI(I_SOFT_COUNT); LI(I_LOST_N) = ln_ + 1; LI(I_DCD) = 0; } dcd = 0; } }   // :516-517
+            else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;
             LI(I_COUNTDOWN) = countdown;
         }
         __syncthreads();                                       // (1) slot done, FIR ring resident
@@ -222,7 +223,6 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
     // ======================================================================================= warp T: input + symbol-timing PLL
     else if (warp == 2) {
         Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
-        const int dcd = LI(I_DCD);
         const int16_t *row = pcm + (size_t)ch * stride;
         // PCM: vector loads of the lane's own channel row, 8 samples at a time, one block ahead of use (see oqpsk_pipe.cu)
         const int4 *row4 = reinterpret_cast<const int4 *>(row);
@@ -241,7 +241,8 @@ msk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, cons
         };
         double dcur = dval_at(a.i0);
         HAND(0, 14) = dcur;
-        __syncthreads();                                       // (1) the slot may have re-centred mixer_center
+        __syncthreads();                                       // (1) the slot may have re-centred mixer_center or (wired) cleared DCD
+        const int dcd = LI(I_DCD);
         Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
         int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
         double2 *bb_row = p.bb + (size_t)ch * p.bb_len;

@@ -134,7 +134,8 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                     LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq;         // warp F reloads mixer_center after the barrier
                 }
             } else countdown = 4;
-            if (mse > p.signalthreshold) LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;   // :674-675
+            if (mse > p.signalthreshold) { LI(I_SIG_FALSE) = LI(I_SIG_FALSE) + 1; if (p.wire_sigstat) { const int ln_ = LI(I_LOST_N); if (ln_ < LOST_CAP) p.lost_pos[(size_t)ln_ * cpad + ch] = LI(I_SOFT_COUNT); LI(I_LOST_N) = ln_ + 1; LI(I_DCD) = 0; } }   // :674-675
+            else LI(I_SIG_TRUE) = LI(I_SIG_TRUE) + 1;
             LI(I_COUNTDOWN) = countdown; LI(I_COUNTDOWN2) = countdown2;
         }
         __syncthreads();                                       // (1) slot done, FIR window resident

@@ -49,7 +49,8 @@ __device__ __forceinline__ int uw_exact(unsigned &sr, int bit)
 
 __global__ void __launch_bounds__(64)
 pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *__restrict__ soft_count, int soft_cap,
-                   int *__restrict__ demod_dcd /* may be null */)
+                   int *__restrict__ demod_dcd /* may be null */, const int *__restrict__ lost_n /* may be null */,
+                   const int *__restrict__ lost_pos, size_t lost_pitch)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= pp.n_channels) return;
@@ -63,7 +64,12 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     const bool vec_ok = ((((size_t)soft_cap * 2) & 15) == 0) && ((((uintptr_t)soft) & 15) == 0);
     int4 grp = make_int4(0, 0, 0, 0), grp_next = make_int4(0, 0, 0, 0);
     if (vec_ok && n > 0) { grp = *reinterpret_cast<const int4 *>(bits); if (n > 8) grp_next = *reinterpret_cast<const int4 *>(bits + 8); }
+    // AeroL::LostSignal (aerol.h:925-931) at the soft-bit positions the demodulator recorded its SignalStatus(false) events
+    int nev = lost_n ? min(lost_n[ch], LOST_CAP) : 0, ev = 0;
+    if (lost_n && lost_n[ch] > LOST_CAP) s.queue_overflow = 1;
+    int next_ev = nev ? lost_pos[ch] : 0x7fffffff;
     for (int i = 0; i < n; i++) {
+        while (i >= next_ev) { s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0; ev++; next_ev = ev < nev ? lost_pos[(size_t)ev * lost_pitch + ch] : 0x7fffffff; }
         int v;
         if (vec_ok) {
             const int k = i & 7;
@@ -140,6 +146,7 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
         }
         if (s.cntr + 1 == pp.total_number_of_bits) { s.scr_pos = 0; s.cntr = -1; }   // :2013-2016
     }
+    if (ev < nev) { s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0; }     // events after the last soft bit
     s.bits_seen += n;
     // carry the partially filled block of slot `blocks_ready` back to slot 0 for the next call
     if (s.blocks_ready > 0 && s.blocks_ready < QD) s.carry_slot = s.blocks_ready; else s.carry_slot = 0;
@@ -262,12 +269,28 @@ int pchan_tick(const PChanParams &pp, int *demod_dcd, cudaStream_t st)
     return 0;
 }
 
+// AeroL::LostSignal for one channel (>= 0) or all (-1)
+__global__ void pchan_lost_kernel(PChanParams pp, int channel, int *__restrict__ demod_dcd)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= pp.n_channels || (channel >= 0 && channel != ch)) return;
+    PChanState &s = pp.state[ch];
+    s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0;
+    if (demod_dcd) demod_dcd[ch] = 0;
+}
+int pchan_lost(const PChanParams &pp, int channel, int *demod_dcd, cudaStream_t st)
+{
+    pchan_lost_kernel<<<(pp.n_channels + 127) / 128, 128, 0, st>>>(pp, channel, demod_dcd);
+    JB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int pchan_process(const PChanParams &pp, const int16_t *d_soft, const int *d_soft_count, int soft_cap, int *demod_dcd,
                   uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, int max_queue, cudaStream_t st,
-                  long long *launches)
+                  long long *launches, const int *lost_n, const int *lost_pos, size_t lost_pitch)
 {
     const int grid = (pp.n_channels + 63) / 64;
-    pchan_frame_kernel<<<grid, 64, 0, st>>>(pp, d_soft, d_soft_count, soft_cap, demod_dcd);
+    pchan_frame_kernel<<<grid, 64, 0, st>>>(pp, d_soft, d_soft_count, soft_cap, demod_dcd, lost_n, lost_pos, lost_pitch);
     JB_CUDA(cudaGetLastError());
     (*launches)++;
     for (int q = 0; q < max_queue; q++) {

@@ -40,5 +40,6 @@ int pchan_init(const PChanParams &pp, cudaStream_t st);
 int pchan_tick(const PChanParams &pp, int *demod_dcd, cudaStream_t st);
 int pchan_process(const PChanParams &pp, const int16_t *d_soft, const int *d_soft_count, int soft_cap, int *demod_dcd,
                   uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, int max_queue, cudaStream_t st,
-                  long long *launches);
+                  long long *launches, const int *lost_n = nullptr, const int *lost_pos = nullptr, size_t lost_pitch = 0);
+int pchan_lost(const PChanParams &pp, int channel, int *demod_dcd, cudaStream_t st);
 }

@@ -48,6 +48,7 @@ def lib():
         L.jor_pchan_new.restype = vp; L.jor_pchan_new.argtypes = [i]
         L.jor_pchan_process.argtypes = [vp, vp, i]; L.jor_pchan_update_dcd.argtypes = [vp]
         L.jor_pchan_dcd.argtypes = [vp]
+        L.jor_pchan_lost_signal.argtypes = [vp]; L.jor_wire_pchan.argtypes = [vp, vp]
         L.jor_pchan_su_count.restype = l; L.jor_pchan_su_count.argtypes = [vp]
         L.jor_pchan_su_take.restype = l; L.jor_pchan_su_take.argtypes = [vp, vp, vp, vp, l]
         L.jor_pchan_free.argtypes = [vp]
@@ -155,6 +156,15 @@ class OraclePChannel:
 
     def update_dcd(self):
         lib().jor_pchan_update_dcd(self.h)
+
+    def lost_signal(self):
+        """AeroL::LostSignal (aerol.h:925-931)"""
+        lib().jor_pchan_lost_signal(self.h)
+
+    def wire(self, demod):
+        """Connect a continuous OracleDemod to this AeroL as JAERO/mainwindow.cpp does (direct connections): soft-bit vectors are
+        decoded inside write(), DCD and LostSignal feed back at once. take_soft() on the demodulator still returns what was emitted."""
+        lib().jor_wire_pchan(demod.h, self.h)
 
     @property
     def dcd(self):

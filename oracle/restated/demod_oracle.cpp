@@ -241,7 +241,8 @@ void OqpskDemodOracle::writeData(const int16_t *ptr, long len)
                     RxDataBits.push_back((short)(unsigned char)ibit);
                     if (RxDataBits.size() >= 32) {                                              // :583-592
                         if (!s.sql || mse < s.signalthreshold || lastmse < s.signalthreshold)
-                            soft_out.insert(soft_out.end(), RxDataBits.begin(), RxDataBits.end());
+                        {   soft_out.insert(soft_out.end(), RxDataBits.begin(), RxDataBits.end());
+                            if (on_emit) on_emit(hook_ctx, RxDataBits.data(), (int)RxDataBits.size()); }
                         RxDataBits.clear();
                     }
                 }
@@ -274,6 +275,7 @@ void OqpskDemodOracle::FreqOffsetEstimateSlot(double est)
         }
     } else countdown = 4;
     if (mse > s.signalthreshold) n_sig_false++; else n_sig_true++;                              // :674-675
+    if (on_sigstat) on_sigstat(hook_ctx, !(mse > s.signalthreshold));
 }
 
 // ------------------------------------------------------------------ MSK
@@ -377,6 +379,7 @@ void MskDemodOracle::writeData(const int16_t *ptr, long len)
             RxDataBits.push_back((short)(unsigned char)ibit);
             if (RxDataBits.size() >= 12) {                                                      // :472-476
                 soft_out.insert(soft_out.end(), RxDataBits.begin(), RxDataBits.end());
+                if (on_emit) on_emit(hook_ctx, RxDataBits.data(), (int)RxDataBits.size());
                 RxDataBits.clear();
             }
         }
@@ -400,5 +403,6 @@ void MskDemodOracle::FreqOffsetEstimateSlot(double est)
         }
     } else countdown = 4;
     if (mse > s.signalthreshold) n_sig_false++; else n_sig_true++;                              // :516-517
+    if (on_sigstat) on_sigstat(hook_ctx, !(mse > s.signalthreshold));
 }
 } // namespace jor

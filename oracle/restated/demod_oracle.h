@@ -36,6 +36,9 @@ struct OqpskDemodOracle                                // oqpskdemodulator.cpp
     JFastFir fir_pre; WaveTable mixer_fir_pre;         // 8400 bps pre-filter (:112-115,280-283)
     // observables
     std::vector<short> soft_out; std::vector<double> cfe_log; long n_sig_true, n_sig_false; long nsamples;
+    // optional direct connections, as JAERO/mainwindow.cpp:198-237,432,508 makes them: processDemodulatedSoftBits(vector) and
+    // SignalStatus(bool) are delivered synchronously, inside writeData
+    void (*on_emit)(void *ctx, const short *bits, int n) = nullptr; void (*on_sigstat)(void *ctx, bool ok) = nullptr; void *hook_ctx = nullptr;
     explicit OqpskDemodOracle(const DemodSettings &);
     void writeData(const int16_t *pcm, long n);        // :334-627
     void FreqOffsetEstimateSlot(double est);           // :629-677
@@ -52,6 +55,7 @@ struct MskDemodOracle                                  // mskdemodulator.cpp
     int countdown;                                     // static at mskdemodulator.cpp:493
     std::vector<short> RxDataBits;
     std::vector<short> soft_out; std::vector<double> cfe_log; long n_sig_true, n_sig_false; long nsamples;
+    void (*on_emit)(void *ctx, const short *bits, int n) = nullptr; void (*on_sigstat)(void *ctx, bool ok) = nullptr; void *hook_ctx = nullptr;
     explicit MskDemodOracle(const DemodSettings &);
     void writeData(const int16_t *pcm, long n);        // :313-488
     void FreqOffsetEstimateSlot(double est);           // :490-519

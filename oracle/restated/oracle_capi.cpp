@@ -113,6 +113,20 @@ int jor_conv_encode(const uint8_t *msg, int msg_len, uint8_t *enc)
   int r = (int)correct_convolutional_encode(c, msg, msg_len, enc); correct_convolutional_destroy(c); return r; }
 
 void *jor_pchan_new(int fb) { return new PChannelOracle(fb); }
+void jor_pchan_lost_signal(void *p) { ((PChannelOracle *)p)->lostSignal(); }
+// The reference's direct connections between one continuous demodulator and one AeroL (JAERO/mainwindow.cpp:198-199,234,237,432,508):
+// every emitted soft-bit vector is decoded at once and the resulting DataCarrierDetect state is back in the demodulator before its
+// next sample; SignalStatus(false) is AeroL::LostSignal.
+struct WireCtx { OrHandle *d; PChannelOracle *p; };
+static void wire_set_dcd(WireCtx *w) { if (w->d->kind == 0) w->d->oq->DCDstatSlot(w->p->datacd); else w->d->msk->DCDstatSlot(w->p->datacd); }
+static void wire_emit(void *ctx, const short *bits, int n) { WireCtx *w = (WireCtx *)ctx; w->p->process(bits, n); wire_set_dcd(w); }
+static void wire_sigstat(void *ctx, bool ok) { WireCtx *w = (WireCtx *)ctx; if (!ok) { w->p->lostSignal(); wire_set_dcd(w); } }
+void jor_wire_pchan(void *hv, void *pv)
+{
+    OrHandle *h = (OrHandle *)hv; WireCtx *w = new WireCtx{h, (PChannelOracle *)pv};   // lives as long as the test process
+    if (h->kind == 0) { h->oq->on_emit = wire_emit; h->oq->on_sigstat = wire_sigstat; h->oq->hook_ctx = w; }
+    else if (h->kind == 1) { h->msk->on_emit = wire_emit; h->msk->on_sigstat = wire_sigstat; h->msk->hook_ctx = w; }
+}
 void jor_pchan_process(void *p, const short *soft, int n) { ((PChannelOracle *)p)->process(soft, n); }
 void jor_pchan_update_dcd(void *p) { ((PChannelOracle *)p)->updateDCD(); }
 int jor_pchan_dcd(void *p) { return ((PChannelOracle *)p)->datacd ? 1 : 0; }

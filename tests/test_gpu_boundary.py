@@ -185,3 +185,100 @@ def test_ingest_router_refuses_a_message_that_does_not_fit():
     assert r.message(b"CHAN1", rate, x) == 1
     assert r.available == 600                                    # channel 0 still holds exactly the first message
     r.close()
+
+
+def _gap_stream(name, secs_a, secs_gap, secs_b, seed=3):
+    """recording, then low-level noise (the carrier disappears), then the recording again"""
+    pcm = load_excerpt(name)
+    rng = np.random.default_rng(seed)
+    gap = np.round(rng.normal(0, 300.0, size=48000 * secs_gap)).astype(np.int16)
+    return np.concatenate([pcm[:48000 * secs_a], gap, pcm[48000 * secs_a:48000 * (secs_a + secs_b)]])
+
+
+def test_write_batch_is_the_reference_wiring_oqpsk(golden):
+    """jaero_pchannel_write_batch = the demodulator and the AeroL connected as JAERO/mainwindow.cpp:198-237,432,508 connects
+    them (direct connections): DCD read by FreqOffsetEstimateSlot reflects every soft bit emitted before that sample, and a
+    SignalStatus(false) is a LostSignal before any later soft bit. Oracle: the restated demodulator with the restated AeroL
+    hooked into its emits (OraclePChannel.wire). A carrier drop in the middle exercises LostSignal and the re-acquisition."""
+    jb = _import()
+    kw = dict(golden["oqpsk_10500"]["kw"])
+    x = _gap_stream("oqpsk_10500", 5, 3, 5)
+    pcm2 = np.stack([x, (x.astype(np.int32) * 2 // 3).astype(np.int16)])
+    b = jb.DemodBatch("oqpsk", 2, **kw)
+    pc = jb.PChannelBatch(2, 10500)
+    got = [[], []]
+    sizes = [4800, 7000, 1234, 48000, 10000]
+    a = 0; k = 0
+    while a < pcm2.shape[1]:
+        n = min(sizes[k % len(sizes)], pcm2.shape[1] - a)
+        pc.write_batch(b, pcm2[:, a:a + n]); a += n; k += 1
+        if a % 48000 < n:                                       # the 1 s DCD timer
+            pc.tick(b)
+        for c, r in enumerate(pc.read_sus()):
+            got[c].append(r)
+    st = b.status(); dcd, tot, okc = pc.stats()
+    b.close(); pc.close()
+    for c in range(2):
+        od = restated.OracleDemod("oqpsk", **kw); op = restated.OraclePChannel(10500); op.wire(od)
+        a = 0; k = 0
+        while a < pcm2.shape[1]:
+            n = min(sizes[k % len(sizes)], pcm2.shape[1] - a)
+            od.write(pcm2[c, a:a + n]); a += n; k += 1
+            if a % 48000 < n:
+                op.update_dcd(); od.set_dcd(op.dcd)
+        rb, rok, _ = op.take_sus()
+        gb = np.concatenate([g[0] for g in got[c]]); gok = np.concatenate([g[1] for g in got[c]])
+        assert np.array_equal(gb, rb) and np.array_equal(gok, rok) and rok.sum() > 100
+        o = od.state()
+        assert st[c]["n_sig_false"] == o["n_sig_false"] and st[c]["n_sig_true"] == o["n_sig_true"] and o["n_sig_false"] >= 5
+        assert dcd[c] == int(op.dcd)
+        for key in ("mixer2_freq", "mse", "agc"):
+            assert abs(st[c][key] - o[key]) <= 1e-6 * max(abs(o[key]), 1e-9), key
+
+
+def test_lost_signal_entry_point(golden):
+    """jaero_pchannel_lost_signal == AeroL::LostSignal (aerol.h:921-931): frame counter parked, DCD and its countdown cleared,
+    the demodulator told at once; decoding resumes at the next unique word exactly as the oracle's does."""
+    jb = _import()
+    kw = dict(golden["oqpsk_10500"]["kw"])
+    pcm = load_excerpt("oqpsk_10500")[:48000 * 9]
+    pcm2 = np.stack([pcm, pcm])
+    b = jb.DemodBatch("oqpsk", 2, **kw); pc = jb.PChannelBatch(2, 10500)
+    od = restated.OracleDemod("oqpsk", **kw); op = restated.OraclePChannel(10500)
+    got = []
+    for k, a in enumerate(range(0, pcm2.shape[1], 4800)):
+        b.write(pcm2[:, a:a + 4800]); pc.process_batch(b)
+        od.set_dcd(op.dcd); od.write(pcm[a:a + 4800]); op.process(od.take_soft())
+        if k == 50:
+            pc.lost_signal(b, channel=0)                        # channel 0 only; channel 1 carries on
+            op.lost_signal(); od.set_dcd(op.dcd)
+            assert pc.stats()[0].tolist() == [0, 1] and b.status()[0]["dcd"] == 0 and b.status()[1]["dcd"] == 1
+        got.append(pc.read_sus())
+    rb, rok, _ = op.take_sus()
+    g0 = np.concatenate([g[0][0] for g in got]); ok0 = np.concatenate([g[0][1] for g in got])
+    g1 = np.concatenate([g[1][0] for g in got])
+    assert np.array_equal(g0, rb) and np.array_equal(ok0, rok)
+    assert len(g1) > len(g0)                                    # the frame in flight on channel 0 was dropped, as in the reference
+    b.close(); pc.close()
+
+
+def test_write_batch_msk_signal_units(golden):
+    """The same wiring for MSK 1200 (cfg 2 signal). The MSK timing loop reads DCD every sample (mskdemodulator.cpp:387-405), the
+    device path switches its gain at the next estimator trigger (<= 2048 samples later than the reference's emit-granular
+    switch): decoded signal units and CRC flags still have to come out identical."""
+    jb = _import()
+    from jaero_b200 import synth
+    kw = dict(fb=1200, freq_center=2000.0, lockingbw=1800, fft_power=13, signalthreshold=0.5, afc=False)
+    pcm = np.tile(synth.msk_pchannel_pcm(4, fc=2013.0, seed=41, ebn0_db=9.0, fb=1200.0, phase=0.7, delay=9), 4)
+    b = jb.DemodBatch("msk", 1, **kw); pc = jb.PChannelBatch(1, 1200)
+    od = restated.OracleDemod("msk", **kw); op = restated.OraclePChannel(1200); op.wire(od)
+    got = []
+    for k, a in enumerate(range(0, len(pcm), 9600)):
+        pc.write_batch(b, pcm[None, a:a + 9600]); od.write(pcm[a:a + 9600])
+        if k % 5 == 4:
+            pc.tick(b); op.update_dcd(); od.set_dcd(op.dcd)
+        got.append(pc.read_sus()[0])
+    rb, rok, _ = op.take_sus()
+    gb = np.concatenate([g[0] for g in got]); gok = np.concatenate([g[1] for g in got])
+    assert np.array_equal(gok, rok) and np.array_equal(gb[gok.astype(bool)], rb[rok.astype(bool)]) and rok.sum() >= 60
+    b.close(); pc.close()
