@@ -82,6 +82,8 @@ typedef struct jaero_status {
     int64_t softbits;     /* soft values emitted so far (drained + still in the ring; burst markers included) */
     int32_t dcd;
     int32_t reserved;
+    double peak_volume;   /* PeakVolume (oqpskdemodulator.cpp:393-405): max |input sample| / 32768 since the previous status read */
+    double scatter[4];    /* ScatterPoints, decimated: the two most recent constellation points (re, im, re, im) as pointbuff holds them */
 } jaero_status;
 
 typedef struct jaero_batch jaero_batch;
@@ -237,6 +239,11 @@ int jaero_rt_create(double fb, int n_channels, int device_ordinal, jaero_rt **ou
 void jaero_rt_destroy(jaero_rt *r);
 /* host soft bits: soft[ch * cap + i], counts[ch] values per channel (AeroL::processDemodulatedSoftBits) */
 int jaero_rt_process_softbits(jaero_rt *r, const int16_t *soft, size_t cap_per_channel, const int32_t *counts);
+/* Opt-in vector semantics: AeroL::Decode returns in the middle of a soft-bit vector when the burst time-out fires
+ * (JAERO/aerol.cpp:2018-2027) and the rest of that vector is lost. With it on, jaero_rt_process_burst drops the rest of the
+ * demodulator's emit (12 / 32 values, +1 with the start marker) and jaero_rt_process_softbits treats each call as one vector.
+ * Off (default): nothing is dropped. */
+int jaero_rt_set_vector_mode(jaero_rt *r, int enabled);
 /* consume (and drain) the soft bits a burst demodulator batch has produced, entirely on the device */
 int jaero_rt_process_burst(jaero_rt *r, jaero_burst *b);
 int jaero_rt_tick(jaero_rt *r);                                                          /* the 1 s updateDCD timer */

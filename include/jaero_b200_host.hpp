@@ -17,6 +17,7 @@
 #include <cstring>
 #include <functional>
 #include <string>
+#include <complex>
 #include <vector>
 
 #include "jaero_b200.h"
@@ -39,6 +40,8 @@ struct ContinuousApi {
     static int set_sql(handle *h, bool s) { return jaero_batch_set_sql(h, s ? 1 : 0); }
     static int set_cpu_reduce(handle *h, bool s) { return jaero_batch_set_cpu_reduce(h, s ? 1 : 0); }
     static void destroy(handle *h) { jaero_batch_destroy(h); }
+    static bool telemetry(const status &s, double &peak, std::vector<std::complex<double> > &pts)
+    { peak = s.peak_volume; pts.clear(); pts.push_back(std::complex<double>(s.scatter[2], s.scatter[3])); pts.push_back(std::complex<double>(s.scatter[0], s.scatter[1])); return true; }
 };
 struct BurstApi {
     typedef jaero_burst handle;
@@ -51,6 +54,7 @@ struct BurstApi {
     static int set_sql(handle *h, bool s) { return jaero_burst_set_sql(h, s ? 1 : 0); }
     static int set_cpu_reduce(handle *, bool) { return JAERO_OK; }   // the burst classes never read cpuReduce on this path
     static void destroy(handle *h) { jaero_burst_destroy(h); }
+    static bool telemetry(const status &, double &, std::vector<std::complex<double> > &) { return false; }
 };
 
 template <class Api> class DemodulatorBase
@@ -65,6 +69,12 @@ public:
     std::function<void(const std::string &str)> WarningTextSignal;
     std::function<void(double Fs)> SampleRateChanged;
     std::function<void(double fb, bool burstmode)> BitRateChanged;
+    // GUI telemetry of the reference (oqpskdemodulator.cpp:403-404,549; mskdemodulator.cpp:343-344,443). The reference paces these
+    // with a wall-clock timer (150 ms); here they fire once per writeData. PeakVolume = max |sample| since the previous emit,
+    // ScatterPoints = the most recent constellation points (decimated pointbuff), OrgOverlapedBuffer = the last 2^13 input samples.
+    std::function<void(double maxval)> PeakVolume;
+    std::function<void(const std::vector<std::complex<double> > &points)> ScatterPoints;
+    std::function<void(const std::vector<double> &buffer)> OrgOverlapedBuffer;
 
     void setAFC(bool state) { afc = state; if (h) check(Api::set_afc(h, state)); }
     void setSQL(bool state) { sql = state; if (h) check(Api::set_sql(h, state)); }
@@ -83,6 +93,10 @@ public:
         const int16_t *pcm = reinterpret_cast<const int16_t *>(data);
         std::vector<int16_t> aligned;
         if (reinterpret_cast<uintptr_t>(data) % sizeof(int16_t)) { aligned.resize(n); memcpy(aligned.data(), data, n * sizeof(int16_t)); pcm = aligned.data(); }
+        if (OrgOverlapedBuffer) {                      // spectrumcycbuff (oqpskdemodulator.cpp:395-396): the last 8192 input samples
+            if (spectrum.size() != 8192) { spectrum.assign(8192, 0.0); spectrum_ptr = 0; }
+            for (size_t k = n > 8192 ? n - 8192 : 0; k < n; k++) { spectrum[spectrum_ptr] = ((double)pcm[k]) / 32768.0; spectrum_ptr = (spectrum_ptr + 1) % 8192; }
+        }
         for (size_t at = 0; at < n;) {                // at most one second per call into the library: the soft-bit ring holds two
             const size_t take = (n - at < max_chunk) ? (n - at) : max_chunk;
             if (!check(Api::write(h, pcm + at, take))) return len;
@@ -153,6 +167,9 @@ protected:
         if (MSESignal) MSESignal(st.mse);
         const int now = st.mse <= signalthreshold ? 1 : 0;      // the reference raises SignalStatus when the gate changes
         if (now != last_status) { last_status = now; if (SignalStatus) SignalStatus(now != 0); }
+        double peak = 0; std::vector<std::complex<double> > pts;
+        if (Api::telemetry(st, peak, pts)) { if (PeakVolume) PeakVolume(peak); if (ScatterPoints) ScatterPoints(pts); }
+        if (OrgOverlapedBuffer && spectrum.size() == 8192) OrgOverlapedBuffer(spectrum);
     }
 
     typename Api::handle *h;
@@ -163,6 +180,7 @@ protected:
     size_t max_chunk;
     std::vector<short> pending;
     std::vector<int16_t> drain;
+    std::vector<double> spectrum; size_t spectrum_ptr = 0;
 };
 
 }  // namespace detail

@@ -31,7 +31,8 @@ class Status(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in
                 ("mixer2_freq", "mixer2_wtptr", "center_freq", "st_freq", "st_wtptr", "agc", "mse", "ebno", "marg",
                  "cfe_est", "n_sig_true", "n_sig_false", "center_wtptr", "st_ref_wtptr")] + \
-               [("samples", ctypes.c_int64), ("softbits", ctypes.c_int64), ("dcd", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+               [("samples", ctypes.c_int64), ("softbits", ctypes.c_int64), ("dcd", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("peak_volume", ctypes.c_double), ("scatter", ctypes.c_double * 4)]
 
 
 class AcarsRecord(ctypes.Structure):
@@ -60,7 +61,7 @@ EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaer
            "jaero_burst_read_softbits", "jaero_burst_set_dcd", "jaero_burst_get_status_all", "jaero_burst_sync",
            "jaero_burst_launch_count",
            "jaero_rt_create", "jaero_rt_destroy", "jaero_rt_process_softbits", "jaero_rt_process_burst", "jaero_rt_tick",
-           "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count",
+           "jaero_rt_read_packets", "jaero_rt_get_stats", "jaero_rt_launch_count", "jaero_rt_set_vector_mode",
            "jaero_cchannel_create", "jaero_cchannel_destroy", "jaero_cchannel_process_batch", "jaero_cchannel_process_softbits",
            "jaero_cchannel_tick", "jaero_cchannel_read_frames", "jaero_cchannel_get_stats", "jaero_cchannel_launch_count",
            "jaero_ingest_create", "jaero_ingest_destroy", "jaero_ingest_message", "jaero_ingest_available", "jaero_ingest_flush",
@@ -128,7 +129,7 @@ def lib():
         L.jaero_rt_destroy.argtypes = [vp]; L.jaero_rt_destroy.restype = None
         L.jaero_rt_process_softbits.argtypes = [vp, vp, sz, vp]
         L.jaero_rt_process_burst.argtypes = [vp, vp]
-        L.jaero_rt_tick.argtypes = [vp]
+        L.jaero_rt_tick.argtypes = [vp]; L.jaero_rt_set_vector_mode.argtypes = [vp, i]
         L.jaero_rt_read_packets.argtypes = [vp, vp, i, vp]
         L.jaero_rt_get_stats.argtypes = [vp, vp, vp, vp]
         L.jaero_rt_launch_count.argtypes = [vp]; L.jaero_rt_launch_count.restype = ctypes.c_int64
@@ -494,6 +495,10 @@ class RTChannelBatch:
 
     def tick(self):
         _check(lib().jaero_rt_tick(self.h))
+
+    def set_vector_mode(self, on=True):
+        """AeroL::Decode's mid-vector return on burst time-out (aerol.cpp:2018-2027)"""
+        _check(lib().jaero_rt_set_vector_mode(self.h, int(bool(on))))
 
     def read_packets(self, cap=8):
         out = np.zeros((self.n, cap, self.RECORD), dtype=np.uint8)

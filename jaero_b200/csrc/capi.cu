@@ -288,6 +288,27 @@ __global__ void set_int_kernel(DemodParams p, int idx, int channel, int value)
     if (ch >= p.n_channels) return;
     if (channel < 0 || channel == ch) p.I[(size_t)idx * p.cpad + ch] = value;
 }
+// PeakVolume (oqpskdemodulator.cpp:393-405, mskdemodulator.cpp:329-344): max |sample| of the input since the last read-out.
+// One warp per channel row, 16-byte loads; the same for every demodulator kernel variant.
+__global__ void peak_kernel(DemodParams p, const int16_t *__restrict__ pcm, size_t stride, int n)
+{
+    const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ch >= p.n_channels) return;
+    const int4 *row = reinterpret_cast<const int4 *>(pcm + (size_t)ch * stride);
+    int m = 0;
+    for (int k = lane; k * 8 < n; k += 32) {
+        const int4 v = __ldg(row + k);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int lo = (int)(short)(w[q] & 0xffff), hi = w[q] >> 16;
+            if (k * 8 + 2 * q < n) m = max(m, abs(lo));
+            if (k * 8 + 2 * q + 1 < n) m = max(m, abs(hi));
+        }
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0) { int &pk = p.I[(size_t)I_PEAK * p.cpad + ch]; pk = max(pk, m); }
+}
 // CenterFreqChangedSlot (oqpskdemodulator.cpp:291-310 / mskdemodulator.cpp:265-282)
 __global__ void center_freq_kernel(DemodParams p, int channel, double freq_center)
 {
@@ -646,6 +667,9 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
             }
         }
     }
+    peak_kernel<<<(p.n_channels + 3) / 4, 128, 0, b->stream>>>(p, d_pcm, stride, (int)n);
+    JB_CUDA(cudaGetLastError());
+    b->launches++;
     const int N = p.bbnfft, trig_every = p.cpu_reduce ? N : N / 4;
     SegmentArgs a;
     memset(&a, 0, sizeof a);
@@ -888,7 +912,11 @@ int jaero_batch_get_status_all(jaero_batch *b, jaero_status *out)
         s.n_sig_true = I(I_SIG_TRUE); s.n_sig_false = I(I_SIG_FALSE);
         s.center_wtptr = D(D_MC_PTR); s.st_ref_wtptr = D(D_SR_PTR);
         s.samples = b->samples; s.softbits = b->h_soft_total[ch] + I(I_SOFT_COUNT); s.dcd = I(I_DCD); s.reserved = 0;
+        s.peak_volume = (double)I(I_PEAK) / 32768.0;
+        s.scatter[0] = D(D_SCAT0_RE); s.scatter[1] = D(D_SCAT0_IM); s.scatter[2] = D(D_SCAT1_RE); s.scatter[3] = D(D_SCAT1_IM);
     }
+    // `emit PeakVolume(maxval); maxval=0;`: the read-out restarts the maximum
+    JB_CUDA(cudaMemsetAsync(b->p.I + (size_t)I_PEAK * cp, 0, cp * sizeof(int), b->stream));
     return JAERO_OK;
 }
 int jaero_batch_get_status(jaero_batch *b, int channel, jaero_status *out)
@@ -1572,6 +1600,7 @@ struct jaero_rt {
     int16_t *d_soft_stage; int *d_count_stage; size_t stage_cap;
     RtState *h_state; uint8_t *h_out;
     long long launches;
+    int vector_mode;
 };
 
 extern "C" {
@@ -1641,7 +1670,7 @@ int jaero_rt_process_softbits(jaero_rt *r, const int16_t *soft, size_t cap, cons
     }
     JB_CUDA(cudaMemcpyAsync(r->d_soft_stage, soft, C * cap * sizeof(int16_t), cudaMemcpyHostToDevice, r->stream));
     JB_CUDA(cudaMemcpyAsync(r->d_count_stage, counts, C * sizeof(int), cudaMemcpyHostToDevice, r->stream));
-    if (rt_process(r->rp, r->d_soft_stage, r->d_count_stage, cap, r->stream, &r->launches)) return JAERO_E_CUDA;
+    if (rt_process(r->rp, r->d_soft_stage, r->d_count_stage, cap, r->stream, &r->launches, r->vector_mode ? -1 : 0)) return JAERO_E_CUDA;
     JB_CUDA(cudaStreamSynchronize(r->stream));
     return JAERO_OK;
 }
@@ -1652,11 +1681,19 @@ int jaero_rt_process_burst(jaero_rt *r, jaero_burst *b)
     const BurstParams &bp = b->p;
     JB_CUDA(cudaStreamSynchronize(r->stream));
     // on the demodulator's stream: ordered after its kernels; its soft ring is drained afterwards
-    if (rt_process(r->rp, bp.soft, bp.BI + (size_t)BI_SOFT_COUNT * bp.cpad, (size_t)bp.soft_cap, b->stream, &r->launches)) return JAERO_E_CUDA;
+    if (rt_process(r->rp, bp.soft, bp.BI + (size_t)BI_SOFT_COUNT * bp.cpad, (size_t)bp.soft_cap, b->stream, &r->launches,
+                   r->vector_mode ? (bp.kind == 1 ? 32 : 12) : 0)) return JAERO_E_CUDA;   // emit sizes: burstoqpskdemodulator.cpp / burstmskdemodulator.cpp:735
     burst_soft_reset_kernel<<<(bp.n_channels + 127) / 128, 128, 0, b->stream>>>(bp);
     JB_CUDA(cudaGetLastError());
     r->launches++;
     JB_CUDA(cudaStreamSynchronize(b->stream));
+    return JAERO_OK;
+}
+// Opt-in: reproduce AeroL::Decode's return in the middle of a soft-bit vector when the burst time-out fires (aerol.cpp:2018-2027)
+int jaero_rt_set_vector_mode(jaero_rt *r, int enabled)
+{
+    if (!r) { set_error("null handle"); return JAERO_E_ARG; }
+    r->vector_mode = enabled ? 1 : 0;
     return JAERO_OK;
 }
 int jaero_rt_tick(jaero_rt *r)

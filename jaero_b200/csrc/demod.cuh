@@ -38,6 +38,7 @@ enum DIdx {
     D_DIFF_LAST,                                        // DiffDecode::lastsoftstate (MSK)
     D_CFE_EST,                                          // last CoarseFreqEstimate::freq_offset_est
     D_LASTMSE,                                          // `lastmse` captured at the start of writeData (:339)
+    D_SCAT0_RE, D_SCAT0_IM, D_SCAT1_RE, D_SCAT1_IM,     // the two most recent constellation points (ScatterPoints, decimated)
     D_COUNT
 };
 // ---- per-channel scalar state, ints: I[idx][channel]
@@ -48,6 +49,7 @@ enum IIdx {
     I_SIG_TRUE, I_SIG_FALSE, I_EMPTYING,                // SignalStatus counters, CoarseFreqEstimate::emptyingcountdown
     I_ZERO_BB,                                          // request: clear the baseband ring (oqpskdemodulator.cpp:667)
     I_LOST_N,                                           // SignalStatus(false) events recorded since the soft ring was last drained
+    I_PEAK,                                             // max |int16 input sample| since the last status read (PeakVolume)
     I_COUNT
 };
 

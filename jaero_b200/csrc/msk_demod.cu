@@ -48,6 +48,7 @@ msk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, c
     Biquad res = {LD(D_RES_X1), LD(D_RES_X2), LD(D_RES_Y1), LD(D_RES_Y2)};
     double marg_sum = LD(D_MARG_SUM), marg_val = LD(D_MARG_VAL);
     double ma_sum = LD(D_MSE_MA_SUM), mse = LD(D_MSE);
+    double2 sc0 = make_double2(LD(D_SCAT0_RE), LD(D_SCAT0_IM)), sc1 = make_double2(LD(D_SCAT1_RE), LD(D_SCAT1_IM));
     double diff_last = LD(D_DIFF_LAST);
     int countdown = LI(I_COUNTDOWN), dcd = LI(I_DCD);
     int marg_pos = LI(I_MARG_POS), dt_pos = LI(I_DT_POS), mse_pos = LI(I_MSE_POS);
@@ -192,6 +193,7 @@ msk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, c
                 pt_msk = p.dt_ring[(size_t)dt_pos * p.cpad + ch];
             }
             pt_msk = cmul(pt_msk, make_double2(cos(marg_val), sin(marg_val)));            // :431
+            sc1 = sc0; sc0 = make_double2(pt_msk.x * 0.75, pt_msk.y * 0.75);                  // pointbuff (:440)
             {   // :446-448
                 const double tda = (fabs((pt_msk).x * 0.75) - 1.0), tdb = (fabs((pt_msk).y * 0.75) - 1.0);
                 const double v = (tda * tda) + (tdb * tdb);
@@ -218,6 +220,7 @@ msk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, c
     LD(D_RES_X1) = res.x1; LD(D_RES_X2) = res.x2; LD(D_RES_Y1) = res.y1; LD(D_RES_Y2) = res.y2;
     LD(D_MARG_SUM) = marg_sum; LD(D_MARG_VAL) = marg_val;
     LD(D_MSE_MA_SUM) = ma_sum; LD(D_MSE) = mse; LD(D_DIFF_LAST) = diff_last;
+    LD(D_SCAT0_RE) = sc0.x; LD(D_SCAT0_IM) = sc0.y; LD(D_SCAT1_RE) = sc1.x; LD(D_SCAT1_IM) = sc1.y;
     LI(I_COUNTDOWN) = countdown;
     LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;
     LI(I_SOFT_COUNT) = soft_count; LI(I_SOFT_PENDING) = soft_pending; LI(I_SOFT_OVERFLOW) = soft_overflow;

@@ -103,6 +103,7 @@ oqpsk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a,
     double marg_sum = LD(D_MARG_SUM), marg_val = LD(D_MARG_VAL);
     double pm_sum = LD(D_MSE_PM_SUM), ma_sum = LD(D_MSE_MA_SUM), mse = LD(D_MSE);
     double lastmse = LD(D_LASTMSE);
+    double2 sc0 = make_double2(LD(D_SCAT0_RE), LD(D_SCAT0_IM)), sc1 = make_double2(LD(D_SCAT1_RE), LD(D_SCAT1_IM));
     int yui = LI(I_YUI), countdown = LI(I_COUNTDOWN), countdown2 = LI(I_COUNTDOWN2), dcd = LI(I_DCD);
     int sig2l_init = LI(I_SIG2L_INIT);
     int marg_pos = LI(I_MARG_POS), dt_pos = LI(I_DT_POS), mse_pos = LI(I_MSE_POS);
@@ -432,6 +433,7 @@ oqpsk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a,
                     pt_qpsk = sy_dt_old;                                  // requested after the previous strobe
                 }
                 pt_qpsk = cmul(pt_qpsk, make_double2(cos(marg_val), sin(marg_val)));   // :537
+                sc1 = sc0; sc0 = pt_qpsk;
                 {   // MSEcalc::Update (DSP.cpp:451-463)
                     const size_t e = (size_t)mse_pos * cpad + ch;
                     const double ab = hypot(pt_qpsk.x, pt_qpsk.y);
@@ -516,6 +518,7 @@ oqpsk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a,
     LD(D_MARG_SUM) = marg_sum; LD(D_MARG_VAL) = marg_val;
     LD(D_MSE_PM_SUM) = pm_sum; LD(D_MSE_MA_SUM) = ma_sum; LD(D_MSE) = mse;
     LD(D_LASTMSE) = lastmse;
+    LD(D_SCAT0_RE) = sc0.x; LD(D_SCAT0_IM) = sc0.y; LD(D_SCAT1_RE) = sc1.x; LD(D_SCAT1_IM) = sc1.y;
     if (PRE) m2_freq_sum[ch] = m2sum;
     LI(I_YUI) = yui; LI(I_COUNTDOWN) = countdown; LI(I_COUNTDOWN2) = countdown2; LI(I_SIG2L_INIT) = sig2l_init;
     LI(I_MARG_POS) = marg_pos; LI(I_DT_POS) = dt_pos; LI(I_MSE_POS) = mse_pos;

@@ -42,7 +42,7 @@ __device__ __forceinline__ int rt_uw(unsigned &sr, int bit, int &inverted)
 }
 
 __global__ void __launch_bounds__(64)
-rt_frame_kernel(RtParams rp, const int16_t *__restrict__ soft, const int *__restrict__ soft_count, size_t soft_stride)
+rt_frame_kernel(RtParams rp, const int16_t *__restrict__ soft, const int *__restrict__ soft_count, size_t soft_stride, int vmode)
 {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= rp.n_channels) return;
@@ -53,8 +53,18 @@ rt_frame_kernel(RtParams rp, const int16_t *__restrict__ soft, const int *__rest
     uint8_t *blocks = rp.blocks + (size_t)ch * RT_SLOTS * RT_BLOCK;
     int cur = s.slot_cur;
     int fill = slots[cur].fill;
+    // vmode != 0: the reference's vector semantics. AeroL::Decode is called once per emitted soft-bit vector and RETURNS when the
+    // burst time-out fires (aerol.cpp:2018-2027), dropping the rest of that vector. vmode > 0: the soft ring holds whole vectors of
+    // the burst demodulator, vmode values each, one more when a vector opens with the start-of-burst marker (the demodulators clear
+    // their buffer, push -1, then add pairs until >= vmode); vmode < 0: the whole call is one vector (host-supplied soft bits).
+    int vec_left = 0; bool skipping = false;
     for (int i = 0; i < n; i++) {
         const int v = bits[i];
+        if (vmode) {
+            if (vec_left == 0) { vec_left = vmode > 0 ? vmode + (v < 0 ? 1 : 0) : n; skipping = false; }
+            vec_left--;
+            if (skipping) continue;
+        }
         s.bits_seen++;
         int bit = (((unsigned char)v) >= 128) ? 1 : 0;                       // aerol.cpp:1136-1139
         int soft_bit = (unsigned short)v;
@@ -94,7 +104,7 @@ rt_frame_kernel(RtParams rp, const int16_t *__restrict__ soft, const int *__rest
             if (fill < RT_BLOCK) { blocks[(size_t)cur * RT_BLOCK + fill] = (uint8_t)soft_bit; fill++; }
         }
         if (gotsync) { s.cntr = -1; s.datacd = 1; s.datacdcountdown = 12; }  // :1990-2011
-        if (s.cntr + 1 == rp.total_number_of_bits) { s.cntr = 1000000000; s.datacd = 0; s.datacdcountdown = 0; }   // :2013-2029
+        if (s.cntr + 1 == rp.total_number_of_bits) { s.cntr = 1000000000; s.datacd = 0; s.datacdcountdown = 0; if (vmode) skipping = true; }   // :2013-2029
     }
     slots[cur].fill = fill;
     s.slot_cur = cur;
@@ -277,9 +287,9 @@ int rt_out_reset(const RtParams &rp, cudaStream_t st)
     JB_CUDA(cudaGetLastError());
     return 0;
 }
-int rt_process(const RtParams &rp, const int16_t *d_soft, const int *d_soft_count, size_t soft_stride, cudaStream_t st, long long *launches)
+int rt_process(const RtParams &rp, const int16_t *d_soft, const int *d_soft_count, size_t soft_stride, cudaStream_t st, long long *launches, int vmode)
 {
-    rt_frame_kernel<<<(rp.n_channels + 63) / 64, 64, 0, st>>>(rp, d_soft, d_soft_count, soft_stride);
+    rt_frame_kernel<<<(rp.n_channels + 63) / 64, 64, 0, st>>>(rp, d_soft, d_soft_count, soft_stride, vmode);
     JB_CUDA(cudaGetLastError());
     const int sb = (RT_BLOCK + 15) & ~15, ob = ((RT_BLOCK / 2) + 15) & ~15;
     const int per_warp = sb + 2 * V_CAP * (int)sizeof(unsigned) + ob;

@@ -32,6 +32,6 @@ int rt_set_scrambler(const uint8_t *seq);
 int rt_init(const RtParams &rp, cudaStream_t st);
 int rt_tick(const RtParams &rp, cudaStream_t st);
 int rt_out_reset(const RtParams &rp, cudaStream_t st);
-int rt_process(const RtParams &rp, const int16_t *d_soft, const int *d_soft_count, size_t soft_stride, cudaStream_t st, long long *launches);
+int rt_process(const RtParams &rp, const int16_t *d_soft, const int *d_soft_count, size_t soft_stride, cudaStream_t st, long long *launches, int vmode = 0);
 
 } // namespace jb

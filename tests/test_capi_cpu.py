@@ -28,10 +28,20 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert set(jaero_b200.EXPORTS) <= set(names)
 
 
-def test_python_structs_match_header_layout():
+def test_python_structs_match_header_layout(tmp_path):
+    """sizeof / offsetof as the C compiler sees include/jaero_b200.h == the ctypes mirrors in jaero_b200/__init__.py"""
+    import subprocess
     import jaero_b200
-    assert ctypes.sizeof(jaero_b200.Settings) == 4 + 4 + 5 * 8 + 4 * 4          # kind, fft_power, 5 doubles, 4 ints
-    assert ctypes.sizeof(jaero_b200.Status) == 14 * 8 + 2 * 8 + 2 * 4
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "jaero_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(jaero_settings), sizeof(jaero_status), offsetof(jaero_status, samples), offsetof(jaero_status, dcd),'
+                   'offsetof(jaero_status, peak_volume), offsetof(jaero_status, scatter), sizeof(jaero_acars_record));return 0;}\n')
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe], check=True)
+    got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    S = jaero_b200.Status
+    assert got == [ctypes.sizeof(jaero_b200.Settings), ctypes.sizeof(S), S.samples.offset, S.dcd.offset, S.peak_volume.offset, S.scatter.offset,
+                   ctypes.sizeof(jaero_b200.AcarsRecord)]
 
 
 @pytest.mark.skipif(has_cuda(), reason="only meaningful on a box without a GPU")

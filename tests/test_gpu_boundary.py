@@ -282,3 +282,71 @@ def test_write_batch_msk_signal_units(golden):
     gb = np.concatenate([g[0] for g in got]); gok = np.concatenate([g[1] for g in got])
     assert np.array_equal(gok, rok) and np.array_equal(gb[gok.astype(bool)], rb[rok.astype(bool)]) and rok.sum() >= 60
     b.close(); pc.close()
+
+
+def _split_vectors(soft, T):
+    """The burst demodulators' emits: an optional start-of-burst marker followed by exactly T values (they clear the buffer,
+    push -1, then add pairs until >= T: burstmskdemodulator.cpp:735-739, burstoqpskdemodulator.cpp)."""
+    out, i = [], 0
+    while i < len(soft):
+        n = T + (1 if soft[i] < 0 else 0)
+        out.append(soft[i:i + n]); i += n
+    return out
+
+
+@pytest.mark.parametrize("name", ["burst_msk_1200_a", "burst_oqpsk_10500"])
+def test_rt_vector_mode_drops_the_rest_of_the_vector_like_the_reference(golden, name):
+    """jaero_rt_set_vector_mode: AeroL::Decode returns in the middle of a soft-bit vector when the burst time-out fires
+    (aerol.cpp:2018-2027). Device path (soft bits never leave the GPU) against the oracle fed vector by vector."""
+    jb = _import()
+    case = golden[name]
+    pcm = load_excerpt(name)
+    oq = case["kind"] == "burst_oqpsk"
+    T = 32 if oq else 12
+    b = (jb.BurstOqpskBatch if oq else jb.BurstMskBatch)(1, **case["kw"])
+    rt = jb.RTChannelBatch(1, case["kw"]["fb"]); rt.set_vector_mode(True)
+    got = []
+    for a in range(0, len(pcm), 48000):
+        b.write(pcm[None, a:a + 48000]); rt.process_burst(b)
+        got += rt.read_packets()[0]
+    tr, bad, dcd = rt.stats()
+    b.close(); rt.close()
+    o = restated.OracleDemod(case["kind"], **case["kw"]); ort = restated.OracleRTChannel(case["kw"]["fb"])
+    nvec = 0
+    for a in range(0, len(pcm), 48000):
+        o.write(pcm[a:a + 48000])
+        for v in _split_vectors(o.take_soft(), T):
+            ort.process(v, vector_semantics=True); nvec += 1
+    ref = ort.packets()
+    assert nvec > 50 and len(ref) == len(got) and len(ref) >= 1 and tr[0] == ort.trials
+    for r, g in zip(ref, got):
+        assert r["type"] == g["type"] and r["nsus"] == g["nsus"] and np.array_equal(r["bytes"], g["bytes"])
+    # host-supplied soft bits: every call is one vector
+    streams = __import__("conftest").synthetic_r_packet_stream(1200, (np.arange(17) * 5 % 256).astype(np.uint8))
+    rt2 = jb.RTChannelBatch(1, 1200); rt2.set_vector_mode(True); ort2 = restated.OracleRTChannel(1200)
+    for a in range(0, len(streams), 40):
+        rt2.process([streams[a:a + 40]]); ort2.process(streams[a:a + 40], vector_semantics=True)
+    g2 = rt2.read_packets()[0]; r2 = ort2.packets()
+    rt2.close()
+    assert len(g2) == len(r2) and all(np.array_equal(x["bytes"], y["bytes"]) for x, y in zip(g2, r2))
+
+
+def test_status_telemetry_peak_volume_and_scatter_points(golden):
+    """PeakVolume (max |sample| since the previous read-out) and the decimated ScatterPoints in jaero_status."""
+    jb = _import()
+    kw = dict(golden["oqpsk_10500"]["kw"])
+    pcm = load_excerpt("oqpsk_10500")[:48000 * 4]
+    pcm2 = np.stack([pcm, (pcm // 2).astype(np.int16), np.zeros_like(pcm)])
+    b = jb.DemodBatch("oqpsk", 3, **kw)
+    b.write(pcm2[:, :100000])
+    st = b.status()
+    for c in range(3):
+        assert st[c]["peak_volume"] == np.abs(pcm2[c, :100000].astype(int)).max() / 32768.0
+    b.write(pcm2[:, 100000:100001])                                    # the read-out restarted the maximum
+    assert b.status()[0]["peak_volume"] == abs(int(pcm2[0, 100000])) / 32768.0
+    b.write(pcm2[:, 100001:])
+    st = b.status()
+    pts = np.array(st[0]["scatter"][:]).reshape(2, 2)
+    assert np.all(np.abs(np.abs(pts) - 1.0) < 0.6)                      # locked OQPSK constellation points sit near (+-1, +-1)
+    assert list(st[2]["scatter"][:]) != list(st[0]["scatter"][:])
+    b.close()
