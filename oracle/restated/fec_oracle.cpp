@@ -531,3 +531,49 @@ void CChannelOracle::updateDCD()
     else { if (datacdcountdown < 0) datacdcountdown = 0; }
     if (datacd && !datacdcountdown) datacd = false;
 }
+
+// ====================================================================================== pinning hooks
+// The pieces of this restatement one by one, for tests/test_fec_pinning.py, which holds them against the reference's own
+// classes compiled verbatim (oracle/ref_fec_driver.cpp -> oracle/_ref/libjaero_ref_fec.so).
+extern "C" {
+// kind 0: PreambleDetector (exact, cleared on a hit); 1: PreambleDetectorPhaseInvariant, tollerence 0, on a bit vector;
+// 2: OQPSKPreambleDetectorAndAmbiguityCorrection (two 52-bit words, tollerence 6); 3: phase-invariant on a shift register with `tol`
+void jor_pin_detect(int kind, int tol, const int *bits, int n, int *out, int *inv)
+{
+    std::vector<int> pre; for (int i = 31; i >= 0; i--) pre.push_back((3780831379ULL >> i) & 1);
+    std::vector<int> buf(32, 0); bool inverted = false; uint32_t sr = 0; uint64_t b1 = 0, b2 = 0;
+    for (int i = 0; i < n; i++) {
+        if (kind == 0) out[i] = uw_update_exact(buf, pre, bits[i]);
+        else if (kind == 1) out[i] = uw_update_invariant(buf, pre, bits[i], inverted);
+        else if (kind == 2) out[i] = c_uw_update(b1, b2, bits[i], inverted);
+        else out[i] = uw_invariant_tol(sr, bits[i], inverted, tol);
+        inv[i] = inverted ? 1 : 0;
+    }
+}
+int jor_pin_crc_bits_check(const int *bits, int n) { return crc_bits_check(bits, n) ? 1 : 0; }
+void jor_pin_scrambler(int *out, int n) { PChannelOracle p(600); for (int i = 0; i < n; i++) out[i] = p.scr[i]; }
+// C-channel frame: 16 blocks of 4 x 64 soft values -> de-interleaved, de-punctured code-order stream (as CChannelOracle::process builds it)
+int jor_pin_c_code_order(const int *frame4096, unsigned char *out)
+{
+    std::vector<uint8_t> deleavered;
+    for (int b = 0; b < 16; b++) {
+        const int *block = frame4096 + 256 * b;
+        for (int j = 0; j < 4; j++) for (int r = 0; r < 64; r++) deleavered.push_back((uint8_t)block[((r * 27) % 64) * 4 + j]);
+    }
+    int ptr = 0, n = 0;
+    for (int k = 0; k + 1 < (int)deleavered.size(); k++) { ptr++; out[n++] = deleavered[k]; if (ptr >= 3) out[n++] = 128; ptr %= 3; }
+    return n;
+}
+void *jor_pin_rt_new(int fb) { return new RTChannelOracle(fb); }
+void jor_pin_rt_free(void *h) { delete (RTChannelOracle *)h; }
+int jor_pin_rt_reset(void *h) { return ((RTChannelOracle *)h)->resetblockptr(); }
+int jor_pin_rt_update(void *h, int msk, int soft) { RTChannelOracle *r = (RTChannelOracle *)h; return msk ? r->rt_updateMSK(soft) : r->rt_update(soft); }
+int jor_pin_rt_info(void *h, unsigned char *out, int cap, int *numberofsus)
+{
+    RTChannelOracle *r = (RTChannelOracle *)h;
+    int n = (int)r->infofield.size() < cap ? (int)r->infofield.size() : cap;
+    for (int i = 0; i < n; i++) out[i] = r->infofield[i];
+    *numberofsus = r->numberofsus;
+    return (int)r->infofield.size();
+}
+}

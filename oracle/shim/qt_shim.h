@@ -140,6 +140,7 @@ public:
         int n = (len < 0 || pos + len > size()) ? size() - pos : len;
         return QByteArray(v.data() + pos, n);
     }
+    void chop(int n) { if (n >= size()) v.clear(); else if (n > 0) v.resize(v.size() - n); }   // QByteArray::chop
     bool operator==(const QByteArray &o) const { return v == o.v; }
     std::vector<char> v;
 };
