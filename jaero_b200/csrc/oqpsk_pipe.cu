@@ -352,7 +352,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             const double st_eta = HAND(sl, 4), d8out = HAND(sl, 5);
             TR(4);
             const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
-            const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
+            const double st_angle_error = atan2_fast(st_out.y, st_out.x);     // :480 std::arg
             TR(11);
             osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
             osc_advance_fraction_of_wave(st, div_exact(-st_angle_error * 0.01, 360.0, 1.0 / 360.0)); // :482
@@ -466,7 +466,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                     agc_sum = agc_sum + fabs(dabval);
                     t_agc[rslot] = fabs(dabval);
                     ring_dirty = true;
-                    agc_val = 1.414213562 / fmax(div_exact(agc_sum, (double)agc_len, r_agc), 0.000001);
+                    agc_val = div_fast(1.414213562, fmax(div_exact(agc_sum, (double)agc_len, r_agc), 0.000001));   // == the IEEE quotient (tools/micro/div_test.cu)
                     agc_val = fmax(agc_val, 0.000001);
                 }
                 double2 sig2 = make_double2(sre * agc_val, sim * agc_val);        // :466
