@@ -644,7 +644,7 @@ burst_back_kernel(const __grid_constant__ BurstParams p, int n)
             }
             const int ts = osc_index(st.ptr);
             const double2 st_out = cmul(make_double2(p.cos_t[ts], p.sin_t[ts]), make_double2(st_eta, -d8out));
-            const double st_angle_error = atan2(st_out.y, st_out.x);
+            const double st_angle_error = atan2_fast(st_out.y, st_out.x);
             if (cntr > p.end_rotation) osc_advance_fraction_of_wave(st, -st_angle_error * 0.002 / 360.0);   // :661-665
             double frac;
             if (osc_have_passed_point(st, p.ee, frac)) {                  // :668
@@ -853,7 +853,7 @@ burst_oqpsk_back_kernel(const __grid_constant__ BurstParams p, long long sample0
           d8out = (w8 * newer + (1.0 - w8) * older); d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta; }
         const int ts = osc_index(st.ptr);
         const double2 st_out = cmul(make_double2(p.cos_t[ts], p.sin_t[ts]), make_double2(st_eta, -d8out));
-        const double st_angle_error = atan2(st_out.y, st_out.x);
+        const double st_angle_error = atan2_fast(st_out.y, st_out.x);
         if (cntr > SPS * (128 + 64)) {
             osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, p.Fs);
             osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0);

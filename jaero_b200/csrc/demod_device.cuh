@@ -186,6 +186,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     asm volatile("{\n\t.reg .pred p;\n\tMBW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBD_%=;\n\tbra MBW_%=;\n\tMBD_%=:\n\t}"
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same for a waiter that is far ahead of its producer (it must not burn the issue slots of the warp it shares a sub-partition with)
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(400);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

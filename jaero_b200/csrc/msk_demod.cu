@@ -161,7 +161,7 @@ msk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, c
         }
         const int ts = osc_index(st.ptr);
         const double2 st_out = cmul(make_double2(p.cos_t[ts], p.sin_t[ts]), make_double2(st_eta, -d8out));   // :389-390
-        const double st_angle_error = atan2(st_out.y, st_out.x);                          // :392
+        const double st_angle_error = atan2_fast(st_out.y, st_out.x);                          // :392
         const double weighting = fabs(tanh(st_angle_error));                              // :395
         if (!dcd) osc_advance_fraction_of_wave(st, -(1.0 - weighting) * st_angle_error * (0.05 / 360.0));    // :397-405
         else osc_advance_fraction_of_wave(st, -(1.0 - weighting) * st_angle_error * (0.003 / 360.0));

@@ -389,7 +389,7 @@ oqpsk_segment_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a,
             d8_2 = d8_1; d8_1 = d8_0; d8_0 = st_eta;
         }
         const double2 st_out = cmul(make_double2(cs_re, cs_im), make_double2(st_eta, -d8out));   // :478-479
-        const double st_angle_error = atan2(st_out.y, st_out.x);          // :480 std::arg
+        const double st_angle_error = atan2_fast(st_out.y, st_out.x);          // :480 std::arg
         osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
         osc_advance_fraction_of_wave(st, -st_angle_error * 0.01 / 360.0); // :482
         if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);

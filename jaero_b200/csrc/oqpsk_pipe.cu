@@ -69,8 +69,8 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
     double *dv = reinterpret_cast<double *>(pp_smem_raw + PP_SM_BASE + PP_SM_HAND);               // [PP_DV][32]
     double2 *bbst = reinterpret_cast<double2 *>(pp_smem_raw + PP_SM_BASE + PP_SM_HAND + PP_SM_DV); // [8][32]
     // Role ids: F 0, E 1, T 2, K1 3, K2 4, S 5, A 6 = physical warp. (Warps w and w+4 share an SM sub-partition and its FP64
-    // pipe. Other placements were measured on B200 - E next to K2, or E / T alone with F, A, S packed together using two
-    // placeholder warps - and were 0-5 % slower than this one: the stages are bound by their own dependent-issue chains.)
+    // pipe. Other placements were measured on B200 inside one GPU call, 9-warp CTAs with placeholder warps: {F,S,A | E | T | K1,K2},
+    // {F,A | E,S | T | K1,K2}, {F,S | E,A | T | K1,K2}: all 8 % slower per epoch than this one.)
     const int lane = threadIdx.x & 31;
     const int warp = (int)(threadIdx.x >> 5);
     const int ch_raw = blockIdx.x * OQ_THREADS + lane;
@@ -599,7 +599,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         int line_first = bb_pos & 7;                            // entries of the open line below this index were written by an earlier launch
         for (int e = 0; e < n; e++) {
             const int tb = (e >> 5) & 1;
-            if ((e & 31) == 0 && e >= PP_DV) { mbar_wait(&bars[7 + tb], (aph >> tb) & 1u); aph ^= (1u << tb); }
+            if ((e & 31) == 0 && e >= PP_DV) { mbar_wait_relaxed(&bars[7 + tb], (aph >> tb) & 1u); aph ^= (1u << tb); }
             const double dcur = dval_at(a.i0 + e);
             dv[(e & (PP_DV - 1)) * 32 + lane] = dcur;
             // ---- A: coarse-estimator ring (:410-429); the host ends the segment on the trigger sample
@@ -625,7 +625,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
-    for (int k = (int)(threadIdx.x >> 5); k < OQ_NT1; k += PP_THREADS / 32) {
+    for (int k = (int)(threadIdx.x >> 5); k < OQ_NT1; k += (int)(blockDim.x >> 5)) {
         p.fir_re[(size_t)k * cpad + ch] = s_re[k * OQ_THREADS + lane];
         p.fir_im[(size_t)k * cpad + ch] = s_im[k * OQ_THREADS + lane];
     }
