@@ -122,6 +122,10 @@ int jaero_batch_set_center_freq(jaero_batch *b, int channel, double hz);  /* Cen
 int jaero_batch_set_afc(jaero_batch *b, int state);
 int jaero_batch_set_sql(jaero_batch *b, int state);
 int jaero_batch_set_cpu_reduce(jaero_batch *b, int state);
+/* Seating of the channels inside the 10500 bps kernel. Channels never interact, so results do not depend on it; throughput does:
+ * the library seats channels with the same symbol-timing phase next to each other (automatically, every JAERO_REGROUP_EPOCHS
+ * estimator epochs; this call does it now when slot_of is NULL, or installs the given permutation slot_of[channel] = seat). */
+int jaero_batch_regroup(jaero_batch *b, const int32_t *slot_of);
 /* connect(demodulator, SIGNAL(SignalStatus(bool)), aerol, SLOT(SignalStatusSlot(bool))) (JAERO/mainwindow.cpp:432,508): with it, a
  * SignalStatus(false) clears the channel's DCD in the kernel and is handed to the device frame layer (jaero_pchannel_process_batch /
  * jaero_cchannel_process_batch) as a LostSignal at its soft-bit position. Off by default (host-driven DCD via jaero_batch_set_dcd). */

@@ -47,7 +47,7 @@ class AcarsRecord(ctypes.Structure):
 EXPORTS = ["jaero_last_error", "jaero_device_count", "jaero_batch_create", "jaero_batch_destroy", "jaero_batch_channels",
            "jaero_batch_write", "jaero_batch_write_device", "jaero_batch_sync", "jaero_batch_read_softbits",
            "jaero_batch_softbits_device", "jaero_batch_reset_softbits", "jaero_batch_set_dcd",
-           "jaero_batch_set_center_freq", "jaero_batch_set_afc", "jaero_batch_set_sql", "jaero_batch_set_cpu_reduce",
+           "jaero_batch_set_center_freq", "jaero_batch_set_afc", "jaero_batch_set_sql", "jaero_batch_set_cpu_reduce", "jaero_batch_regroup",
            "jaero_burst_set_afc", "jaero_burst_set_sql", "jaero_batch_get_status", "jaero_batch_get_status_all",
            "jaero_batch_launch_count", "jaero_batch_set_stream", "jaero_batch_set_profiling",
            "jaero_batch_get_profile", "jaero_viterbi_create", "jaero_viterbi_destroy",
@@ -116,6 +116,7 @@ def lib():
         L.jaero_pchannel_lost_signal.argtypes = [vp, vp, i]; L.jaero_cchannel_lost_signal.argtypes = [vp, vp, i]
         L.jaero_pchannel_write_batch.argtypes = [vp, vp, vp, sz, sz]; L.jaero_cchannel_write_batch.argtypes = [vp, vp, vp, sz, sz]
         L.jaero_batch_wire_signal_status.argtypes = [vp, i]
+        L.jaero_batch_regroup.argtypes = [vp, vp]
         L.jaero_burst_msk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_oqpsk_create.argtypes = [ctypes.POINTER(Settings), i, i, ctypes.POINTER(vp)]
         L.jaero_burst_destroy.argtypes = [vp]; L.jaero_burst_destroy.restype = None
@@ -214,6 +215,15 @@ class DemodBatch:
 
     def set_cpu_reduce(self, state):
         _check(lib().jaero_batch_set_cpu_reduce(self.h, int(bool(state))))
+
+    def regroup(self, slot_of=None):
+        """seat the channels by symbol-timing phase now (slot_of None) or as the given permutation; never changes results"""
+        if slot_of is None:
+            _check(lib().jaero_batch_regroup(self.h, None))
+        else:
+            a = np.ascontiguousarray(slot_of, dtype=np.int32)
+            assert len(a) == self.n
+            _check(lib().jaero_batch_regroup(self.h, _p(a)))
 
     def wire_signal_status(self, on=True):
         """connect(demodulator, SignalStatus, aerol, SignalStatusSlot) (mainwindow.cpp:432,508)"""

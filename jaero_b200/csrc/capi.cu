@@ -237,6 +237,10 @@ struct jaero_batch {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_seg, ev_cfe;
     double prof_samples;
     int trace_state;            // JAERO_PIPE_TRACE: 0 = armed, 1 = done
+    // seating of the channels in the pipelined 10500 bps kernel (regroup)
+    int *d_chan_of; double *d_keys, *h_keys; double *d_ring_scratch; size_t ring_scratch_count;
+    std::vector<int> slot_of;   // [cpad] seat of channel c
+    long long epochs, next_regroup; int regroup_every; long long regroups;
 };
 
 namespace {
@@ -328,6 +332,101 @@ __global__ void center_freq_kernel(DemodParams p, int channel, double freq_cente
     if ((D(D_M2_FREQ) - D(D_MC_FREQ)) < (-p.lockingbw / 2.0)) set_m2(D(D_MC_FREQ) - (p.lockingbw / 2.0));
     double2 *row = p.bb + (size_t)ch * p.bb_len;
     for (int j = 0; j < p.bb_len; j++) row[j] = make_double2(0.0, 0.0);
+}
+// ---- seating by symbol-timing phase (pipelined 10500 bps kernel)
+// key[c] = samples until channel c's next carrier-update strobe, in [0, 2 * samples per strobe): st_osc passes the point ee
+// (oqpskdemodulator.cpp:488) every Fs/fb samples and every second passage (yui, :496-503) is a carrier update.
+__global__ void regroup_key_kernel(DemodParams p, double *__restrict__ key)
+{
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= p.n_channels) return;
+    const double ptr = p.D[(size_t)D_ST_PTR * p.cpad + ch], step = p.D[(size_t)D_ST_STEP * p.cpad + ch];
+    const int yui = p.I[(size_t)I_YUI * p.cpad + ch];
+    const double N = (double)jb::WTSIZE;
+    double d = p.ee * N - ptr; if (d < 0) d += N;
+    const double per = step > 0 ? N / step : 1.0;
+    double k = step > 0 ? d / step : 0.0;
+    if (yui) k += per;                                    // the next passage only stores pt_d; the one after it updates the carrier
+    key[ch] = fmod(k, 2.0 * per);
+}
+// ring_new[(cta', k, lane')] = ring_old[(cta, k, lane)] for the channel that moves from seat (cta, lane) to (cta', lane')
+__global__ void regroup_ring_kernel(const double *__restrict__ src, double *__restrict__ dst, const int *__restrict__ old_seat_of_new, int len, int n_ctas)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // (cta', k)
+    if (row >= (long long)n_ctas * len) return;
+    const int cta_n = (int)(row / len), k = (int)(row % len);
+    const int so = old_seat_of_new[cta_n * 32 + lane];
+    dst[row * 32 + lane] = src[((size_t)(so >> 5) * len + k) * 32 + (so & 31)];
+}
+// New seating: slot_of[c] for every channel (pads keep their seats). The rings follow; everything else is indexed by channel.
+int batch_apply_seating(jaero_batch *b, const std::vector<int> &new_slot_of)
+{
+    DemodParams &p = b->p;
+    const int cp = p.cpad, n_ctas = cp / 32;
+    std::vector<int> old_seat_of_new(cp), chan_of(cp);
+    for (int c = 0; c < cp; c++) { old_seat_of_new[new_slot_of[c]] = b->slot_of[c]; chan_of[new_slot_of[c]] = c; }
+    const size_t need = (size_t)p.agc_len * cp;
+    if (!b->d_ring_scratch) {
+        if (cudaMalloc(&b->d_ring_scratch, need * sizeof(double)) != cudaSuccess) { cudaGetLastError(); b->regroup_every = 0; return 0; }   // no room: keep the seating
+        b->ring_scratch_count = need;
+    }
+    int *d_map = b->d_chan_of + cp;                          // second half of the allocation: old seat of each new seat
+    JB_CUDA(cudaMemcpyAsync(d_map, old_seat_of_new.data(), cp * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    auto move = [&](double *ring, int len) -> int {
+        if (!ring) return 0;
+        const long long rows = (long long)n_ctas * len;
+        regroup_ring_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, b->stream>>>(ring, b->d_ring_scratch, d_map, len, n_ctas);
+        JB_CUDA(cudaGetLastError());
+        JB_CUDA(cudaMemcpyAsync(ring, b->d_ring_scratch, (size_t)rows * 32 * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+        b->launches++;
+        return 0;
+    };
+    if (move(p.agc_ring, p.agc_len) || move(p.ebno_e1, p.ebno_len) || move(p.ebno_e2, p.ebno_len)) return -1;
+    JB_CUDA(cudaMemcpyAsync(b->d_chan_of, chan_of.data(), cp * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    JB_CUDA(cudaStreamSynchronize(b->stream));               // the host vectors above go out of scope
+    b->slot_of = new_slot_of;
+    b->regroups++;
+    return 0;
+}
+int batch_regroup_by_phase(jaero_batch *b, bool force)
+{
+    DemodParams &p = b->p;
+    const int C = p.n_channels, cp = p.cpad;
+    regroup_key_kernel<<<(C + 127) / 128, 128, 0, b->stream>>>(p, b->d_keys);
+    JB_CUDA(cudaGetLastError());
+    JB_CUDA(cudaMemcpyAsync(b->h_keys, b->d_keys, C * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    JB_CUDA(cudaStreamSynchronize(b->stream));
+    b->launches++;
+    // Is the present seating still coherent? A CTA is coherent when the carrier-update strobes of its channels fall within 1.5
+    // samples of each other (circularly, period = two strobe intervals). Moving the rings costs ~10 ms per 4096 channels, so the
+    // seating is only changed when more than a tenth of the CTAs have drifted apart (never, for transmitters on one clock).
+    if (!force) {
+        const double period = 2.0 * p.Fs / p.fb;                                     // keys are in [0, 2*Fs/fb)
+        int bad = 0, ctas = 0;
+        std::vector<double> ks;
+        std::vector<std::vector<int>> members(cp / 32);
+        for (int c = 0; c < C; c++) members[b->slot_of[c] >> 5].push_back(c);
+        for (auto &m : members) {
+            if (m.size() < 2) continue;
+            ctas++;
+            ks.clear();
+            for (int c : m) ks.push_back(b->h_keys[c]);
+            std::sort(ks.begin(), ks.end());
+            double gap = ks.front() + period - ks.back();
+            for (size_t i = 1; i < ks.size(); i++) gap = std::max(gap, ks[i] - ks[i - 1]);
+            if (period - gap > 1.5) bad++;
+        }
+        if (bad * 10 <= ctas) return 0;
+    }
+    std::vector<int> order(C);
+    for (int c = 0; c < C; c++) order[c] = c;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return b->h_keys[x] < b->h_keys[y]; });
+    std::vector<int> slot_of(cp);
+    for (int k = 0; k < C; k++) slot_of[order[k]] = k;
+    for (int c = C; c < cp; c++) slot_of[c] = c;
+    if (slot_of == b->slot_of) return 0;
+    return batch_apply_seating(b, slot_of);
 }
 } // namespace
 
@@ -553,6 +652,23 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         JB_CUDA(cudaStreamSynchronize(b->stream));
         cudaFree(dfc);
     }
+    b->d_chan_of = 0; b->d_keys = 0; b->h_keys = 0; b->d_ring_scratch = 0; b->ring_scratch_count = 0; b->epochs = 0; b->regroups = 0;
+    b->regroup_every = 0; b->next_regroup = 0;
+    if (s->kind == JAERO_KIND_OQPSK && s->fb > 8400 && b->use_pipe && !s->cpu_reduce) {
+        // the pipelined kernel seats channels by symbol-timing phase: first after 2.4 s of signal (loops locked), a check 2.7 s later,
+        // then every JAERO_REGROUP_EPOCHS estimator epochs (default 128 = 11 s; 0 = never: symbol clocks of different transmitters
+        // drift by a sample in minutes, not seconds)
+        const char *e = getenv("JAERO_REGROUP_EPOCHS");
+        b->regroup_every = e ? atoi(e) : 128;
+        if (batch_alloc(b, &b->d_chan_of, (size_t)2 * cp) || batch_alloc(b, &b->d_keys, (size_t)cp)) return JAERO_E_CUDA;
+        JB_CUDA(cudaMallocHost(&b->h_keys, cp * sizeof(double)));
+        b->slot_of.resize(cp);
+        std::vector<int> ident(cp);
+        for (size_t c = 0; c < cp; c++) { ident[c] = (int)c; b->slot_of[c] = (int)c; }
+        JB_CUDA(cudaMemcpy(b->d_chan_of, ident.data(), cp * sizeof(int), cudaMemcpyHostToDevice));
+        p.chan_of = b->d_chan_of;
+        b->next_regroup = b->regroup_every > 0 ? 28 : -1;
+    }
     JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)I_COUNT * cp * sizeof(int)));
     JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)D_COUNT * cp * sizeof(double)));
     JB_CUDA(cudaMallocHost(&b->h_soft_total, cp * sizeof(long long)));
@@ -575,7 +691,8 @@ void jaero_batch_destroy(jaero_batch *b)
     for (int k = 0; k < 2; k++) if (b->ev_cfe_done[k]) cudaEventDestroy(b->ev_cfe_done[k]);
     for (void *q : b->allocs) cudaFree(q);
     cudaFree(b->d_stage); cudaFree(b->d_x);
-    cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage); cudaFreeHost(b->h_soft_total);
+    cudaFreeHost(b->h_ints); cudaFreeHost(b->h_dbls); cudaFreeHost(b->h_soft_stage); cudaFreeHost(b->h_soft_total); cudaFreeHost(b->h_keys);
+    cudaFree(b->d_ring_scratch);
     for (auto &e : b->ev_seg) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (auto &e : b->ev_cfe) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
@@ -667,6 +784,10 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
             }
         }
     }
+    if (b->regroup_every > 0 && b->next_regroup >= 0 && b->epochs >= b->next_regroup) {
+        if (batch_regroup_by_phase(b, false)) return JAERO_E_CUDA;
+        b->next_regroup = b->epochs + (b->epochs < 64 ? 32 : b->regroup_every);
+    }
     peak_kernel<<<(p.n_channels + 3) / 4, 128, 0, b->stream>>>(p, d_pcm, stride, (int)n);
     JB_CUDA(cudaGetLastError());
     b->launches++;
@@ -746,6 +867,7 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
                 if (cfe_in_flight) JB_CUDA(cudaStreamWaitEvent(b->stream, b->ev_cfe_done[(b->cfe_count - 1) & 1], 0));
                 cfe_in_flight = true;
             }
+            b->epochs++;
             cc = 0;                                                // :426
             seg_start = i; resume = true; seg_bb = bbp; seg_cc = 0;
         }
@@ -886,6 +1008,20 @@ int jaero_batch_wire_signal_status(jaero_batch *b, int enabled)
     if (!b) { set_error("null handle"); return JAERO_E_ARG; }
     b->p.wire_sigstat = enabled ? 1 : 0;
     return JAERO_OK;
+}
+// Seat the channels of the pipelined 10500 bps kernel: slot_of[c] = seat of channel c (a permutation of 0..n_channels-1), or NULL
+// to seat them by symbol-timing phase now. Results never depend on the seating (channels do not interact); throughput does.
+int jaero_batch_regroup(jaero_batch *b, const int32_t *slot_of)
+{
+    if (!b) { set_error("null handle"); return JAERO_E_ARG; }
+    if (!b->d_chan_of) return JAERO_OK;                        // this batch's kernel has a fixed seating
+    JB_CUDA(cudaSetDevice(b->device));
+    if (!slot_of) return batch_regroup_by_phase(b, true) ? JAERO_E_CUDA : JAERO_OK;
+    const int C = b->p.n_channels, cp = b->p.cpad;
+    std::vector<int> v(cp), seen(C, 0);
+    for (int c = 0; c < C; c++) { if (slot_of[c] < 0 || slot_of[c] >= C || seen[slot_of[c]]) { set_error("jaero_batch_regroup: not a permutation"); return JAERO_E_ARG; } seen[slot_of[c]] = 1; v[c] = slot_of[c]; }
+    for (int c = C; c < cp; c++) v[c] = c;
+    return batch_apply_seating(b, v) ? JAERO_E_CUDA : JAERO_OK;
 }
 int jaero_batch_set_cpu_reduce(jaero_batch *b, int state)
 {

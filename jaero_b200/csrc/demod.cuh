@@ -86,6 +86,7 @@ struct DemodParams {
     // DataCarrierDetect(false) at once: the kernel clears the channel's DCD and records the soft-bit position of the event for
     // the device frame layer (lost_pos[k][ch] = soft values emitted before event k).
     int wire_sigstat; int *lost_pos;  // [LOST_CAP][cpad]
+    const int *chan_of;               // [cpad] channel seated at (cta, lane) of the pipelined 10500 bps kernel (null: identity)
     const double *sin_t, *cos_t;      // the reference's 19999-entry tables (DSP.cpp:19-20), built on the host
     double *cfe_est_out;              // [ch] value CoarseFreqEstimate would emit this epoch
     const double2 *xpre;              // 8400 bps: K6 output of the current call [ch][xstride] (null otherwise)

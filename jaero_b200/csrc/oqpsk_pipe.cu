@@ -73,9 +73,13 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
     // {F,A | E,S | T | K1,K2}, {F,S | E,A | T | K1,K2}: all 8 % slower per epoch than this one.)
     const int lane = threadIdx.x & 31;
     const int warp = (int)(threadIdx.x >> 5);
-    const int ch_raw = blockIdx.x * OQ_THREADS + lane;
-    const bool live = ch_raw < p.n_channels;
-    const int ch = ch_raw;                                    // dead lanes run on their (allocated) pad column with zero input
+    // Which channel this lane carries. Channels are independent, so the library may seat them as it likes: it regroups them by
+    // symbol-timing phase (capi.cu, regroup) so that the 32 channels of a CTA strobe on the same samples - the expensive
+    // carrier-update path of warps K1 / K2 then runs on one sample in nine instead of (some lane) on every sample. All state
+    // stays indexed by channel; only the sample-rate rings, which are laid out by seat, move when the seating changes.
+    const int seat = blockIdx.x * OQ_THREADS + lane;
+    const int ch = p.chan_of ? p.chan_of[seat] : seat;       // dead lanes run on their (allocated) pad column with zero input
+    const bool live = ch < p.n_channels;
     const size_t cpad = p.cpad;
     if (threadIdx.x == 0) { for (int k = 0; k < 3; k++) mbar_init(&bars[k], 1); for (int k = 3; k < 9; k++) mbar_init(&bars[k], 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -350,3 +350,51 @@ def test_status_telemetry_peak_volume_and_scatter_points(golden):
     assert np.all(np.abs(np.abs(pts) - 1.0) < 0.6)                      # locked OQPSK constellation points sit near (+-1, +-1)
     assert list(st[2]["scatter"][:]) != list(st[0]["scatter"][:])
     b.close()
+
+
+def test_regrouping_never_changes_results(golden):
+    """The 10500 bps kernel may seat channels in any lane (the library regroups them by symbol-timing phase for speed): soft
+    bits and loop state must be bit-identical whatever the seating and whenever it changes - random permutations in the middle
+    of the stream, phase regrouping, and no regrouping at all."""
+    jb = _import()
+    kw = dict(golden["oqpsk_10500"]["kw"])
+    pcm = load_excerpt("oqpsk_10500")[:48000 * 5]
+    C = 70
+    rng = np.random.default_rng(7)
+    variants = np.stack([pcm, (pcm.astype(np.int32) * 2 // 3).astype(np.int16), np.roll(pcm, 5), np.roll(pcm, 123), pcm[::-1].copy()])
+    idx = rng.integers(0, 5, size=C)
+    pcm2 = np.ascontiguousarray(variants[idx])
+
+    def run(mode):
+        os.environ["JAERO_REGROUP_EPOCHS"] = "0" if mode == "fixed" else "24"
+        b = jb.DemodBatch("oqpsk", C, **kw)
+        acc = [[] for _ in range(C)]
+        for k, a in enumerate(range(0, pcm2.shape[1], 7000)):
+            if mode == "random" and k % 3 == 1:
+                b.regroup(rng.permutation(C))
+            if mode == "phase" and k == 20:
+                b.regroup()
+            b.write(pcm2[:, a:a + 7000])
+            if k % 4 == 3:
+                for c, s in enumerate(b.read_softbits()):
+                    acc[c].append(s)
+        for c, s in enumerate(b.read_softbits()):
+            acc[c].append(s)
+        st = b.status()
+        b.close()
+        return [np.concatenate(x) for x in acc], st
+
+    import os
+    try:
+        ref, st_ref = run("fixed")
+        for mode in ("random", "phase"):
+            got, st = run(mode)
+            for c in range(C):
+                assert np.array_equal(got[c], ref[c]), (mode, c)
+                for key in ("mixer2_wtptr", "st_wtptr", "mse", "agc", "ebno", "mixer2_freq"):
+                    assert st[c][key] == st_ref[c][key], (mode, c, key)
+    finally:
+        os.environ.pop("JAERO_REGROUP_EPOCHS", None)
+    so, sto = restated.OracleDemod("oqpsk", **kw), None
+    so.write(variants[idx[C - 1]])
+    assert np.array_equal(so.take_soft() >= 128, ref[C - 1] >= 128)
