@@ -806,7 +806,7 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
         }
         long long *d_trace = 0;
         if (const char *tf = getenv("JAERO_PIPE_TRACE")) {   // development aid: stage time stamps of one K1a launch
-            if (!b->trace_state && b->launches > 40 && (i1 - i0) > 4000 && p.kind == JAERO_KIND_OQPSK && b->use_pipe && !p.xpre && p.fb > 8400) {
+            if (!b->trace_state && b->launches > 300 && (i1 - i0) > 4000 && p.kind == JAERO_KIND_OQPSK && b->use_pipe && !p.xpre && p.fb > 8400) {
                 (void)tf; cudaMalloc(&d_trace, 64 * 16 * sizeof(long long)); cudaMemset(d_trace, 0, 64 * 16 * sizeof(long long));
                 a.trace = d_trace; a.trace_j0 = 2000;
             }

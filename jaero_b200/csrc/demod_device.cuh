@@ -91,15 +91,17 @@ __device__ __forceinline__ void osc_next_frame(Osc &o)               // DSP.cpp:
     if (o.step < 0) o.step = 0;
     o.last = o.ptr;
     o.ptr += o.step;
-    // `while(((int)WTptr)>=WTSIZE)`: for the non-negative finite pointer, (int)x >= N  <=>  x >= (double)N
-    while (o.ptr >= (double)WTSIZE) o.ptr -= WTSIZE;
+    // `while(((int)WTptr)>=WTSIZE)`: for the non-negative finite pointer, (int)x >= N  <=>  x >= (double)N. The step is below N
+    // (frequencies below Fs), so the loop body runs at most once: written as a branch around the (then idle) loop, which costs
+    // a compare instead of a divergent loop on every sample
+    if (o.ptr >= (double)WTSIZE) { o.ptr -= WTSIZE; while (o.ptr >= (double)WTSIZE) o.ptr -= WTSIZE; }
 }
 // table index the oscillator will have after its next WTnextFrame(), without committing the advance
 __device__ __forceinline__ int osc_next_index(const Osc &o)
 {
     double s = o.step; if (s < 0) s = 0;
     double q = o.ptr + s;
-    while (q >= (double)WTSIZE) q -= WTSIZE;
+    if (q >= (double)WTSIZE) { q -= WTSIZE; while (q >= (double)WTSIZE) q -= WTSIZE; }
     return osc_index(q);
 }
 __device__ __forceinline__ void osc_set_phase_deg(Osc &o, double p)  // DSP.cpp:175-180
@@ -116,8 +118,8 @@ __device__ __forceinline__ void osc_increase_phase_deg(Osc &o, double p)   // DS
 __device__ __forceinline__ void osc_advance_fraction_of_wave(Osc &o, double x)   // DSP.h:56
 {
     o.ptr += x * WTSIZE;
-    while (o.ptr >= WTSIZE) o.ptr -= WTSIZE;
-    while (o.ptr < 0) o.ptr += WTSIZE;
+    if (o.ptr >= WTSIZE) { o.ptr -= WTSIZE; while (o.ptr >= WTSIZE) o.ptr -= WTSIZE; }
+    if (o.ptr < 0) { o.ptr += WTSIZE; while (o.ptr < 0) o.ptr += WTSIZE; }
 }
 // IfHavePassedPoint (DSP.cpp:222-238); frac receives FractionOfSampleItPassesBy
 __device__ __forceinline__ bool osc_have_passed_point(const Osc &o, double fraction_of_wave, double &frac)

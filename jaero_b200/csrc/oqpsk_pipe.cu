@@ -172,8 +172,6 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 }
                 // a carrier update moves the pointer by ct_ec degrees = 55.6 * ct_ec entries: a few entries in lock, so the
                 // entry needed after an update sits in the speculated 128-byte line or one of its neighbours
-                l1_prefetch(cos_t + max(m2_spec - 16, 0)); l1_prefetch(cos_t + min(m2_spec + 16, WTSIZE - 1));
-                l1_prefetch(sin_t + max(m2_spec - 16, 0)); l1_prefetch(sin_t + min(m2_spec + 16, WTSIZE - 1));
                 nb_sync(BAR_P + sl);                           // P_j: carrier error of this sample (warp K1)
                 TR(8);
                 const double upd = HAND(sl, 14), ct_ec = HAND(sl, 15);
