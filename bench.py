@@ -545,7 +545,7 @@ def run_burst(a):
     base = torch.zeros(len(base_np), dtype=torch.int16, device=dev)
     if rank == 0:
         base.copy_(torch.from_numpy(base_np))
-    shard.broadcast_(base, 0)                       # the one collective of this workload: the shared recording over NCCL/NVLink
+    shard.broadcast_(base.view(torch.uint8), 0)     # (NCCL has no int16: the same bytes as uint8) the one collective of this workload: the shared recording over NCCL/NVLink
     offs = synth.replica_offsets(rank * C, rank * C + C)
     n = len(base_np)
     pitch = (n + 7) & ~7
@@ -651,7 +651,7 @@ def run_mix(a):
     b8 = torch.zeros(len(base8), dtype=torch.int16, device=dev)
     if rank == 0:
         b8.copy_(torch.from_numpy(base8))
-    shard.broadcast_(b8, 0)
+    shard.broadcast_(b8.view(torch.uint8), 0)       # NCCL has no int16 type: the same bytes as uint8
     sA, sB = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     pipe = Pipeline("oqpsk10500", cp, p_lo, 10.0, envs_t, dev, local, sA) if cp > 0 else None
     cb = cl = pcm8 = None

@@ -162,7 +162,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 const int sl = j & 1;
                 // speculative request for mixer2's next entry (right unless this sample turns out to be a carrier-update strobe)
                 const int m2_spec = osc_next_index(m2);
-                const double n2_re = cos_t[m2_spec], n2_im = sin_t[m2_spec];
+                const double n2_re = __ldcg(cos_t + m2_spec), n2_im = __ldcg(sin_t + m2_spec);
                 double dnext = 0.0;                            // input sample j+1, decoded by warp A a tile or two ahead
                 if (j + 1 < nB) {
                     const int e = j + 1, tb = (e >> 5) & 1;
@@ -182,7 +182,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
                 osc_next_frame(m2);                                               // :600 (st_osc / st_osc_ref live in warp T, mixer_center in warp T)
                 {
                     const int t = osc_index(m2.ptr);
-                    if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = cos_t[t]; c2_im = sin_t[t]; }
+                    if (t == m2_spec) { c2_re = n2_re; c2_im = n2_im; } else { c2_re = __ldcg(cos_t + t); c2_im = __ldcg(sin_t + t); }
                 }
                 TR(13);
                 if (j + 1 < nB) {   // the next sample's mixed value enters the FIR ring (:453-456)
@@ -338,7 +338,7 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
     // ======================================================================================= warp T: symbol-timing PLL
     else if (warp == 2) {
         Osc st = {LD(D_ST_PTR), LD(D_ST_STEP), LD(D_ST_FREQ), LD(D_ST_LAST)};
-        Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};
+        const double sr_freq = LD(D_SR_FREQ);                  // st_osc_ref: only its (constant) frequency is read here; warp A advances it
         __syncthreads();                                       // (1)
         const double ee = p.ee;
         double cs_re, cs_im;
@@ -358,8 +358,8 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             TR(11);
             osc_set_freq(st, (-st_angle_error * 0.00000001) + st.freq, Fs);   // :481 IncreseFreqHz
             osc_advance_fraction_of_wave(st, div_exact(-st_angle_error * 0.01, 360.0, 1.0 / 360.0)); // :482
-            if (st.freq < (sr.freq - 0.1)) osc_set_freq(st, (sr.freq - 0.1), Fs);
-            if (st.freq > (sr.freq + 0.1)) osc_set_freq(st, (sr.freq + 0.1), Fs);
+            if (st.freq < (sr_freq - 0.1)) osc_set_freq(st, (sr_freq - 0.1), Fs);
+            if (st.freq > (sr_freq + 0.1)) osc_set_freq(st, (sr_freq + 0.1), Fs);
             double frac = 0.0;
             const bool strobe = osc_have_passed_point(st, ee, frac);          // :488
             // slot sl's T->K1 fields were read by K1(j-2), which precedes X_{j-1} -> Z_j -> (E) -> this point: free
@@ -367,11 +367,10 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             __threadfence_block();
             nb_arrive(BAR_U + sl);
             TR(5);
-            osc_next_frame(st); osc_next_frame(sr);                           // :602-603
+            osc_next_frame(st);                                               // :602 (st_osc_ref, :603, advances in warp A)
             { const int t = osc_index(st.ptr); if (t == st_spec) { cs_re = ns_re; cs_im = ns_im; } else { cs_re = cos_t[t]; cs_im = sin_t[t]; } }
         }
         LD(D_ST_PTR) = st.ptr; LD(D_ST_STEP) = st.step; LD(D_ST_FREQ) = st.freq; LD(D_ST_LAST) = st.last;
-        LD(D_SR_PTR) = sr.ptr; LD(D_SR_STEP) = sr.step; LD(D_SR_FREQ) = sr.freq; LD(D_SR_LAST) = sr.last;
     }
     // ======================================================================================= warp E: envelope chain
     else if (warp == 1) {
@@ -587,12 +586,13 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
         };
         __syncthreads();                                       // (1) the slot may have re-centred mixer_center
         Osc mc = {LD(D_MC_PTR), LD(D_MC_STEP), LD(D_MC_FREQ), LD(D_MC_LAST)};
+        Osc sr = {LD(D_SR_PTR), LD(D_SR_STEP), LD(D_SR_FREQ), LD(D_SR_LAST)};   // st_osc_ref (:603): nothing in the loop reads its pointer
         int bb_pos = a.bb_pos, coarse_counter = a.coarse_counter;
         double2 *bb_row = p.bb + (size_t)ch * p.bb_len;
         const int bbn = p.bb_len;                               // a multiple of 8
         const bool cpu_reduce = p.cpu_reduce != 0;
         double cc_re, cc_im;
-        { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+        { const int t = osc_index(mc.ptr); cc_re = __ldcg(cos_t + t); cc_im = __ldcg(sin_t + t); }
         // This warp runs ahead of the demodulator loop: nothing it computes depends on the loop (PCM, mixer_center, the estimator
         // ring). It decodes the input into a two-tile ring for warp K2 and writes the estimator ring one full 128-byte line (8
         // samples) per lane at a time, so that every 32-byte sector reaches HBM whole.
@@ -618,13 +618,15 @@ oqpsk_pipe_kernel(const __grid_constant__ DemodParams p, const SegmentArgs a, co
             if (!(e == n - 1 && a.stop_after_a)) {
                 coarse_counter++;                                                 // :431
                 osc_next_frame(mc);                                               // :601
-                { const int t = osc_index(mc.ptr); cc_re = cos_t[t]; cc_im = sin_t[t]; }
+                osc_next_frame(sr);                                               // :603
+                { const int t = osc_index(mc.ptr); cc_re = __ldcg(cos_t + t); cc_im = __ldcg(sin_t + t); }   // L2 only: L1 is kept for warp T's entries
             }
             if ((e & 31) == 31 || e == n - 1)
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[3 + tb])) : "memory");   // tile (or the rest) complete
         }
         if (live) for (int k = line_first; k < (bb_pos & 7); k++) bb_row[(bb_pos & ~7) + k] = bbst[k * 32 + lane];   // the open line
         LD(D_MC_PTR) = mc.ptr; LD(D_MC_STEP) = mc.step; LD(D_MC_FREQ) = mc.freq; LD(D_MC_LAST) = mc.last;
+        LD(D_SR_PTR) = sr.ptr; LD(D_SR_LAST) = sr.last;
     }
     __syncthreads();                                           // (2) every warp is done with the FIR window
     for (int k = (int)(threadIdx.x >> 5); k < OQ_NT1; k += (int)(blockDim.x >> 5)) {
