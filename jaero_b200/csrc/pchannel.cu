@@ -58,6 +58,8 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     const int n = soft_count[ch];
     const int16_t *bits = soft + (size_t)ch * soft_cap;
     const int block_len = pp.block_len, QD = pp.queue;
+    // while the frame counter sits at its idle value 1e9 the block index is the constant (1e9 - BitsInHeader) % block_len
+    const int idle_idx = (1000000000 - pp.bits_in_header) % block_len;
     s.blocks_ready = 0;
     // the soft-bit row is read 8 values (16 B) at a time, the next group requested while the current one is consumed
     // (soft and soft_cap*2 are 16-byte multiples: cudaMalloc base, capacity rounded by the caller)
@@ -106,10 +108,9 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
             const unsigned short t = s.frameinfo; s.frameinfo = s.lastframeinfo; s.lastframeinfo = t;
         }
         if (s.cntr >= 16) {                                                  // :1540-1552
-            int idx = s.cntr - pp.bits_in_header;                            // (cntr-BitsInHeader)%block_len, negative -> 0, without a division
-            if (idx < 0) idx = 0;
-            if (idx >= 8 * block_len) idx %= block_len;                      // only while cntr sits at its 1e9 idle value
-            while (idx >= block_len) idx -= block_len;
+            int idx;                                                         // (cntr-BitsInHeader)%block_len, negative -> 0, without a division
+            if (s.cntr >= 1000000000) idx = idle_idx;
+            else { idx = s.cntr - pp.bits_in_header; if (idx < 0) idx = 0; while (idx >= block_len) idx -= block_len; }
             // every slot holds a completed block the Viterbi stage has not decoded yet: this bit has nowhere to go. Flag it
             // (read_sus / get_stats report JAERO_E_OVERFLOW) instead of overwriting a queued block.
             if (s.blocks_ready >= QD) s.queue_overflow = 1;
@@ -129,9 +130,12 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
                     if (m.frame_done) s.nframes++;
                     s.blocks_ready++;
                 } else s.queue_overflow = 1;
-                // the partially filled next block starts from the same buffer contents in the reference (it reuses
-                // `block`); copy forward so stale positions match if a frame is cut short
-                if (s.blocks_ready < QD) {
+                // The reference reuses one `block` buffer, so a block that completed without every position rewritten would carry
+                // the previous block's values. That cannot happen while the counter runs: the index goes 0, 1, 2 ... (or back to 0
+                // at a unique word), so by the time it reaches block_len-1 every position has been written since the last restart.
+                // Only the idle index could complete a stale block, and only if it were block_len-1 (it is 2366 / 240 / 48 for the
+                // three rates): then, and only then, the previous contents are copied forward.
+                if (idle_idx == block_len - 1 && s.blocks_ready < QD) {
                     const uint8_t *srcb = pp.blocks + ((size_t)ch * QD + (s.blocks_ready - 1)) * block_len;
                     uint8_t *dstb = pp.blocks + ((size_t)ch * QD + s.blocks_ready) * block_len;
                     if ((block_len & 15) == 0) {
@@ -225,7 +229,10 @@ pchan_su_kernel(PChanParams pp, int *__restrict__ demod_dcd)
     if (s.carry_slot > 0) {
         const uint8_t *srcb = pp.blocks + ((size_t)ch * QD + s.carry_slot) * block_len;
         uint8_t *dstb = pp.blocks + ((size_t)ch * QD) * block_len;
-        for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
+        if ((block_len & 15) == 0) {
+            const int4 *s4 = reinterpret_cast<const int4 *>(srcb); int4 *d4 = reinterpret_cast<int4 *>(dstb);
+            for (int k = 0; k < block_len / 16; k++) d4[k] = s4[k];
+        } else for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
         s.carry_slot = 0;
     }
     s.blocks_ready = 0;
