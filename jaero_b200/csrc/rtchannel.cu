@@ -136,9 +136,8 @@ rt_trial_kernel(RtParams rp, int smem_per_warp, int sbuf_bytes)
     if (ch >= rp.n_channels) return;
     unsigned char *base = rt_smem + (size_t)warp * smem_per_warp;
     uint8_t *sbuf = base;
-    unsigned *h0 = reinterpret_cast<unsigned *>(base + sbuf_bytes);
-    unsigned *h1 = h0 + V_CAP;
-    uint8_t *obits = reinterpret_cast<uint8_t *>(h1 + V_CAP);
+    uint2 *hist = reinterpret_cast<uint2 *>(base + sbuf_bytes);
+    uint8_t *obits = reinterpret_cast<uint8_t *>(hist + V_CAP);
     RtState *sp = rp.state + ch;
     RtSlot *slots = rp.slots + (size_t)ch * RT_SLOTS;
     int rc = sp->rc, lastpacketstate = sp->lastpacketstate, n_bad = sp->n_bad, out_count = sp->out_count, trials = sp->n_trials;
@@ -165,7 +164,7 @@ rt_trial_kernel(RtParams rp, int smem_per_warp, int sbuf_bytes)
                 const int sets = bp >> 1;
                 for (int k = lane; k < sets; k += 32) obits[k] = 0;
                 __syncwarp();
-                viterbi_decode_warp(sbuf, sets, h0, h1, obits, rc, lane);
+                viterbi_decode_warp(sbuf, sets, hist, obits, rc, lane);
                 __syncwarp();
                 for (int k = lane; k < sets; k += 32) obits[k] ^= c_rt_scr[k];            // scrambler.reset(); scrambler.update(deconvol)
                 __syncwarp();

@@ -33,9 +33,8 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, size_t in_stride, size_t 
     if (active_count && active_count[ch] <= active_q) return;      // nothing queued for this channel
     unsigned char *base = smem + (size_t)warp * smem_per_warp;
     uint8_t *sbuf = base;
-    unsigned *h0 = reinterpret_cast<unsigned *>(base + sbuf_bytes);
-    unsigned *h1 = h0 + V_CAP;
-    uint8_t *obits = reinterpret_cast<uint8_t *>(h1 + V_CAP);
+    uint2 *hist = reinterpret_cast<uint2 *>(base + sbuf_bytes);
+    uint8_t *obits = sbuf;                 // decoded bits overwrite the consumed head of the soft buffer (viterbi_core.cuh)
 
     // ---- stage the code-order soft buffer: overlap ‖ (de-interleaved) block ‖ erasure padding
     const int ov = (mode == 0) ? overlap_len[ch] : 0;
@@ -54,10 +53,17 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, size_t in_stride, size_t 
     }
     __syncwarp();
     const int sets = total >> 1;
-    for (int k = lane; k < sets; k += 32) obits[k] = 0;
+    // right(62) of the new code-order block, zero-extended to 62: taken before the decoded bits overwrite the buffer
+    const int kk = n_soft < 62 ? n_soft : 62;
+    uint8_t keep0 = 0, keep1 = 0;
+    if (mode == 0) {
+        if (lane < kk) keep0 = sbuf[ov + n_soft - kk + lane];
+        if (lane + 32 < kk) keep1 = sbuf[ov + n_soft - kk + lane + 32];
+    }
+    __syncwarp();
 
     int rc = renorm_counter[ch];
-    viterbi_decode_warp(sbuf, sets, h0, h1, obits, rc, lane);
+    const int nout = viterbi_decode_warp(sbuf, sets, hist, obits, rc, lane);
     renorm_counter[ch] = rc;
     __syncwarp();
 
@@ -67,14 +73,13 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, size_t in_stride, size_t 
     if (mode == 0) {
         // Decode_Continuous: mid(paddinglength+1, n/2); positions never written by the decoder read as 0
         const int pos = pad + 1;
-        for (int k = lane; k < nbits; k += 32) out[k] = (pos + k < sets) ? obits[pos + k] : (uint8_t)0;
+        for (int k = lane; k < nbits; k += 32) out[k] = (pos + k < nout) ? obits[pos + k] : (uint8_t)0;
         if (lane == 0 && n_valid) { int nv = (sets - pos < nbits) ? (sets - pos) : nbits; n_valid[ch] = nv < 0 ? 0 : nv; }   // QVector::mid truncation (empty, never negative)
-        // keep right(62) of the new (code-order) block, zero-extended to 62
-        const int kk = n_soft < 62 ? n_soft : 62;
-        for (int k = lane; k < 62; k += 32) overlap[ch * 64 + k] = (k < kk) ? sbuf[ov + n_soft - kk + k] : (uint8_t)0;
+        overlap[ch * 64 + lane] = keep0;
+        if (lane + 32 < 62) overlap[ch * 64 + lane + 32] = keep1;
         if (lane == 0) overlap_len[ch] = 62;
     } else {
-        for (int k = lane; k < nbits; k += 32) out[k] = obits[k];   // last K-1 positions stay 0
+        for (int k = lane; k < nbits; k += 32) out[k] = (k < nout) ? obits[k] : (uint8_t)0;   // last K-1 positions stay 0
         if (lane == 0 && n_valid) n_valid[ch] = nbits;
     }
 }
@@ -82,10 +87,9 @@ viterbi_k7_kernel(const uint8_t *__restrict__ soft_in, size_t in_stride, size_t 
 size_t viterbi_smem_per_warp(int n_soft, int pad, int *sbuf_bytes)
 {
     int total = 62 + n_soft + pad;
-    int sb = (total + 15) & ~15;
-    int ob = ((total / 2) + 15) & ~15;
+    int sb = (total + 2 + 15) & ~15;              // + one look-ahead pair
     *sbuf_bytes = sb;
-    return (size_t)sb + 2 * V_CAP * sizeof(unsigned) + ob;
+    return (size_t)sb + V_CAP * sizeof(uint2);
 }
 
 int viterbi_launch(const uint8_t *d_soft, int n_soft, int cols, int mode, int pad, uint8_t *d_overlap,

@@ -18,7 +18,7 @@ __device__ __forceinline__ unsigned parity7(unsigned x) { return __popc(x) & 1u;
 __device__ __forceinline__ unsigned conv_out(unsigned sr) { return parity7(sr & 109u) | (parity7(sr & 79u) << 1); }
 
 struct WarpHist {
-    unsigned *h0, *h1;       // decision words of even / odd successors, V_CAP entries each
+    uint2 *h;                // decision words of a step: x = even successors 2l, y = odd successors 2l+1; V_CAP entries
     uint8_t *obits;          // decoded bits, oldest first
     int index, len, nout;
 };
@@ -29,78 +29,116 @@ __device__ __forceinline__ void traceback(WarpHist &H, unsigned state, int min_t
     int idx = H.index;
     const int len = H.len;
     const int g = len - min_tb;
+    uint8_t *ob = H.obits + H.nout + (g - 1) + min_tb;          // step j of the walk decides position ob[-j]
     for (int j = 0; j < len; j++) {
         idx = (idx == 0) ? V_CAP - 1 : idx - 1;
-        unsigned w = (state & 1u) ? H.h1[idx] : H.h0[idx];
-        unsigned h = (w >> (state >> 1)) & 1u;
+        const uint2 d = H.h[idx];
+        const unsigned w = (state & 1u) ? d.y : d.x;
+        const unsigned h = (w >> (state >> 1)) & 1u;
         state = (state >> 1) | (h << 5);
-        if (j >= min_tb && lane == 0) H.obits[H.nout + (g - 1 - (j - min_tb))] = (uint8_t)h;
+        if (j >= min_tb && lane == 0) ob[-j] = (uint8_t)h;
     }
     if (g > 0) { H.nout += g; H.len -= g; }
 }
 
-// Decode `sets` trellis steps from sbuf[0 .. 2*sets) (soft values 0..255, code order). obits must be zero-filled for
-// [0, sets); h0/h1 are V_CAP-entry decision rings. rc = libcorrect's renormalisation counter (persists across calls).
-__device__ __forceinline__ void viterbi_decode_warp(const uint8_t *__restrict__ sbuf, int sets, unsigned *h0, unsigned *h1, uint8_t *obits, int &rc, int lane)
+// Lane constants of the add-compare-select step. Both generator polynomials (109, 79) have their first and last taps set,
+// so the four branch labels a lane needs are one label t = table[2l] and its complement: table[2l | 64] = table[2l + 1] =
+// t ^ 3, table[(2l + 1) | 64] = t. With soft values a, b in 0..255 the distance to label t is (a ^ ma) + (b ^ mb) where
+// ma / mb = 0xff when the label's bit is set (|soft - 255| = soft ^ 0xff), and the distance to t ^ 3 is 510 minus it.
+struct VitLane {
+    unsigned s0, s1, m16, psel;
+    int src_lo, src_hi, lane;
+};
+
+struct VitState { unsigned m; int rc; WarpHist H; };
+
+// One trellis step with history. TAIL: the zero-tail steps (ties go to the high predecessor, only states whose low bits
+// are zero compete for the best state).
+template <bool TAIL>
+__device__ __forceinline__ void acs_step(VitState &S, const VitLane &L, unsigned d, int i, int sets)
 {
-    // per-lane branch outputs for successors 2l (e=0) and 2l+1 (e=1)
-    const unsigned s0 = 2u * lane, s1 = 2u * lane + 1u;
-    const unsigned tl0 = conv_out(s0), th0 = conv_out(s0 | 64u), tl1 = conv_out(s1), th1 = conv_out(s1 | 64u);
-    const int src_lo = lane >> 1, src_hi = 16 + (lane >> 1);
-    const bool odd = lane & 1;
-
-    unsigned m = 0;                       // packed metrics: e0 | e1<<16 (error_buffer_reset -> 0)
-    WarpHist H; H.h0 = h0; H.h1 = h1; H.obits = obits; H.index = 0; H.len = 0; H.nout = 0;
-
-    for (int i = 0; i < sets; i++) {
-        const unsigned a0 = sbuf[2 * i], b0 = sbuf[2 * i + 1];
-        const unsigned a1 = 255u - a0, b1 = 255u - b0;    // |soft-255|
-        const unsigned vlo = __shfl_sync(FULL, m, src_lo), vhi = __shfl_sync(FULL, m, src_hi);
-        const unsigned mlo = odd ? (vlo >> 16) : (vlo & 0xffffu);
-        const unsigned mhi = odd ? (vhi >> 16) : (vhi & 0xffffu);
-#define DSEL(t) (((t) & 1u ? a1 : a0) + ((t) & 2u ? b1 : b0))
-        if (i < VK - 1) {
-            // warm-up: errors[j] = dist(table[j]) + errors[j>>1] for the states reachable so far; no history
-            unsigned e0 = (DSEL(tl0) + mlo) & 0xffffu, e1 = (DSEL(tl1) + mlo) & 0xffffu;
-            unsigned lim = 1u << (i + 1);
-            unsigned o0 = m & 0xffffu, o1 = m >> 16;
-            if (s0 < lim) o0 = e0;
-            if (s1 < lim) o1 = e1;
-            m = o0 | (o1 << 16);
-            continue;
+    const unsigned dn = 510u - d;
+    const unsigned vlo = __shfl_sync(FULL, S.m, L.src_lo), vhi = __shfl_sync(FULL, S.m, L.src_hi);
+    const unsigned mlo = __byte_perm(vlo, 0u, L.psel), mhi = __byte_perm(vhi, 0u, L.psel);
+    const unsigned lo0 = (d + mlo) & 0xffffu, hi0 = (dn + mhi) & 0xffffu;
+    const unsigned lo1 = (dn + mlo) & 0xffffu, hi1 = (d + mhi) & 0xffffu;
+    // inner: ties -> low predecessor (<=); tail: ties -> high predecessor (<). The survivor's metric is the minimum either way.
+    const bool take_hi0 = TAIL ? (lo0 >= hi0) : (lo0 > hi0);
+    const bool take_hi1 = TAIL ? (lo1 >= hi1) : (lo1 > hi1);
+    unsigned e0 = min(lo0, hi0), e1 = min(lo1, hi1);
+    const unsigned w0 = __ballot_sync(FULL, take_hi0), w1 = __ballot_sync(FULL, take_hi1);
+    if (L.lane == 0) S.H.h[S.H.index] = make_uint2(w0, w1);
+    // history_buffer_process_skip
+    S.H.index++; if (S.H.index == V_CAP) S.H.index = 0;
+    S.rc++; S.H.len++;
+    const bool renorm = (S.rc == V_RENORM);
+    const bool tb = (S.H.len == V_CAP);
+    if (renorm || tb) {
+        const unsigned skip = TAIL ? (1u << (VK - (sets - i))) : 1u;
+        unsigned k0 = ((L.s0 & (skip - 1u)) == 0u) ? ((e0 << 6) | L.s0) : 0xffffffffu;
+        unsigned k1 = ((L.s1 & (skip - 1u)) == 0u) ? ((e1 << 6) | L.s1) : 0xffffffffu;
+        unsigned best = __reduce_min_sync(FULL, min(k0, k1));
+        if (renorm) {
+            S.rc = 0;
+            unsigned mn = best >> 6;
+            if ((L.s0 & (skip - 1u)) == 0u) e0 = (e0 - mn) & 0xffffu;
+            if ((L.s1 & (skip - 1u)) == 0u) e1 = (e1 - mn) & 0xffffu;
         }
-        const bool tail = (i + (VK - 1) >= sets);
-        const unsigned lo0 = (DSEL(tl0) + mlo) & 0xffffu, hi0 = (DSEL(th0) + mhi) & 0xffffu;
-        const unsigned lo1 = (DSEL(tl1) + mlo) & 0xffffu, hi1 = (DSEL(th1) + mhi) & 0xffffu;
-#undef DSEL
-        // inner: ties -> low predecessor (<=); tail: ties -> high predecessor (<)
-        const bool pick_lo0 = tail ? (lo0 < hi0) : (lo0 <= hi0);
-        const bool pick_lo1 = tail ? (lo1 < hi1) : (lo1 <= hi1);
-        unsigned e0 = pick_lo0 ? lo0 : hi0, e1 = pick_lo1 ? lo1 : hi1;
-        const unsigned w0 = __ballot_sync(FULL, !pick_lo0), w1 = __ballot_sync(FULL, !pick_lo1);
-        if (lane == 0) { h0[H.index] = w0; h1[H.index] = w1; }
-        __syncwarp();
-        const unsigned skip = tail ? (1u << (VK - (sets - i))) : 1u;
-        // history_buffer_process_skip
-        H.index++; if (H.index == V_CAP) H.index = 0;
-        rc++; H.len++;
-        const bool renorm = (rc == V_RENORM);
-        const bool tb = (H.len == V_CAP);
-        if (renorm || tb) {
-            unsigned k0 = ((s0 & (skip - 1u)) == 0u) ? ((e0 << 6) | s0) : 0xffffffffu;
-            unsigned k1 = ((s1 & (skip - 1u)) == 0u) ? ((e1 << 6) | s1) : 0xffffffffu;
-            unsigned best = __reduce_min_sync(FULL, min(k0, k1));
-            if (renorm) {
-                rc = 0;
-                unsigned mn = best >> 6;
-                if ((s0 & (skip - 1u)) == 0u) e0 = (e0 - mn) & 0xffffu;
-                if ((s1 & (skip - 1u)) == 0u) e1 = (e1 - mn) & 0xffffu;
-            }
-            if (tb) traceback(H, best & 63u, V_MIN_TB, lane);
-        }
-        m = e0 | (e1 << 16);
+        if (tb) { __syncwarp(); traceback(S.H, best & 63u, V_MIN_TB, L.lane); }
     }
-    traceback(H, 0u, 0, lane);            // history_buffer_flush
+    S.m = e0 | (e1 << 16);
+}
+
+// Decode `sets` trellis steps from sbuf[0 .. 2*sets) (soft values 0..255, code order; 2-byte aligned). hist is a V_CAP-entry
+// decision ring. rc = libcorrect's renormalisation counter (persists across calls). Returns the number of decoded bits
+// written to obits[0 ..) (= sets - (K-1) once sets >= K-1); later positions are not touched. obits may be sbuf itself: the
+// bit of step p is written after step p + V_MIN_TB has been read, at byte p < 2p.
+__device__ __forceinline__ int viterbi_decode_warp(const uint8_t *sbuf, int sets, uint2 *hist, uint8_t *obits, int &rc, int lane)
+{
+    VitLane L;
+    L.lane = lane; L.s0 = 2u * lane; L.s1 = L.s0 + 1u;
+    const unsigned t = conv_out(L.s0);
+    L.m16 = ((t & 1u) ? 0x00ffu : 0u) | ((t & 2u) ? 0xff00u : 0u);
+    L.psel = (lane & 1) ? 0x4432u : 0x4410u;         // byte_perm selector: the odd / even half of a packed metric pair
+    L.src_lo = lane >> 1; L.src_hi = 16 + (lane >> 1);
+    const unsigned short *sb16 = reinterpret_cast<const unsigned short *>(sbuf);
+#define VDIST(x16) ((((unsigned)(x16) ^ L.m16) & 0xffu) + (((unsigned)(x16) ^ L.m16) >> 8))
+
+    VitState S;
+    S.m = 0;                              // packed metrics: e0 | e1<<16 (error_buffer_reset -> 0)
+    S.rc = rc;
+    S.H.h = hist; S.H.obits = obits; S.H.index = 0; S.H.len = 0; S.H.nout = 0;
+
+    // warm-up: errors[j] = dist(table[j]) + errors[j>>1] for the states reachable so far; no history
+    const int nwarm = sets < VK - 1 ? sets : VK - 1;
+    for (int i = 0; i < nwarm; i++) {
+        const unsigned d = VDIST(sb16[i]), dn = 510u - d;
+        const unsigned vlo = __shfl_sync(FULL, S.m, L.src_lo);
+        const unsigned mlo = __byte_perm(vlo, 0u, L.psel);
+        const unsigned e0 = (d + mlo) & 0xffffu, e1 = (dn + mlo) & 0xffffu;
+        const unsigned lim = 1u << (i + 1);
+        unsigned o0 = S.m & 0xffffu, o1 = S.m >> 16;
+        if (L.s0 < lim) o0 = e0;
+        if (L.s1 < lim) o1 = e1;
+        S.m = o0 | (o1 << 16);
+    }
+    const int tail_start = (sets - (VK - 1) > VK - 1) ? sets - (VK - 1) : VK - 1;
+    int i = VK - 1;
+    unsigned x = (i < sets) ? sb16[i] : 0u;
+    for (; i < tail_start; i++) {
+        const unsigned d = VDIST(x);
+        x = sb16[i + 1];                  // i + 1 <= sets - (K-1): inside the staged buffer
+        acs_step<false>(S, L, d, i, sets);
+    }
+    for (; i < sets; i++) {
+        const unsigned d = VDIST(sb16[i]);
+        acs_step<true>(S, L, d, i, sets);
+    }
+#undef VDIST
+    __syncwarp();
+    traceback(S.H, 0u, 0, lane);          // history_buffer_flush
+    rc = S.rc;
+    return S.H.nout;
 }
 
 } // namespace jb

@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-per_unit = float(sys.argv[2]) if len(sys.argv) > 2 else None      # warp-samples in the launch: warps * samples
+per_unit = float(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] else None      # warp-samples in the launch: warps * samples
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
