@@ -47,12 +47,106 @@ __device__ __forceinline__ int uw_exact(unsigned &sr, int bit)
     return 0;
 }
 
-__global__ void __launch_bounds__(64)
+// One soft bit through AeroL::Decode's continuous branch. Every lane of the channel's warp runs it with the same state
+// (the state is warp-uniform); lane 0 does the stores.
+__device__ __forceinline__ void pchan_frame_bit(const PChanParams &pp, PChanState &s, int ch, int v, int idle_idx, int lane)
+{
+    const int block_len = pp.block_len, QD = pp.queue;
+    int bit = (((unsigned char)v) >= 128) ? 1 : 0;                           // aerol.cpp:1136-1139
+    int soft_bit = (unsigned short)v;
+    if (v < 0) return;                                                       // burst marker: never in continuous modes
+    int gotsync;
+    if (pp.oqpsk) {                                                          // :1156-1233
+        s.realimag++; s.realimag %= 2;
+        const bool search = (s.cntr > pp.number_of_bits - 68 || s.cntr <= 0 || !s.datacd);
+        int inv;
+        if (s.realimag) {                                                    // explicit arms: the state stays in registers
+            if (search) gotsync = uw_invariant(s.sr_imag, bit, s.inv_imag);
+            inv = s.inv_imag;
+        } else {
+            if (search) gotsync = uw_invariant(s.sr_real, bit, s.inv_real);
+            inv = s.inv_real;
+        }
+        if (search) { if (!s.gotsync_last) { s.gotsync_last = gotsync; gotsync = 0; } else s.gotsync_last = 0; }
+        else { gotsync = 0; s.gotsync_last = 0; }
+        if (inv) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
+    } else gotsync = uw_exact(s.sr_plain, bit);                              // :1269-1272
+
+    if (s.cntr < 1000000000) s.cntr++;
+    if (s.cntr < 16) {                                                       // :1275-1300
+        if (s.cntr == 0) { s.frameinfo = (unsigned short)bit; s.info_len = 0; }
+        else s.frameinfo = (unsigned short)((s.frameinfo << 1) | bit);
+    }
+    if (s.cntr == 15) {                                                      // :1301-1319
+        const unsigned short t = s.frameinfo; s.frameinfo = s.lastframeinfo; s.lastframeinfo = t;
+    }
+    if (s.cntr >= 16) {                                                      // :1540-1552
+        int idx;                                                             // (cntr-BitsInHeader)%block_len, negative -> 0
+        if (s.cntr >= 1000000000) idx = idle_idx;
+        else { idx = s.cntr - pp.bits_in_header; if (idx < 0) idx = 0; idx %= block_len; }
+        // every slot holds a completed block the Viterbi stage has not decoded yet: this bit has nowhere to go. Flag it
+        // (read_sus / get_stats report JAERO_E_OVERFLOW) instead of overwriting a queued block.
+        if (s.blocks_ready >= QD) s.queue_overflow = 1;
+        else if (lane == 0) pp.blocks[((size_t)ch * QD + s.blocks_ready) * block_len + idx] = (uint8_t)soft_bit;
+        if (idx == block_len - 1) {
+            // block complete: queue it for the Viterbi stage with what the SU stage needs to know
+            if (s.blocks_ready < QD) {
+                PChanBlockMeta m;
+                const int nbits = s.first_decode_done ? block_len / 2 : block_len / 2 - (pp.paddinglength / 2 + 1);
+                m.scr_pos = s.scr_pos; m.info_off = s.info_len; m.n_valid = nbits;
+                m.frame_done = ((s.cntr - pp.bits_in_header) == (pp.number_of_bits - 1)) ? 1 : 0;   // :1582
+                m.frame_index = s.nframes;
+                if (lane == 0) pp.meta[(size_t)ch * QD + s.blocks_ready] = m;
+                s.scr_pos += nbits;                                          // scrambler.update advances by deconvol.size()
+                s.info_len += nbits / 8;                                     // whole bytes appended (:1568-1580)
+                s.first_decode_done = 1;
+                if (m.frame_done) s.nframes++;
+                s.blocks_ready++;
+            } else s.queue_overflow = 1;
+            // The reference reuses one `block` buffer, so a block that completed without every position rewritten would carry
+            // the previous block's values. That cannot happen while the counter runs: the index goes 0, 1, 2 ... (or back to 0
+            // at a unique word), so by the time it reaches block_len-1 every position has been written since the last restart.
+            // Only the idle index could complete a stale block, and only if it were block_len-1 (it is 2366 / 240 / 48 for the
+            // three rates): then, and only then, the previous contents are copied forward.
+            if (idle_idx == block_len - 1 && s.blocks_ready < QD) {
+                __syncwarp();
+                const uint8_t *srcb = pp.blocks + ((size_t)ch * QD + (s.blocks_ready - 1)) * block_len;
+                uint8_t *dstb = pp.blocks + ((size_t)ch * QD + s.blocks_ready) * block_len;
+                for (int k = lane; k < block_len; k += 32) dstb[k] = srcb[k];
+                __syncwarp();
+            }
+        }
+    }
+    if (gotsync) {                                                           // :1990-2011
+        s.cntr = -1; s.datacd = 1; s.datacdcountdown = 12; s.scr_pos = 0; s.dcd_rises++;
+    }
+    if (s.cntr + 1 == pp.total_number_of_bits) { s.scr_pos = 0; s.cntr = -1; }   // :2013-2016
+}
+
+// bits 0, 2, 4 ... of x packed into the low 16 bits
+__device__ __forceinline__ unsigned even_bits(unsigned x)
+{
+    x &= 0x55555555u;
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0f0f0f0fu;
+    x = (x | (x >> 4)) & 0x00ff00ffu;
+    x = (x | (x >> 8)) & 0x0000ffffu;
+    return x;
+}
+
+// One warp per channel. The bit loop of AeroL::Decode is a state machine, but between its events it is regular: while the
+// frame counter runs inside a block (or idles at 1e9) and no unique word appears, soft bit i + j goes to block position
+// idx + j, the real / imaginary arm alternates, and nothing else changes. Those stretches are taken 32 bits at a time, one
+// bit per lane (the unique-word shift registers of all 32 positions are formed from a ballot and compared in parallel);
+// header bits, block completions, frame wrap, unique-word hits, LostSignal events and the 600 / 1200 bps framing take the
+// bit-serial path above. Both paths apply the same updates, so the result does not depend on where the stretches end.
+__global__ void __launch_bounds__(128)
 pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *__restrict__ soft_count, int soft_cap,
                    int *__restrict__ demod_dcd /* may be null */, const int *__restrict__ lost_n /* may be null */,
                    const int *__restrict__ lost_pos, size_t lost_pitch)
 {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ch >= pp.n_channels) return;
     PChanState s = pp.state[ch];
     const int n = soft_count[ch];
@@ -61,102 +155,85 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     // while the frame counter sits at its idle value 1e9 the block index is the constant (1e9 - BitsInHeader) % block_len
     const int idle_idx = (1000000000 - pp.bits_in_header) % block_len;
     s.blocks_ready = 0;
-    // the soft-bit row is read 8 values (16 B) at a time, the next group requested while the current one is consumed
-    // (soft and soft_cap*2 are 16-byte multiples: cudaMalloc base, capacity rounded by the caller)
-    const bool vec_ok = ((((size_t)soft_cap * 2) & 15) == 0) && ((((uintptr_t)soft) & 15) == 0);
-    int4 grp = make_int4(0, 0, 0, 0), grp_next = make_int4(0, 0, 0, 0);
-    if (vec_ok && n > 0) { grp = *reinterpret_cast<const int4 *>(bits); if (n > 8) grp_next = *reinterpret_cast<const int4 *>(bits + 8); }
     // AeroL::LostSignal (aerol.h:925-931) at the soft-bit positions the demodulator recorded its SignalStatus(false) events
     int nev = lost_n ? min(lost_n[ch], LOST_CAP) : 0, ev = 0;
     if (lost_n && lost_n[ch] > LOST_CAP) s.queue_overflow = 1;
     int next_ev = nev ? lost_pos[ch] : 0x7fffffff;
-    for (int i = 0; i < n; i++) {
+    int i = 0;
+    while (i < n) {
         while (i >= next_ev) { s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0; ev++; next_ev = ev < nev ? lost_pos[(size_t)ev * lost_pitch + ch] : 0x7fffffff; }
-        int v;
-        if (vec_ok) {
-            const int k = i & 7;
-            if (k == 0 && i > 0) { grp = grp_next; if (i + 8 < n) grp_next = *reinterpret_cast<const int4 *>(bits + i + 8); }
-            const int w = (k < 2) ? grp.x : (k < 4) ? grp.y : (k < 6) ? grp.z : grp.w;
-            v = (k & 1) ? (w >> 16) : (int)(short)(w & 0xffff);
-        } else v = bits[i];
-        int bit = (((unsigned char)v) >= 128) ? 1 : 0;                       // aerol.cpp:1136-1139
-        int soft_bit = (unsigned short)v;
-        if (v < 0) continue;                                                 // burst marker: never in continuous modes
-        int gotsync;
-        if (pp.oqpsk) {                                                      // :1156-1233
-            s.realimag++; s.realimag %= 2;
-            const bool search = (s.cntr > pp.number_of_bits - 68 || s.cntr <= 0 || !s.datacd);
-            int inv;
-            if (s.realimag) {                                                // explicit arms: the state stays in registers
-                if (search) gotsync = uw_invariant(s.sr_imag, bit, s.inv_imag);
-                inv = s.inv_imag;
-            } else {
-                if (search) gotsync = uw_invariant(s.sr_real, bit, s.inv_real);
-                inv = s.inv_real;
+        int r = min(32, min(n, next_ev) - i);                                // bits this round may take (>= 1)
+        const int v = (lane < r) ? (int)bits[i + lane] : 0;
+        const unsigned negm = __ballot_sync(0xffffffffu, v < 0);
+        if (negm) r = min(r, __ffs(negm) - 1);
+        const int c = s.cntr;
+        const bool idle = (c >= 1000000000);
+        bool fast = pp.oqpsk && r > 0 && s.blocks_ready < QD;
+        bool searching = true;
+        int idx0 = idle_idx;
+        if (fast && !idle) {
+            // the counter runs: stay clear of the header (cntr < 16), the end of the block and the frame wrap
+            fast = (c >= 16) && (c + 1 >= pp.bits_in_header);
+            if (fast) {
+                idx0 = (c + 1 - pp.bits_in_header) % block_len;
+                r = min(r, block_len - 1 - idx0);
+                r = min(r, pp.total_number_of_bits - 2 - c);
+                searching = (!s.datacd) || (c > pp.number_of_bits - 68);
+                if (!searching) r = min(r, pp.number_of_bits - 68 - c + 1);
+                fast = r > 0;
             }
-            if (search) { if (!s.gotsync_last) { s.gotsync_last = gotsync; gotsync = 0; } else s.gotsync_last = 0; }
-            else { gotsync = 0; s.gotsync_last = 0; }
-            if (inv) { bit = 1 - bit; if (soft_bit != 128) soft_bit = 255 - soft_bit; }
-        } else gotsync = uw_exact(s.sr_plain, bit);                          // :1269-1272
-
-        if (s.cntr < 1000000000) s.cntr++;
-        if (s.cntr < 16) {                                                   // :1275-1300
-            if (s.cntr == 0) { s.frameinfo = (unsigned short)bit; s.info_len = 0; }
-            else s.frameinfo = (unsigned short)((s.frameinfo << 1) | bit);
-        }
-        if (s.cntr == 15) {                                                  // :1301-1319
-            const unsigned short t = s.frameinfo; s.frameinfo = s.lastframeinfo; s.lastframeinfo = t;
-        }
-        if (s.cntr >= 16) {                                                  // :1540-1552
-            int idx;                                                         // (cntr-BitsInHeader)%block_len, negative -> 0, without a division
-            if (s.cntr >= 1000000000) idx = idle_idx;
-            else { idx = s.cntr - pp.bits_in_header; if (idx < 0) idx = 0; while (idx >= block_len) idx -= block_len; }
-            // every slot holds a completed block the Viterbi stage has not decoded yet: this bit has nowhere to go. Flag it
-            // (read_sus / get_stats report JAERO_E_OVERFLOW) instead of overwriting a queued block.
-            if (s.blocks_ready >= QD) s.queue_overflow = 1;
-            else pp.blocks[((size_t)ch * QD + s.blocks_ready) * block_len + idx] = (uint8_t)soft_bit;
-            if (idx == block_len - 1) {
-                // block complete: queue it for the Viterbi stage with what the SU stage needs to know
-                if (s.blocks_ready < QD) {
-                    PChanBlockMeta m;
-                    const int nbits = s.first_decode_done ? block_len / 2 : block_len / 2 - (pp.paddinglength / 2 + 1);
-                    m.scr_pos = s.scr_pos; m.info_off = s.info_len; m.n_valid = nbits;
-                    m.frame_done = ((s.cntr - pp.bits_in_header) == (pp.number_of_bits - 1)) ? 1 : 0;   // :1582
-                    m.frame_index = s.nframes;
-                    pp.meta[(size_t)ch * QD + s.blocks_ready] = m;
-                    s.scr_pos += nbits;                                      // scrambler.update advances by deconvol.size()
-                    s.info_len += nbits / 8;                                 // whole bytes appended (:1568-1580)
-                    s.first_decode_done = 1;
-                    if (m.frame_done) s.nframes++;
-                    s.blocks_ready++;
-                } else s.queue_overflow = 1;
-                // The reference reuses one `block` buffer, so a block that completed without every position rewritten would carry
-                // the previous block's values. That cannot happen while the counter runs: the index goes 0, 1, 2 ... (or back to 0
-                // at a unique word), so by the time it reaches block_len-1 every position has been written since the last restart.
-                // Only the idle index could complete a stale block, and only if it were block_len-1 (it is 2366 / 240 / 48 for the
-                // three rates): then, and only then, the previous contents are copied forward.
-                if (idle_idx == block_len - 1 && s.blocks_ready < QD) {
-                    const uint8_t *srcb = pp.blocks + ((size_t)ch * QD + (s.blocks_ready - 1)) * block_len;
-                    uint8_t *dstb = pp.blocks + ((size_t)ch * QD + s.blocks_ready) * block_len;
-                    if ((block_len & 15) == 0) {
-                        const int4 *s4 = reinterpret_cast<const int4 *>(srcb); int4 *d4 = reinterpret_cast<int4 *>(dstb);
-                        for (int k = 0; k < block_len / 16; k++) d4[k] = s4[k];
-                    } else for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
+        } else if (fast) fast = (idle_idx != block_len - 1);
+        if (fast) {
+            const unsigned valid = (r == 32) ? 0xffffffffu : ((1u << r) - 1u);
+            // lane j carries bit i + j; its arm: realimag after the increment
+            const int a_imag = ((s.realimag + 1) & 1) ? 0 : 1;               // offset of the first imaginary-arm bit in this round
+            const bool mine_imag = ((lane & 1) == a_imag);
+            if (searching) {
+                const int bit = (((unsigned char)v) >= 128) ? 1 : 0;
+                const unsigned B = __ballot_sync(0xffffffffu, bit != 0) & valid;
+                const unsigned E0 = even_bits(B), E1 = even_bits(B >> 1);    // bits of the even / odd lanes, in order
+                const unsigned Em = (lane & 1) ? E1 : E0;
+                const unsigned srp = mine_imag ? s.sr_imag : s.sr_real;
+                const int k = lane >> 1;
+                const unsigned W = (srp << (k + 1)) | (__brev(Em) >> (31 - k));   // the register after this lane's bit
+                const bool hit = (lane < r) && (W == UWORD || W == ~UWORD);
+                if (__any_sync(0xffffffffu, hit)) fast = false;              // a unique word inside the round: bit-serial
+                else {
+                    const int n0 = (r + 1) >> 1, n1 = r >> 1;                // bits taken by the even / odd lanes
+                    const unsigned sr_e = s.sr_imag, sr_r = s.sr_real;
+                    const unsigned imag_E = a_imag ? E1 : E0, real_E = a_imag ? E0 : E1;
+                    const int imag_n = a_imag ? n1 : n0, real_n = a_imag ? n0 : n1;
+                    if (imag_n) s.sr_imag = (sr_e << imag_n) | (__brev(imag_E) >> (32 - imag_n));
+                    if (real_n) s.sr_real = (sr_r << real_n) | (__brev(real_E) >> (32 - real_n));
                 }
             }
         }
-        if (gotsync) {                                                       // :1990-2011
-            s.cntr = -1; s.datacd = 1; s.datacdcountdown = 12; s.scr_pos = 0; s.dcd_rises++;
+        if (fast) {
+            const bool mine_imag = ((lane & 1) == (((s.realimag + 1) & 1) ? 0 : 1));
+            const int inv = mine_imag ? s.inv_imag : s.inv_real;
+            int soft_bit = (unsigned short)v;
+            if (inv && soft_bit != 128) soft_bit = 255 - soft_bit;
+            uint8_t *blk = pp.blocks + ((size_t)ch * QD + s.blocks_ready) * block_len;
+            if (idle) { if (lane == r - 1) blk[idle_idx] = (uint8_t)soft_bit; }      // every bit lands on the idle index: the last one stays
+            else { if (lane < r) blk[idx0 + lane] = (uint8_t)soft_bit; s.cntr = c + r; }
+            s.realimag = (s.realimag + r) & 1;
+            s.gotsync_last = 0;
+            i += r;
+        } else {
+            // one bit, serially (lane 0 holds bit i; a burst marker is only skipped)
+            pchan_frame_bit(pp, s, ch, __shfl_sync(0xffffffffu, v, 0), idle_idx, lane);
+            i++;
         }
-        if (s.cntr + 1 == pp.total_number_of_bits) { s.scr_pos = 0; s.cntr = -1; }   // :2013-2016
     }
     if (ev < nev) { s.cntr = 1000000000; s.datacdcountdown = 0; s.datacd = 0; }     // events after the last soft bit
     s.bits_seen += n;
     // carry the partially filled block of slot `blocks_ready` back to slot 0 for the next call
     if (s.blocks_ready > 0 && s.blocks_ready < QD) s.carry_slot = s.blocks_ready; else s.carry_slot = 0;
-    pp.state[ch] = s;
-    pp.ready[ch] = s.blocks_ready;
-    if (demod_dcd) demod_dcd[ch] = s.datacd;
+    if (lane == 0) {
+        pp.state[ch] = s;
+        pp.ready[ch] = s.blocks_ready;
+        if (demod_dcd) demod_dcd[ch] = s.datacd;
+    }
 }
 
 __global__ void __launch_bounds__(64)
@@ -297,7 +374,7 @@ int pchan_process(const PChanParams &pp, const int16_t *d_soft, const int *d_sof
                   long long *launches, const int *lost_n, const int *lost_pos, size_t lost_pitch)
 {
     const int grid = (pp.n_channels + 63) / 64;
-    pchan_frame_kernel<<<grid, 64, 0, st>>>(pp, d_soft, d_soft_count, soft_cap, demod_dcd, lost_n, lost_pos, lost_pitch);
+    pchan_frame_kernel<<<(pp.n_channels + 3) / 4, 128, 0, st>>>(pp, d_soft, d_soft_count, soft_cap, demod_dcd, lost_n, lost_pos, lost_pitch);
     JB_CUDA(cudaGetLastError());
     (*launches)++;
     for (int q = 0; q < max_queue; q++) {
