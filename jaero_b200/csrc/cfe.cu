@@ -269,7 +269,8 @@ namespace cgx = cooperative_groups;
 
 static const int CC_CL = 8, CC_T = 256, CC_SEQ = 16, CC_RS = 143;             // cluster size, threads, sequences per CTA, row stride
 static const int CC_BUF = CC_SEQ * CC_RS * 16;                                // one working buffer (bytes)
-static const int CC_SM_TOTAL = 2 * CC_BUF + 128 * 16;
+static const int CC_TW2 = 128, CC_TW3 = 152;                                  // offsets (in double2) of the per-pass twiddle copies
+static const int CC_SM_TOTAL = 2 * CC_BUF + (128 + 24 + 32) * 16;
 
 __device__ __forceinline__ int cc_ph(int e) { return e + (e >> 3); }          // padded position inside a 128-point sequence
 
@@ -277,11 +278,13 @@ __device__ __forceinline__ int cc_ph(int e) { return e + (e >> 3); }          //
 // sequences w and w+8 through all three passes, so the passes are ordered by __syncwarp() only: each pass reads its
 // butterflies' inputs into registers, __syncwarp, writes the outputs back into the same rows. `last` receives
 // (sequence, position, value) of the final pass and normally stores it back (mask / square are fused there).
-template <bool INV, class Store>
+// FIRST = false: the caller has already run the first (radix-8) pass from registers — the values it pulled from the ring or
+// from its peers are exactly one butterfly's inputs — stored the outputs (row[8j + t]) and passed a __syncthreads().
+template <bool INV, bool FIRST, class Store>
 __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 *__restrict__ tws, Store last)
 {
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    {   // radix 8, Ns = 1: lanes 0-15 -> sequence w, lanes 16-31 -> sequence w+8
+    if (FIRST) {   // radix 8, Ns = 1: lanes 0-15 -> sequence w, lanes 16-31 -> sequence w+8
         double2 *row = buf + (w + ((l & 16) >> 1)) * CC_RS;
         const int j = l & 15;
         double2 v[8];
@@ -294,8 +297,11 @@ __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 
         __syncwarp();
     }
     double2 *r0 = buf + w * CC_RS, *r1 = buf + (w + 8) * CC_RS;
-    auto radix4 = [&](double2 &v0, double2 &v1, double2 &v2, double2 &v3, int k, int wm) {
-        double2 w1 = tws[(k * wm) & 127], w2 = tws[(2 * k * wm) & 127], w3 = tws[(3 * k * wm) & 127];
+    // The twiddles of a pass depend on the lane only. Read straight from the 128-entry table the second pass's strides
+    // (4k, 8k, 12k) put a quarter-warp's eight 16-byte loads on two, one and two bank groups (4-, 8- and 4-way conflicts) and
+    // the third pass's 2l on four (2-way); the kernel keeps compact copies instead: tws[CC_TW2 + 8(m-1) + k] = W^(4mk),
+    // tws[CC_TW3 + l] = W^(2l). Same table values, so the arithmetic is unchanged.
+    auto radix4 = [&](double2 &v0, double2 &v1, double2 &v2, double2 &v3, double2 w1, double2 w2, double2 w3) {
         if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
         v1 = c_mul(v1, w1); v2 = c_mul(v2, w2); v3 = c_mul(v3, w3);
         dft4<INV>(v0, v1, v2, v3);
@@ -305,7 +311,8 @@ __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 
         double2 b0 = r1[cc_ph(l)], b1 = r1[cc_ph(l + 32)], b2 = r1[cc_ph(l + 64)], b3 = r1[cc_ph(l + 96)];
         __syncwarp();
         const int k = l & 7, ob = (l >> 3) * 32 + k;
-        radix4(a0, a1, a2, a3, k, 4); radix4(b0, b1, b2, b3, k, 4);
+        const double2 w1 = tws[CC_TW2 + k], w2 = tws[CC_TW2 + 8 + k], w3 = tws[CC_TW2 + 16 + k];
+        radix4(a0, a1, a2, a3, w1, w2, w3); radix4(b0, b1, b2, b3, w1, w2, w3);
         r0[cc_ph(ob)] = a0; r0[cc_ph(ob + 8)] = a1; r0[cc_ph(ob + 16)] = a2; r0[cc_ph(ob + 24)] = a3;
         r1[cc_ph(ob)] = b0; r1[cc_ph(ob + 8)] = b1; r1[cc_ph(ob + 16)] = b2; r1[cc_ph(ob + 24)] = b3;
         __syncwarp();
@@ -314,7 +321,8 @@ __device__ __forceinline__ void cc_fft(double2 *__restrict__ buf, const double2 
         double2 a0 = r0[cc_ph(l)], a1 = r0[cc_ph(l + 32)], a2 = r0[cc_ph(l + 64)], a3 = r0[cc_ph(l + 96)];
         double2 b0 = r1[cc_ph(l)], b1 = r1[cc_ph(l + 32)], b2 = r1[cc_ph(l + 64)], b3 = r1[cc_ph(l + 96)];
         __syncwarp();
-        radix4(a0, a1, a2, a3, l, 1); radix4(b0, b1, b2, b3, l, 1);
+        const double2 w1 = tws[l], w2 = tws[CC_TW3 + l], w3 = tws[3 * l];
+        radix4(a0, a1, a2, a3, w1, w2, w3); radix4(b0, b1, b2, b3, w1, w2, w3);
         last(w, l, a0); last(w, l + 32, a1); last(w, l + 64, a2); last(w, l + 96, a3);
         last(w + 8, l, b0); last(w + 8, l + 32, b1); last(w + 8, l + 64, b2); last(w + 8, l + 96, b3);
         __syncwarp();
@@ -334,6 +342,8 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
     const int N = 16384, ring_len = p.bb_len;
     const double2 *__restrict__ twN = pl.tw;
     if (threadIdx.x < 128) tws[threadIdx.x] = twN[threadIdx.x * (N / 128)];
+    else if (threadIdx.x < 128 + 24) { const int e = threadIdx.x - 128, m = e >> 3, k = e & 7; tws[CC_TW2 + e] = twN[(4 * (m + 1) * k) * (N / 128)]; }
+    else if (threadIdx.x < 128 + 24 + 32) { const int l = threadIdx.x - 152; tws[CC_TW3 + l] = twN[(2 * l) * (N / 128)]; }
     // The four-step twiddles W_N^(c*k1) are read from the same table the reference-order transforms use (a product of two
     // smaller tables breaks the exact conjugate symmetry of the table and with it the estimator's tie-breaks on symmetric
     // spectra). Their indices do not depend on the data, so the loads are issued ahead of the cluster barrier they follow.
@@ -358,15 +368,17 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
                 colv[i] = ring[n];
             }
         }
+        // ---- P1: column FFT over r                                                   A[cc][k1]
+        // this thread's eight samples r = r0i + 16 i of column cc are butterfly r0i of the first pass: it runs from registers
+        dft8<false>(colv);
         if (arrived) { cluster.barrier_wait(); arrived = false; }   // the peers have pulled the previous channel's P3 result out of A
         {
             const int cc = threadIdx.x & 15, r0i = threadIdx.x >> 4;
 #pragma unroll
-            for (int i = 0; i < 8; i++) bufA[cc * CC_RS + cc_ph(r0i + 16 * i)] = colv[i];
+            for (int i = 0; i < 8; i++) bufA[cc * CC_RS + cc_ph(8 * r0i + i)] = colv[i];
         }
         __syncthreads();
-        // ---- P1: column FFT over r, in place                                         A[cc][k1]
-        cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+        cc_fft<false, false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
         double2 tw8[8];
         {
             const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
@@ -377,21 +389,22 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
         // rows k1 = 16q+kk, all c: B[kk][c] = A_src[cc][k1] * W_N^{c k1}   (kk fastest: contiguous remote reads)
         {
             const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
+            double2 x[8];
 #pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const double2 x = rA[s][cc * CC_RS + cc_ph(16 * q + kk)];
-                bufB[kk * CC_RS + cc_ph(16 * s + cc)] = c_mul(x, tw8[s]);
-            }
+            for (int s = 0; s < 8; s++) x[s] = c_mul(rA[s][cc * CC_RS + cc_ph(16 * q + kk)], tw8[s]);
+            dft8<false>(x);                // c = cc + 16 s: butterfly cc of row kk's first pass
+#pragma unroll
+            for (int s = 0; s < 8; s++) bufB[kk * CC_RS + cc_ph(8 * cc + s)] = x[s];
         }
         __syncthreads();
         // ---- P2: row FFT over c -> mask (:99-100) -> row IFFT, in place               B[kk][c]
-        cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) {
+        cc_fft<false, false>(bufB, tws, [&](int f, int e, double2 v) {
             const int k = (16 * q + f) + 128 * e;          // X[k1 + n1*k2]
             if (!pl.is8400) { if (k >= pl.startbin && k <= pl.stopbin) v = make_double2(0.0, 0.0); }
             else { const double w = pl.window[k]; v = make_double2(v.x * w, v.y * w); }
             bufB[f * CC_RS + cc_ph(e)] = v;
         });
-        cc_fft<true>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
+        cc_fft<true, true>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
         {
             const int cc = threadIdx.x & 15, kk = threadIdx.x >> 4;
 #pragma unroll
@@ -401,19 +414,22 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
         // columns c = 16q+cc, all k1: A[cc][k1] = B_src[kk][c] * conj(W_N^{c k1})   (cc fastest: contiguous remote reads)
         {
             const int cc = threadIdx.x & 15, kk = threadIdx.x >> 4;
+            double2 x[8];
 #pragma unroll
             for (int s = 0; s < 8; s++) {
-                const double2 x = rB[s][kk * CC_RS + cc_ph(16 * q + cc)];
                 double2 w = tw8[s]; w.y = -w.y;
-                bufA[cc * CC_RS + cc_ph(16 * s + kk)] = c_mul(x, w);
+                x[s] = c_mul(rB[s][kk * CC_RS + cc_ph(16 * q + cc)], w);
             }
+            dft8<true>(x);                 // k1 = kk + 16 s: butterfly kk of column cc's first pass
+#pragma unroll
+            for (int s = 0; s < 8; s++) bufA[cc * CC_RS + cc_ph(8 * kk + s)] = x[s];
         }
         __syncthreads();
         // ---- P3: column IFFT over k1 -> square (:103) -> column FFT over r, in place  A[cc][k1]
-        cc_fft<true>(bufA, tws, [&](int f, int e, double2 v) {
+        cc_fft<true, false>(bufA, tws, [&](int f, int e, double2 v) {
             bufA[f * CC_RS + cc_ph(e)] = make_double2(v.x * v.x - v.y * v.y, v.x * v.y + v.y * v.x);
         });
-        cc_fft<false>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
+        cc_fft<false, true>(bufA, tws, [&](int f, int e, double2 v) { bufA[f * CC_RS + cc_ph(e)] = v; });
         {
             const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
 #pragma unroll
@@ -422,11 +438,12 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
         cluster.sync();
         {
             const int kk = threadIdx.x & 15, cc = threadIdx.x >> 4;
+            double2 x[8];
 #pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const double2 x = rA[s][cc * CC_RS + cc_ph(16 * q + kk)];
-                bufB[kk * CC_RS + cc_ph(16 * s + cc)] = c_mul(x, tw8[s]);
-            }
+            for (int s = 0; s < 8; s++) x[s] = c_mul(rA[s][cc * CC_RS + cc_ph(16 * q + kk)], tw8[s]);
+            dft8<false>(x);
+#pragma unroll
+            for (int s = 0; s < 8; s++) bufB[kk * CC_RS + cc_ph(8 * cc + s)] = x[s];
         }
         cluster.barrier_arrive();          // split barrier: this CTA is done reading its peers' A (waited on before A is refilled)
         arrived = true;
@@ -445,7 +462,7 @@ cfe_cluster_kernel(CfePlan pl, DemodParams p, int oldest)
                 const int i_sh = (16 * q + kk) + 128 * ((k2b + 16 * i + 64) & 127);
                 yo[i] = (bigchange || i_sh < need_lo || i_sh > need_hi) ? 20.0 : y[i_sh];
             }
-            cc_fft<false>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
+            cc_fft<false, false>(bufB, tws, [&](int f, int e, double2 v) { bufB[f * CC_RS + cc_ph(e)] = v; });
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 8; i++) {
