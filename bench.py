@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-saturation", action="store_true", help="skip the 8192/16384/32768-channel saturation block (N=1, default workload)")
+    ap.add_argument("--streams", type=int, default=1, help="continuous workloads: split a GPU's channels into this many batches, each on its own CUDA stream "
+                    "(the demodulator epoch of one batch then overlaps the estimator epoch of another)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="mix16384: weak = 2048 channels per GPU, strong = 16384 in total")
     return ap.parse_args()
 
@@ -301,6 +303,7 @@ class Pipeline:
         self.layer = jaero_b200.PChannelBatch(C, m["fb"], device=local)
         if stream is not None:
             self.batch.set_stream(stream.cuda_stream)      # demod segments, estimator, frame layer, Viterbi all launch here
+        self.stream = stream
         self.stride = self.pcm.stride(0)
 
     def step_device(self):
@@ -332,12 +335,17 @@ def timed_steps(pipes, stream, steps, warmup, rank, local, dev):
     for p in pipes:
         p.batch.set_profiling(True); p.batch.get_profile()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    others = [p.stream for p in pipes if getattr(p, "stream", None) is not None and p.stream is not stream]
     torch.cuda.synchronize(); shard.barrier()
     clocks.mark_begin()
     e0.record(stream)
+    for so in others:
+        so.wait_event(e0)                 # no batch starts before e0 ...
     for _ in range(steps):
         for p in pipes:
             p.step_device()
+    for so in others:
+        ej = torch.cuda.Event(); ej.record(so); stream.wait_event(ej)   # ... and e1 fires when every batch is done
     e1.record(stream)
     torch.cuda.synchronize(); shard.barrier()
     ms_local = e0.elapsed_time(e1)
@@ -417,27 +425,40 @@ def run_continuous(a, mode):
     shard.broadcast_(torch.view_as_real(envs_t), 0)
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: handle 0 would mean "library's own stream"
     assert stream.cuda_stream != 0
-    pipe = Pipeline(mode, C, ch0, ebn0, envs_t, dev, local, stream)
+    G = max(1, a.streams)
+    if C % (32 * G):
+        raise SystemExit("bench.py: --streams must divide the channel count into multiples of 32")
+    Cg = C // G
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(G - 1)]
+    pipes = [Pipeline(mode, Cg, ch0 + g * Cg, ebn0, envs_t, dev, local, streams[g]) for g in range(G)]
+    pipe = pipes[0]
     torch.cuda.synchronize()
-    ms, ms_local, launches, profs, clk = timed_steps([pipe], stream, a.steps, a.warmup, rank, local, dev)
-    dcd, su_tot, su_ok = pipe.layer.stats()
+    ms, ms_local, launches, profs, clk = timed_steps(pipes, stream, a.steps, a.warmup, rank, local, dev)
+    st = [p.layer.stats() for p in pipes]
+    dcd, su_tot, su_ok = (np.concatenate([x[i] for x in st]) for i in range(3))
     total_samples = float(C) * STEP_SAMPLES * a.steps * world
     value = total_samples / (ms * 1e-3) / 1e6
 
     # ---- end-to-end through the C ABI with HOST buffers
     e2e = None
     if not a.no_e2e:
-        host = torch.empty((C, STEP_SAMPLES), dtype=torch.int16).pin_memory()
-        host.copy_(pipe.pcm.cpu())
-        hnp = host.numpy()
-        pch, batch = pipe.layer, pipe.batch
-        su_buf = np.empty((C, pch.su_cap, 16), dtype=np.uint8); su_cnt = np.zeros(C, dtype=np.int32)
+        hosts, bufs = [], []
+        for p in pipes:
+            host = torch.empty((Cg, STEP_SAMPLES), dtype=torch.int16).pin_memory()
+            host.copy_(p.pcm.cpu())
+            hosts.append(host.numpy())
+            bufs.append((np.empty((Cg, p.layer.su_cap, 16), dtype=np.uint8), np.zeros(Cg, dtype=np.int32)))
+        pch = pipe.layer
 
         def step_e2e():
-            batch.write(hnp)                       # H2D of the step's PCM (pinned) inside the call
-            pch.process_batch(batch)
-            pch.tick(batch)
-            return pch.read_sus_raw(su_buf, su_cnt)   # D2H of the decoded signal units + CRC flags (bulk records)
+            for p, h in zip(pipes, hosts):
+                p.batch.write(h)                   # H2D of the step's PCM (pinned) inside the call
+                p.layer.process_batch(p.batch)
+                p.layer.tick(p.batch)
+            n = 0
+            for p, (su_buf, su_cnt) in zip(pipes, bufs):
+                n += p.layer.read_sus_raw(su_buf, su_cnt)   # D2H of the decoded signal units + CRC flags (bulk records)
+            return n
         step_e2e()
         torch.cuda.synchronize(); shard.barrier()
         t0 = time.perf_counter()
@@ -451,14 +472,18 @@ def run_continuous(a, mode):
 
     tot = shard.reduce_sum([float(su_tot.sum()), float(su_ok.sum()), float(dcd.sum())], device=dev)
     peaks = load_peaks()
-    roofline = roofline_block(mode, profs[0], C, ms_local, peaks)
+    prof = {k: sum(pr[k] for pr in profs) for k in profs[0]} if G > 1 else profs[0]
+    if G > 1:
+        prof["samples"] = profs[0]["samples"]; prof["batches"] = G
+    roofline = roofline_block(mode, prof, C, ms_local, peaks)
 
     # ---- saturation: what the same pipeline reaches with more channels per GPU (the metric's 4096 leave most issue slots idle)
     saturation = None
     if rank == 0 and world == 1 and mode == "oqpsk10500" and not a.no_saturation and not a.channels:
         saturation = []
         pcm0, fcs0 = pipe.pcm, pipe.fcs
-        pipe.close()
+        for p in pipes:
+            p.close()
         for Cs in (8192, 16384, 32768):
             try:
                 ps = Pipeline(mode, Cs, 0, ebn0, envs_t, dev, local, stream)
@@ -496,7 +521,7 @@ def run_continuous(a, mode):
                 "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "channels_rt": value * 1e6 / FS,
                 "config": {"workload": m["label"], "channels_per_gpu": C, "seconds_per_step": 1.0, "ebn0_db": ebn0,
-                           "parallelism": "channels sharded x%d, no data-path collective" % world,
+                           "parallelism": "channels sharded x%d GPUs x %d concurrent batches per GPU, no data-path collective" % (world, G),
                            "l2": "inputs (%.0f MB int16 + %.1f GB of ring state per step) exceed the 126 MB L2" % (C * STEP_SAMPLES * 2 / 1e6, C * 3.4e-3)},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_base,
                 "decode": {"su_total": tot[0], "su_crc_ok": tot[1], "channels_with_dcd": tot[2]}}
@@ -504,7 +529,8 @@ def run_continuous(a, mode):
             line["saturation"] = saturation
         print(json.dumps(line))
     if pipe is not None:
-        pipe.close()
+        for p in pipes:
+            p.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier(); dist.destroy_process_group()

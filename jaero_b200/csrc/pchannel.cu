@@ -21,11 +21,11 @@
 
 namespace jb {
 
-__constant__ uint8_t c_scr[5000];          // AeroLScrambler::pre_state
+__device__ uint8_t g_scr[5000];            // AeroLScrambler::pre_state (global, not constant: it is indexed per lane)
 
 int pchan_set_scrambler(const uint8_t *seq)
 {
-    JB_CUDA(cudaMemcpyToSymbol(c_scr, seq, 5000));
+    JB_CUDA(cudaMemcpyToSymbol(g_scr, seq, 5000));
     return 0;
 }
 
@@ -236,69 +236,84 @@ pchan_frame_kernel(PChanParams pp, const int16_t *__restrict__ soft, const int *
     }
 }
 
-__global__ void __launch_bounds__(64)
+// One warp per channel. The delay line, the scrambler and the byte packing are position-wise, so they run 32 decoded bits
+// at a time (the delay line is far longer than 32, so a round's reads never see the round's own writes; the packed bytes are
+// the ballot of the descrambled bits); the CRCs of a frame's signal units are computed one unit per lane, and only the
+// DCD countdown and the output-ring bookkeeping walk the units in order.
+__global__ void __launch_bounds__(128)
 pchan_su_kernel(PChanParams pp, int *__restrict__ demod_dcd)
 {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned FULLM = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ch >= pp.n_channels) return;
     PChanState s = pp.state[ch];
-    const int block_len = pp.block_len, half = block_len / 2, QD = pp.queue;
-    uint8_t *dl2 = pp.dl2 + (size_t)ch * pp.dl2_len;
+    const int block_len = pp.block_len, half = block_len / 2, QD = pp.queue, L = pp.dl2_len;
+    uint8_t *dl2 = pp.dl2 + (size_t)ch * L;
     uint8_t *info = pp.infofield + (size_t)ch * pp.info_cap;
     for (int q = 0; q < s.blocks_ready; q++) {
         const PChanBlockMeta m = pp.meta[(size_t)ch * QD + q];
         const uint8_t *dec = pp.decoded + ((size_t)ch * QD + q) * half;
-        int charptr = 0; unsigned ch8 = 0; int outb = m.info_off;
-        // DelayLine::update (aerol.h:465-473) writes slot ptr and returns slot ptr+1, a value stored dl2_len-1 steps earlier:
-        // groups of 16 steps read their 16 outputs and 16 inputs first (independent loads), then write
-        for (int h0 = 0; h0 < m.n_valid; h0 += 16) {
-            const int cnt = min(16, m.n_valid - h0);
-            uint8_t oldv[16], newv[16];
-            {
-                int rp = s.dl2_ptr + 1; if (rp >= pp.dl2_len) rp = 0;
-#pragma unroll
-                for (int k = 0; k < 16; k++) if (k < cnt) { oldv[k] = dl2[rp]; newv[k] = dec[h0 + k]; rp++; if (rp >= pp.dl2_len) rp = 0; }
-            }
-#pragma unroll
-            for (int k = 0; k < 16; k++) if (k < cnt) {
-                dl2[s.dl2_ptr] = newv[k]; s.dl2_ptr++; if (s.dl2_ptr >= pp.dl2_len) s.dl2_ptr = 0;
-                int b = oldv[k];
-                b ^= c_scr[m.scr_pos + h0 + k];                              // aerol.h:421-429
-                ch8 |= (unsigned)b * 128u;                                   // aerol.cpp:1568-1580
-                charptr++; charptr %= 8;
-                if (charptr == 0) { if (outb < pp.info_cap) info[outb] = (uint8_t)ch8; outb++; ch8 = 0; } else ch8 >>= 1;
-            }
+        int outb = m.info_off;
+        // DelayLine::update (aerol.h:465-473) writes slot ptr and returns slot ptr+1, a value stored dl2_len-1 steps earlier
+        for (int h0 = 0; h0 < m.n_valid; h0 += 32) {
+            const int cnt = min(32, m.n_valid - h0);
+            int rp = s.dl2_ptr + 1 + lane; if (rp >= L) rp -= L;
+            int wp = s.dl2_ptr + lane; if (wp >= L) wp -= L;
+            int b = 0; uint8_t newv = 0;
+            if (lane < cnt) { b = dl2[rp]; newv = dec[h0 + lane]; b ^= g_scr[m.scr_pos + h0 + lane]; }   // aerol.h:421-429
+            __syncwarp();
+            if (lane < cnt) dl2[wp] = newv;
+            __syncwarp();
+            s.dl2_ptr += cnt; if (s.dl2_ptr >= L) s.dl2_ptr -= L;
+            // LSB-first bytes (aerol.cpp:1568-1580): a trailing partial byte is dropped, as the reference drops ch8 at the next block
+            const unsigned word = __ballot_sync(FULLM, b & 1);
+            const int nbytes = cnt >> 3;
+            if (lane < nbytes && outb + lane < pp.info_cap) info[outb + lane] = (uint8_t)(word >> (8 * lane));
+            outb += nbytes;
         }
         if (m.frame_done) {                                                  // :1582-1610
+            __syncwarp();
             const int nsu = outb / 12;
-            for (int k = 0; k < nsu; k++) {
-                const uint8_t *su = info + k * 12;
-                unsigned crc = 0xFFFF;                                       // AeroLcrc16::calcusingbytes (aerol.h:334-362)
-                for (int i = 0; i < 10; i++) {
-                    unsigned byte = su[i];
-                    for (int t = 0; t < 8; t++) {
-                        const unsigned mb = byte & 1u; byte >>= 1;
-                        const unsigned cb = crc & 1u; crc >>= 1;
-                        if (cb ^ mb) crc ^= 0x8408u;
+            for (int k0 = 0; k0 < nsu; k0 += 32) {
+                const int k = k0 + lane;
+                int ok = 0;
+                if (k < nsu) {
+                    const uint8_t *su = info + k * 12;
+                    unsigned crc = 0xFFFF;                                   // AeroLcrc16::calcusingbytes (aerol.h:334-362)
+                    int tsum = 0;
+                    for (int i = 0; i < 10; i++) {
+                        unsigned byte = su[i];
+                        tsum += (int)byte;
+                        for (int t = 0; t < 8; t++) {
+                            const unsigned mb = byte & 1u; byte >>= 1;
+                            const unsigned cb = crc & 1u; crc >>= 1;
+                            if (cb ^ mb) crc ^= 0x8408u;
+                        }
                     }
+                    unsigned crc_calc = (~crc) & 0xFFFFu;
+                    const unsigned crc_rec = ((unsigned)su[11] << 8) | su[10];
+                    if ((!crc_rec) && (crc_calc != crc_rec) && tsum == 0) crc_calc = 0;
+                    ok = (crc_calc == crc_rec);
                 }
-                unsigned crc_calc = (~crc) & 0xFFFFu;
-                const unsigned crc_rec = ((unsigned)su[11] << 8) | su[10];
-                if ((!crc_rec) && (crc_calc != crc_rec)) {
-                    int tsum = 0; for (int i = 0; i < 10; i++) tsum += su[i];
-                    if (tsum == 0) crc_calc = 0;
+                const int gcnt = min(32, nsu - k0);
+                for (int j = 0; j < gcnt; j++) {
+                    const int okj = __shfl_sync(FULLM, ok, j);
+                    if (okj) { if (s.datacdcountdown < 12) s.datacdcountdown += 2; }
+                    else { if (s.datacdcountdown > 0) s.datacdcountdown -= 3; }
+                    if (!s.datacd && s.datacdcountdown > 2) { s.datacd = 1; s.dcd_rises++; }
+                    if (s.su_count < pp.su_cap) {
+                        uint8_t *o = pp.su_out + ((size_t)ch * pp.su_cap + s.su_count) * 16;
+                        const uint8_t *su = info + (k0 + j) * 12;
+                        if (lane < 12) o[lane] = su[lane];
+                        else if (lane == 12) o[12] = (uint8_t)okj;
+                        else if (lane == 13) o[13] = (uint8_t)(k0 + j);
+                        else if (lane == 14) o[14] = (uint8_t)(m.frame_index & 255);
+                        else if (lane == 15) o[15] = (uint8_t)((m.frame_index >> 8) & 255);
+                        s.su_count++;
+                    } else s.queue_overflow = 1;
+                    s.su_total++; s.su_ok += okj;
                 }
-                const int ok = (crc_calc == crc_rec);
-                if (ok) { if (s.datacdcountdown < 12) s.datacdcountdown += 2; }
-                else { if (s.datacdcountdown > 0) s.datacdcountdown -= 3; }
-                if (!s.datacd && s.datacdcountdown > 2) { s.datacd = 1; s.dcd_rises++; }
-                if (s.su_count < pp.su_cap) {
-                    uint8_t *o = pp.su_out + ((size_t)ch * pp.su_cap + s.su_count) * 16;
-                    for (int i = 0; i < 12; i++) o[i] = su[i];
-                    o[12] = (uint8_t)ok; o[13] = (uint8_t)k; o[14] = (uint8_t)(m.frame_index & 255); o[15] = (uint8_t)((m.frame_index >> 8) & 255);
-                    s.su_count++;
-                } else s.queue_overflow = 1;
-                s.su_total++; s.su_ok += ok;
             }
         }
     }
@@ -308,13 +323,15 @@ pchan_su_kernel(PChanParams pp, int *__restrict__ demod_dcd)
         uint8_t *dstb = pp.blocks + ((size_t)ch * QD) * block_len;
         if ((block_len & 15) == 0) {
             const int4 *s4 = reinterpret_cast<const int4 *>(srcb); int4 *d4 = reinterpret_cast<int4 *>(dstb);
-            for (int k = 0; k < block_len / 16; k++) d4[k] = s4[k];
-        } else for (int k = 0; k < block_len; k++) dstb[k] = srcb[k];
+            for (int k = lane; k < block_len / 16; k += 32) d4[k] = s4[k];
+        } else for (int k = lane; k < block_len; k += 32) dstb[k] = srcb[k];
         s.carry_slot = 0;
     }
     s.blocks_ready = 0;
-    pp.state[ch] = s;
-    if (demod_dcd) demod_dcd[ch] = s.datacd;
+    if (lane == 0) {
+        pp.state[ch] = s;
+        if (demod_dcd) demod_dcd[ch] = s.datacd;
+    }
 }
 
 // AeroL::updateDCD (aerol.cpp:1109-1122), the reference's 1 s QTimer
@@ -373,7 +390,6 @@ int pchan_process(const PChanParams &pp, const int16_t *d_soft, const int *d_sof
                   uint8_t *vit_overlap, int *vit_overlap_len, int *vit_renorm, int *vit_valid, int max_queue, cudaStream_t st,
                   long long *launches, const int *lost_n, const int *lost_pos, size_t lost_pitch)
 {
-    const int grid = (pp.n_channels + 63) / 64;
     pchan_frame_kernel<<<(pp.n_channels + 3) / 4, 128, 0, st>>>(pp, d_soft, d_soft_count, soft_cap, demod_dcd, lost_n, lost_pos, lost_pitch);
     JB_CUDA(cudaGetLastError());
     (*launches)++;
@@ -383,7 +399,7 @@ int pchan_process(const PChanParams &pp, const int16_t *d_soft, const int *d_sof
                            (size_t)pp.queue * pp.block_len, (size_t)pp.queue * (pp.block_len / 2), pp.ready, q)) return -1;
         (*launches)++;
     }
-    pchan_su_kernel<<<grid, 64, 0, st>>>(pp, demod_dcd);
+    pchan_su_kernel<<<(pp.n_channels + 3) / 4, 128, 0, st>>>(pp, demod_dcd);
     JB_CUDA(cudaGetLastError());
     (*launches)++;
     return 0;
