@@ -232,7 +232,28 @@ cfe_search_kernel(CfePlan pl, DemodParams p)
     const double *y = pl.y + (size_t)ch * pl.nfft;
     const int N = pl.nfft, epb = pl.expectedpeakbin;
     double best = 0.0; int besti = 0x7fffffff;
-    for (int i = pl.lo + lane; i < pl.hi; i += 32) {
+    int i0 = pl.lo;
+    if (pl.lo - epb - 1 >= 0 && pl.hi + epb + 1 < N) {
+        // every index of the fold is inside the spectrum (true for all four rates): no per-bin range tests, and four
+        // candidate bins per lane and round, their 24 loads requested together (the loop is load-latency bound otherwise)
+        for (; i0 + 128 <= pl.hi; i0 += 128) {
+            double a[4][3], c[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + lane + 32 * u;
+#pragma unroll
+                for (int j = -1; j <= 1; j++) { a[u][j + 1] = y[i - epb - j]; c[u][j + 1] = y[i + epb + j]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                double val = 0;
+#pragma unroll
+                for (int j = 0; j < 3; j++) val += (a[u][j] + c[u][j]);
+                if (val > best) { best = val; besti = i0 + lane + 32 * u; }   // ascending i per lane: the first maximum wins
+            }
+        }
+    }
+    for (int i = i0 + lane; i < pl.hi; i += 32) {
         if ((i < 0) || (i >= N)) continue;
         double val = 0;
         for (int j = -1; j <= 1; j++) {
