@@ -399,12 +399,13 @@ int batch_regroup_by_phase(jaero_batch *b, bool force)
     JB_CUDA(cudaStreamSynchronize(b->stream));
     b->launches++;
     // Is the present seating still coherent? A CTA is coherent when the carrier-update strobes of its channels fall within 1.5
-    // samples of each other (circularly, period = two strobe intervals). Moving the rings costs ~10 ms per 4096 channels, so the
-    // seating is only changed when more than a tenth of the CTAs have drifted apart (never, for transmitters on one clock).
+    // samples of each other (circularly, period = two strobe intervals). Moving the rings costs ~30 ms per 4096 channels, so the
+    // seating is only changed when more than a quarter of the CTAs have drifted apart (never, for transmitters on one clock).
     if (!force) {
         const double period = 2.0 * p.Fs / p.fb;                                     // keys are in [0, 2*Fs/fb)
+        static const double thr = getenv("JAERO_REGROUP_SPREAD") ? atof(getenv("JAERO_REGROUP_SPREAD")) : 1.5;
         int bad = 0, ctas = 0;
-        std::vector<double> ks;
+        std::vector<double> ks, spreads;
         std::vector<std::vector<int>> members(cp / 32);
         for (int c = 0; c < C; c++) members[b->slot_of[c] >> 5].push_back(c);
         for (auto &m : members) {
@@ -415,9 +416,15 @@ int batch_regroup_by_phase(jaero_batch *b, bool force)
             std::sort(ks.begin(), ks.end());
             double gap = ks.front() + period - ks.back();
             for (size_t i = 1; i < ks.size(); i++) gap = std::max(gap, ks[i] - ks[i - 1]);
-            if (period - gap > 1.5) bad++;
+            spreads.push_back(period - gap);
+            if (period - gap > thr) bad++;
         }
-        if (bad * 10 <= ctas) return 0;
+        if (getenv("JAERO_DEBUG") && !spreads.empty()) {
+            std::sort(spreads.begin(), spreads.end());
+            fprintf(stderr, "[jaero_b200] seating check at epoch %lld: %d of %d CTAs spread > %.1f samples (median %.2f, p90 %.2f, max %.2f)\n", b->epochs, bad, ctas, thr,
+                    spreads[spreads.size() / 2], spreads[spreads.size() * 9 / 10], spreads.back());
+        }
+        if (bad * 4 <= ctas) return 0;
     }
     std::vector<int> order(C);
     for (int c = 0; c < C; c++) order[c] = c;
@@ -655,7 +662,8 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
     b->d_chan_of = 0; b->d_keys = 0; b->h_keys = 0; b->d_ring_scratch = 0; b->ring_scratch_count = 0; b->epochs = 0; b->regroups = 0;
     b->regroup_every = 0; b->next_regroup = 0;
     if (s->kind == JAERO_KIND_OQPSK && s->fb > 8400 && b->use_pipe && !s->cpu_reduce) {
-        // the pipelined kernel seats channels by symbol-timing phase: first after 2.4 s of signal (loops locked), a check 2.7 s later,
+        // the pipelined kernel seats channels by symbol-timing phase: first after 2.9 s of signal (the timing loops' phases are final
+        // to a few hundredths of a sample by then; at 2 s they are not), a check 2.7 s later (a no-op unless they moved),
         // then every JAERO_REGROUP_EPOCHS estimator epochs (default 128 = 11 s; 0 = never: symbol clocks of different transmitters
         // drift by a sample in minutes, not seconds)
         const char *e = getenv("JAERO_REGROUP_EPOCHS");
@@ -667,7 +675,7 @@ int jaero_batch_create(const jaero_settings *s, int n_channels, const double *fr
         for (size_t c = 0; c < cp; c++) { ident[c] = (int)c; b->slot_of[c] = (int)c; }
         JB_CUDA(cudaMemcpy(b->d_chan_of, ident.data(), cp * sizeof(int), cudaMemcpyHostToDevice));
         p.chan_of = b->d_chan_of;
-        b->next_regroup = b->regroup_every > 0 ? 28 : -1;
+        b->next_regroup = b->regroup_every > 0 ? 34 : -1;
     }
     JB_CUDA(cudaMallocHost(&b->h_ints, (size_t)I_COUNT * cp * sizeof(int)));
     JB_CUDA(cudaMallocHost(&b->h_dbls, (size_t)D_COUNT * cp * sizeof(double)));
@@ -784,10 +792,6 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
             }
         }
     }
-    if (b->regroup_every > 0 && b->next_regroup >= 0 && b->epochs >= b->next_regroup) {
-        if (batch_regroup_by_phase(b, false)) return JAERO_E_CUDA;
-        b->next_regroup = b->epochs + (b->epochs < 64 ? 32 : b->regroup_every);
-    }
     peak_kernel<<<(p.n_channels + 3) / 4, 128, 0, b->stream>>>(p, d_pcm, stride, (int)n);
     JB_CUDA(cudaGetLastError());
     b->launches++;
@@ -868,6 +872,12 @@ int jaero_batch_write_device(jaero_batch *b, const int16_t *d_pcm, size_t n, siz
                 cfe_in_flight = true;
             }
             b->epochs++;
+            // seating check between two launches (the segment kernel has written its ring tiles back; per-channel state is indexed
+            // by channel, only the ring rows and chan_of move)
+            if (b->regroup_every > 0 && b->next_regroup >= 0 && b->epochs >= b->next_regroup) {
+                if (batch_regroup_by_phase(b, false)) return JAERO_E_CUDA;
+                b->next_regroup = b->epochs + (b->epochs < 64 ? std::min(32, b->regroup_every) : b->regroup_every);
+            }
             cc = 0;                                                // :426
             seg_start = i; resume = true; seg_bb = bbp; seg_cc = 0;
         }

@@ -369,13 +369,14 @@ def test_regrouping_never_changes_results(golden):
         os.environ["JAERO_REGROUP_EPOCHS"] = "0" if mode == "fixed" else "24"
         b = jb.DemodBatch("oqpsk", C, **kw)
         acc = [[] for _ in range(C)]
-        for k, a in enumerate(range(0, pcm2.shape[1], 7000)):
+        step = 90000 if mode == "long_writes" else 7000                 # long_writes: the scheduled seating (epoch 34) falls between two launches inside the second call
+        for k, a in enumerate(range(0, pcm2.shape[1], step)):
             if mode == "random" and k % 3 == 1:
                 b.regroup(rng.permutation(C))
             if mode == "phase" and k == 20:
                 b.regroup()
-            b.write(pcm2[:, a:a + 7000])
-            if k % 4 == 3:
+            b.write(pcm2[:, a:a + step])
+            if k % 4 == 3 or mode == "long_writes":
                 for c, s in enumerate(b.read_softbits()):
                     acc[c].append(s)
         for c, s in enumerate(b.read_softbits()):
@@ -387,7 +388,7 @@ def test_regrouping_never_changes_results(golden):
     import os
     try:
         ref, st_ref = run("fixed")
-        for mode in ("random", "phase"):
+        for mode in ("random", "phase", "long_writes"):
             got, st = run(mode)
             for c in range(C):
                 assert np.array_equal(got[c], ref[c]), (mode, c)
