@@ -297,7 +297,7 @@ __device__ __forceinline__ int cc_ph(int e) { return e + (e >> 3); }          //
 
 // log10 for finite x >= 1 (the argument is max(|X|^2, 1)): fdlibm's log kernel — x = 2^k m, m in [sqrt(1/2), sqrt(2)),
 // s = (m-1)/(m+1), degree-14 polynomial in s — with the quotient by div_fast and the final scaling split as in fdlibm's
-// e_log10.c. Within 2 ulp of glibc's log10 on 5 M arguments in [1, 1e40] (host twin of this function; the library call it
+// e_log10.c. Within 2 ulp of glibc's log10 on 5 M arguments in [1, 1e40] (host twin: tools/micro/log10_test.c; the library call it
 // replaces is itself only specified to 1 ulp), about half the instructions; the smoothed spectrum feeds an arg-max over
 // sums of six bins, where differences of that size cannot matter unless the library's own rounding would.
 __device__ __forceinline__ double log10_ge1(double x)
