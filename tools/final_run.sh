@@ -1,3 +1,4 @@
+# Round-end evidence run (one GPU): full GPU test suite, the four workloads, the ncu launch list and the --set full captures that profiles/r02_* are made from
 set -u
 O=gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -8 > $O/r2_final_gputest.log
@@ -11,3 +12,4 @@ ncu --clock-control none --set full --import-source on -k regex:oqpsk_pipe_kerne
 ncu --clock-control none --set full --import-source on -k regex:pchan_frame_kernel -s 3 -c 1 -f -o $O/r02_pchan_frame_kernel $B > $O/ncu_3.log 2>&1
 ncu --clock-control none --set full --import-source on -k regex:pchan_su_kernel -s 3 -c 1 -f -o $O/r02_pchan_su_kernel $B > $O/ncu_4.log 2>&1
 ncu --clock-control none --set full --import-source on -k regex:viterbi_k7_kernel -s 18 -c 1 -f -o $O/r02_viterbi_k7_kernel $B > $O/ncu_5.log 2>&1
+ncu --clock-control none --set full --import-source on -k regex:cfe_cluster_kernel -s 30 -c 1 -f -o $O/r02_cfe_cluster_kernel $B > $O/ncu_6.log 2>&1
